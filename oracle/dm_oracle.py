@@ -1,0 +1,426 @@
+# -*- coding: utf-8 -*-
+"""
+CPU oracle for the DeepMatching-for-stereo hot path  --  TEST INFRASTRUCTURE ONLY.
+
+This module is a vectorised numpy restatement of the reference algorithm.  It is the
+checker the CUDA path is compared against.  Only ``tests/``, ``__graft_entry__.smoke()``
+and the ``cpu_baseline`` / ``--impl reference`` legs of ``bench.py`` may import it; the
+product package (``deepmatching_stereo_matching_b200``) never does and has no CPU
+fallback.
+
+Parity pin: the reference ships no tests or golden vectors, so the
+oracle is pinned against outputs of the *live, unmodified* reference generated in the
+build container by ``tests/golden/make_golden.py`` (committed ``tests/golden/*.npz``)
+and, where OpenCV is importable, directly against ``cv2.matchTemplate``.
+
+Every function cites the reference lines it restates (paths relative to the reference
+repository root).  The correlation arithmetic itself lives in a third-party dependency
+of the reference -- OpenCV ``cv2.matchTemplate`` (pinned ``opencv==3.4.1`` in
+``environment.yml:7``; 4.13.0 in this image), file
+``modules/imgproc/src/templmatch.cpp::common_matchTemplate`` -- which is restated here
+from its published algorithm: exact cross-correlation, integral-image window sums in
+float64, the ``|num| < t`` / ``1.125 t`` clamp rule, float32 result.
+"""
+
+import numpy as np
+
+LAM = 1.4                     # misc/Correlation_map.py:41  (self.lam)
+NEAR_ZERO = 0.0001            # misc/Matching.py:74
+
+TM_CCOEFF = 4                 # cv2.TM_CCOEFF
+TM_CCOEFF_NORMED = 5          # cv2.TM_CCOEFF_NORMED
+FEATURE_NAMES = {'cv2.TM_CCOEFF_NORMED': TM_CCOEFF_NORMED, 'cv2.TM_CCOEFF': TM_CCOEFF}  # misc/Feature_value.py:24
+
+_FLT_EPSILON = float(np.finfo(np.float32).eps)
+_DBL_EPSILON = float(np.finfo(np.float64).eps)
+
+
+# --------------------------------------------------------------------------------------
+# descriptors
+# --------------------------------------------------------------------------------------
+def atomic_patches(img, ws):
+    """misc/Correlation_map.py:51-67 -- every ws x ws window, (T0,T1,ws,ws) uint8."""
+    img = np.asarray(img)
+    win = np.lib.stride_tricks.sliding_window_view(img, (ws, ws))
+    return np.ascontiguousarray(win).astype(np.uint8)
+
+
+def _im2col(img, ws):
+    """(T0*T1, ws*ws) float64 matrix of the windows of ``img`` (row-major positions)."""
+    win = np.lib.stride_tricks.sliding_window_view(np.asarray(img), (ws, ws))
+    t0, t1 = win.shape[:2]
+    return win.reshape(t0 * t1, ws * ws).astype(np.float64), (t0, t1)
+
+
+# --------------------------------------------------------------------------------------
+# correlation  (OpenCV matchTemplate restated)  +  min-max
+# --------------------------------------------------------------------------------------
+def match_template_matrix(img, template, ws, method=TM_CCOEFF_NORMED):
+    """All patches of ``img`` against all windows of ``template`` at once.
+
+    Restates ``cv2.matchTemplate(patch, template, method)`` (call site
+    misc/Feature_value.py:41) for every atomic patch: returns a float32 matrix
+    ``R[p, q]`` with p = patch index in ``img`` and q = window index in ``template``.
+    OpenCV algorithm (templmatch.cpp::common_matchTemplate): ``num = sum(T*I) -
+    mean(T)*sum(I)``; for the normed variant ``t = sqrt(max(sum(I^2) - sum(I)^2/K, 0)) *
+    sqrt(K)*std(T)`` and ``num/t`` if ``|num| < t``, ``+-1`` if ``|num| < 1.125 t``, else
+    0; a flat template yields an all-ones map; result stored as float32.
+    """
+    a1, _ = _im2col(img, ws)
+    a2, _ = _im2col(template, ws)
+    k = float(ws * ws)
+    inv_area = 1.0 / k
+    cc = a1 @ a2.T                                   # exact: integer sums < 2^53
+    s1 = a1.sum(1)
+    q1 = (a1 * a1).sum(1)
+    s2 = a2.sum(1)
+    q2 = (a2 * a2).sum(1)
+    templ_mean = s1 * inv_area
+    num = cc - templ_mean[:, None] * s2[None, :]
+    if method == TM_CCOEFF:
+        return num.astype(np.float32)
+    # meanStdDev of the template (population std)
+    templ_var = np.maximum(q1 * inv_area - templ_mean * templ_mean, 0.0)
+    templ_sdv = np.sqrt(templ_var)
+    templ_norm2 = templ_sdv * templ_sdv
+    flat_templ = templ_norm2 < _DBL_EPSILON
+    templ_norm = np.sqrt(templ_norm2) / np.sqrt(inv_area)
+    wnd_mean2 = s2 * s2 * inv_area
+    wnd_sum2 = q2
+    diff2 = np.maximum(wnd_sum2 - wnd_mean2, 0.0)
+    t_w = np.where(diff2 <= np.minimum(0.5, 10.0 * _FLT_EPSILON * wnd_sum2), 0.0, np.sqrt(diff2))
+    t = templ_norm[:, None] * t_w[None, :]
+    absn = np.abs(num)
+    with np.errstate(divide='ignore', invalid='ignore'):
+        res = np.where(absn < t, num / t, np.where(absn < t * 1.125, np.sign(num), 0.0))
+    res[flat_templ, :] = 1.0
+    return res.astype(np.float32)
+
+
+def min_max(x):
+    """misc/Feature_value.py:32-37 -- (x - min) / (max - min) in the array's dtype."""
+    with np.errstate(divide='ignore', invalid='ignore'):
+        mn = x.min(axis=-1, keepdims=True)
+        mx = x.max(axis=-1, keepdims=True)
+        return (x - mn) / (mx - mn)
+
+
+def feature_value(patch, image, method=TM_CCOEFF_NORMED):
+    """misc/Feature_value.py:39-43 for one patch: float32 map, min-maxed over the map.
+
+    ``patch`` and ``image`` are any sizes with patch <= image (for_igarss/cor_map.py:33-35).
+    """
+    patch = np.asarray(patch)
+    image = np.asarray(image)
+    ph, pw = patch.shape
+    win = np.lib.stride_tricks.sliding_window_view(image, (ph, pw))
+    oh, ow = win.shape[:2]
+    a2 = win.reshape(oh * ow, ph * pw).astype(np.float64)
+    a1 = patch.reshape(1, ph * pw).astype(np.float64)
+    k = float(ph * pw)
+    inv_area = 1.0 / k
+    cc = a1 @ a2.T
+    s1 = a1.sum(1); q1 = (a1 * a1).sum(1); s2 = a2.sum(1); q2 = (a2 * a2).sum(1)
+    templ_mean = s1 * inv_area
+    num = cc - templ_mean[:, None] * s2[None, :]
+    if method == TM_CCOEFF_NORMED:
+        templ_sdv = np.sqrt(np.maximum(q1 * inv_area - templ_mean * templ_mean, 0.0))
+        templ_norm2 = templ_sdv * templ_sdv
+        if templ_norm2[0] < _DBL_EPSILON:
+            res = np.ones_like(num)
+        else:
+            templ_norm = np.sqrt(templ_norm2) / np.sqrt(inv_area)
+            diff2 = np.maximum(q2 - s2 * s2 * inv_area, 0.0)
+            t_w = np.where(diff2 <= np.minimum(0.5, 10.0 * _FLT_EPSILON * q2), 0.0, np.sqrt(diff2))
+            t = templ_norm[:, None] * t_w[None, :]
+            absn = np.abs(num)
+            with np.errstate(divide='ignore', invalid='ignore'):
+                res = np.where(absn < t, num / t, np.where(absn < t * 1.125, np.sign(num), 0.0))
+    else:
+        res = num
+    res = res.astype(np.float32).reshape(oh, ow)
+    return min_max(res.reshape(1, -1)).reshape(oh, ow)
+
+
+def initial_co_map(img, template, ws, method=TM_CCOEFF_NORMED):
+    """misc/Correlation_map.py:69-87 -- 4-D (T0,T1,T0,T1) float64 holding float32 values,
+    each [i,j] slice independently min-maxed (misc/Feature_value.py:42)."""
+    raw = match_template_matrix(img, template, ws, method)          # float32 [P,Q]
+    t0 = img.shape[0] - ws + 1
+    t1 = img.shape[1] - ws + 1
+    norm = min_max(raw)                                              # float32 arithmetic
+    return norm.astype(np.float64).reshape(t0, t1, t0, t1)
+
+
+# --------------------------------------------------------------------------------------
+# pyramid
+# --------------------------------------------------------------------------------------
+def rectify(m, lam=LAM):
+    """misc/Correlation_map.py:158-159."""
+    return m ** lam
+
+
+def maxpool_3s2p1(m):
+    """torch.nn.MaxPool2d(3, 2, padding=1) over the last two axes
+    (misc/Correlation_map.py:176-184, used :100-103).  -inf padding, NaN propagates."""
+    c, d = m.shape[-2:]
+    oc, od = (c - 1) // 2 + 1, (d - 1) // 2 + 1
+    pad = np.full(m.shape[:-2] + (c + 2, d + 2), -np.inf, dtype=m.dtype)
+    pad[..., 1:c + 1, 1:d + 1] = m
+    out = None
+    nan = None
+    for dy in range(3):
+        for dx in range(3):
+            v = pad[..., dy:dy + 2 * oc:2, dx:dx + 2 * od:2][..., :oc, :od]
+            nan = np.isnan(v) if nan is None else (nan | np.isnan(v))
+            out = v.copy() if out is None else np.fmax(out, v)
+    if nan.any():
+        out[nan] = np.nan
+    return out
+
+
+def aggregate(m):
+    """misc/Correlation_map.py:89-130 -- max-pool every slice, then average the four
+    children of each parent without any shift; add order ((ul+ur)+ll)+lr, then /4."""
+    res = maxpool_3s2p1(m)
+    l1, l2 = m.shape[2] // 2, m.shape[3] // 2
+    ul = res[0:2 * l1:2, 0:2 * l2:2]
+    ur = res[0:2 * l1:2, 1:2 * l2:2]
+    ll = res[1:2 * l1:2, 0:2 * l2:2]
+    lr = res[1:2 * l1:2, 1:2 * l2:2]
+    return (ul + ur + ll + lr) / 4
+
+
+def pyramid(co_map, lam=LAM):
+    """misc/Correlation_map.py:132-156 -> (co_map_list, iteration, N_map)."""
+    lst = []
+    cur = rectify(co_map, lam)
+    lst.append(cur)
+    n = 1
+    iteration = 1
+    while n < min(co_map.shape[:2]):
+        cur = rectify(aggregate(cur), lam)
+        lst.append(cur)
+        n *= 2
+        iteration += 1
+    return lst, iteration, n
+
+
+def correlation_map(img, template, ws, method=TM_CCOEFF_NORMED):
+    """misc/Correlation_map.py:161-173 -> dict(co_map, co_map_list, iteration, N_map)."""
+    co = initial_co_map(img, template, ws, method)
+    lst, it, n = pyramid(co)
+    return dict(co_map=co, co_map_list=lst, iteration=it, N_map=n)
+
+
+# --------------------------------------------------------------------------------------
+# backtracking
+# --------------------------------------------------------------------------------------
+def _near_match_vec(level, p0, p1, d0, d1):
+    """misc/Matching.py:58-78 vectorised over arrays of children.
+
+    level: (A,B,C,D); p*: patch coordinates; d*: p_dot.  Returns (row, col, score) with
+    first-max row-major tie-break over the zero-padded 3x3 window, NaN winning like
+    np.argmax, and the ``max < 1e-4 -> centre`` rule.  Arithmetic in level.dtype.
+    """
+    a, b, c, d = level.shape
+    pad = np.zeros((a, b, c + 2, d + 2), dtype=level.dtype)
+    pad[:, :, 1:c + 1, 1:d + 1] = level
+    wins = np.empty(p0.shape + (9,), dtype=level.dtype)
+    n = 0
+    for dy in range(3):
+        for dx in range(3):
+            wins[..., n] = pad[p0, p1, d0 + dy, d1 + dx]
+            n += 1
+    m = np.argmax(wins, axis=-1)                     # first max; first NaN if any
+    mx = np.max(wins, axis=-1)                       # NaN propagates
+    with np.errstate(invalid='ignore'):
+        small = mx < level.dtype.type(NEAR_ZERO)
+    m = np.where(small, 4, m)
+    m0, m1 = m // 3, m % 3
+    centre = pad[p0, p1, d0 + 1, d1 + 1]
+    best = np.take_along_axis(wins, m[..., None], axis=-1)[..., 0]
+    score = best + centre
+    return d0 + m0 - 1, d1 + m1 - 1, score
+
+
+def initial_move_map(top):
+    """misc/Matching.py:80-96 -- (3,a,b) float64 at the pyramid top."""
+    a, b = top.shape[:2]
+    ii, jj = np.meshgrid(np.arange(a), np.arange(b), indexing='ij')
+    r, c, s = _near_match_vec(top, ii, jj, ii, jj)
+    out = np.zeros((3, a, b))
+    out[0], out[1], out[2] = r, c, s
+    return out
+
+
+def backtrack_level(level, parent_map):
+    """misc/Matching.py:98-139 (filtering off) -- (3,h,w) -> (3,2h,2w)."""
+    h, w = parent_map.shape[1:]
+    ii, jj = np.meshgrid(np.arange(2 * h), np.arange(2 * w), indexing='ij')
+    pd0 = (parent_map[0] * 2).astype('int64')
+    pd1 = (parent_map[1] * 2).astype('int64')
+    d0 = pd0[ii // 2, jj // 2] + (ii & 1)
+    d1 = pd1[ii // 2, jj // 2] + (jj & 1)
+    r, c, s = _near_match_vec(level, ii, jj, d0, d1)
+    out = np.empty((3, 2 * h, 2 * w))
+    out[0], out[1], out[2] = r, c, s
+    return out
+
+
+def sub_pix(l0, mp):
+    """misc/Matching.py:165-209 -- parabola fit on level 0; wraps at index -1, skips at
+    the upper edge (IndexError swallowed); arithmetic in l0.dtype, result float64."""
+    t0, t1, c, d = l0.shape
+    out = mp.copy()
+    ii, jj = np.meshgrid(np.arange(t0), np.arange(t1), indexing='ij')
+    c0 = mp[0].astype('int64')
+    c1 = mp[1].astype('int64')
+    two = l0.dtype.type(2)
+
+    def fit(r0, r1, r_):
+        with np.errstate(divide='ignore', invalid='ignore'):
+            ok = (r0 > r1) & (r0 > r_)
+            diff = -(r1 - r_) / (two * (r1 + r_ - two * r0))
+        return np.where(ok, diff, 0).astype(np.float64)
+
+    r0 = l0[ii, jj, c0, c1]
+    # rows
+    valid = (c0 + 1) < c
+    r1 = l0[ii, jj, np.minimum(c0 + 1, c - 1), c1]
+    r_ = l0[ii, jj, (c0 - 1) % c, c1]
+    d_x = ii - mp[0]
+    out[0] = np.where(valid, ii - d_x + fit(r0, r1, r_), ii - d_x)
+    # cols
+    valid = (c1 + 1) < d
+    r1 = l0[ii, jj, c0, np.minimum(c1 + 1, d - 1)]
+    r_ = l0[ii, jj, c0, (c1 - 1) % d]
+    d_y = jj - mp[1]
+    out[1] = np.where(valid, jj - d_y + fit(r0, r1, r_), jj - d_y)
+    return out
+
+
+def matching(co_map_list, sub_pix_on=True, return_levels=False):
+    """misc/Matching.py:211-222 with filtering off -> (3,T0,T1) float64."""
+    mp = initial_move_map(co_map_list[-1])
+    levels = [mp]
+    idx = len(co_map_list) - 1
+    while idx > 0:
+        idx -= 1
+        mp = backtrack_level(co_map_list[idx], mp)
+        levels.append(mp)
+    pre = mp
+    if sub_pix_on:
+        mp = sub_pix(co_map_list[0], mp)
+    if return_levels:
+        return mp, pre, levels
+    return mp
+
+
+# --------------------------------------------------------------------------------------
+# disparity planes, post-hoc sub-pixel, tiling
+# --------------------------------------------------------------------------------------
+MODES = ['elevation', 'elevation2', 'distance']      # misc/Calc_difference.py:30
+
+
+def cal_map(mp, mode='elevation'):
+    """misc/Calc_difference.py:25-49."""
+    if mode not in MODES:
+        raise SystemExit
+    t0, t1 = mp.shape[1:]
+    ii, jj = np.meshgrid(np.arange(t0, dtype=np.float64), np.arange(t1, dtype=np.float64), indexing='ij')
+    if mode == 'elevation':
+        return jj - mp[1]
+    if mode == 'elevation2':
+        return ii - mp[0]
+    d0 = ii - mp[0]
+    d1 = jj - mp[1]
+    # np.linalg.norm of a 1-D 2-vector evaluates sqrt(dot(x, x)); the BLAS ddot kernel
+    # of this image fuses the second product: sqrt(fma(d1, d1, d0*d0))  (checked against
+    # the live reference on 1e5 random vectors: 0 mismatches; plain d0*d0+d1*d1 differs
+    # by 1 ulp in 8 % of them).
+    return np.sqrt(_fma(d1, d1, d0 * d0))
+
+
+def _fma(a, b, c):
+    import ctypes
+    import ctypes.util
+    libm = ctypes.CDLL(ctypes.util.find_library('m') or 'libm.so.6')
+    libm.fma.restype = ctypes.c_double
+    libm.fma.argtypes = [ctypes.c_double] * 3
+    f = np.frompyfunc(lambda x, y, z: libm.fma(float(x), float(y), float(z)), 3, 1)
+    return f(a, b, c).astype(np.float64)
+
+
+def image_threshold(arr, threshold=(0, 10)):
+    """misc/optimize_loop.py:40-44."""
+    arr = np.where(arr > threshold[1], threshold[1], arr)
+    arr = np.where(arr < threshold[0], threshold[0], arr)
+    return arr
+
+
+def sub_pix_cal(arr, co_map, direction=0, ratio=100.):
+    """misc/sub_pix_cal.py:22-53 -- post-hoc 2-D parabola refinement of a mosaic."""
+    arr = image_threshold(np.asarray(arr), threshold=[-3, 3]).astype(float)
+    co = np.asarray(co_map, dtype=np.float64)
+    s0, s1 = arr.shape
+    if s0 > 2 and s1 > 2:
+        d = arr[1:-1, 1:-1]
+        r0 = co[1:-1, 1:-1] * ratio
+        if direction == 0:
+            r1 = co[2:, 1:-1] * ratio
+            r_ = co[:-2, 1:-1] * ratio
+        else:
+            r1 = co[1:-1, 2:] * ratio
+            r_ = co[1:-1, :-2] * ratio
+        with np.errstate(divide='ignore', invalid='ignore'):
+            dis = d - (r1 - r_) / (2 * (r1 + r_ - 2 * r0))
+            dis = np.where(np.abs(d - dis) > 1, d, dis)
+        arr = arr.copy()
+        arr[1:-1, 1:-1] = dis
+    return image_threshold(arr, threshold=[-3, 3])
+
+
+def solve_tile(img1, img2, ws, modes=('elevation',), sub_pix_on=True, method=TM_CCOEFF_NORMED):
+    """misc/image_cut_solver.py:115-142 -> ((nmodes,T0,T1), (T0,T1))."""
+    cm = correlation_map(img1, img2, ws, method)
+    out = matching(cm['co_map_list'], sub_pix_on)
+    return np.array([cal_map(out, m) for m in modes]), out[2]
+
+
+def tile_grid(img_shape, image_size, stride, ws):
+    """misc/image_cut_solver.py:53-62 -> (len0, len1); the last fitting tile is dropped."""
+    e = int((ws - 1) / 2)
+    trimmed = [image_size[i] + 2 * e for i in range(2)]
+    return [int(np.floor((img_shape[i] - trimmed[i]) / stride[i])) for i in range(2)], trimmed
+
+
+def image_cut_solver(img1, img2, image_size=(32, 32), stride=(32, 32), ws=5,
+                     modes=('elevation',), sub_pix_on=True, method=TM_CCOEFF_NORMED,
+                     tile_rows=None):
+    """misc/image_cut_solver.py:95-113,144-184 -> (d_map (nmodes,S0',S1'), out_map (S0',S1')).
+
+    ``tile_rows=(lo,hi)`` restricts the solve to tile-row indices lo..hi-1 (everything
+    else is left NaN) -- used to check the multi-GPU strip partition.
+    """
+    ln, trimmed = tile_grid(img1.shape, image_size, stride, ws)
+    if ln[0] <= 0 or ln[1] <= 0:
+        raise IndexError('list index out of range')         # img_index[-1] on an empty list
+    size = [stride[i] * (ln[i] - 1) + image_size[i] for i in range(2)]
+    d_map = np.full([len(modes)] + size, np.nan)
+    out_map = np.full(size, np.nan)
+    lo, hi = (0, ln[0]) if tile_rows is None else tile_rows
+    for j in range(ln[1]):
+        for i in range(lo, hi):
+            y, x = stride[0] * i, stride[1] * j
+            d, s = solve_tile(img1[y:y + trimmed[0], x:x + trimmed[1]],
+                              img2[y:y + trimmed[0], x:x + trimmed[1]], ws, modes, sub_pix_on, method)
+            d_map[:, y:y + image_size[0], x:x + image_size[1]] = d
+            out_map[y:y + image_size[0], x:x + image_size[1]] = s
+    return d_map, out_map
+
+
+def raw_read(path, size=(6000, 6000), rate=1):
+    """misc/raw_read.py:36-45 -- int8 read, * rate, cast to uint8 (wraps)."""
+    c = np.fromfile(path, dtype=np.int8, count=size[0] * size[1]).reshape(1, size[1], size[0])
+    return (c * rate)[0].astype(np.uint8)
