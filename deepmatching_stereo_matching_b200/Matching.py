@@ -1,0 +1,130 @@
+# -*- coding: utf-8 -*-
+"""
+Matching -- top-down backtracking over the correlation pyramid and the level-0 parabola
+refinement, on the GPU.
+
+Mirror of misc/Matching.py:20-268 of the reference: same constructor, same (3,T0,T1)
+float64 result.  ``Co_obj`` may be this package's Correlation_map (device-resident
+pyramid, float32) or any object with ``co_map_list`` (4-D numpy arrays, float32 or
+float64 -- processed in their own dtype, so indices are bit-exact with the reference) and
+``N_map``.
+"""
+
+import sys
+
+import numpy as np
+
+from . import _native
+from .Correlation_map import DeviceLevels
+
+
+class Zero_padding(object):
+    """misc/Matching.py:258-268 -- ZeroPad2d(1); the kernels read zeros outside the map."""
+
+    def eval(self):
+        return self
+
+    def forward(self, x):
+        import torch
+        return torch.nn.functional.pad(x, (1, 1, 1, 1))
+
+    __call__ = forward
+
+
+class Matching():
+
+    def __init__(
+        self,
+        Co_obj=None,
+        filter_window_size=3,
+        filtering=False,
+        filtering_num=3,
+        filtering_mode='median',
+        sub_pix=True
+    ):
+        try:
+            Co_obj.co_map_list
+        except AttributeError as e:
+            print('Error!: {}'.format(e))
+            print('please run \'obj=Correlation_map()\' and \'obj()\' first.')
+            sys.exit()
+
+        MODES = ['average', 'median']
+        assert filtering_mode in MODES, 'invalid filtering mode is input!: {}'.format(filtering_mode)
+
+        self.obj = Co_obj
+        self.Padding = Zero_padding()
+        self.Padding.eval()
+
+        self.filtering_num = filtering_num
+        self.filter_window_size = filter_window_size
+        self.filtering = filtering
+        self.filtering_mode = filtering_mode
+        self.sub_pix = sub_pix
+
+    # ------------------------------------------------------------------ device levels
+    def _device_levels(self):
+        torch = _native.require_cuda()
+        lst = self.obj.co_map_list
+        if isinstance(lst, DeviceLevels):
+            return lst.device, False
+        out = []
+        f64 = any(np.asarray(x).dtype != np.float32 for x in lst)
+        for x in lst:
+            a = np.ascontiguousarray(x, dtype=np.float64 if f64 else np.float32)
+            out.append(torch.from_numpy(a).cuda())
+        return out, f64
+
+    def _filter(self, map_here):
+        """misc/Matching.py:224-255 on the small (3,h,w) host map (default off; includes the
+        reference's square-grid sizing of d_map)."""
+        map_shape = map_here.shape
+        if map_shape[1] >= self.filter_window_size and map_shape[2] >= self.filter_window_size:
+            e = int((self.filter_window_size - 1) / 2)
+            n = map_shape[1]
+            jj = np.arange(n)
+            d_map = (map_here[1, :n, :n] - jj[None, :]).astype('int64')
+            d_map2 = (map_here[0, :n, :n] - jj[:, None]).astype('int64')
+            red = np.mean if self.filtering_mode == 'average' else np.median
+            for i in range(e, map_shape[1] - e):
+                for j in range(e, map_shape[2] - e):
+                    map_here[1, i, j] = round(red(d_map[i - e:i + e + 1, j - e:j + e + 1])) + j
+                    map_here[0, i, j] = round(red(d_map2[i - e:i + e + 1, j - e:j + e + 1])) + i
+        return map_here
+
+    def _filter_device(self, match, score, torch):
+        mp = np.concatenate([match.cpu().numpy().astype(np.float64), score.cpu().numpy().astype(np.float64)[None]], 0)
+        mp = self._filter(mp)
+        self.filtering_num -= 1
+        return torch.from_numpy(np.ascontiguousarray(mp[:2]).astype(np.int32)).cuda()
+
+    # ------------------------------------------------------------------ reference API
+    def __call__(self):
+        torch = _native.require_cuda()
+        lib = _native.lib()
+        levels, f64 = self._device_levels()
+        sdt = torch.float64 if f64 else torch.float32
+        st = _native.stream_ptr
+        top = levels[-1]
+        a, b = top.shape[:2]
+        match = torch.empty((2, a, b), dtype=torch.int32, device='cuda')
+        score = torch.empty((a, b), dtype=sdt, device='cuda')
+        _native.check(lib.dm_backtrack_top(_native.ptr(top), int(f64), 1, a, b, _native.ptr(match), _native.ptr(score), st()))
+        if self.filtering and self.filtering_num > 0:
+            match = self._filter_device(match, score, torch)
+        for k in range(len(levels) - 2, -1, -1):
+            lv = levels[k]
+            A, B, C, D = lv.shape
+            nmatch = torch.empty((2, A, B), dtype=torch.int32, device='cuda')
+            nscore = torch.empty((A, B), dtype=sdt, device='cuda')
+            _native.check(lib.dm_backtrack_level(_native.ptr(lv), int(f64), 1, A, B, C, D, _native.ptr(match),
+                                                 _native.ptr(nmatch), _native.ptr(nscore), st()))
+            match, score = nmatch, nscore
+            if self.filtering and self.filtering_num > 0:
+                match = self._filter_device(match, score, torch)
+        t0, t1 = levels[0].shape[:2]
+        out = torch.empty((3, t0, t1), dtype=torch.float64, device='cuda')
+        _native.check(lib.dm_match_map(_native.ptr(levels[0]), int(f64), 1, t0, t1, _native.ptr(match), _native.ptr(score),
+                                       1 if self.sub_pix else 0, _native.ptr(out), st()))
+        self.map = out.cpu().numpy()
+        return self.map

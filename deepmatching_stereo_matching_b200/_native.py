@@ -1,0 +1,190 @@
+# -*- coding: utf-8 -*-
+"""
+ctypes binding of libdmstereo.so (include/dmstereo.h).  There is no CPU fallback: if the
+library cannot be loaded (or built with nvcc) every entry point of the package raises.
+"""
+
+import ctypes
+import os
+from ctypes import POINTER, Structure, byref, c_char_p, c_double, c_float, c_int, c_int32, c_longlong, c_size_t, c_void_p
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, 'libdmstereo.so')
+
+TM_CCOEFF = 4
+TM_CCOEFF_NORMED = 5
+MODE_IDS = {'elevation': 0, 'elevation2': 1, 'distance': 2}
+CORR_AUTO, CORR_SIMT, CORR_UMMA = 0, 1, 2
+STAGES = ['descriptors', 'correlation', 'normalize', 'aggregate', 'backtrack', 'planes']
+
+
+class DmError(RuntimeError):
+    pass
+
+
+class SceneParams(Structure):
+    _fields_ = [('scene_h', c_int32), ('scene_w', c_int32), ('t0', c_int32), ('t1', c_int32),
+                ('s0', c_int32), ('s1', c_int32), ('ws', c_int32), ('method', c_int32),
+                ('n_modes', c_int32), ('modes', c_int32 * 4), ('sub_pix', c_int32),
+                ('tile_row_lo', c_int32), ('tile_row_hi', c_int32), ('fused', c_int32),
+                ('reserved', c_int32 * 3)]
+
+
+class SceneInfo(Structure):
+    _fields_ = [('len0', c_int32), ('len1', c_int32), ('out_h', c_int32), ('out_w', c_int32),
+                ('row_lo', c_int32), ('row_hi', c_int32), ('n_tiles', c_int32), ('levels', c_int32),
+                ('n_map', c_int32), ('used_fused', c_int32), ('chunk_tiles', c_int32),
+                ('kernel_launches', c_int32)]
+
+
+# name -> (restype, argtypes); every symbol include/dmstereo.h declares
+SIGNATURES = {
+    'dm_version': (c_int, []),
+    'dm_last_error': (c_char_p, []),
+    'dm_device_cc': (c_int, []),
+    'dm_kpad': (c_int, [c_int]),
+    'dm_descriptors': (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    'dm_correlation': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
+    'dm_feature_value': (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
+    'dm_minmax_rectify': (c_int, [c_void_p, c_longlong, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    'dm_aggregate': (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
+    'dm_backtrack_top': (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    'dm_backtrack_level': (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
+    'dm_match_map': (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
+    'dm_cal_map': (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
+    'dm_sub_pix_cal': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_double, c_void_p, c_void_p]),
+    'dm_ctx_create': (c_int, [POINTER(c_void_p)]),
+    'dm_ctx_destroy': (None, [c_void_p]),
+    'dm_ctx_set_stream': (c_int, [c_void_p, c_void_p]),
+    'dm_ctx_set_workspace_limit': (c_int, [c_void_p, c_size_t]),
+    'dm_ctx_workspace_bytes': (c_size_t, [c_void_p]),
+    'dm_scene_geometry': (c_int, [POINTER(SceneParams), POINTER(SceneInfo)]),
+    'dm_solve_scene': (c_int, [c_void_p, POINTER(SceneParams), c_void_p, c_void_p, c_void_p, c_void_p, POINTER(SceneInfo)]),
+    'dm_solve_scene_host': (c_int, [c_void_p, POINTER(SceneParams), c_void_p, c_void_p, c_void_p, c_void_p, POINTER(SceneInfo)]),
+    'dm_ctx_enable_timing': (c_int, [c_void_p, c_int]),
+    'dm_ctx_stage_ms': (c_int, [c_void_p, POINTER(c_float), POINTER(c_int)]),
+}
+
+_lib = None
+
+
+def lib():
+    """The loaded library; builds it in-tree with nvcc if it is missing.  Raises on failure."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        from . import build as _build
+        try:
+            _build.build()
+        except Exception as exc:                                   # no silent fallback
+            raise DmError('libdmstereo.so is missing and could not be built: %s' % exc)
+    try:
+        handle = ctypes.CDLL(LIB_PATH)
+    except OSError as exc:
+        raise DmError('cannot load %s: %s' % (LIB_PATH, exc))
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(handle, name)                                 # AttributeError if a symbol is missing
+        fn.restype = res
+        fn.argtypes = args
+    _lib = handle
+    return _lib
+
+
+def check(rc):
+    if rc != 0:
+        raise DmError('libdmstereo error %d: %s' % (rc, lib().dm_last_error().decode('utf-8', 'replace')))
+
+
+def require_cuda():
+    """torch is plumbing only: device memory, streams, torch.distributed."""
+    import torch
+    if not torch.cuda.is_available():
+        raise DmError('deepmatching_stereo_matching_b200 needs a CUDA device (sm_100a); there is no CPU fallback')
+    return torch
+
+
+def stream_ptr():
+    import torch
+    return c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def ptr(t):
+    return c_void_p(t.data_ptr()) if t is not None else c_void_p(None)
+
+
+def method_id(feature_name):
+    return {'cv2.TM_CCOEFF_NORMED': TM_CCOEFF_NORMED, 'cv2.TM_CCOEFF': TM_CCOEFF}[feature_name]
+
+
+class Context(object):
+    """Owns a dm_ctx (workspace + staging buffers) bound to torch's current stream."""
+
+    def __init__(self, workspace_limit=None, timing=False):
+        require_cuda()
+        self._h = c_void_p()
+        check(lib().dm_ctx_create(byref(self._h)))
+        if workspace_limit:
+            check(lib().dm_ctx_set_workspace_limit(self._h, int(workspace_limit)))
+        if timing:
+            check(lib().dm_ctx_enable_timing(self._h, 1))
+        self.timing = timing
+
+    def close(self):
+        if getattr(self, '_h', None):
+            lib().dm_ctx_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def bind_stream(self):
+        check(lib().dm_ctx_set_stream(self._h, stream_ptr()))
+
+    def solve_device(self, prm, img1, img2, d_map, out_map):
+        info = SceneInfo()
+        self.bind_stream()
+        check(lib().dm_solve_scene(self._h, byref(prm), ptr(img1), ptr(img2), ptr(d_map), ptr(out_map), byref(info)))
+        return info
+
+    def solve_host(self, prm, img1_np, img2_np, d_map_np, out_map_np):
+        info = SceneInfo()
+        self.bind_stream()
+        check(lib().dm_solve_scene_host(self._h, byref(prm), c_void_p(img1_np.ctypes.data), c_void_p(img2_np.ctypes.data),
+                                        c_void_p(d_map_np.ctypes.data), c_void_p(out_map_np.ctypes.data), byref(info)))
+        return info
+
+    def stage_ms(self):
+        ms = (c_float * len(STAGES))()
+        ln = (c_int * len(STAGES))()
+        check(lib().dm_ctx_stage_ms(self._h, ms, ln))
+        return {s: float(ms[i]) for i, s in enumerate(STAGES)}, {s: int(ln[i]) for i, s in enumerate(STAGES)}
+
+    @property
+    def workspace_bytes(self):
+        return int(lib().dm_ctx_workspace_bytes(self._h))
+
+
+def scene_params(shape, image_size, stride, window_size, feature_name, modes, sub_pix, tile_rows=None, fused=-1):
+    prm = SceneParams()
+    prm.scene_h, prm.scene_w = int(shape[0]), int(shape[1])
+    prm.t0, prm.t1 = int(image_size[0]), int(image_size[1])
+    prm.s0, prm.s1 = int(stride[0]), int(stride[1])
+    prm.ws = int(window_size)
+    prm.method = method_id(feature_name)
+    prm.n_modes = len(modes)
+    for i, m in enumerate(modes):
+        prm.modes[i] = MODE_IDS[m]
+    prm.sub_pix = 1 if sub_pix else 0
+    prm.tile_row_lo, prm.tile_row_hi = (0, 0) if tile_rows is None else (int(tile_rows[0]), int(tile_rows[1]))
+    prm.fused = int(fused)
+    return prm
+
+
+def scene_geometry(prm):
+    info = SceneInfo()
+    check(lib().dm_scene_geometry(byref(prm), byref(info)))
+    return info

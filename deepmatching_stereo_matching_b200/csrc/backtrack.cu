@@ -1,0 +1,206 @@
+// Top-down backtracking and the level-0 parabola refinement.
+// Replaces Matching._calc_near_match (misc/Matching.py:58-78), _initial_move_map
+// (:80-96), _B (:98-139, filtering off), _sub_pix_compute/_sub_pix_cal (:165-209) and the
+// assembly of the (3,T0,T1) float64 result (:211-222).
+//
+// Index results are bit-exact with the reference given the same level data: only
+// comparisons and one addition are involved, and the kernels are instantiated for both
+// float (the pipeline's dtype) and double (the reference's dtype).
+#include "dm_common.cuh"
+
+namespace {
+
+template <typename T> struct Near { static __device__ __forceinline__ T zero_thr(); };
+template <> struct Near<float>  { static __device__ __forceinline__ float  zero_thr() { return DM_NEAR_ZERO_F; } };
+template <> struct Near<double> { static __device__ __forceinline__ double zero_thr() { return DM_NEAR_ZERO_D; } };
+
+// misc/Matching.py:58-78.  map = one (C,D) slice; (d0,d1) = p_dot.
+// np.argmax: first maximum in row-major order, the first NaN wins; zero padding outside.
+template <typename T>
+__device__ __forceinline__ void near_match(const T* __restrict__ map, int C, int D, int d0, int d1,
+                                           int& r0, int& r1, T& score) {
+    T best = T(0);
+    int bi = 0;
+    bool best_nan = false;
+#pragma unroll
+    for (int k = 0; k < 9; ++k) {
+        const int y = d0 + k / 3 - 1, x = d1 + k % 3 - 1;
+        T v = T(0);
+        if (y >= 0 && y < C && x >= 0 && x < D) v = map[(size_t)y * D + x];
+        if (k == 0) { best = v; best_nan = (v != v); }
+        else if (!best_nan && (v > best || v != v)) { best = v; bi = k; best_nan = (v != v); }
+    }
+    T centre = T(0);
+    if (d0 >= 0 && d0 < C && d1 >= 0 && d1 < D) centre = map[(size_t)d0 * D + d1];
+    if (best < Near<T>::zero_thr()) { bi = 4; best = centre; }      // false for NaN, like numpy
+    r0 = d0 + bi / 3 - 1;
+    r1 = d1 + bi % 3 - 1;
+    score = best + centre;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+dm_backtrack_kernel(const T* __restrict__ level, long long total, int A, int B, int C, int D,
+                    const int32_t* __restrict__ parent, int32_t* __restrict__ match, T* __restrict__ score) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const int j = (int)(idx % B);
+    long long t = idx / B;
+    const int i = (int)(t % A);
+    const long long n = t / A;
+    int d0, d1;
+    if (parent) {
+        const int hA = A >> 1, hB = B >> 1;
+        const size_t pbase = (size_t)n * 2 * hA * hB;
+        const size_t pidx = (size_t)(i >> 1) * hB + (j >> 1);
+        d0 = 2 * parent[pbase + pidx] + (i & 1);
+        d1 = 2 * parent[pbase + (size_t)hA * hB + pidx] + (j & 1);
+    } else {
+        d0 = i; d1 = j;
+    }
+    const T* map = level + (((size_t)n * A + i) * B + j) * (size_t)C * D;
+    int r0, r1;
+    T s;
+    near_match<T>(map, C, D, d0, d1, r0, r1, s);
+    const size_t mbase = (size_t)n * 2 * A * B;
+    const size_t midx = (size_t)i * B + j;
+    match[mbase + midx] = r0;
+    match[mbase + (size_t)A * B + midx] = r1;
+    score[(size_t)n * A * B + midx] = s;
+}
+
+// misc/Matching.py:165-175
+template <typename T>
+__device__ __forceinline__ T sub_pix_fit(T r0, T r1, T rm) {
+    if (r0 > r1 && r0 > rm) return -(r1 - rm) / (T(2) * (r1 + rm - T(2) * r0));
+    return T(0);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+dm_match_map_kernel(const T* __restrict__ l0, long long total, int T0, int T1,
+                    const int32_t* __restrict__ match, const T* __restrict__ score, int sub_pix,
+                    double* __restrict__ out) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const int P = T0 * T1;
+    const long long n = idx / P;
+    const int p = (int)(idx - n * P);
+    const int c0 = match[(size_t)n * 2 * P + p];
+    const int c1 = match[(size_t)n * 2 * P + P + p];
+    double m0 = (double)c0, m1 = (double)c1;
+    if (sub_pix) {
+        const T* map = l0 + ((size_t)n * P + p) * (size_t)P;    // (C,D) = (T0,T1)
+        const T r0 = map[(size_t)c0 * T1 + c1];
+        if (c0 + 1 < T0) {                                      // else IndexError swallowed (:196)
+            const T r1 = map[(size_t)(c0 + 1) * T1 + c1];
+            const T rm = map[(size_t)(c0 == 0 ? T0 - 1 : c0 - 1) * T1 + c1];   // index -1 wraps
+            m0 += (double)sub_pix_fit<T>(r0, r1, rm);
+        }
+        if (c1 + 1 < T1) {
+            const T r1 = map[(size_t)c0 * T1 + c1 + 1];
+            const T rm = map[(size_t)c0 * T1 + (c1 == 0 ? T1 - 1 : c1 - 1)];
+            m1 += (double)sub_pix_fit<T>(r0, r1, rm);
+        }
+    }
+    double* o = out + (size_t)n * 3 * P;
+    o[p] = m0;
+    o[P + p] = m1;
+    o[2 * P + p] = (double)score[(size_t)n * P + p];
+}
+
+// misc/Calc_difference.py:25-49
+__global__ void dm_cal_map_kernel(const double* __restrict__ map, int T0, int T1, int mode, double* __restrict__ out) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    const int P = T0 * T1;
+    if (idx >= P) return;
+    const int i = idx / T1, j = idx - i * T1;
+    const double d0 = __dsub_rn((double)i, map[idx]);
+    const double d1 = __dsub_rn((double)j, map[P + idx]);
+    double v;
+    if (mode == DM_MODE_ELEVATION) v = d1;
+    else if (mode == DM_MODE_ELEVATION2) v = d0;
+    else v = __dsqrt_rn(__fma_rn(d1, d1, __dmul_rn(d0, d0)));   // np.linalg.norm = sqrt(ddot) with the fused second product
+    out[idx] = v;
+}
+
+// misc/sub_pix_cal.py:22-53 (+ misc/optimize_loop.py:40-44).  All float64, no contraction,
+// so the result is bit-identical to numpy.
+__device__ __forceinline__ double clamp3(double v) {
+    if (v > 3.0) v = 3.0;          // np.where(arr > 3, 3, arr): NaN stays
+    if (v < -3.0) v = -3.0;
+    return v;
+}
+__global__ void dm_sub_pix_cal_kernel(const double* __restrict__ arr, const double* __restrict__ co,
+                                      int S0, int S1, int direction, double ratio, double* __restrict__ out) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= S0 * S1) return;
+    const int i = idx / S1, j = idx - i * S1;
+    double d = clamp3(arr[idx]);
+    double dis = d;
+    if (i >= 1 && i < S0 - 1 && j >= 1 && j < S1 - 1) {
+        const int step = direction == 0 ? S1 : 1;
+        const double r0 = __dmul_rn(co[idx], ratio);
+        const double r1 = __dmul_rn(co[idx + step], ratio);
+        const double rm = __dmul_rn(co[idx - step], ratio);
+        const double den = __dmul_rn(2.0, __dsub_rn(__dadd_rn(r1, rm), __dmul_rn(2.0, r0)));
+        dis = __dsub_rn(d, __ddiv_rn(__dsub_rn(r1, rm), den));
+        if (fabs(__dsub_rn(d, dis)) > 1.0) dis = d;
+    }
+    out[idx] = clamp3(dis);
+}
+
+}  // namespace
+
+template <typename T>
+static int backtrack_launch(const void* level, long long n, int a, int b, int c, int d,
+                            const int32_t* parent, int32_t* match, void* score, cudaStream_t st) {
+    const long long total = n * a * b;
+    dm_backtrack_kernel<T><<<dm_div_up(total, 256), 256, 0, st>>>((const T*)level, total, a, b, c, d, parent, match, (T*)score);
+    DM_LAUNCH_CHECK();
+    return DM_OK;
+}
+
+extern "C" int dm_backtrack_top(const void* top_dev, int is_f64, int n, int a, int b,
+                                int32_t* match_dev, void* score_dev, void* stream) {
+    DM_REQUIRE(n > 0 && a > 0 && b > 0, DM_ERR_INVALID, "dm_backtrack_top: bad shape");
+    return is_f64 ? backtrack_launch<double>(top_dev, n, a, b, a, b, nullptr, match_dev, score_dev, (cudaStream_t)stream)
+                  : backtrack_launch<float>(top_dev, n, a, b, a, b, nullptr, match_dev, score_dev, (cudaStream_t)stream);
+}
+
+extern "C" int dm_backtrack_level(const void* level_dev, int is_f64, int n, int a, int b, int c, int d,
+                                  const int32_t* parent_match_dev, int32_t* match_dev, void* score_dev, void* stream) {
+    DM_REQUIRE(n > 0 && a >= 2 && b >= 2 && !(a & 1) && !(b & 1) && c > 0 && d > 0, DM_ERR_INVALID, "dm_backtrack_level: bad shape");
+    DM_REQUIRE(parent_match_dev != nullptr, DM_ERR_INVALID, "dm_backtrack_level: parent matches missing");
+    return is_f64 ? backtrack_launch<double>(level_dev, n, a, b, c, d, parent_match_dev, match_dev, score_dev, (cudaStream_t)stream)
+                  : backtrack_launch<float>(level_dev, n, a, b, c, d, parent_match_dev, match_dev, score_dev, (cudaStream_t)stream);
+}
+
+extern "C" int dm_match_map(const void* level0_dev, int is_f64, int n, int t0, int t1,
+                            const int32_t* match_dev, const void* score_dev, int sub_pix,
+                            double* map_dev, void* stream) {
+    DM_REQUIRE(n > 0 && t0 > 0 && t1 > 0, DM_ERR_INVALID, "dm_match_map: bad shape");
+    const long long total = (long long)n * t0 * t1;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (is_f64)
+        dm_match_map_kernel<double><<<dm_div_up(total, 256), 256, 0, st>>>((const double*)level0_dev, total, t0, t1, match_dev, (const double*)score_dev, sub_pix, map_dev);
+    else
+        dm_match_map_kernel<float><<<dm_div_up(total, 256), 256, 0, st>>>((const float*)level0_dev, total, t0, t1, match_dev, (const float*)score_dev, sub_pix, map_dev);
+    DM_LAUNCH_CHECK();
+    return DM_OK;
+}
+
+extern "C" int dm_cal_map(const double* map_dev, int t0, int t1, int mode, double* out_dev, void* stream) {
+    DM_REQUIRE(mode >= 0 && mode <= 2, DM_ERR_INVALID, "dm_cal_map: invalid mode %d", mode);
+    dm_cal_map_kernel<<<dm_div_up((long long)t0 * t1, 256), 256, 0, (cudaStream_t)stream>>>(map_dev, t0, t1, mode, out_dev);
+    DM_LAUNCH_CHECK();
+    return DM_OK;
+}
+
+extern "C" int dm_sub_pix_cal(const double* arr_dev, const double* co_map_dev, int s0, int s1,
+                              int direction, double ratio, double* out_dev, void* stream) {
+    DM_REQUIRE(s0 > 0 && s1 > 0 && (direction == 0 || direction == 1), DM_ERR_INVALID, "dm_sub_pix_cal: bad arguments");
+    dm_sub_pix_cal_kernel<<<dm_div_up((long long)s0 * s1, 256), 256, 0, (cudaStream_t)stream>>>(arr_dev, co_map_dev, s0, s1, direction, ratio, out_dev);
+    DM_LAUNCH_CHECK();
+    return DM_OK;
+}

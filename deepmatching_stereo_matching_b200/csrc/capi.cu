@@ -1,0 +1,419 @@
+// C-ABI glue: error reporting, the correlation dispatcher, the workspace-owning context
+// and the batched scene solver that replaces ImageCutSolver._cut_and_pool / _solver /
+// _execute_matching (misc/image_cut_solver.py:95-184).
+#include <stdarg.h>
+#include <string.h>
+
+#include <vector>
+
+#include "dm_common.cuh"
+#include "dm_internal.h"
+
+// ------------------------------------------------------------------ errors
+static thread_local char g_err[512] = "";
+
+void dm_set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+extern "C" const char* dm_last_error(void) { return g_err; }
+extern "C" int dm_version(void) { return 100; }
+
+extern "C" int dm_device_cc(void) {
+    int dev = 0, major = 0, minor = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return DM_ERR_CUDA;
+    if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess) return DM_ERR_CUDA;
+    if (cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, dev) != cudaSuccess) return DM_ERR_CUDA;
+    return major * 10 + minor;
+}
+
+// ------------------------------------------------------------------ correlation dispatch
+extern "C" int dm_correlation(const void* desc1_dev, const float* stat1_dev,
+                              const void* desc2_dev, const float* stat2_dev,
+                              int n_tiles, int p, int kpad, int ws, int method, int engine,
+                              float* raw_dev, void* stream) {
+    DM_REQUIRE(method == DM_TM_CCOEFF || method == DM_TM_CCOEFF_NORMED, DM_ERR_INVALID, "dm_correlation: invalid method %d", method);
+    DM_REQUIRE(n_tiles > 0 && p > 0 && kpad == dm_kpad(ws), DM_ERR_INVALID, "dm_correlation: bad shape (kpad %d for ws %d)", kpad, ws);
+    cudaStream_t st = (cudaStream_t)stream;
+    const bool umma_ok = dm_correlation_umma_supported(p, kpad);
+    if (engine == DM_CORR_UMMA) {
+        DM_REQUIRE(umma_ok, DM_ERR_UNSUPPORTED, "dm_correlation: tcgen05 engine needs P %% 128 == 0 and kpad <= 256 (P=%d kpad=%d)", p, kpad);
+        return dm_correlation_umma(desc1_dev, stat1_dev, desc2_dev, stat2_dev, n_tiles, p, kpad, method, raw_dev, st);
+    }
+    if (engine == DM_CORR_AUTO && umma_ok)
+        return dm_correlation_umma(desc1_dev, stat1_dev, desc2_dev, stat2_dev, n_tiles, p, kpad, method, raw_dev, st);
+    return dm_correlation_simt(desc1_dev, stat1_dev, desc2_dev, stat2_dev, n_tiles, p, kpad, method, raw_dev, st);
+}
+
+// ------------------------------------------------------------------ context
+extern "C" int dm_ctx_create(dm_ctx** out) {
+    DM_REQUIRE(out != nullptr, DM_ERR_INVALID, "dm_ctx_create: null out");
+    int cc = dm_device_cc();
+    DM_REQUIRE(cc >= 100, DM_ERR_UNSUPPORTED, "dm_ctx_create: this library is built for sm_100a only (device cc %d)", cc);
+    *out = new dm_ctx();
+    return DM_OK;
+}
+
+extern "C" void dm_ctx_destroy(dm_ctx* ctx) {
+    if (!ctx) return;
+    cudaFree(ctx->ws); cudaFree(ctx->scene1); cudaFree(ctx->scene2); cudaFree(ctx->planes);
+    for (auto& v : ctx->ev) for (auto e : v) cudaEventDestroy(e);
+    delete ctx;
+}
+
+extern "C" int dm_ctx_set_stream(dm_ctx* ctx, void* stream) { ctx->stream = (cudaStream_t)stream; return DM_OK; }
+extern "C" int dm_ctx_set_workspace_limit(dm_ctx* ctx, size_t bytes) { ctx->ws_limit = bytes; return DM_OK; }
+extern "C" size_t dm_ctx_workspace_bytes(const dm_ctx* ctx) { return ctx->ws_bytes; }
+extern "C" int dm_ctx_enable_timing(dm_ctx* ctx, int on) { ctx->timing = on != 0; return DM_OK; }
+
+static int ctx_reserve(dm_ctx* ctx, size_t bytes) {
+    if (bytes <= ctx->ws_bytes) return DM_OK;
+    DM_REQUIRE(bytes <= ctx->ws_limit, DM_ERR_NOMEM, "workspace of %zu bytes exceeds the limit of %zu", bytes, ctx->ws_limit);
+    DM_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    if (ctx->ws) DM_CUDA_CHECK(cudaFree(ctx->ws));
+    ctx->ws = nullptr; ctx->ws_bytes = 0;
+    DM_CUDA_CHECK(cudaMalloc(&ctx->ws, bytes));
+    ctx->ws_bytes = bytes;
+    return DM_OK;
+}
+
+int StageTimer::begin(size_t chunk) {
+    if (!ctx->timing) return DM_OK;
+    auto& v = ctx->ev[stage];
+    slot = chunk * 2;
+    while (v.size() < slot + 2) { cudaEvent_t e; DM_CUDA_CHECK(cudaEventCreate(&e)); v.push_back(e); }
+    DM_CUDA_CHECK(cudaEventRecord(v[slot], ctx->stream));
+    return DM_OK;
+}
+int StageTimer::end() {
+    if (!ctx->timing) return DM_OK;
+    DM_CUDA_CHECK(cudaEventRecord(ctx->ev[stage][slot + 1], ctx->stream));
+    return DM_OK;
+}
+
+extern "C" int dm_ctx_stage_ms(dm_ctx* ctx, float* ms_out, int* launches_out) {
+    DM_REQUIRE(ctx->timing, DM_ERR_INVALID, "dm_ctx_stage_ms: timing not enabled");
+    DM_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    for (int s = 0; s < DM_STAGE_COUNT; ++s) {
+        float total = 0.f;
+        for (size_t c = 0; c < ctx->chunks_last && 2 * c + 1 < ctx->ev[s].size(); ++c) {
+            float ms = 0.f;
+            DM_CUDA_CHECK(cudaEventElapsedTime(&ms, ctx->ev[s][2 * c], ctx->ev[s][2 * c + 1]));
+            total += ms;
+        }
+        if (ms_out) ms_out[s] = total;
+        if (launches_out) launches_out[s] = ctx->launches[s];
+    }
+    return DM_OK;
+}
+
+// ------------------------------------------------------------------ geometry
+static int ilog2_exact(int v) { int l = 0; while ((1 << l) < v) ++l; return ((1 << l) == v) ? l : -1; }
+
+extern "C" int dm_scene_geometry(const dm_scene_params* prm, dm_scene_info* info) {
+    DM_REQUIRE(prm && info, DM_ERR_INVALID, "dm_scene_geometry: null argument");
+    DM_REQUIRE(prm->ws >= 1 && (prm->ws & 1) && prm->ws <= 31, DM_ERR_INVALID, "window_size must be odd and <= 31 (got %d)", prm->ws);
+    DM_REQUIRE(prm->t0 > 0 && prm->t1 > 0 && prm->s0 > 0 && prm->s1 > 0, DM_ERR_INVALID, "image_size and stride must be positive");
+    const int mn = prm->t0 < prm->t1 ? prm->t0 : prm->t1, mxs = prm->t0 < prm->t1 ? prm->t1 : prm->t0;
+    const int lg = ilog2_exact(mn);
+    // misc/Correlation_map.py:192 -- the patch grid's short side must be a power of two and
+    // the long side a multiple of it; the reference fails with a
+    // broadcast error otherwise.
+    DM_REQUIRE(lg >= 0 && mxs % mn == 0, DM_ERR_INVALID, "image_size (%d,%d): short side must be a power of two dividing the long side", prm->t0, prm->t1);
+    DM_REQUIRE(prm->method == DM_TM_CCOEFF || prm->method == DM_TM_CCOEFF_NORMED, DM_ERR_INVALID, "invalid feature method %d", prm->method);
+    DM_REQUIRE(prm->n_modes >= 1 && prm->n_modes <= 4, DM_ERR_INVALID, "1..4 disparity modes supported (got %d)", prm->n_modes);
+    for (int m = 0; m < prm->n_modes; ++m)
+        DM_REQUIRE(prm->modes[m] >= 0 && prm->modes[m] <= 2, DM_ERR_INVALID, "invalid disparity mode %d", prm->modes[m]);
+    memset(info, 0, sizeof(*info));
+    const int e2 = prm->ws - 1;
+    // misc/image_cut_solver.py:62: floor((S - trimmed) / stride) -- the last fitting tile is dropped
+    const int d0 = prm->scene_h - (prm->t0 + e2), d1 = prm->scene_w - (prm->t1 + e2);
+    info->len0 = d0 >= 0 ? d0 / prm->s0 : -1;
+    info->len1 = d1 >= 0 ? d1 / prm->s1 : -1;
+    DM_REQUIRE(info->len0 >= 1 && info->len1 >= 1, DM_ERR_INVALID, "scene %dx%d yields no tiles (len = %d,%d)", prm->scene_h, prm->scene_w, info->len0, info->len1);
+    info->out_h = prm->s0 * (info->len0 - 1) + prm->t0;
+    info->out_w = prm->s1 * (info->len1 - 1) + prm->t1;
+    int lo = prm->tile_row_lo, hi = prm->tile_row_hi;
+    if (hi <= 0) { lo = 0; hi = info->len0; }
+    DM_REQUIRE(lo >= 0 && lo < hi && hi <= info->len0, DM_ERR_INVALID, "tile row strip [%d,%d) outside [0,%d)", lo, hi, info->len0);
+    info->row_lo = prm->s0 * lo;
+    info->row_hi = (hi == info->len0) ? info->out_h : prm->s0 * hi;
+    info->n_tiles = (hi - lo) * info->len1;
+    info->levels = lg + 1;
+    info->n_map = mn;
+    return DM_OK;
+}
+
+// ------------------------------------------------------------------ scene kernels
+namespace {
+
+__global__ void dm_tile_origin_kernel(int32_t* origin, int n, int first_tile, int len1, int s0, int s1) {
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    int g = first_tile + t;
+    origin[2 * t] = s0 * (g / len1);
+    origin[2 * t + 1] = s1 * (g % len1);
+}
+
+struct PlaneArgs {
+    int n_modes; int modes[4];
+    int T0, T1, s0, s1, len0, len1, out_h, out_w;
+    int first_tile; int sub_pix;
+};
+
+// misc/Matching.py:165-209 + misc/Calc_difference.py:25-49 + the paste of
+// misc/image_cut_solver.py:165-175.  Overlaps: the reference pastes tiles j-outer/i-inner,
+// so a pixel ends up owned by the covering tile with the largest (i,j); this kernel writes
+// a pixel only from its owner, which makes the scatter race-free and order-free.
+__global__ void __launch_bounds__(256)
+dm_planes_kernel(const float* __restrict__ l0, long long total, PlaneArgs a,
+                 const int32_t* __restrict__ match, const float* __restrict__ score,
+                 double* __restrict__ d_map, double* __restrict__ out_map) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const int P = a.T0 * a.T1;
+    const long long n = idx / P;
+    const int p = (int)(idx - n * P);
+    const int i = p / a.T1, j = p - i * a.T1;
+    const int g = a.first_tile + (int)n;
+    const int gi = g / a.len1, gj = g - gi * a.len1;
+    const int Y = a.s0 * gi + i, X = a.s1 * gj + j;
+    if (min(Y / a.s0, a.len0 - 1) != gi || min(X / a.s1, a.len1 - 1) != gj) return;
+    const int c0 = match[(size_t)n * 2 * P + p];
+    const int c1 = match[(size_t)n * 2 * P + P + p];
+    double m0 = (double)c0, m1 = (double)c1;
+    if (a.sub_pix) {
+        const float* map = l0 + ((size_t)n * P + p) * (size_t)P;
+        const float r0 = map[(size_t)c0 * a.T1 + c1];
+        if (c0 + 1 < a.T0) {
+            const float r1 = map[(size_t)(c0 + 1) * a.T1 + c1];
+            const float rm = map[(size_t)(c0 == 0 ? a.T0 - 1 : c0 - 1) * a.T1 + c1];
+            if (r0 > r1 && r0 > rm) m0 += (double)(-(r1 - rm) / (2.0f * (r1 + rm - 2.0f * r0)));
+        }
+        if (c1 + 1 < a.T1) {
+            const float r1 = map[(size_t)c0 * a.T1 + c1 + 1];
+            const float rm = map[(size_t)c0 * a.T1 + (c1 == 0 ? a.T1 - 1 : c1 - 1)];
+            if (r0 > r1 && r0 > rm) m1 += (double)(-(r1 - rm) / (2.0f * (r1 + rm - 2.0f * r0)));
+        }
+    }
+    const double e0 = __dsub_rn((double)i, m0), e1 = __dsub_rn((double)j, m1);
+    const size_t plane = (size_t)a.out_h * a.out_w, pix = (size_t)Y * a.out_w + X;
+    for (int m = 0; m < a.n_modes; ++m) {
+        double v = a.modes[m] == DM_MODE_ELEVATION ? e1
+                 : a.modes[m] == DM_MODE_ELEVATION2 ? e0
+                 : __dsqrt_rn(__fma_rn(e1, e1, __dmul_rn(e0, e0)));
+        d_map[m * plane + pix] = v;
+    }
+    out_map[pix] = (double)score[(size_t)n * P + p];
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------ materialising solver
+struct Carve {
+    char* base; size_t off;
+    explicit Carve(char* b) : base(b), off(0) {}
+    template <typename T> T* take(size_t count) {
+        off = (off + 255) & ~(size_t)255;
+        T* p = base ? (T*)(base + off) : nullptr;
+        off += count * sizeof(T);
+        return p;
+    }
+};
+
+struct TileBuffers {
+    int32_t* origin; void* desc1; void* desc2; float* stat1; float* stat2;
+    std::vector<float*> level;
+    int32_t* match[2]; float* score[2];
+};
+
+static size_t carve_tiles(char* base, int nt, int t0, int t1, int kpad, int levels, TileBuffers& tb) {
+    Carve c(base);
+    const size_t P = (size_t)t0 * t1;
+    tb.origin = c.take<int32_t>((size_t)nt * 2);
+    tb.desc1 = c.take<__nv_bfloat16>((size_t)nt * P * kpad);
+    tb.desc2 = c.take<__nv_bfloat16>((size_t)nt * P * kpad);
+    tb.stat1 = c.take<float>((size_t)nt * P * 4);
+    tb.stat2 = c.take<float>((size_t)nt * P * 4);
+    tb.level.clear();
+    size_t a = t0, b = t1;
+    for (int k = 0; k < levels; ++k) {
+        tb.level.push_back(c.take<float>((size_t)nt * a * b * a * b));
+        a >>= 1; b >>= 1;
+    }
+    for (int s = 0; s < 2; ++s) {
+        tb.match[s] = c.take<int32_t>((size_t)nt * 2 * P);
+        tb.score[s] = c.take<float>((size_t)nt * P);
+    }
+    return (c.off + 255) & ~(size_t)255;
+}
+
+extern "C" int dm_solve_scene(dm_ctx* ctx, const dm_scene_params* prm,
+                              const uint8_t* img1_dev, const uint8_t* img2_dev,
+                              double* d_map_dev, double* out_map_dev, dm_scene_info* info_out) {
+    DM_REQUIRE(ctx && prm && img1_dev && img2_dev && d_map_dev && out_map_dev, DM_ERR_INVALID, "dm_solve_scene: null argument");
+    dm_scene_info info;
+    int rc = dm_scene_geometry(prm, &info);
+    if (rc != DM_OK) return rc;
+    cudaStream_t st = ctx->stream;
+    const int t0 = prm->t0, t1 = prm->t1, P = t0 * t1, kpad = dm_kpad(prm->ws), L = info.levels;
+    int lo = prm->tile_row_lo, hi = prm->tile_row_hi;
+    if (hi <= 0) { lo = 0; hi = info.len0; }
+
+    const bool want_fused = prm->fused != 0;
+    const bool fused = want_fused && dm_fused_supported(t0, t1, kpad);
+    DM_REQUIRE(!(prm->fused == 1 && !fused), DM_ERR_UNSUPPORTED, "fused path does not support image_size (%d,%d) with window %d", t0, t1, prm->ws);
+
+    // tiles per chunk from the workspace limit
+    TileBuffers tb;
+    const size_t per_tile = fused ? dm_fused_workspace(nullptr, 1, t0, t1, kpad, L, nullptr)
+                                  : carve_tiles(nullptr, 1, t0, t1, kpad, L, tb);
+    long long max_chunk = (long long)(ctx->ws_limit / (per_tile + 4096));
+    if (max_chunk > 16384) max_chunk = 16384;
+    DM_REQUIRE(max_chunk >= 1, DM_ERR_NOMEM, "one tile needs %zu bytes of workspace, limit is %zu", per_tile, ctx->ws_limit);
+    const int n_chunks = dm_div_up(info.n_tiles, max_chunk);
+    const int chunk = dm_div_up(info.n_tiles, n_chunks);
+    const size_t need = fused ? dm_fused_workspace(nullptr, chunk, t0, t1, kpad, L, nullptr)
+                              : carve_tiles(nullptr, chunk, t0, t1, kpad, L, tb);
+    rc = ctx_reserve(ctx, need);
+    if (rc != DM_OK) return rc;
+    for (int s = 0; s < DM_STAGE_COUNT; ++s) ctx->launches[s] = 0;
+    ctx->chunks_last = n_chunks;
+
+    PlaneArgs pa;
+    pa.n_modes = prm->n_modes;
+    for (int m = 0; m < 4; ++m) pa.modes[m] = prm->modes[m];
+    pa.T0 = t0; pa.T1 = t1; pa.s0 = prm->s0; pa.s1 = prm->s1; pa.len0 = info.len0; pa.len1 = info.len1;
+    pa.out_h = info.out_h; pa.out_w = info.out_w; pa.sub_pix = prm->sub_pix;
+
+    int launches = 0;
+    for (int ck = 0; ck < n_chunks; ++ck) {
+        const int first = lo * info.len1 + ck * chunk;
+        const int nt = (ck == n_chunks - 1) ? info.n_tiles - ck * chunk : chunk;
+        pa.first_tile = first;
+        if (fused) {
+            dm_fused_args fa;
+            fa.img1 = img1_dev; fa.img2 = img2_dev; fa.scene_h = prm->scene_h; fa.scene_w = prm->scene_w;
+            fa.t0 = t0; fa.t1 = t1; fa.ws = prm->ws; fa.kpad = kpad; fa.levels = L; fa.method = prm->method;
+            fa.first_tile = first; fa.n_tiles = nt; fa.len0 = info.len0; fa.len1 = info.len1;
+            fa.s0 = prm->s0; fa.s1 = prm->s1; fa.out_h = info.out_h; fa.out_w = info.out_w;
+            fa.n_modes = prm->n_modes; for (int m = 0; m < 4; ++m) fa.modes[m] = prm->modes[m];
+            fa.sub_pix = prm->sub_pix; fa.d_map = d_map_dev; fa.out_map = out_map_dev;
+            rc = dm_fused_solve_chunk(ctx, &fa, ck);
+            if (rc != DM_OK) return rc;
+            continue;
+        }
+        carve_tiles(ctx->ws, nt, t0, t1, kpad, L, tb);
+        {
+            StageTimer tm(ctx, DM_STAGE_DESCRIPTORS);
+            if ((rc = tm.begin(ck)) != DM_OK) return rc;
+            dm_tile_origin_kernel<<<dm_div_up(nt, 128), 128, 0, st>>>(tb.origin, nt, first, info.len1, prm->s0, prm->s1);
+            DM_LAUNCH_CHECK();
+            if ((rc = dm_descriptors(img1_dev, prm->scene_h, prm->scene_w, prm->scene_w, tb.origin, nt, t0, t1, prm->ws, tb.desc1, tb.stat1, st)) != DM_OK) return rc;
+            if ((rc = dm_descriptors(img2_dev, prm->scene_h, prm->scene_w, prm->scene_w, tb.origin, nt, t0, t1, prm->ws, tb.desc2, tb.stat2, st)) != DM_OK) return rc;
+            ctx->launches[DM_STAGE_DESCRIPTORS] += 3;
+            if ((rc = tm.end()) != DM_OK) return rc;
+        }
+        {
+            StageTimer tm(ctx, DM_STAGE_CORRELATION);
+            if ((rc = tm.begin(ck)) != DM_OK) return rc;
+            if ((rc = dm_correlation(tb.desc1, tb.stat1, tb.desc2, tb.stat2, nt, P, kpad, prm->ws, prm->method, DM_CORR_AUTO, tb.level[0], st)) != DM_OK) return rc;
+            ctx->launches[DM_STAGE_CORRELATION] += 1;
+            if ((rc = tm.end()) != DM_OK) return rc;
+        }
+        {
+            StageTimer tm(ctx, DM_STAGE_NORMALIZE);
+            if ((rc = tm.begin(ck)) != DM_OK) return rc;
+            if ((rc = dm_minmax_rectify(tb.level[0], (long long)nt * P, P, nullptr, tb.level[0], nullptr, nullptr, st)) != DM_OK) return rc;
+            ctx->launches[DM_STAGE_NORMALIZE] += 1;
+            if ((rc = tm.end()) != DM_OK) return rc;
+        }
+        {
+            StageTimer tm(ctx, DM_STAGE_AGGREGATE);
+            if ((rc = tm.begin(ck)) != DM_OK) return rc;
+            for (int k = 0; k + 1 < L; ++k) {
+                if ((rc = dm_aggregate(tb.level[k], nt, t0 >> k, t1 >> k, t0 >> k, t1 >> k, 1, tb.level[k + 1], st)) != DM_OK) return rc;
+                ctx->launches[DM_STAGE_AGGREGATE] += 1;
+            }
+            if ((rc = tm.end()) != DM_OK) return rc;
+        }
+        int cur = 0;
+        {
+            StageTimer tm(ctx, DM_STAGE_BACKTRACK);
+            if ((rc = tm.begin(ck)) != DM_OK) return rc;
+            if ((rc = dm_backtrack_top(tb.level[L - 1], 0, nt, t0 >> (L - 1), t1 >> (L - 1), tb.match[cur], tb.score[cur], st)) != DM_OK) return rc;
+            ctx->launches[DM_STAGE_BACKTRACK] += 1;
+            for (int k = L - 2; k >= 0; --k) {
+                if ((rc = dm_backtrack_level(tb.level[k], 0, nt, t0 >> k, t1 >> k, t0 >> k, t1 >> k, tb.match[cur], tb.match[cur ^ 1], tb.score[cur ^ 1], st)) != DM_OK) return rc;
+                cur ^= 1;
+                ctx->launches[DM_STAGE_BACKTRACK] += 1;
+            }
+            if ((rc = tm.end()) != DM_OK) return rc;
+        }
+        {
+            StageTimer tm(ctx, DM_STAGE_PLANES);
+            if ((rc = tm.begin(ck)) != DM_OK) return rc;
+            const long long total = (long long)nt * P;
+            dm_planes_kernel<<<dm_div_up(total, 256), 256, 0, st>>>(tb.level[0], total, pa, tb.match[cur], tb.score[cur], d_map_dev, out_map_dev);
+            DM_LAUNCH_CHECK();
+            ctx->launches[DM_STAGE_PLANES] += 1;
+            if ((rc = tm.end()) != DM_OK) return rc;
+        }
+    }
+    for (int s = 0; s < DM_STAGE_COUNT; ++s) launches += ctx->launches[s];
+    info.used_fused = fused ? 1 : 0;
+    info.chunk_tiles = chunk;
+    info.kernel_launches = launches;
+    if (info_out) *info_out = info;
+    return DM_OK;
+}
+
+extern "C" int dm_solve_scene_host(dm_ctx* ctx, const dm_scene_params* prm,
+                                   const uint8_t* img1_host, const uint8_t* img2_host,
+                                   double* d_map_host, double* out_map_host, dm_scene_info* info_out) {
+    DM_REQUIRE(ctx && prm && img1_host && img2_host && d_map_host && out_map_host, DM_ERR_INVALID, "dm_solve_scene_host: null argument");
+    dm_scene_info info;
+    int rc = dm_scene_geometry(prm, &info);
+    if (rc != DM_OK) return rc;
+    cudaStream_t st = ctx->stream;
+    const size_t sb = (size_t)prm->scene_h * prm->scene_w;
+    if (sb > ctx->scene_bytes) {
+        DM_CUDA_CHECK(cudaStreamSynchronize(st));
+        cudaFree(ctx->scene1); cudaFree(ctx->scene2); ctx->scene1 = ctx->scene2 = nullptr; ctx->scene_bytes = 0;
+        DM_CUDA_CHECK(cudaMalloc(&ctx->scene1, sb));
+        DM_CUDA_CHECK(cudaMalloc(&ctx->scene2, sb));
+        ctx->scene_bytes = sb;
+    }
+    const size_t plane = (size_t)info.out_h * info.out_w;
+    const size_t pb = plane * (prm->n_modes + 1) * sizeof(double);
+    if (pb > ctx->planes_bytes) {
+        DM_CUDA_CHECK(cudaStreamSynchronize(st));
+        cudaFree(ctx->planes); ctx->planes = nullptr; ctx->planes_bytes = 0;
+        DM_CUDA_CHECK(cudaMalloc(&ctx->planes, pb));
+        ctx->planes_bytes = pb;
+    }
+    // only the rows the strip's tiles read: [s0*lo, s0*(hi-1) + t0 + ws - 1)
+    int lo = prm->tile_row_lo, hi = prm->tile_row_hi;
+    if (hi <= 0) { lo = 0; hi = info.len0; }
+    const size_t in_lo = (size_t)prm->s0 * lo, in_hi = (size_t)prm->s0 * (hi - 1) + prm->t0 + prm->ws - 1;
+    const size_t in_off = in_lo * prm->scene_w, in_bytes = (in_hi - in_lo) * prm->scene_w;
+    DM_CUDA_CHECK(cudaMemcpyAsync(ctx->scene1 + in_off, img1_host + in_off, in_bytes, cudaMemcpyHostToDevice, st));
+    DM_CUDA_CHECK(cudaMemcpyAsync(ctx->scene2 + in_off, img2_host + in_off, in_bytes, cudaMemcpyHostToDevice, st));
+    double* d_map = ctx->planes;
+    double* out_map = ctx->planes + plane * prm->n_modes;
+    if (prm->s0 > prm->t0 || prm->s1 > prm->t1)      // gaps between tiles: np.empty in the reference, zeros here
+        DM_CUDA_CHECK(cudaMemsetAsync(ctx->planes, 0, pb, st));
+    rc = dm_solve_scene(ctx, prm, ctx->scene1, ctx->scene2, d_map, out_map, &info);
+    if (rc != DM_OK) return rc;
+    const size_t row_off = (size_t)info.row_lo * info.out_w;
+    const size_t row_bytes = (size_t)(info.row_hi - info.row_lo) * info.out_w * sizeof(double);
+    for (int m = 0; m < prm->n_modes; ++m)
+        DM_CUDA_CHECK(cudaMemcpyAsync(d_map_host + m * plane + row_off, d_map + m * plane + row_off, row_bytes, cudaMemcpyDeviceToHost, st));
+    DM_CUDA_CHECK(cudaMemcpyAsync(out_map_host + row_off, out_map + row_off, row_bytes, cudaMemcpyDeviceToHost, st));
+    DM_CUDA_CHECK(cudaStreamSynchronize(st));
+    if (info_out) *info_out = info;
+    return DM_OK;
+}

@@ -1,0 +1,83 @@
+// Shared device helpers and host-side error plumbing for libdmstereo (sm_100a only).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <math_constants.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/dmstereo.h"
+
+#define DM_LAM 1.4f                 // misc/Correlation_map.py:41
+#define DM_NEAR_ZERO_F 0.0001f      // misc/Matching.py:74
+#define DM_NEAR_ZERO_D 0.0001
+
+void dm_set_error(const char* fmt, ...);
+
+#define DM_CUDA_CHECK(expr)                                                              \
+    do {                                                                                 \
+        cudaError_t err__ = (expr);                                                      \
+        if (err__ != cudaSuccess) {                                                      \
+            dm_set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(err__),      \
+                         __FILE__, __LINE__);                                            \
+            return DM_ERR_CUDA;                                                          \
+        }                                                                                \
+    } while (0)
+
+#define DM_REQUIRE(cond, code, ...)                                                      \
+    do {                                                                                 \
+        if (!(cond)) {                                                                   \
+            dm_set_error(__VA_ARGS__);                                                   \
+            return (code);                                                               \
+        }                                                                                \
+    } while (0)
+
+#define DM_LAUNCH_CHECK() DM_CUDA_CHECK(cudaGetLastError())
+
+// ---- per-patch statistics written by the descriptor kernel -------------------------
+// x = S'  (residual sum of the mean-centred window, |S'| <= K/2)
+// y = inv (1/sqrt(sum a'^2 - S'^2/K); 0 for a flat window)
+// z = S'/K
+// w = 1 if the window is flat (all pixels equal) else 0
+typedef float4 dm_stat;
+
+// NaN-propagating max/min: torch.nn.MaxPool2d and numpy max/min keep NaN
+// (misc/Correlation_map.py:103, misc/Feature_value.py:34-35); fmaxf would drop it.
+__device__ __forceinline__ float dm_max_nan(float a, float b) {
+    float r;
+    asm("max.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b));
+    return r;
+}
+__device__ __forceinline__ float dm_min_nan(float a, float b) {
+    float r;
+    asm("min.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b));
+    return r;
+}
+
+// ---- the one ZNCC formula every kernel shares ---------------------------------------
+// dot = sum a1'*a2' (exact integer in fp32), returns z = (dot - S1'*S2'/K) * inv2.
+// The row factor inv1 (>0) and the [-1,1] clamp are monotone, so kernels that max-pool
+// apply dm_zncc_finish after pooling and still get bit-identical values.
+__device__ __forceinline__ float dm_zncc_partial(float dot, float s1, float s2k, float inv2) {
+    return __fmul_rn(__fmaf_rn(-s1, s2k, dot), inv2);
+}
+__device__ __forceinline__ float dm_zncc_finish(float z, float inv1, bool flat1, bool normed) {
+    if (!normed) return z;                       // TM_CCOEFF: numerator only (inv2 == 1)
+    if (flat1) return 1.0f;                      // OpenCV: flat template -> map of ones
+    float r = __fmul_rn(z, inv1);
+    return fminf(fmaxf(r, -1.0f), 1.0f);
+}
+
+// (x - min) / (max - min), then ** 1.4   (misc/Feature_value.py:36, Correlation_map.py:159)
+__device__ __forceinline__ float dm_normalize(float x, float mn, float mx) {
+    return __fdiv_rn(__fsub_rn(x, mn), __fsub_rn(mx, mn));
+}
+__device__ __forceinline__ float dm_rectify(float x) { return powf(x, DM_LAM); }
+
+__device__ __forceinline__ int dm_round_mean(int sum, int k) {
+    // nearest integer to sum/k for sum >= 0 (pixels are unsigned)
+    return (2 * sum + k) / (2 * k);
+}
+
+static inline int dm_div_up(long long a, long long b) { return (int)((a + b - 1) / b); }

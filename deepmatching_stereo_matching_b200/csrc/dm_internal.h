@@ -1,0 +1,52 @@
+// Internal (non-ABI) declarations shared between the translation units of libdmstereo.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <vector>
+
+#include "../../include/dmstereo.h"
+
+int dm_correlation_simt(const void* desc1, const float* stat1, const void* desc2, const float* stat2,
+                        int n_tiles, int p, int kpad, int method, float* raw, cudaStream_t stream);
+
+// tcgen05 / TMEM / TMA engine (correlation_umma.cu)
+bool dm_correlation_umma_supported(int p, int kpad);
+int dm_correlation_umma(const void* desc1, const float* stat1, const void* desc2, const float* stat2,
+                        int n_tiles, int p, int kpad, int method, float* raw, cudaStream_t stream);
+
+struct dm_ctx {
+    cudaStream_t stream = nullptr;
+    char* ws = nullptr;             // workspace
+    size_t ws_bytes = 0;
+    size_t ws_limit = (size_t)48 << 30;
+    // host-API staging
+    uint8_t* scene1 = nullptr; uint8_t* scene2 = nullptr; size_t scene_bytes = 0;
+    double* planes = nullptr; size_t planes_bytes = 0;
+    // timing
+    bool timing = false;
+    std::vector<cudaEvent_t> ev[DM_STAGE_COUNT];   // pairs (start, stop) per chunk
+    int launches[DM_STAGE_COUNT] = {};
+    size_t chunks_last = 0;
+};
+
+// Records a CUDA-event pair around one stage of one chunk when ctx->timing is on.
+struct StageTimer {
+    dm_ctx* ctx; int stage; size_t slot;
+    StageTimer(dm_ctx* c, int s) : ctx(c), stage(s), slot(0) {}
+    int begin(size_t chunk);
+    int end();
+};
+
+// Fused solver (fused.cu): level 0 is never written to HBM.
+struct dm_fused_args {
+    const uint8_t* img1; const uint8_t* img2; int scene_h, scene_w;
+    int t0, t1, ws, kpad, levels, method;
+    int first_tile, n_tiles, len0, len1, s0, s1, out_h, out_w;
+    int n_modes, modes[4], sub_pix;
+    double* d_map; double* out_map;
+};
+bool dm_fused_supported(int t0, int t1, int kpad);
+size_t dm_fused_workspace(char* base, int n_tiles, int t0, int t1, int kpad, int levels, void* buffers_out);
+int dm_fused_solve_chunk(dm_ctx* ctx, const dm_fused_args* a, int chunk_index);

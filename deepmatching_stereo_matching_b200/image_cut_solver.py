@@ -1,0 +1,163 @@
+# -*- coding: utf-8 -*-
+"""
+ImageCutSolver -- cuts a scene into halo'd tiles, matches every tile and mosaics the
+disparity planes.  Mirror of misc/image_cut_solver.py:26-197 of the reference (same
+constructor, same (d_map, out_map) float64 result, same tile grid and overlap rule).
+
+The reference solves the tiles one after the other on the CPU; here all tiles of the
+scene (or of this rank's strip of tile rows) go through libdmstereo in a few batched
+launches: descriptors -> tcgen05 correlation -> pyramid -> backtracking -> planes.
+"""
+
+import numpy as np
+
+from . import _native
+from .Correlation_map import Correlation_map
+from .Matching import Matching
+from .Calc_difference import Calc_difference
+
+_CTX = {}
+
+
+def _context():
+    """One dm_ctx (workspace, staging buffers) per CUDA device of this process."""
+    torch = _native.require_cuda()
+    dev = torch.cuda.current_device()
+    if dev not in _CTX:
+        _CTX[dev] = _native.Context()
+    return _CTX[dev]
+
+
+def pinned_empty(shape, dtype):
+    """numpy array backed by page-locked host memory (torch owns the allocation)."""
+    torch = _native.require_cuda()
+    t = torch.empty(tuple(int(x) for x in shape), dtype=getattr(torch, np.dtype(dtype).name), pin_memory=True)
+    return t.numpy()
+
+
+class ImageCutSolver():
+
+    def __init__(
+        self, img1, img2,
+        image_size=[32, 32], stride=[32, 32], window_size=5,
+        feature_name='cv2.TM_CCOEFF_NORMED', degree_map_mode=['elevation'],
+        padding=False,
+        sub_pix=True,
+        filtering=False,
+        filtering_window_size=3,
+        filtering_num=3,
+        filtering_mode='average'
+    ):
+        self.img_shape = img1.shape
+        assert self.img_shape == img2.shape, '2枚の画像は同じサイズ！'
+        self.img1 = img1
+        self.img2 = img2
+        self.stride = stride
+        self.window_size = window_size
+        self.degree_map_mode = degree_map_mode
+        self.exclusive_pix = int((window_size - 1) / 2)
+        self.image_size = image_size
+        self.trimed_size = [image_size[i] + 2 * self.exclusive_pix for i in range(2)]
+        self.feature_name = feature_name
+
+        if padding:
+            self._padding()
+
+        # misc/image_cut_solver.py:62 -- the last fitting tile is dropped (no +1)
+        self.len = [int(np.floor((self.img_shape[i] - self.trimed_size[i]) / self.stride[i])) for i in range(2)]
+
+        self.padding = padding
+        self.sub_pix = sub_pix
+        self.filtering = filtering
+        self.filtering_window_size = filtering_window_size
+        self.filtering_num = filtering_num
+        self.filtering_mode = filtering_mode
+
+        self.log_flg = True
+        # extensions (keyword-only use): strip of tile rows for the multi-GPU partition and
+        # the engine selector (-1 auto, 0 materialising, 1 fused)
+        self.tile_rows = None
+        self.fused = -1
+
+    def _padding(self):
+        # misc/image_cut_solver.py:73-93 zeroes image 2 and leaves img_shape stale, so every
+        # window of image 2 is flat and the whole result is NaN.  Fenced, not accelerated.
+        raise NotImplementedError('padding=True is broken in the reference (image_cut_solver.py:85-93) and not supported')
+
+    def _cut_and_pool(self):
+        """misc/image_cut_solver.py:95-113 -- tile views, j outer / i inner."""
+        self.img1_sub = []
+        self.img2_sub = []
+        self.img_index = []
+        for j in range(self.len[1]):
+            for i in range(self.len[0]):
+                ys, xs = self.stride[0] * i, self.stride[1] * j
+                self.img1_sub.append(self.img1[ys:ys + self.trimed_size[0], xs:xs + self.trimed_size[1]])
+                self.img2_sub.append(self.img2[ys:ys + self.trimed_size[0], xs:xs + self.trimed_size[1]])
+                self.img_index.append([i, j])
+
+    def _solver(self, solve_image, solve_template):
+        """misc/image_cut_solver.py:115-142 -- one tile through the class API (device kernels)."""
+        co_cls = Correlation_map(solve_image, solve_template, window_size=self.window_size, feature_name=self.feature_name)
+        co_cls()
+        if self.log_flg:
+            print('complete to create multi-level correlation pyramid')
+            print('pyramid level: {}, N={}'.format(co_cls.iteration, co_cls.N_map))
+            self.log_flg = False
+        cls = Matching(co_cls, sub_pix=self.sub_pix, filtering=self.filtering, filter_window_size=self.filtering_window_size,
+                       filtering_num=self.filtering_num, filtering_mode=self.filtering_mode)
+        out = cls()
+        del co_cls
+        del cls
+        return np.array([Calc_difference.cal_map(out, mode=m) for m in self.degree_map_mode]), out[2, :, :]
+
+    def _params(self):
+        return _native.scene_params(self.img_shape, self.image_size, self.stride, self.window_size, self.feature_name,
+                                    list(self.degree_map_mode), self.sub_pix, self.tile_rows, self.fused)
+
+    def _execute_matching(self):
+        """misc/image_cut_solver.py:144-179 -- all tiles batched on the GPU."""
+        size_list = [self.stride[i] * self.img_index[-1][i] + self.image_size[i] for i in range(2)]   # IndexError when no tile fits, as in the reference
+        MODES = ['elevation', 'elevation2', 'distance']
+        for m in self.degree_map_mode:
+            if m not in MODES:
+                print('please input valid mode! {} are ok. yours is \'{}\''.format(MODES, m))
+                import sys
+                sys.exit()
+        if self.filtering:
+            return self._execute_matching_per_tile(size_list)
+        img1 = np.ascontiguousarray(self.img1, dtype=np.uint8)
+        img2 = np.ascontiguousarray(self.img2, dtype=np.uint8)
+        prm = self._params()
+        self.d_map = pinned_empty([len(self.degree_map_mode)] + size_list, np.float64)
+        self.out_map = pinned_empty(size_list, np.float64)
+        self.info = _context().solve_host(prm, img1, img2, self.d_map, self.out_map)
+        if self.log_flg:
+            print('complete to create multi-level correlation pyramid')
+            print('pyramid level: {}, N={}'.format(self.info.levels, self.info.n_map))
+            self.log_flg = False
+
+    def _execute_matching_per_tile(self, size_list):
+        """Tile-by-tile variant used when the displacement filter is on (Matching._filter,
+        misc/Matching.py:224-255, runs between the levels on the host)."""
+        self.d_map = np.empty([len(self.degree_map_mode)] + size_list, dtype=float)
+        self.out_map = np.empty(size_list, dtype=float)
+        for idx in range(len(self.img_index)):
+            i, j = self.img_index[idx]
+            ys, xs = self.stride[0] * i, self.stride[1] * j
+            d, s = self._solver(self.img1_sub[idx], self.img2_sub[idx])
+            self.d_map[:, ys:ys + self.image_size[0], xs:xs + self.image_size[1]] = d
+            self.out_map[ys:ys + self.image_size[0], xs:xs + self.image_size[1]] = s
+
+    def __call__(self):
+        self._cut_and_pool()
+        self._execute_matching()
+        return self.d_map, self.out_map
+
+    @staticmethod
+    def image_save(path, arr, threshold=[100, 190]):
+        """misc/image_cut_solver.py:186-197."""
+        from PIL import Image
+        arr = np.where(arr > threshold[1], threshold[1], arr)
+        arr = np.where(arr < threshold[0], threshold[0], arr)
+        Image.fromarray(arr.astype(np.uint8)).save(path)

@@ -1,0 +1,204 @@
+/*
+ * dmstereo.h -- C-ABI of libdmstereo.so, the B200 (sm_100a) implementation of the
+ * DeepMatching-for-stereo hot path of Yuki-Kumon/deepmatching_stereo_matching.
+ *
+ * The reference has no FFI of its own: its boundary is the Python class API
+ * (SURVEY.md section 8(b)).  Each entry point below names the reference function it
+ * replaces (paths relative to the reference repository).  The Python mirror of that API
+ * (package deepmatching_stereo_matching_b200, re-exported as misc.*) binds these symbols
+ * through ctypes; INTEGRATION.md shows the stub.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no C++/torch types cross the boundary.
+ *   - "dev" pointers are CUDA device pointers on the current device; "host" pointers are
+ *     ordinary (ideally pinned) host memory.
+ *   - stream is a cudaStream_t passed as void* (NULL = legacy default stream).  Stage
+ *     functions only enqueue work on it and return; they never synchronise.
+ *   - return value: 0 on success, <0 on error (DM_ERR_*); dm_last_error() returns a
+ *     thread-local human readable message.  Nothing throws.
+ *   - 4-D correlation maps are row-major [n][A][B][C][D]: n tiles, (A,B) the patch grid
+ *     of image 1, (C,D) the position grid in image 2.
+ */
+#ifndef DMSTEREO_H_
+#define DMSTEREO_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DM_OK                 0
+#define DM_ERR_INVALID       -1   /* bad argument (shape, window size, method ...) */
+#define DM_ERR_CUDA          -2   /* a CUDA runtime / driver call failed          */
+#define DM_ERR_NOMEM         -3   /* workspace would exceed the configured limit   */
+#define DM_ERR_UNSUPPORTED   -4   /* shape not supported by the requested kernel   */
+
+/* cv2 enum values accepted as `method` (misc/Feature_value.py:24) */
+#define DM_TM_CCOEFF          4
+#define DM_TM_CCOEFF_NORMED   5
+
+/* disparity planes (misc/Calc_difference.py:30) */
+#define DM_MODE_ELEVATION     0   /* j - map[1]              */
+#define DM_MODE_ELEVATION2    1   /* i - map[0]              */
+#define DM_MODE_DISTANCE      2   /* ||(i,j) - map[:2]||     */
+
+/* correlation engine selector for dm_correlation */
+#define DM_CORR_AUTO          0   /* tcgen05 when the shape allows it, else SIMT   */
+#define DM_CORR_SIMT          1   /* CUDA-core exact reference kernel              */
+#define DM_CORR_UMMA          2   /* tcgen05.mma + TMEM + TMA (errors if unsupported) */
+
+int         dm_version(void);
+const char* dm_last_error(void);
+/* compute capability of the current device as major*10+minor, or <0 */
+int         dm_device_cc(void);
+
+/* ---------------------------------------------------------------- descriptors ------
+ * Replaces Correlation_map._create_atomic_patch (misc/Correlation_map.py:51-67) plus the
+ * per-patch statistics cv2.matchTemplate derives internally (misc/Feature_value.py:41).
+ * For each of n tiles with top-left corner origin_yx[2*t..] in the scene, and each patch
+ * centre (i,j) of the t0 x t1 grid, writes the ws*ws window as bf16 values (pixel minus
+ * the patch's rounded mean, exact), zero padded to kpad, plus stat[p] = {S', inv} with
+ * S' the residual sum and inv = 1/sqrt(sum a'^2 - S'^2/K) (0 for a flat window).
+ * kpad = dm_kpad(ws).
+ */
+int dm_kpad(int ws);
+int dm_descriptors(const uint8_t* scene_dev, int scene_h, int scene_w, int pitch,
+                   const int32_t* origin_yx_dev, int n_tiles, int t0, int t1, int ws,
+                   void* desc_bf16_dev, float* stat_dev, void* stream);
+
+/* ---------------------------------------------------------------- correlation ------
+ * Replaces Correlation_map._create_simple_initial_co_map (misc/Correlation_map.py:69-87)
+ * = P x cv2.matchTemplate (misc/Feature_value.py:41), without the min-max.
+ * raw[t][p][q] = ZNCC(patch p of image 1, window q of image 2) (or the un-normalised
+ * TM_CCOEFF numerator), fp32, for n tiles.  p,q in [0, P) with P = t0*t1.
+ */
+int dm_correlation(const void* desc1_dev, const float* stat1_dev,
+                   const void* desc2_dev, const float* stat2_dev,
+                   int n_tiles, int p, int kpad, int ws, int method, int engine,
+                   float* raw_dev, void* stream);
+
+/* Feature_value.__call__ for arbitrary patch / image sizes (misc/Feature_value.py:39-43,
+ * for_igarss/cor_map.py:33-35): float32 (ih-ph+1) x (iw-pw+1) map, min-maxed. */
+int dm_feature_value(const uint8_t* patch_dev, int ph, int pw,
+                     const uint8_t* image_dev, int ih, int iw,
+                     int method, float* out_dev, void* stream);
+
+/* Feature_value.min_max per row (misc/Feature_value.py:32-37) fused with the
+ * rectification map**1.4 (misc/Correlation_map.py:158-159).  rows x q fp32.
+ * norm_dev and rect_dev may each be NULL (skip) and may alias raw_dev. */
+int dm_minmax_rectify(const float* raw_dev, long long rows, int q,
+                      float* norm_dev, float* rect_dev,
+                      float* rowmin_dev, float* rowmax_dev, void* stream);
+
+/* ---------------------------------------------------------------- pyramid ----------
+ * Replaces Correlation_map._aggregation + _rectification for one level transition
+ * (misc/Correlation_map.py:89-130,158-159): 3x3/stride-2/pad-1 max-pool of every (C,D)
+ * slice, average of the four children of each parent (no shift), then **1.4.
+ * in  [n][A][B][C][D]  ->  out [n][A/2][B/2][C/2][D/2]      (A,B,C,D even)
+ * rectify = 0 returns the plain average (Correlation_map._aggregation alone).
+ */
+int dm_aggregate(const float* in_dev, int n, int a, int b, int c, int d, int rectify,
+                 float* out_dev, void* stream);
+
+/* ---------------------------------------------------------------- backtracking -----
+ * Matching._initial_move_map (misc/Matching.py:80-96): top level [n][a][b][a][b].
+ * Matching._B (misc/Matching.py:98-139, filtering off): level [n][A][B][C][D] with the
+ * parent matches of the (A/2,B/2) grid.  match = int32 [n][2][A][B] (row, col);
+ * score [n][A][B] in the level's dtype.  is_f64 selects double input (bit-exact check
+ * against the reference's float64 pyramid).
+ */
+int dm_backtrack_top(const void* top_dev, int is_f64, int n, int a, int b,
+                     int32_t* match_dev, void* score_dev, void* stream);
+int dm_backtrack_level(const void* level_dev, int is_f64, int n, int a, int b, int c, int d,
+                       const int32_t* parent_match_dev,
+                       int32_t* match_dev, void* score_dev, void* stream);
+
+/* Matching._sub_pix_cal (misc/Matching.py:165-209) + assembly of Matching.__call__'s
+ * return value (misc/Matching.py:211-222): map_dev = double [n][3][T0][T1] =
+ * (row (+diff), col (+diff), score).  sub_pix = 0 skips the parabola fit. */
+int dm_match_map(const void* level0_dev, int is_f64, int n, int t0, int t1,
+                 const int32_t* match_dev, const void* score_dev, int sub_pix,
+                 double* map_dev, void* stream);
+
+/* Calc_difference.cal_map (misc/Calc_difference.py:25-49): double (3,T0,T1) -> (T0,T1) */
+int dm_cal_map(const double* map_dev, int t0, int t1, int mode, double* out_dev, void* stream);
+
+/* sub_pix_cal (misc/sub_pix_cal.py:22-53) incl. both image_threshold clamps
+ * (misc/optimize_loop.py:40-44): double (s0,s1) planes. */
+int dm_sub_pix_cal(const double* arr_dev, const double* co_map_dev, int s0, int s1,
+                   int direction, double ratio, double* out_dev, void* stream);
+
+/* ---------------------------------------------------------------- scene solver -----
+ * Replaces ImageCutSolver._cut_and_pool/_solver/_execute_matching
+ * (misc/image_cut_solver.py:95-184) for a whole scene or for a strip of tile rows.
+ */
+typedef struct dm_scene_params {
+    int32_t scene_h, scene_w;       /* S0, S1 of both images                              */
+    int32_t t0, t1;                 /* image_size (patch grid of a tile)                  */
+    int32_t s0, s1;                 /* stride                                             */
+    int32_t ws;                     /* window_size (odd)                                  */
+    int32_t method;                 /* DM_TM_*                                            */
+    int32_t n_modes;                /* number of disparity planes                         */
+    int32_t modes[4];               /* DM_MODE_*                                          */
+    int32_t sub_pix;                /* Matching(sub_pix=...)                              */
+    int32_t tile_row_lo, tile_row_hi; /* strip of tile rows [lo,hi); hi<=0 means all      */
+    int32_t fused;                  /* 1: fused tcgen05 path (no level-0 in HBM) when the
+                                       shape allows it, 0: materialising path, -1: auto  */
+    int32_t reserved[3];
+} dm_scene_params;
+
+typedef struct dm_scene_info {
+    int32_t len0, len1;             /* tile grid (misc/image_cut_solver.py:62)            */
+    int32_t out_h, out_w;           /* S0', S1' of the full mosaic                        */
+    int32_t row_lo, row_hi;         /* output rows owned by the strip                     */
+    int32_t n_tiles;                /* tiles in the strip                                 */
+    int32_t levels;                 /* pyramid depth ("iteration")                        */
+    int32_t n_map;                  /* N_map                                              */
+    int32_t used_fused;             /* which path ran                                     */
+    int32_t chunk_tiles;            /* tiles per batch                                    */
+    int32_t kernel_launches;        /* kernels enqueued by the last solve                 */
+} dm_scene_info;
+
+typedef struct dm_ctx dm_ctx;
+
+int  dm_ctx_create(dm_ctx** out);                 /* on the current CUDA device          */
+void dm_ctx_destroy(dm_ctx* ctx);
+int  dm_ctx_set_stream(dm_ctx* ctx, void* stream);
+int  dm_ctx_set_workspace_limit(dm_ctx* ctx, size_t bytes);
+size_t dm_ctx_workspace_bytes(const dm_ctx* ctx);
+
+/* geometry only (no GPU work): fills info for the given params */
+int dm_scene_geometry(const dm_scene_params* prm, dm_scene_info* info);
+
+/* Device-resident solve.  img*_dev: uint8 [scene_h][scene_w].  d_map_dev: double
+ * [n_modes][out_h][out_w], out_map_dev: double [out_h][out_w]; only rows
+ * [row_lo,row_hi) are written.  Asynchronous on the ctx stream. */
+int dm_solve_scene(dm_ctx* ctx, const dm_scene_params* prm,
+                   const uint8_t* img1_dev, const uint8_t* img2_dev,
+                   double* d_map_dev, double* out_map_dev, dm_scene_info* info);
+
+/* Host-buffer solve: copies both scenes host->device, solves, copies the owned rows of
+ * the planes device->host, and synchronises the ctx stream before returning. */
+int dm_solve_scene_host(dm_ctx* ctx, const dm_scene_params* prm,
+                        const uint8_t* img1_host, const uint8_t* img2_host,
+                        double* d_map_host, double* out_map_host, dm_scene_info* info);
+
+/* per-stage device time of the last dm_solve_scene* call in milliseconds (CUDA events on
+ * the ctx stream; enabled by dm_ctx_enable_timing).  Stage ids: DM_STAGE_*. */
+#define DM_STAGE_DESCRIPTORS  0
+#define DM_STAGE_CORRELATION  1
+#define DM_STAGE_NORMALIZE    2
+#define DM_STAGE_AGGREGATE    3
+#define DM_STAGE_BACKTRACK    4
+#define DM_STAGE_PLANES       5
+#define DM_STAGE_COUNT        6
+int dm_ctx_enable_timing(dm_ctx* ctx, int on);
+int dm_ctx_stage_ms(dm_ctx* ctx, float* ms_out /* [DM_STAGE_COUNT] */,
+                    int* launches_out /* [DM_STAGE_COUNT] */);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DMSTEREO_H_ */

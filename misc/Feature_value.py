@@ -1,0 +1,4 @@
+# Drop-in shim: the reference's scripts do `from misc.Feature_value import ...`
+# (deep_dem_mathing.py:11-13, ex_deepmatching_rawinput.py:17-18); the implementation lives
+# in deepmatching_stereo_matching_b200.Feature_value and runs on the GPU through libdmstereo.
+from deepmatching_stereo_matching_b200.Feature_value import Feature_value  # noqa: F401

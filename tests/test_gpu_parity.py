@@ -1,0 +1,225 @@
+"""Parity of the CUDA path (through the C-ABI / the reference-shaped classes) against the
+golden vectors of the live reference and against the numpy oracle.  Needs a B200."""
+import numpy as np
+import pytest
+
+from conftest import load_golden, TILE_CASES, SOLVER_CASES, co_map_atol
+from oracle import dm_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+# float32 pyramid on the GPU vs the reference's float64 pyramid (north star: 1e-3 relative)
+LEVEL_RTOL, LEVEL_ATOL = 1e-3, 2e-5
+# integer-disparity disagreement allowed end to end (north star: <= 0.1 %)
+MAX_INDEX_DISAGREEMENT = 1e-3
+
+
+@pytest.fixture(scope='module')
+def dm():
+    import torch
+    assert torch.cuda.is_available(), 'GPU tests need a CUDA device'
+    import deepmatching_stereo_matching_b200 as pkg
+    from deepmatching_stereo_matching_b200 import _native
+    assert _native.lib().dm_device_cc() >= 100
+    return pkg
+
+
+def _levels(g):
+    return [g['level%d' % k] for k in range(int(g['nlevels']))]
+
+
+class Stub(object):
+    pass
+
+
+@pytest.mark.parametrize('engine', [1, 0])
+@pytest.mark.parametrize('name', TILE_CASES)
+def test_correlation_and_pyramid_vs_reference(dm, name, engine):
+    g = load_golden(name)
+    co = dm.Correlation_map(g['img1'], g['img2'], window_size=int(g['ws']), feature_name=str(g['feature']))
+    co._create_atomic_patch()
+    assert np.array_equal(co.atomic_patch, O.atomic_patches(g['img1'], int(g['ws'])))
+    co._create_simple_initial_co_map(engine=engine)
+    ref = g['co_map'].astype(np.float64)
+    got = co.co_map
+    assert got.shape == ref.shape and got.dtype == np.float64
+    assert np.array_equal(np.isnan(got), np.isnan(ref))
+    assert np.nanmax(np.abs(got - ref)) <= co_map_atol(name)
+    # tighter: against the oracle's exact-integer ZNCC
+    exact = O.initial_co_map(g['img1'], g['img2'], int(g['ws']), O.FEATURE_NAMES[str(g['feature'])])
+    assert np.nanmax(np.abs(got - exact)) <= 2e-6
+    co._multi_level_correlation_pyramid()
+    assert co.N_map == int(g['N_map']) and co.iteration == int(g['iteration'])
+    assert len(co.co_map_list) == int(g['nlevels'])
+    for a, b in zip(co.co_map_list, _levels(g)):
+        assert a.shape == b.shape
+        assert np.array_equal(np.isnan(a), np.isnan(b))
+        assert np.allclose(a, b, rtol=LEVEL_RTOL, atol=LEVEL_ATOL, equal_nan=True)
+
+
+@pytest.mark.parametrize('name', TILE_CASES)
+def test_aggregate_kernel_given_reference_level(dm, name):
+    import torch
+    from deepmatching_stereo_matching_b200 import _native
+    g = load_golden(name)
+    lv = _levels(g)
+    for k in range(len(lv) - 1):
+        src = torch.from_numpy(lv[k].astype(np.float32)).cuda()
+        a, b, c, d = src.shape
+        out = torch.empty((a // 2, b // 2, c // 2, d // 2), dtype=torch.float32, device='cuda')
+        _native.check(_native.lib().dm_aggregate(_native.ptr(src), 1, a, b, c, d, 1, _native.ptr(out), _native.stream_ptr()))
+        got = out.cpu().numpy()
+        assert np.array_equal(np.isnan(got), np.isnan(lv[k + 1]))
+        assert np.allclose(got, lv[k + 1], rtol=2e-5, atol=1e-6, equal_nan=True)
+        # un-rectified variant == oracle.aggregate
+        _native.check(_native.lib().dm_aggregate(_native.ptr(src), 1, a, b, c, d, 0, _native.ptr(out), _native.stream_ptr()))
+        ref = O.aggregate(lv[k].astype(np.float32).astype(np.float64))
+        assert np.allclose(out.cpu().numpy(), ref, rtol=1e-6, atol=1e-7, equal_nan=True)
+
+
+def test_aggregate_batched_and_banded(dm):
+    """n > 1, wide rows (banded staging) and a non-square grid against the oracle."""
+    import torch
+    from deepmatching_stereo_matching_b200 import _native
+    rng = np.random.default_rng(0)
+    for (n, a, b, c, d) in [(3, 4, 4, 64, 64), (2, 2, 2, 128, 128), (2, 2, 4, 8, 32), (5, 8, 8, 8, 8), (1, 2, 2, 2, 2), (2, 2, 2, 6, 6)]:
+        x = rng.random((n, a, b, c, d)).astype(np.float32)
+        src = torch.from_numpy(x).cuda()
+        out = torch.empty((n, a // 2, b // 2, c // 2, d // 2), dtype=torch.float32, device='cuda')
+        _native.check(_native.lib().dm_aggregate(_native.ptr(src), n, a, b, c, d, 1, _native.ptr(out), _native.stream_ptr()))
+        ref = np.stack([O.rectify(O.aggregate(x[i].astype(np.float64))) for i in range(n)])
+        assert np.allclose(out.cpu().numpy(), ref, rtol=2e-5, atol=1e-6), (n, a, b, c, d)
+
+
+@pytest.mark.parametrize('name', TILE_CASES)
+def test_backtracking_bit_exact(dm, name):
+    g = load_golden(name)
+    lv = _levels(g)
+    st = Stub()
+    st.co_map_list = lv                      # float64, as the reference holds it
+    st.N_map = int(g['N_map'])
+    assert np.array_equal(dm.Matching(st, sub_pix=False)(), g['map_nosub'], equal_nan=True)
+    got = dm.Matching(st, sub_pix=True)()
+    assert got.dtype == np.float64 and got.shape == g['map_sub'].shape
+    assert np.array_equal(got[2], g['map_sub'][2], equal_nan=True)
+    assert np.array_equal(got[:2].astype(np.int64), g['map_sub'][:2].astype(np.int64))
+    assert np.allclose(got, g['map_sub'], rtol=0, atol=1e-12, equal_nan=True)
+    st.co_map_list = [x.astype(np.float32) for x in lv]
+    assert np.array_equal(dm.Matching(st, sub_pix=False)(), g['map_f32_nosub'], equal_nan=True)
+    assert np.array_equal(dm.Matching(st, sub_pix=True)(), g['map_f32_sub'], equal_nan=True)
+
+
+@pytest.mark.parametrize('name', TILE_CASES)
+def test_cal_map_bit_exact(dm, name):
+    g = load_golden(name)
+    for m in O.MODES:
+        assert np.array_equal(dm.Calc_difference.cal_map(g['map_sub'], m), g['cal_' + m], equal_nan=True)
+
+
+def test_sub_pix_cal_bit_exact(dm):
+    g = load_golden('sub_pix_cal')
+    for d in (0, 1):
+        assert np.array_equal(dm.sub_pix_cal(g['arr'], g['co'], direction=d), g['out_dir%d' % d], equal_nan=True)
+    assert np.array_equal(dm.sub_pix_cal(g['arr'], g['co'], direction=0, ratio=1.), g['out_ratio1'], equal_nan=True)
+    s = load_golden(SOLVER_CASES[0])
+    for i, m in enumerate(s['modes']):
+        direction = 1 if str(m) == 'elevation' else 0
+        assert np.array_equal(dm.sub_pix_cal(s['d_map'][i], s['out_map'], direction=direction), s['spc_' + str(m)], equal_nan=True)
+
+
+def test_feature_value_general_sizes(dm):
+    g = load_golden('feature_value')
+    a = dm.Feature_value('cv2.TM_CCOEFF_NORMED')(g['patch'], g['img'])
+    assert a.dtype == np.float32 and a.shape == g['normed_49'].shape
+    assert np.abs(a - g['normed_49']).max() <= 6e-5
+    assert np.abs(a - O.feature_value(g['patch'], g['img'])).max() <= 1e-6
+    b = dm.Feature_value('cv2.TM_CCOEFF')(g['patch'], g['img'])
+    assert np.abs(b - g['ccoeff_49']).max() <= 6e-5
+    c = dm.Feature_value()(g['img'], g['small'])           # swapped argument order, like cv2
+    assert np.abs(c - g['normed_small']).max() <= 6e-5
+
+
+def _end_to_end_tile(dm, img1, img2, ws, sub_pix):
+    co = dm.Correlation_map(img1, img2, window_size=ws)
+    co()
+    return co, dm.Matching(co, sub_pix=sub_pix)()
+
+
+@pytest.mark.parametrize('name', ['tile_16x16_ws5_noise', 'tile_16x16_ws5_sine', 'tile_8x32_ws3', 'tile_32x8_ws5',
+                                  'tile_16x16_ws15', 'tile_32x32_ws5'])
+def test_end_to_end_tile_vs_reference(dm, name):
+    g = load_golden(name)
+    _, got = _end_to_end_tile(dm, g['img1'], g['img2'], int(g['ws']), False)
+    ref = g['map_nosub']
+    bad = np.mean((got[:2] != ref[:2]).any(0))
+    assert bad <= max(MAX_INDEX_DISAGREEMENT, 1.0 / ref[0].size), bad
+    ok = (got[:2] == ref[:2]).all(0)
+    assert np.allclose(got[2][ok], ref[2][ok], rtol=LEVEL_RTOL, atol=LEVEL_ATOL)
+    _, got = _end_to_end_tile(dm, g['img1'], g['img2'], int(g['ws']), True)
+    ref = g['map_sub']
+    close = np.abs(got[:2] - ref[:2]).max(0) <= 1e-3 * np.maximum(1.0, np.abs(ref[:2]).max(0))
+    assert 1.0 - close.mean() <= max(MAX_INDEX_DISAGREEMENT, 1.0 / ref[0].size)
+
+
+def test_flat_patch_gives_nan_like_reference(dm):
+    g = load_golden('tile_8x8_ws5_flat')
+    co, got = _end_to_end_tile(dm, g['img1'], g['img2'], int(g['ws']), True)
+    assert np.isnan(g['co_map']).any()
+    assert np.array_equal(np.isnan(co.co_map), np.isnan(g['co_map']))
+    assert np.array_equal(np.isnan(got), np.isnan(g['map_sub']))
+
+
+@pytest.mark.parametrize('name', SOLVER_CASES)
+def test_image_cut_solver_vs_reference(dm, name):
+    g = load_golden(name)
+    s = dm.ImageCutSolver(g['img1'], g['img2'], image_size=list(g['image_size']), stride=list(g['stride']),
+                          window_size=int(g['ws']), degree_map_mode=[str(m) for m in g['modes']], sub_pix=bool(g['sub_pix']))
+    d, sc = s()
+    assert list(s.len) == list(g['len'])
+    assert d.shape == g['d_map'].shape and sc.shape == g['out_map'].shape and d.dtype == np.float64
+    assert np.mean(np.abs(d - g['d_map']) > 0.5) <= MAX_INDEX_DISAGREEMENT
+    close = np.abs(d - g['d_map']) <= 1e-3 * np.maximum(1.0, np.abs(g['d_map']))
+    assert close.mean() >= 1.0 - MAX_INDEX_DISAGREEMENT
+    assert np.mean(np.abs(sc - g['out_map']) > 1e-3) <= MAX_INDEX_DISAGREEMENT
+    # the batched path and the tile-by-tile class path are the same kernels
+    s2 = dm.ImageCutSolver(g['img1'], g['img2'], image_size=list(g['image_size']), stride=list(g['stride']),
+                           window_size=int(g['ws']), degree_map_mode=[str(m) for m in g['modes']], sub_pix=bool(g['sub_pix']))
+    s2.log_flg = False
+    s2._cut_and_pool()
+    s2._execute_matching_per_tile(list(d.shape[1:]))
+    assert np.array_equal(s2.d_map, d) and np.array_equal(s2.out_map, sc)
+
+
+def test_oracle_tile_t64_ws15(dm):
+    """One tile at the C2/C3 geometry (T=64, ws=15) against the numpy oracle."""
+    from deepmatching_stereo_matching_b200.synth import stereo_pair
+    i1, i2 = stereo_pair((78, 78), seed=21, mode='sine', amp=5)
+    cm = O.correlation_map(i1, i2, 15)
+    ref = O.matching(cm['co_map_list'], True)
+    co, got = _end_to_end_tile(dm, i1, i2, 15, True)
+    assert np.abs(co.co_map - cm['co_map']).max() <= 2e-6
+    for a, b in zip(co.co_map_list, cm['co_map_list']):
+        assert np.allclose(a, b, rtol=LEVEL_RTOL, atol=LEVEL_ATOL)
+    bad = np.mean((np.floor(got[:2] + 0.5) != np.floor(ref[:2] + 0.5)).any(0))
+    assert bad <= MAX_INDEX_DISAGREEMENT
+
+
+def test_scene_c2_properties(dm):
+    """Full C2 size (1024^2, T=64, ws=15, stride 60): constant-shift recovery,
+    determinism, and strip partition == whole-scene solve (bit-exact)."""
+    from deepmatching_stereo_matching_b200.synth import stereo_pair
+    i1, i2 = stereo_pair((1024, 1024), seed=1, mode='shift', amp=3)
+    kw = dict(image_size=[64, 64], stride=[60, 60], window_size=15, degree_map_mode=['elevation', 'elevation2'], sub_pix=False)
+    s = dm.ImageCutSolver(i1, i2, **kw)
+    d, sc = s()
+    assert d.shape == (2, 904, 904) and list(s.len) == [15, 15]
+    assert np.mean(d[0] == 3.0) > 0.97 and np.mean(d[1] == 0.0) > 0.97
+    d2, sc2 = dm.ImageCutSolver(i1, i2, **kw)()
+    assert np.array_equal(d, d2) and np.array_equal(sc, sc2)
+    merged = np.zeros_like(d)
+    for lo, hi in [(0, 7), (7, 15)]:
+        p = dm.ImageCutSolver(i1, i2, **kw)
+        p.tile_rows = (lo, hi)
+        dp, _ = p()
+        merged[:, p.info.row_lo:p.info.row_hi] = dp[:, p.info.row_lo:p.info.row_hi]
+    assert np.array_equal(merged, d)

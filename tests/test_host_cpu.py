@@ -1,0 +1,141 @@
+"""CPU-only checks: the C-ABI library loads and exports what include/dmstereo.h declares,
+geometry, argument validation of the reference-shaped classes, strip partition."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+from conftest import REPO
+from oracle import dm_oracle as O
+
+
+def test_library_exports_every_declared_symbol():
+    from deepmatching_stereo_matching_b200 import _native
+    header = open(os.path.join(REPO, 'include', 'dmstereo.h')).read()
+    header = re.sub(r'/\*.*?\*/', '', header, flags=re.S)
+    declared = set(re.findall(r'\b(dm_[a-z0-9_]+)\s*\(', header))
+    assert len(declared) >= 20
+    lib = _native.lib()
+    raw = ctypes.CDLL(_native.LIB_PATH)
+    for name in declared:
+        assert hasattr(raw, name), 'libdmstereo.so does not export %s' % name
+    assert declared == set(_native.SIGNATURES), declared ^ set(_native.SIGNATURES)
+    assert lib.dm_version() >= 100
+    assert lib.dm_kpad(15) == 256 and lib.dm_kpad(5) == 64 and lib.dm_kpad(3) == 64
+
+
+def test_struct_layout_matches_header():
+    from deepmatching_stereo_matching_b200 import _native
+    assert ctypes.sizeof(_native.SceneParams) == 4 * (9 + 4 + 4 + 3)
+    assert ctypes.sizeof(_native.SceneInfo) == 4 * 12
+
+
+@pytest.mark.parametrize('shape,size,stride,ws', [((256, 256), (32, 32), (32, 32), 5), ((1024, 1024), (64, 64), (60, 60), 15),
+                                                   ((4096, 4096), (64, 64), (60, 60), 15), ((8192, 8192), (128, 128), (124, 124), 15),
+                                                   ((80, 112), (16, 16), (16, 16), 3), ((100, 300), (8, 32), (8, 30), 5)])
+def test_geometry_matches_oracle(shape, size, stride, ws):
+    from deepmatching_stereo_matching_b200 import _native
+    info = _native.scene_geometry(_native.scene_params(shape, size, stride, ws, 'cv2.TM_CCOEFF_NORMED', ['elevation'], True))
+    ln, _ = O.tile_grid(shape, size, stride, ws)
+    assert [info.len0, info.len1] == ln
+    assert info.out_h == stride[0] * (ln[0] - 1) + size[0] and info.out_w == stride[1] * (ln[1] - 1) + size[1]
+    assert info.n_tiles == ln[0] * ln[1] and info.n_map == min(size) and info.levels == int(np.log2(min(size))) + 1
+    assert (info.row_lo, info.row_hi) == (0, info.out_h)
+
+
+def test_geometry_table_of_survey():
+    from deepmatching_stereo_matching_b200 import _native
+    for shape, size, stride, ws, tiles, out in [((256, 256), 32, 32, 5, 36, 192), ((1024, 1024), 64, 60, 15, 225, 904),
+                                                 ((4096, 4096), 64, 60, 15, 4356, 3964), ((8192, 8192), 128, 124, 15, 4096, 7940),
+                                                 ((512, 512), 32, 32, 5, 196, 448)]:
+        info = _native.scene_geometry(_native.scene_params(shape, (size, size), (stride, stride), ws, 'cv2.TM_CCOEFF_NORMED', ['elevation'], True))
+        assert info.n_tiles == tiles and info.out_h == out
+
+
+def test_geometry_rejects_bad_arguments():
+    from deepmatching_stereo_matching_b200 import _native
+    ok = dict(shape=(256, 256), image_size=(32, 32), stride=(32, 32), window_size=5, feature_name='cv2.TM_CCOEFF_NORMED', modes=['elevation'], sub_pix=True)
+    for bad in [dict(window_size=4), dict(image_size=(12, 12)), dict(image_size=(8, 20)), dict(shape=(30, 30)), dict(stride=(0, 32))]:
+        kw = dict(ok); kw.update(bad)
+        with pytest.raises(_native.DmError):
+            _native.scene_geometry(_native.scene_params(**kw))
+    prm = _native.scene_params(**dict(ok, tile_rows=(3, 9)))
+    with pytest.raises(_native.DmError):
+        _native.scene_geometry(prm)       # only 6 tile rows
+
+
+def test_strip_geometry():
+    from deepmatching_stereo_matching_b200 import _native
+    from deepmatching_stereo_matching_b200.strips import partition_tile_rows, strip_rows, input_rows
+    assert [hi - lo for lo, hi in partition_tile_rows(66, 8)] == [9, 9, 8, 8, 8, 8, 8, 8]
+    assert partition_tile_rows(3, 4) == [(0, 1), (1, 2), (2, 3), (3, 3)]
+    parts = partition_tile_rows(66, 8)
+    rows = [strip_rows(lo, hi, 66, 60, 64) for lo, hi in parts]
+    assert rows[0][0] == 0 and rows[-1][1] == 3964
+    assert all(rows[i][1] == rows[i + 1][0] for i in range(7))
+    for (lo, hi), rr in zip(parts, rows):
+        info = _native.scene_geometry(_native.scene_params((4096, 4096), (64, 64), (60, 60), 15, 'cv2.TM_CCOEFF_NORMED', ['elevation'], True, (lo, hi)))
+        assert (info.row_lo, info.row_hi) == rr and info.n_tiles == (hi - lo) * 66
+    a, b = input_rows(9, 18, 60, 64, 15)
+    assert (a, b) == (540, 60 * 17 + 78)
+
+
+def test_reference_shaped_validation(capsys):
+    import deepmatching_stereo_matching_b200 as dm
+    with pytest.raises(SystemExit):
+        dm.Feature_value('cv2.TM_SQDIFF')
+    with pytest.raises(SystemExit):
+        dm.Correlation_map(np.zeros((10, 10), np.uint8), np.zeros((10, 11), np.uint8))
+    with pytest.raises(SystemExit):
+        dm.Matching(object())
+    class Co:
+        co_map_list = []
+    with pytest.raises(AssertionError):
+        dm.Matching(Co(), filtering_mode='mean')
+    with pytest.raises(AssertionError):
+        dm.ImageCutSolver(np.zeros((64, 64), np.uint8), np.zeros((64, 65), np.uint8))
+    with pytest.raises(SystemExit):
+        dm.Calc_difference.cal_map(np.zeros((3, 4, 4)), 'nope')
+    s = dm.ImageCutSolver(np.zeros((256, 256), np.uint8), np.zeros((256, 256), np.uint8))
+    assert s.len == [6, 6] and s.trimed_size == [36, 36] and s.exclusive_pix == 2
+    s._cut_and_pool()
+    assert len(s.img_index) == 36 and s.img_index[1] == [1, 0] and s.img1_sub[0].shape == (36, 36)
+    m = dm.Matching(Co())
+    assert (m.filter_window_size, m.filtering, m.filtering_num, m.filtering_mode, m.sub_pix) == (3, False, 3, 'median', True)
+    assert np.array_equal(dm.image_threshold(np.array([-5., 0.5, 20.])), np.array([0., 0.5, 10.]))
+
+
+def test_no_cpu_fallback_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip('GPU present')
+    import deepmatching_stereo_matching_b200 as dm
+    from deepmatching_stereo_matching_b200._native import DmError
+    img = np.random.default_rng(0).integers(0, 255, (20, 20), dtype=np.uint8)
+    with pytest.raises(DmError):
+        dm.Correlation_map(img, img, 5)()
+    with pytest.raises(DmError):
+        dm.ImageCutSolver(np.zeros((256, 256), np.uint8), np.zeros((256, 256), np.uint8))()
+    with pytest.raises(DmError):
+        dm.sub_pix_cal(np.zeros((5, 5)), np.zeros((5, 5)))
+
+
+def test_misc_shims_resolve_to_the_package():
+    import misc.Correlation_map, misc.Matching, misc.image_cut_solver, misc.Feature_value, misc.raw_read
+    import misc.sub_pix_cal, misc.Calc_difference, misc.optimize_loop
+    import deepmatching_stereo_matching_b200 as dm
+    assert misc.Correlation_map.Correlation_map is dm.Correlation_map
+    assert misc.image_cut_solver.ImageCutSolver is dm.ImageCutSolver
+    assert misc.Matching.Matching is dm.Matching and misc.sub_pix_cal.sub_pix_cal is dm.sub_pix_cal
+    assert misc.raw_read.RawRead is dm.RawRead and misc.optimize_loop.image_threshold is dm.image_threshold
+
+
+def test_raw_read(tmp_path):
+    import deepmatching_stereo_matching_b200 as dm
+    a = (np.arange(12 * 10) * 3 % 256).astype(np.uint8).reshape(10, 12)
+    p = tmp_path / 'x.raw'
+    a.tofile(p)
+    assert np.array_equal(dm.RawRead.read(str(p), size=(12, 10)), O.raw_read(str(p), size=(12, 10)))
+    assert np.array_equal(dm.RawRead.read(str(p), size=(12, 10), rate=2), O.raw_read(str(p), size=(12, 10), rate=2))
