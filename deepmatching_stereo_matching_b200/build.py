@@ -54,7 +54,7 @@ def build(force=False, verbose=False):
         failed |= p.returncode != 0
     if failed:
         raise RuntimeError('nvcc failed')
-    cmd = [_nvcc(), '-shared', '-o', LIB] + objs + ['-lcuda', '-lcudart']
+    cmd = [_nvcc(), '-shared', '-Wno-deprecated-gpu-targets', '-o', LIB] + objs + ['-lcudart']
     subprocess.check_call(cmd)
     return LIB
 

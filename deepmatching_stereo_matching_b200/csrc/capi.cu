@@ -236,8 +236,8 @@ static size_t carve_tiles(char* base, int nt, int t0, int t1, int kpad, int leve
     tb.origin = c.take<int32_t>((size_t)nt * 2);
     tb.desc1 = c.take<__nv_bfloat16>((size_t)nt * P * kpad);
     tb.desc2 = c.take<__nv_bfloat16>((size_t)nt * P * kpad);
-    tb.stat1 = c.take<float>((size_t)nt * P * 4);
-    tb.stat2 = c.take<float>((size_t)nt * P * 4);
+    tb.stat1 = c.take<float>((size_t)nt * P * DM_STAT_FLOATS);
+    tb.stat2 = c.take<float>((size_t)nt * P * DM_STAT_FLOATS);
     tb.level.clear();
     size_t a = t0, b = t1;
     for (int k = 0; k < levels; ++k) {

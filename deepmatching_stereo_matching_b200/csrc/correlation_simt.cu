@@ -61,7 +61,7 @@ dm_correlation_simt_kernel(const __nv_bfloat16* __restrict__ d1, const dm_stat* 
             if (q >= P) continue;
             dm_stat sq = s2[q];
             float z = dm_zncc_partial(acc[u][v], sp.x, sq.z, normed ? sq.y : 1.0f);
-            raw[((size_t)tile * P + p) * P + q] = dm_zncc_finish(z, sp.y, sp.w != 0.f, normed != 0);
+            raw[((size_t)tile * P + p) * P + q] = dm_zncc_finish(z, sp.y, sp.y == 0.f, normed != 0);
         }
     }
 }

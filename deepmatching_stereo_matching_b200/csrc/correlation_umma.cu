@@ -1,6 +1,334 @@
+// tcgen05 / TMEM / TMA correlation engine (sm_100a).
+//
+// Replaces the P calls of cv2.matchTemplate in
+// Correlation_map._create_simple_initial_co_map (misc/Correlation_map.py:69-87):
+// per tile the dense contraction C[p][q] = sum_k A1[p][k] * A2[q][k] over the bf16
+// descriptor matrices (exact integers, fp32 accumulate exact), followed by the ZNCC
+// epilogue.  Two epilogues:
+//   MODE_RAW  : writes raw ZNCC  [tile][p][q]                    (materialising path)
+//   MODE_POOL : 3x3/s2/p1 max-pools the raw ZNCC of every patch on the fly (the first
+//               half of Correlation_map._aggregation, misc/Correlation_map.py:100-103;
+//               min-max and **1.4 are monotone, so pooling commutes with them) and writes
+//               only the pooled map [tile][p][C/2][D/2] plus the per-patch min / max that
+//               Feature_value.min_max (misc/Feature_value.py:32-37) needs.  Level 0 never
+//               reaches HBM.
+//
+// Work item = 256 patches of one tile (two M=128 accumulator halves) x all P positions,
+// swept in N-tiles of 128 positions.  Persistent grid, one CTA per SM, 10 warps:
+//   warp 0      TMA producer   A (2 halves x KB boxes, once per item), B ring of STAGES
+//   warp 1      MMA issuer     tcgen05.mma cta_group::1 kind::f16, M=128 N=128 K=16;
+//                              TMEM: 2 halves x 2 accumulator stages x 128 columns = 512
+//   warps 2..9  epilogue       tcgen05.ld 32x32b, thread == patch row, so the 3x3 pooling,
+//                              the running row minimum and the halo row carried between
+//                              N-tiles are all thread-local registers.
+// B traffic: every CTA streams the tile's whole position matrix once per item; with
+// M = 256 rows per item that is 32 B/clk/SM from L2 at the MMA's full rate.
 #include "dm_common.cuh"
 #include "dm_internal.h"
-bool dm_correlation_umma_supported(int, int) { return false; }
-int dm_correlation_umma(const void*, const float*, const void*, const float*, int, int, int, int, float*, cudaStream_t) {
-    dm_set_error("tcgen05 engine not built"); return DM_ERR_UNSUPPORTED;
+#include "umma.cuh"
+
+namespace {
+
+constexpr int BM = 128;                 // rows per accumulator half = TMEM lanes
+constexpr int HALVES = 2;
+constexpr int BN = 128;                 // positions per N-tile
+constexpr int BK = 64;                  // bf16 per 128-byte swizzle row
+constexpr int UMMA_K = 16;
+constexpr int STAGES = 5;
+constexpr int MAX_KB = 4;               // kpad <= 256
+constexpr int BOX_BYTES = BM * BK * 2;  // 16 KiB: one [128 rows x 64] bf16 box
+constexpr int EPI_WARPS = 8;
+constexpr int THREADS = 32 * (2 + EPI_WARPS);
+constexpr int TMEM_COLS = 512;
+constexpr size_t SMEM_BYTES = 1024 /*align slack*/ + (size_t)(HALVES * MAX_KB + STAGES) * BOX_BYTES + 256;
+
+struct Params {
+    const dm_stat* stat1;       // [n*P] float4 {S', inv, S'/K, mean}
+    const float2* cstat2;       // [n*P] {S'/K, inv} of image 2
+    int n_items, P, KB, items_per_tile, normed;
+    float* raw;                 // MODE_RAW : [n][P][P]
+    float* pooled;              // MODE_POOL: [n][P][P/4]
+    float* rowmin; float* rowmax;   // MODE_POOL: [n][P]
+};
+
+enum { MODE_RAW = 0, MODE_POOL = 1 };
+
+template <int MODE, int D>      // D = positions per map row (T1); only used by MODE_POOL
+__global__ void __launch_bounds__(THREADS, 1)
+dm_correlation_umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const Params prm) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* smemA = smem;
+    uint8_t* smemB = smem + (size_t)HALVES * MAX_KB * BOX_BYTES;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smemB + (size_t)STAGES * BOX_BYTES);
+    uint64_t* a_full = bars;
+    uint64_t* a_empty = bars + 1;
+    uint64_t* b_full = bars + 2;
+    uint64_t* b_empty = bars + 2 + STAGES;
+    uint64_t* t_full = bars + 2 + 2 * STAGES;
+    uint64_t* t_empty = bars + 4 + 2 * STAGES;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 6 + 2 * STAGES);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int P = prm.P, KB = prm.KB, NT = P / BN;
+
+    if (threadIdx.x == 0) {
+        umma::mbar_init(a_full, 1);
+        umma::mbar_init(a_empty, 1);
+        for (int s = 0; s < STAGES; ++s) { umma::mbar_init(b_full + s, 1); umma::mbar_init(b_empty + s, 1); }
+        for (int s = 0; s < 2; ++s) { umma::mbar_init(t_full + s, 1); umma::mbar_init(t_empty + s, EPI_WARPS); }
+        umma::fence_barrier_init();
+        umma::tma_prefetch_desc(&mapA);
+        umma::tma_prefetch_desc(&mapB);
+    }
+    if (warp == 1) {
+        umma::tmem_alloc(tmem_slot, TMEM_COLS);
+        umma::tmem_relinquish();
+    }
+    umma::tc_fence_before();
+    __syncthreads();
+    umma::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ------------------------------------------------------------ TMA producer
+        if (lane == 0) {
+            int bs = 0; uint32_t bph = 0, aph = 0;
+            for (int item = blockIdx.x; item < prm.n_items; item += gridDim.x) {
+                const int tile = item / prm.items_per_tile;
+                const int row0 = tile * P + (item - tile * prm.items_per_tile) * (HALVES * BM);
+                umma::mbar_wait(a_empty, aph ^ 1);
+                umma::mbar_expect_tx(a_full, (uint32_t)(HALVES * KB * BOX_BYTES));
+                for (int h = 0; h < HALVES; ++h)
+                    for (int kb = 0; kb < KB; ++kb)
+                        umma::tma_load_2d(smemA + (size_t)(h * MAX_KB + kb) * BOX_BYTES, &mapA, kb * BK, row0 + h * BM, a_full);
+                aph ^= 1;
+                for (int j = 0; j < NT; ++j)
+                    for (int kb = 0; kb < KB; ++kb) {
+                        umma::mbar_wait(b_empty + bs, bph ^ 1);
+                        umma::mbar_expect_tx(b_full + bs, (uint32_t)BOX_BYTES);
+                        umma::tma_load_2d(smemB + (size_t)bs * BOX_BYTES, &mapB, kb * BK, tile * P + j * BN, b_full + bs);
+                        if (++bs == STAGES) { bs = 0; bph ^= 1; }
+                    }
+            }
+        }
+    } else if (warp == 1) {
+        // ------------------------------------------------------------ MMA issuer
+        if (lane == 0) {
+            constexpr uint32_t idesc = umma::instr_desc_bf16(BM, BN);
+            int bs = 0; uint32_t bph = 0, aph = 0; int acc = 0; uint32_t accph = 0;
+            for (int item = blockIdx.x; item < prm.n_items; item += gridDim.x) {
+                umma::mbar_wait(a_full, aph);
+                aph ^= 1;
+                for (int j = 0; j < NT; ++j) {
+                    umma::mbar_wait(t_empty + acc, accph ^ 1);
+                    umma::tc_fence_after();
+                    for (int kb = 0; kb < KB; ++kb) {
+                        umma::mbar_wait(b_full + bs, bph);
+                        umma::tc_fence_after();
+                        const uint64_t bdesc = umma::smem_desc_sw128(smemB + (size_t)bs * BOX_BYTES);
+#pragma unroll
+                        for (int h = 0; h < HALVES; ++h) {
+                            const uint64_t adesc = umma::smem_desc_sw128(smemA + (size_t)(h * MAX_KB + kb) * BOX_BYTES);
+                            const uint32_t d = tmem_base + (uint32_t)((h * 2 + acc) * BN);
+#pragma unroll
+                            for (int k = 0; k < BK / UMMA_K; ++k)      // +32 B per K step inside the swizzle atom
+                                umma::mma_bf16(d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+                        }
+                        umma::mma_commit(b_empty + bs);                // frees the B stage when these MMAs retire
+                        if (++bs == STAGES) { bs = 0; bph ^= 1; }
+                    }
+                    umma::mma_commit(t_full + acc);                    // accumulators of this N-tile complete
+                    if (++acc == 2) { acc = 0; accph ^= 1; }
+                }
+                umma::mma_commit(a_empty);                             // A may be overwritten
+            }
+        }
+    } else {
+        // ------------------------------------------------------------ epilogue
+        const int e = warp - 2;
+        const int half = e >> 2;
+        const int quarter = warp & 3;                   // TMEM lanes a warp may touch: 32*(warp_id % 4)..+31
+        const int row_local = half * BM + quarter * 32 + lane;
+        const bool normed = prm.normed != 0;
+        int acc = 0; uint32_t accph = 0;
+        for (int item = blockIdx.x; item < prm.n_items; item += gridDim.x) {
+            const int tile = item / prm.items_per_tile;
+            const size_t prow = (size_t)tile * P + (size_t)(item - tile * prm.items_per_tile) * (HALVES * BM) + row_local;
+            const dm_stat s1 = prm.stat1[prow];
+            const bool flat1 = (s1.y == 0.0f);
+            const float2* cs = prm.cstat2 + (size_t)tile * P;
+            // MODE_POOL state: st[] = horizontally pooled previous row (odd rows) / running
+            // vertical max (even rows); rmin = running row minimum of the raw values
+            constexpr int HW = (MODE == MODE_POOL) ? D / 2 : 1;
+            float st[HW];
+            float rmin = CUDART_INF_F, rmax = -CUDART_INF_F;
+            if (MODE == MODE_POOL) {
+#pragma unroll
+                for (int i = 0; i < HW; ++i) st[i] = -CUDART_INF_F;
+            }
+            float* out_raw = (MODE == MODE_RAW) ? prm.raw + prow * (size_t)P : nullptr;
+            float* out_pool = (MODE == MODE_POOL) ? prm.pooled + prow * (size_t)(P / 4) : nullptr;
+            for (int j = 0; j < NT; ++j) {
+                umma::mbar_wait(t_full + acc, accph);
+                umma::tc_fence_after();
+                const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)((half * 2 + acc) * BN);
+                float zprev = -CUDART_INF_F;            // last raw value of the previous 32-column chunk
+                float4 ob;                              // MODE_POOL: 4 pooled outputs being assembled
+#pragma unroll
+                for (int c = 0; c < BN / 32; ++c) {
+                    float v[32];
+                    umma::tmem_ld_32x32(taddr + (uint32_t)(c * 32), v);
+                    if (c == BN / 32 - 1) {             // whole accumulator stage is in registers
+                        umma::tc_fence_before();
+                        if (lane == 0) umma::mbar_arrive(t_empty + acc);
+                    }
+                    const float4* cs4 = reinterpret_cast<const float4*>(cs + (size_t)j * BN + c * 32);
+#pragma unroll
+                    for (int i = 0; i < 32; i += 2) {
+                        const float4 cp = __ldg(cs4 + (i >> 1));         // {s2k, inv2} of two columns
+                        v[i] = dm_zncc_partial(v[i], s1.x, cp.x, normed ? cp.y : 1.0f);
+                        v[i + 1] = dm_zncc_partial(v[i + 1], s1.x, cp.z, normed ? cp.w : 1.0f);
+                    }
+                    if (MODE == MODE_RAW) {
+#pragma unroll
+                        for (int i = 0; i < 32; i += 4) {
+                            float4 o;
+                            o.x = dm_zncc_finish(v[i], s1.y, flat1, normed);
+                            o.y = dm_zncc_finish(v[i + 1], s1.y, flat1, normed);
+                            o.z = dm_zncc_finish(v[i + 2], s1.y, flat1, normed);
+                            o.w = dm_zncc_finish(v[i + 3], s1.y, flat1, normed);
+                            *reinterpret_cast<float4*>(out_raw + (size_t)j * BN + c * 32 + i) = o;
+                        }
+                    } else {
+                        constexpr int R = BN / D;               // map rows per N-tile (even)
+#pragma unroll
+                        for (int i = 0; i < 32; i += 2) {
+                            const int n = c * 32 + i;           // column inside the N-tile
+                            const int x = n % D, r = n / D;     // position inside the map row / row inside the N-tile
+                            const int xh = x >> 1;
+                            const float left = (x == 0) ? -CUDART_INF_F : (i == 0 ? zprev : v[i - 1]);
+                            const float h = fmaxf(fmaxf(left, v[i]), v[i + 1]);
+                            rmin = fminf(rmin, fminf(v[i], v[i + 1]));
+                            if ((r & 1) == 0) {
+                                st[xh] = fmaxf(st[xh], h);      // rows 2y-1 (carried) and 2y
+                            } else {
+                                const float o = dm_zncc_finish(fmaxf(st[xh], h), s1.y, flat1, normed);
+                                st[xh] = h;                     // becomes row 2(y+1)-1 of the next pooled row
+                                rmax = fmaxf(rmax, o);
+                                if ((xh & 3) == 0) ob.x = o; else if ((xh & 3) == 1) ob.y = o; else if ((xh & 3) == 2) ob.z = o; else ob.w = o;
+                                if ((xh & 3) == 3) {
+                                    const int yo = (j * R + r) >> 1;        // pooled row
+                                    *reinterpret_cast<float4*>(out_pool + (size_t)yo * (D / 2) + (xh - 3)) = ob;
+                                }
+                            }
+                        }
+                        zprev = v[31];
+                    }
+                }
+                if (++acc == 2) { acc = 0; accph ^= 1; }
+            }
+            if (MODE == MODE_POOL) {
+                prm.rowmin[prow] = dm_zncc_finish(rmin, s1.y, flat1, normed);
+                prm.rowmax[prow] = rmax;
+            }
+        }
+    }
+
+    umma::tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        umma::tc_fence_after();
+        umma::tmem_dealloc(tmem_base, TMEM_COLS);
+    }
+}
+
+dm_encode_tiled_fn get_encode_fn() {
+    static dm_encode_tiled_fn fn = nullptr;
+    if (fn) return fn;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess)
+        return nullptr;
+    fn = (dm_encode_tiled_fn)p;
+    return fn;
+}
+
+template <int MODE, int D>
+int launch(const CUtensorMap& mapA, const CUtensorMap& mapB, const Params& prm, cudaStream_t stream) {
+    static bool configured = false;
+    auto kern = dm_correlation_umma_kernel<MODE, D>;
+    if (!configured) {
+        DM_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+        configured = true;
+    }
+    int dev = 0, sms = 0;
+    DM_CUDA_CHECK(cudaGetDevice(&dev));
+    DM_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    const int grid = prm.n_items < sms ? prm.n_items : sms;
+    kern<<<grid, THREADS, SMEM_BYTES, stream>>>(mapA, mapB, prm);
+    DM_LAUNCH_CHECK();
+    return DM_OK;
+}
+
+}  // namespace
+
+int dm_make_desc_tensor_map(CUtensorMap* map, const void* base, uint64_t rows, uint32_t kpad, uint32_t box_rows) {
+    dm_encode_tiled_fn enc = get_encode_fn();
+    DM_REQUIRE(enc != nullptr, DM_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+    cuuint64_t gdim[2] = {kpad, rows};
+    cuuint64_t gstride[1] = {(cuuint64_t)kpad * 2};
+    cuuint32_t box[2] = {(cuuint32_t)BK, box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    DM_REQUIRE(r == CUDA_SUCCESS, DM_ERR_CUDA, "cuTensorMapEncodeTiled failed with %d", (int)r);
+    return DM_OK;
+}
+
+bool dm_correlation_umma_supported(int p, int kpad) {
+    return p >= HALVES * BM && p % (HALVES * BM) == 0 && kpad % BK == 0 && kpad <= MAX_KB * BK;
+}
+
+bool dm_correlation_umma_pool_supported(int t0, int t1, int kpad) {
+    return dm_correlation_umma_supported(t0 * t1, kpad) && (t1 == 16 || t1 == 32 || t1 == 64) && t0 % 2 == 0;
+}
+
+static int fill_params(Params& prm, CUtensorMap& mapA, CUtensorMap& mapB, const void* desc1, const float* stat1,
+                       const void* desc2, const float* stat2, int n_tiles, int p, int kpad, int method) {
+    const uint64_t rows = (uint64_t)n_tiles * p;
+    int rc = dm_make_desc_tensor_map(&mapA, desc1, rows, kpad, BM);
+    if (rc != DM_OK) return rc;
+    rc = dm_make_desc_tensor_map(&mapB, desc2, rows, kpad, BN);
+    if (rc != DM_OK) return rc;
+    prm.stat1 = (const dm_stat*)stat1;
+    prm.cstat2 = reinterpret_cast<const float2*>((const dm_stat*)stat2 + rows);
+    prm.P = p; prm.KB = kpad / BK; prm.items_per_tile = p / (HALVES * BM);
+    prm.n_items = n_tiles * prm.items_per_tile;
+    prm.normed = method == DM_TM_CCOEFF_NORMED;
+    prm.raw = prm.pooled = prm.rowmin = prm.rowmax = nullptr;
+    return DM_OK;
+}
+
+int dm_correlation_umma(const void* desc1, const float* stat1, const void* desc2, const float* stat2,
+                        int n_tiles, int p, int kpad, int method, float* raw, cudaStream_t stream) {
+    Params prm; CUtensorMap mapA, mapB;
+    int rc = fill_params(prm, mapA, mapB, desc1, stat1, desc2, stat2, n_tiles, p, kpad, method);
+    if (rc != DM_OK) return rc;
+    prm.raw = raw;
+    return launch<MODE_RAW, 64>(mapA, mapB, prm, stream);
+}
+
+int dm_correlation_umma_pool(const void* desc1, const float* stat1, const void* desc2, const float* stat2,
+                             int n_tiles, int t0, int t1, int kpad, int method,
+                             float* pooled, float* rowmin, float* rowmax, cudaStream_t stream) {
+    DM_REQUIRE(dm_correlation_umma_pool_supported(t0, t1, kpad), DM_ERR_UNSUPPORTED, "pooled tcgen05 correlation: unsupported grid (%d,%d)", t0, t1);
+    Params prm; CUtensorMap mapA, mapB;
+    int rc = fill_params(prm, mapA, mapB, desc1, stat1, desc2, stat2, n_tiles, t0 * t1, kpad, method);
+    if (rc != DM_OK) return rc;
+    prm.pooled = pooled; prm.rowmin = rowmin; prm.rowmax = rowmax;
+    if (t1 == 64) return launch<MODE_POOL, 64>(mapA, mapB, prm, stream);
+    if (t1 == 32) return launch<MODE_POOL, 32>(mapA, mapB, prm, stream);
+    return launch<MODE_POOL, 16>(mapA, mapB, prm, stream);
 }

@@ -62,7 +62,9 @@ dm_descriptor_kernel(const uint8_t* __restrict__ scene, int pitch,
         const float var = __fsub_rn((float)rq, __fmul_rn(s, sk));     // sum a'^2 - S'^2/K
         const bool flat = (rq == 0);
         const float inv = flat ? 0.0f : __frcp_rn(__fsqrt_rn(var));
-        stat[warp] = make_float4(s, inv, sk, flat ? 1.0f : 0.0f);
+        stat[warp] = make_float4(s, inv, sk, (float)mean);
+        // compact column parameters for the tcgen05 epilogue: {S'/K, inv}
+        reinterpret_cast<float2*>(stat + n_patches)[warp] = make_float2(sk, inv);
     }
 }
 

@@ -37,9 +37,9 @@ void dm_set_error(const char* fmt, ...);
 
 // ---- per-patch statistics written by the descriptor kernel -------------------------
 // x = S'  (residual sum of the mean-centred window, |S'| <= K/2)
-// y = inv (1/sqrt(sum a'^2 - S'^2/K); 0 for a flat window)
+// y = inv (1/sqrt(sum a'^2 - S'^2/K); 0 exactly when the window is flat)
 // z = S'/K
-// w = 1 if the window is flat (all pixels equal) else 0
+// w = the rounded mean the window was centred on (integer 0..255)
 typedef float4 dm_stat;
 
 // NaN-propagating max/min: torch.nn.MaxPool2d and numpy max/min keep NaN

@@ -59,10 +59,13 @@ int         dm_device_cc(void);
  * per-patch statistics cv2.matchTemplate derives internally (misc/Feature_value.py:41).
  * For each of n tiles with top-left corner origin_yx[2*t..] in the scene, and each patch
  * centre (i,j) of the t0 x t1 grid, writes the ws*ws window as bf16 values (pixel minus
- * the patch's rounded mean, exact), zero padded to kpad, plus stat[p] = {S', inv} with
- * S' the residual sum and inv = 1/sqrt(sum a'^2 - S'^2/K) (0 for a flat window).
- * kpad = dm_kpad(ws).
+ * the patch's rounded mean, exact), zero padded to kpad, plus the window statistics:
+ * stat_dev holds DM_STAT_FLOATS (6) floats per patch -- first n*P float4 {S', inv, S'/K,
+ * mean} with S' the residual sum and inv = 1/sqrt(sum a'^2 - S'^2/K) (0 for a flat
+ * window), then n*P float2 {S'/K, inv} (the compact column table of the tcgen05
+ * epilogue).  kpad = dm_kpad(ws).
  */
+#define DM_STAT_FLOATS 6
 int dm_kpad(int ws);
 int dm_descriptors(const uint8_t* scene_dev, int scene_h, int scene_w, int pitch,
                    const int32_t* origin_yx_dev, int n_tiles, int t0, int t1, int ws,
