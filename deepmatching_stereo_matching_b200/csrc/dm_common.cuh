@@ -73,7 +73,10 @@ __device__ __forceinline__ float dm_zncc_finish(float z, float inv1, bool flat1,
 __device__ __forceinline__ float dm_normalize(float x, float mn, float mx) {
     return __fdiv_rn(__fsub_rn(x, mn), __fsub_rn(mx, mn));
 }
-__device__ __forceinline__ float dm_rectify(float x) { return powf(x, DM_LAM); }
+// x ** 1.4 for x in [0,1] as exp2(1.4 * log2 x) on the special-function unit: 0 -> 0 and
+// 1 -> 1 exactly, NaN propagates, absolute error < 2e-7 (relative < 3e-6 down to 1e-3).
+// libdevice powf costs ~10x more and made the pyramid kernels ALU-bound instead of HBM-bound.
+__device__ __forceinline__ float dm_rectify(float x) { return exp2f(__fmul_rn(DM_LAM, __log2f(x))); }
 
 __device__ __forceinline__ int dm_round_mean(int sum, int k) {
     // nearest integer to sum/k for sum >= 0 (pixels are unsigned)

@@ -1,6 +1,336 @@
-// placeholder until the fused tcgen05 solver lands
+// Fused scene solver: the level-0 correlation map never reaches HBM.
+//
+//   descriptors -> tcgen05 correlation with pooled epilogue (correlation_umma.cu, MODE_POOL)
+//   -> first aggregation from the pooled raw map (this file) -> generic aggregation for
+//   the upper levels (pyramid.cu) -> backtracking down to level 1 (backtrack.cu) -> final
+//   level: the 3x3 window of level-0 values around each predicted match and the four
+//   parabola neighbours are recomputed from the two images (exact integer dot products,
+//   the same ZNCC / min-max / **1.4 formula as everywhere else), then the disparity planes
+//   are written straight into the mosaic.
+//
+// Replaces, for a batch of tiles, Correlation_map.__call__ (misc/Correlation_map.py:161-173),
+// Matching.__call__ (misc/Matching.py:211-222), Calc_difference.cal_map
+// (misc/Calc_difference.py:25-49) and the paste of misc/image_cut_solver.py:165-175.
+// HBM traffic per tile drops from ~2.1 * 4 P^2 bytes (write raw, read+write level 0, read
+// level 0) to ~0.6 * 4 P^2.
 #include "dm_common.cuh"
 #include "dm_internal.h"
-bool dm_fused_supported(int, int, int) { return false; }
-size_t dm_fused_workspace(char*, int, int, int, int, int, void*) { return 0; }
-int dm_fused_solve_chunk(dm_ctx*, const dm_fused_args*, int) { dm_set_error("fused path not built"); return DM_ERR_UNSUPPORTED; }
+
+namespace {
+
+struct FusedBuffers {
+    int32_t* origin; void* desc1; void* desc2; float* stat1; float* stat2;
+    float* pooled; float* rowmin; float* rowmax;
+    float* level[16];           // level[0] unused
+    int32_t* match[2]; float* score[2];
+};
+
+struct Carve {
+    char* base; size_t off;
+    explicit Carve(char* b) : base(b), off(0) {}
+    template <typename T> T* take(size_t count) {
+        off = (off + 255) & ~(size_t)255;
+        T* p = base ? (T*)(base + off) : nullptr;
+        off += count * sizeof(T);
+        return p;
+    }
+};
+
+size_t carve(char* base, int nt, int t0, int t1, int kpad, int levels, FusedBuffers& fb) {
+    Carve c(base);
+    const size_t P = (size_t)t0 * t1;
+    fb.origin = c.take<int32_t>((size_t)nt * 2);
+    fb.desc1 = c.take<__nv_bfloat16>((size_t)nt * P * kpad);
+    fb.desc2 = c.take<__nv_bfloat16>((size_t)nt * P * kpad);
+    fb.stat1 = c.take<float>((size_t)nt * P * DM_STAT_FLOATS);
+    fb.stat2 = c.take<float>((size_t)nt * P * DM_STAT_FLOATS);
+    fb.pooled = c.take<float>((size_t)nt * P * (P / 4));
+    fb.rowmin = c.take<float>((size_t)nt * P);
+    fb.rowmax = c.take<float>((size_t)nt * P);
+    size_t a = t0 >> 1, b = t1 >> 1;
+    fb.level[0] = nullptr;
+    for (int k = 1; k < levels; ++k) {
+        fb.level[k] = c.take<float>((size_t)nt * a * b * a * b);
+        a >>= 1; b >>= 1;
+    }
+    for (int s = 0; s < 2; ++s) {
+        fb.match[s] = c.take<int32_t>((size_t)nt * 2 * (P / 4));
+        fb.score[s] = c.take<float>((size_t)nt * (P / 4));
+    }
+    return (c.off + 255) & ~(size_t)255;
+}
+
+__global__ void dm_tile_origin_kernel2(int32_t* origin, int n, int first_tile, int len1, int s0, int s1) {
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    int g = first_tile + t;
+    origin[2 * t] = s0 * (g / len1);
+    origin[2 * t + 1] = s1 * (g % len1);
+}
+
+// ---------------------------------------------------------------------------------------
+// First aggregation from the pooled raw ZNCC: per child min-max + **1.4 (monotone, so they
+// commute with the max-pool the GEMM epilogue already did), average of the four children,
+// **1.4.  (misc/Feature_value.py:36, misc/Correlation_map.py:109-128,158-159)
+// pooled [n][t0*t1][t0/2][t1/2] -> level 1 [n][t0/2][t1/2][t0/2][t1/2]; 4 outputs / thread.
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+dm_aggregate_first_kernel(const float* __restrict__ pooled, const float* __restrict__ rowmin,
+                          const float* __restrict__ rowmax, long long total4, int t0, int t1,
+                          float* __restrict__ out) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total4) return;
+    const int P = t0 * t1, Q4 = P / 16;                 // float4 per pooled map
+    const int hA = t0 >> 1, hB = t1 >> 1;
+    const int m4 = (int)(idx % Q4);
+    long long t = idx / Q4;
+    const int J = (int)(t % hB); t /= hB;
+    const int I = (int)(t % hA);
+    const long long n = t / hA;
+    float4 sum;
+#pragma unroll
+    for (int ch = 0; ch < 4; ++ch) {
+        const size_t p = (size_t)n * P + (size_t)(2 * I + (ch >> 1)) * t1 + (2 * J + (ch & 1));
+        const float mn = __ldg(rowmin + p), mx = __ldg(rowmax + p);
+        float4 v = __ldg(reinterpret_cast<const float4*>(pooled + p * (size_t)(P / 4)) + m4);
+        v.x = dm_rectify(dm_normalize(v.x, mn, mx));
+        v.y = dm_rectify(dm_normalize(v.y, mn, mx));
+        v.z = dm_rectify(dm_normalize(v.z, mn, mx));
+        v.w = dm_rectify(dm_normalize(v.w, mn, mx));
+        if (ch == 0) sum = v;
+        else { sum.x = __fadd_rn(sum.x, v.x); sum.y = __fadd_rn(sum.y, v.y); sum.z = __fadd_rn(sum.z, v.z); sum.w = __fadd_rn(sum.w, v.w); }
+    }
+    float4 o;
+    o.x = dm_rectify(__fmul_rn(sum.x, 0.25f)); o.y = dm_rectify(__fmul_rn(sum.y, 0.25f));
+    o.z = dm_rectify(__fmul_rn(sum.z, 0.25f)); o.w = dm_rectify(__fmul_rn(sum.w, 0.25f));
+    reinterpret_cast<float4*>(out)[idx] = o;
+}
+
+// ---------------------------------------------------------------------------------------
+// Final level.  One warp per patch p = (i,j) of a tile.
+// ---------------------------------------------------------------------------------------
+struct FinalArgs {
+    const uint8_t* img1; const uint8_t* img2; int pitch;
+    const int32_t* origin; const dm_stat* stat1; const dm_stat* stat2;
+    const float* rowmin; const float* rowmax;
+    const int32_t* parent;      // level-1 matches [n][2][t0/2][t1/2]
+    int t0, t1, ws, normed, sub_pix;
+    int n_modes, modes[4];
+    int s0, s1, len0, len1, out_h, out_w, first_tile;
+    double* d_map; double* out_map;
+};
+
+constexpr int MAXK_REG = 8;     // window pixels per lane kept in registers (ws <= 15)
+
+// sum over the window of (a_k - m1) * (b_k(q) - m2(q)) for up to NQ positions q, exact int32
+template <int NQ>
+__device__ __forceinline__ void window_dots(const uint8_t* __restrict__ a_base, const uint8_t* __restrict__ b_img,
+                                            int pitch, int ws, int K, int lane, int m1,
+                                            const int (&qy)[NQ], const int (&qx)[NQ], const int (&m2)[NQ],
+                                            const bool (&ok)[NQ], int (&dot)[NQ]) {
+#pragma unroll
+    for (int s = 0; s < NQ; ++s) dot[s] = 0;
+    for (int k = lane; k < K; k += 32) {
+        const int ky = k / ws, kx = k - ky * ws;
+        const int a = (int)a_base[ky * pitch + kx] - m1;
+#pragma unroll
+        for (int s = 0; s < NQ; ++s)
+            if (ok[s]) dot[s] += a * ((int)b_img[(size_t)(qy[s] + ky) * pitch + qx[s] + kx] - m2[s]);
+    }
+#pragma unroll
+    for (int s = 0; s < NQ; ++s) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) dot[s] += __shfl_xor_sync(0xffffffffu, dot[s], o);
+    }
+}
+
+__global__ void __launch_bounds__(256)
+dm_final_level_kernel(const FinalArgs a, long long n_patches) {
+    const int lane = threadIdx.x & 31;
+    const long long w = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (w >= n_patches) return;
+    const int T0 = a.t0, T1 = a.t1, P = T0 * T1, K = a.ws * a.ws;
+    const long long n = w / P;
+    const int p = (int)(w - n * P);
+    const int i = p / T1, j = p - i * T1;
+    const int oy = a.origin[2 * n], ox = a.origin[2 * n + 1];
+    const bool normed = a.normed != 0;
+
+    // misc/Matching.py:116-124: p_dot = 2 * parent match + o
+    const int hA = T0 >> 1, hB = T1 >> 1;
+    const size_t pb = (size_t)n * 2 * hA * hB, pi = (size_t)(i >> 1) * hB + (j >> 1);
+    const int d0 = 2 * a.parent[pb + pi] + (i & 1);
+    const int d1 = 2 * a.parent[pb + (size_t)hA * hB + pi] + (j & 1);
+
+    const dm_stat s1 = a.stat1[(size_t)n * P + p];
+    const bool flat1 = (s1.y == 0.0f);
+    const float mn = a.rowmin[(size_t)n * P + p], mx = a.rowmax[(size_t)n * P + p];
+    const uint8_t* a_base = a.img1 + (size_t)(oy + i) * a.pitch + ox + j;
+    const uint8_t* b_img = a.img2 + (size_t)oy * a.pitch + ox;          // window q=(y,x) starts at b_img[y*pitch + x]
+    const dm_stat* st2 = a.stat2 + (size_t)n * P;
+    const int m1 = (int)s1.w;
+
+    // level-0 value of position (y,x) from its exact dot product
+    auto value = [&](int dot, const dm_stat& sq) -> float {
+        const float z = dm_zncc_partial((float)dot, s1.x, sq.z, normed ? sq.y : 1.0f);
+        return dm_rectify(dm_normalize(dm_zncc_finish(z, s1.y, flat1, normed), mn, mx));
+    };
+
+    // ---- misc/Matching.py:58-78 on the recomputed 3x3 window (zero padding outside)
+    int qy[9], qx[9], m2[9], dot[9];
+    bool ok[9];
+    dm_stat sq[9];
+#pragma unroll
+    for (int s = 0; s < 9; ++s) {
+        qy[s] = d0 + s / 3 - 1; qx[s] = d1 + s % 3 - 1;
+        ok[s] = qy[s] >= 0 && qy[s] < T0 && qx[s] >= 0 && qx[s] < T1;
+        sq[s] = ok[s] ? st2[qy[s] * T1 + qx[s]] : make_float4(0.f, 0.f, 0.f, 0.f);
+        m2[s] = (int)sq[s].w;
+    }
+    window_dots<9>(a_base, b_img, a.pitch, a.ws, K, lane, m1, qy, qx, m2, ok, dot);
+    float best = 0.f, centre = 0.f;
+    int bi = 0;
+    bool best_nan = false;
+#pragma unroll
+    for (int s = 0; s < 9; ++s) {
+        const float v = ok[s] ? value(dot[s], sq[s]) : 0.0f;
+        if (s == 4) centre = v;
+        if (s == 0) { best = v; best_nan = (v != v); }
+        else if (!best_nan && (v > best || v != v)) { best = v; bi = s; best_nan = (v != v); }
+    }
+    if (best < DM_NEAR_ZERO_F) { bi = 4; best = centre; }
+    const int c0 = d0 + bi / 3 - 1, c1 = d1 + bi % 3 - 1;
+    const float score = best + centre;
+
+    // ---- misc/Matching.py:165-209 parabola fit (index -1 wraps, upper edge skipped)
+    double mrow = (double)c0, mcol = (double)c1;
+    if (a.sub_pix) {
+        int ny[4], nx[4], nm[4], nd[4];
+        bool nok[4];
+        dm_stat ns[4];
+        ny[0] = c0 + 1; nx[0] = c1; ny[1] = (c0 == 0 ? T0 - 1 : c0 - 1); nx[1] = c1;
+        ny[2] = c0; nx[2] = c1 + 1; ny[3] = c0; nx[3] = (c1 == 0 ? T1 - 1 : c1 - 1);
+        const bool in = c0 >= 0 && c0 < T0 && c1 >= 0 && c1 < T1;      // always true when filtering is off
+        nok[0] = nok[1] = in && (c0 + 1 < T0);
+        nok[2] = nok[3] = in && (c1 + 1 < T1);
+#pragma unroll
+        for (int s = 0; s < 4; ++s) {
+            ns[s] = nok[s] ? st2[ny[s] * T1 + nx[s]] : make_float4(0.f, 0.f, 0.f, 0.f);
+            nm[s] = (int)ns[s].w;
+        }
+        window_dots<4>(a_base, b_img, a.pitch, a.ws, K, lane, m1, ny, nx, nm, nok, nd);
+        const float r0 = best;                      // level-0 value at the match itself
+        if (nok[0]) {
+            const float r1 = value(nd[0], ns[0]), rm = value(nd[1], ns[1]);
+            if (r0 > r1 && r0 > rm) mrow += (double)(-(r1 - rm) / (2.0f * (r1 + rm - 2.0f * r0)));
+        }
+        if (nok[2]) {
+            const float r1 = value(nd[2], ns[2]), rm = value(nd[3], ns[3]);
+            if (r0 > r1 && r0 > rm) mcol += (double)(-(r1 - rm) / (2.0f * (r1 + rm - 2.0f * r0)));
+        }
+    }
+    if (lane != 0) return;
+
+    // ---- planes + paste (misc/Calc_difference.py:36-48, misc/image_cut_solver.py:165-175)
+    const int g = a.first_tile + (int)n;
+    const int gi = g / a.len1, gj = g - gi * a.len1;
+    const int Y = a.s0 * gi + i, X = a.s1 * gj + j;
+    if (min(Y / a.s0, a.len0 - 1) != gi || min(X / a.s1, a.len1 - 1) != gj) return;   // a later tile owns this pixel
+    const double e0 = __dsub_rn((double)i, mrow), e1 = __dsub_rn((double)j, mcol);
+    const size_t plane = (size_t)a.out_h * a.out_w, pix = (size_t)Y * a.out_w + X;
+    for (int m = 0; m < a.n_modes; ++m) {
+        const double v = a.modes[m] == DM_MODE_ELEVATION ? e1
+                       : a.modes[m] == DM_MODE_ELEVATION2 ? e0
+                       : __dsqrt_rn(__fma_rn(e1, e1, __dmul_rn(e0, e0)));
+        a.d_map[m * plane + pix] = v;
+    }
+    a.out_map[pix] = (double)score;
+}
+
+}  // namespace
+
+bool dm_fused_supported(int t0, int t1, int kpad) {
+    return dm_correlation_umma_pool_supported(t0, t1, kpad) && t0 >= 4 && t1 >= 4;
+}
+
+size_t dm_fused_workspace(char* base, int n_tiles, int t0, int t1, int kpad, int levels, void* buffers_out) {
+    FusedBuffers fb;
+    size_t n = carve(base, n_tiles, t0, t1, kpad, levels, fb);
+    if (buffers_out) *(FusedBuffers*)buffers_out = fb;
+    return n;
+}
+
+int dm_fused_solve_chunk(dm_ctx* ctx, const dm_fused_args* a, int ck) {
+    cudaStream_t st = ctx->stream;
+    FusedBuffers fb;
+    const int nt = a->n_tiles, t0 = a->t0, t1 = a->t1, P = t0 * t1, L = a->levels;
+    carve(ctx->ws, nt, t0, t1, a->kpad, L, fb);
+    int rc;
+    {
+        StageTimer tm(ctx, DM_STAGE_DESCRIPTORS);
+        if ((rc = tm.begin(ck)) != DM_OK) return rc;
+        dm_tile_origin_kernel2<<<dm_div_up(nt, 128), 128, 0, st>>>(fb.origin, nt, a->first_tile, a->len1, a->s0, a->s1);
+        DM_LAUNCH_CHECK();
+        if ((rc = dm_descriptors(a->img1, a->scene_h, a->scene_w, a->scene_w, fb.origin, nt, t0, t1, a->ws, fb.desc1, fb.stat1, st)) != DM_OK) return rc;
+        if ((rc = dm_descriptors(a->img2, a->scene_h, a->scene_w, a->scene_w, fb.origin, nt, t0, t1, a->ws, fb.desc2, fb.stat2, st)) != DM_OK) return rc;
+        ctx->launches[DM_STAGE_DESCRIPTORS] += 3;
+        if ((rc = tm.end()) != DM_OK) return rc;
+    }
+    {
+        StageTimer tm(ctx, DM_STAGE_CORRELATION);
+        if ((rc = tm.begin(ck)) != DM_OK) return rc;
+        if ((rc = dm_correlation_umma_pool(fb.desc1, fb.stat1, fb.desc2, fb.stat2, nt, t0, t1, a->kpad, a->method,
+                                           fb.pooled, fb.rowmin, fb.rowmax, st)) != DM_OK) return rc;
+        ctx->launches[DM_STAGE_CORRELATION] += 1;
+        if ((rc = tm.end()) != DM_OK) return rc;
+    }
+    {
+        StageTimer tm(ctx, DM_STAGE_NORMALIZE);        // min-max + rectify + first child average
+        if ((rc = tm.begin(ck)) != DM_OK) return rc;
+        const long long total4 = (long long)nt * (P / 4) * (P / 16);
+        dm_aggregate_first_kernel<<<dm_div_up(total4, 256), 256, 0, st>>>(fb.pooled, fb.rowmin, fb.rowmax, total4, t0, t1, fb.level[1]);
+        DM_LAUNCH_CHECK();
+        ctx->launches[DM_STAGE_NORMALIZE] += 1;
+        if ((rc = tm.end()) != DM_OK) return rc;
+    }
+    {
+        StageTimer tm(ctx, DM_STAGE_AGGREGATE);
+        if ((rc = tm.begin(ck)) != DM_OK) return rc;
+        for (int k = 1; k + 1 < L; ++k) {
+            if ((rc = dm_aggregate(fb.level[k], nt, t0 >> k, t1 >> k, t0 >> k, t1 >> k, 1, fb.level[k + 1], st)) != DM_OK) return rc;
+            ctx->launches[DM_STAGE_AGGREGATE] += 1;
+        }
+        if ((rc = tm.end()) != DM_OK) return rc;
+    }
+    int cur = 0;
+    {
+        StageTimer tm(ctx, DM_STAGE_BACKTRACK);
+        if ((rc = tm.begin(ck)) != DM_OK) return rc;
+        if ((rc = dm_backtrack_top(fb.level[L - 1], 0, nt, t0 >> (L - 1), t1 >> (L - 1), fb.match[cur], fb.score[cur], st)) != DM_OK) return rc;
+        ctx->launches[DM_STAGE_BACKTRACK] += 1;
+        for (int k = L - 2; k >= 1; --k) {
+            if ((rc = dm_backtrack_level(fb.level[k], 0, nt, t0 >> k, t1 >> k, t0 >> k, t1 >> k, fb.match[cur], fb.match[cur ^ 1], fb.score[cur ^ 1], st)) != DM_OK) return rc;
+            cur ^= 1;
+            ctx->launches[DM_STAGE_BACKTRACK] += 1;
+        }
+        if ((rc = tm.end()) != DM_OK) return rc;
+    }
+    {
+        StageTimer tm(ctx, DM_STAGE_PLANES);           // level-0 backtracking + sub-pixel + planes
+        if ((rc = tm.begin(ck)) != DM_OK) return rc;
+        FinalArgs fa;
+        fa.img1 = a->img1; fa.img2 = a->img2; fa.pitch = a->scene_w;
+        fa.origin = fb.origin; fa.stat1 = (const dm_stat*)fb.stat1; fa.stat2 = (const dm_stat*)fb.stat2;
+        fa.rowmin = fb.rowmin; fa.rowmax = fb.rowmax; fa.parent = fb.match[cur];
+        fa.t0 = t0; fa.t1 = t1; fa.ws = a->ws; fa.normed = a->method == DM_TM_CCOEFF_NORMED; fa.sub_pix = a->sub_pix;
+        fa.n_modes = a->n_modes; for (int m = 0; m < 4; ++m) fa.modes[m] = a->modes[m];
+        fa.s0 = a->s0; fa.s1 = a->s1; fa.len0 = a->len0; fa.len1 = a->len1; fa.out_h = a->out_h; fa.out_w = a->out_w;
+        fa.first_tile = a->first_tile; fa.d_map = a->d_map; fa.out_map = a->out_map;
+        const long long n_patches = (long long)nt * P;
+        dm_final_level_kernel<<<dm_div_up(n_patches, 8), 256, 0, st>>>(fa, n_patches);
+        DM_LAUNCH_CHECK();
+        ctx->launches[DM_STAGE_PLANES] += 1;
+        if ((rc = tm.end()) != DM_OK) return rc;
+    }
+    return DM_OK;
+}

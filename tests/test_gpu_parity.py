@@ -235,6 +235,27 @@ def test_image_cut_solver_vs_reference(dm, name):
     assert np.array_equal(s2.d_map, d) and np.array_equal(s2.out_map, sc)
 
 
+@pytest.mark.parametrize('shape,size,stride,ws,sub', [((96, 96), 16, 12, 5, True), ((200, 168), 32, 30, 5, True),
+                                                      ((300, 300), 64, 60, 15, True), ((150, 230), 32, 32, 3, False)])
+def test_fused_path_equals_materialising_path(dm, shape, size, stride, ws, sub):
+    """The fused tcgen05 path (level 0 never in HBM) recomputes level-0 values with the same
+    formula from exact dot products: planes must agree with the materialising path."""
+    from deepmatching_stereo_matching_b200.synth import stereo_pair
+    i1, i2 = stereo_pair(shape, seed=5, mode='sine', amp=4)
+    res = []
+    for fused in (0, 1):
+        s = dm.ImageCutSolver(i1, i2, image_size=[size, size], stride=[stride, stride], window_size=ws,
+                              degree_map_mode=['elevation', 'elevation2', 'distance'], sub_pix=sub)
+        s.log_flg = False
+        s.fused = fused
+        d, sc = s()
+        assert s.info.used_fused == fused
+        res.append((d, sc))
+    (d0, s0), (d1, s1) = res
+    assert np.mean(np.abs(d0 - d1) > 1e-4) <= 2e-4
+    assert np.mean(np.abs(s0 - s1) > 1e-5) <= 2e-4
+
+
 def test_oracle_tile_t64_ws15(dm):
     """One tile at the C2/C3 geometry (T=64, ws=15) against the numpy oracle."""
     from deepmatching_stereo_matching_b200.synth import stereo_pair
