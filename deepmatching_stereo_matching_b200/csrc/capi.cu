@@ -264,7 +264,7 @@ extern "C" int dm_solve_scene(dm_ctx* ctx, const dm_scene_params* prm,
     if (hi <= 0) { lo = 0; hi = info.len0; }
 
     const bool want_fused = prm->fused != 0;
-    const bool fused = want_fused && dm_fused_supported(t0, t1, kpad);
+    const bool fused = want_fused && dm_fused_supported(t0, t1, kpad) && dm_fused_supported_ws(prm->ws);
     DM_REQUIRE(!(prm->fused == 1 && !fused), DM_ERR_UNSUPPORTED, "fused path does not support image_size (%d,%d) with window %d", t0, t1, prm->ws);
 
     // tiles per chunk from the workspace limit

@@ -14,6 +14,7 @@ extern "C" int dm_kpad(int ws) {
     return ((k + 63) / 64) * 64;       // multiple of 64 bf16 = one 128-byte swizzle row
 }
 
+// Generic kernel (any odd ws <= 31): one warp per patch, two passes over the window.
 __global__ void __launch_bounds__(256)
 dm_descriptor_kernel(const uint8_t* __restrict__ scene, int pitch,
                      const int32_t* __restrict__ origin_yx, long long n_patches,
@@ -68,6 +69,91 @@ dm_descriptor_kernel(const uint8_t* __restrict__ scene, int pitch,
     }
 }
 
+// Fast kernel for the window sizes the repo uses (ws <= 15): the window is read once, every
+// lane owns 8 consecutive K entries of its patch and writes them as one 16-byte store, so a
+// descriptor row leaves the warp as coalesced 128..512-byte segments.  G = lanes per patch.
+template <int WS>
+__global__ void __launch_bounds__(256)
+dm_descriptor_fast_kernel(const uint8_t* __restrict__ scene, int pitch,
+                          const int32_t* __restrict__ origin_yx, long long n_patches, int t0, int t1,
+                          __nv_bfloat16* __restrict__ desc, dm_stat* __restrict__ stat) {
+    constexpr int K = WS * WS;
+    constexpr int KPAD = ((K + 63) / 64) * 64;
+    constexpr int LANES = KPAD / 8;                                   // lanes that store
+    constexpr int G = LANES <= 8 ? 8 : (LANES <= 16 ? 16 : 32);       // lanes per patch
+    constexpr int PER_WARP = 32 / G;
+    const int lane = threadIdx.x & 31, gl = lane % G;
+    const long long warp = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    long long pidx = warp * PER_WARP + lane / G;
+    const bool live = pidx < n_patches;
+    if (!live) pidx = n_patches - 1;                                  // keep the warp converged for the shuffles
+    const int P = t0 * t1;
+    const int tile = (int)(pidx / P);
+    const int p = (int)(pidx - (long long)tile * P);
+    const int i = p / t1, j = p - i * t1;
+    const uint8_t* base = scene + (size_t)(origin_yx[2 * tile] + i) * pitch + origin_yx[2 * tile + 1] + j;
+    int px[8];
+    int sum = 0;
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+        const int k = gl * 8 + u;
+        px[u] = 0;
+        if (k < K) {
+            const int ky = k / WS, kx = k - ky * WS;
+            px[u] = base[ky * pitch + kx];
+            sum += px[u];
+        }
+    }
+#pragma unroll
+    for (int o = G / 2; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    const int mean = dm_round_mean(sum, K);
+    int rs = 0, rq = 0;
+    float f[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+        const int k = gl * 8 + u;
+        const int v = (k < K) ? px[u] - mean : 0;
+        rs += v;
+        rq += v * v;
+        f[u] = (float)v;
+    }
+#pragma unroll
+    for (int o = G / 2; o > 0; o >>= 1) {
+        rs += __shfl_xor_sync(0xffffffffu, rs, o);
+        rq += __shfl_xor_sync(0xffffffffu, rq, o);
+    }
+    if (!live) return;
+    if (gl < LANES) {
+        __nv_bfloat162 h0 = __floats2bfloat162_rn(f[0], f[1]), h1 = __floats2bfloat162_rn(f[2], f[3]);
+        __nv_bfloat162 h2 = __floats2bfloat162_rn(f[4], f[5]), h3 = __floats2bfloat162_rn(f[6], f[7]);
+        uint4 pk;
+        pk.x = *reinterpret_cast<uint32_t*>(&h0); pk.y = *reinterpret_cast<uint32_t*>(&h1);
+        pk.z = *reinterpret_cast<uint32_t*>(&h2); pk.w = *reinterpret_cast<uint32_t*>(&h3);
+        *reinterpret_cast<uint4*>(desc + (size_t)pidx * KPAD + gl * 8) = pk;
+    }
+    if (gl == 0) {
+        const float s = (float)rs;
+        const float sk = __fdiv_rn(s, (float)K);
+        const float var = __fsub_rn((float)rq, __fmul_rn(s, sk));
+        const bool flat = (rq == 0);
+        const float inv = flat ? 0.0f : __frcp_rn(__fsqrt_rn(var));
+        stat[pidx] = make_float4(s, inv, sk, (float)mean);
+        reinterpret_cast<float2*>(stat + n_patches)[pidx] = make_float2(sk, inv);
+    }
+}
+
+template <int WS>
+static void launch_descriptor_fast(const uint8_t* scene, int pitch, const int32_t* origin, long long n_patches,
+                                   int t0, int t1, void* desc, float* stat, cudaStream_t st) {
+    constexpr int K = WS * WS;
+    constexpr int KPAD = ((K + 63) / 64) * 64;
+    constexpr int LANES = KPAD / 8;
+    constexpr int G = LANES <= 8 ? 8 : (LANES <= 16 ? 16 : 32);
+    const long long warps = (n_patches + (32 / G) - 1) / (32 / G);
+    dm_descriptor_fast_kernel<WS><<<dm_div_up(warps, 8), 256, 0, st>>>(scene, pitch, origin, n_patches, t0, t1,
+                                                                        (__nv_bfloat16*)desc, (dm_stat*)stat);
+}
+
 extern "C" int dm_descriptors(const uint8_t* scene_dev, int scene_h, int scene_w, int pitch,
                               const int32_t* origin_yx_dev, int n_tiles, int t0, int t1, int ws,
                               void* desc_bf16_dev, float* stat_dev, void* stream) {
@@ -76,10 +162,22 @@ extern "C" int dm_descriptors(const uint8_t* scene_dev, int scene_h, int scene_w
     DM_REQUIRE(scene_h >= t0 + ws - 1 && scene_w >= t1 + ws - 1 && pitch >= scene_w, DM_ERR_INVALID,
                "dm_descriptors: scene %dx%d smaller than a tile", scene_h, scene_w);
     const long long n_patches = (long long)n_tiles * t0 * t1;
-    const int warps = 8;
-    dm_descriptor_kernel<<<dm_div_up(n_patches, warps), warps * 32, 0, (cudaStream_t)stream>>>(
-        scene_dev, pitch, origin_yx_dev, n_patches, t0, t1, ws, dm_kpad(ws),
-        (__nv_bfloat16*)desc_bf16_dev, (dm_stat*)stat_dev);
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (ws) {
+        case 3:  launch_descriptor_fast<3>(scene_dev, pitch, origin_yx_dev, n_patches, t0, t1, desc_bf16_dev, stat_dev, st); break;
+        case 5:  launch_descriptor_fast<5>(scene_dev, pitch, origin_yx_dev, n_patches, t0, t1, desc_bf16_dev, stat_dev, st); break;
+        case 7:  launch_descriptor_fast<7>(scene_dev, pitch, origin_yx_dev, n_patches, t0, t1, desc_bf16_dev, stat_dev, st); break;
+        case 9:  launch_descriptor_fast<9>(scene_dev, pitch, origin_yx_dev, n_patches, t0, t1, desc_bf16_dev, stat_dev, st); break;
+        case 11: launch_descriptor_fast<11>(scene_dev, pitch, origin_yx_dev, n_patches, t0, t1, desc_bf16_dev, stat_dev, st); break;
+        case 13: launch_descriptor_fast<13>(scene_dev, pitch, origin_yx_dev, n_patches, t0, t1, desc_bf16_dev, stat_dev, st); break;
+        case 15: launch_descriptor_fast<15>(scene_dev, pitch, origin_yx_dev, n_patches, t0, t1, desc_bf16_dev, stat_dev, st); break;
+        default: {
+            const int warps = 8;
+            dm_descriptor_kernel<<<dm_div_up(n_patches, warps), warps * 32, 0, st>>>(
+                scene_dev, pitch, origin_yx_dev, n_patches, t0, t1, ws, dm_kpad(ws),
+                (__nv_bfloat16*)desc_bf16_dev, (dm_stat*)stat_dev);
+        }
+    }
     DM_LAUNCH_CHECK();
     return DM_OK;
 }

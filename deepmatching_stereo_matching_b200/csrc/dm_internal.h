@@ -54,5 +54,6 @@ struct dm_fused_args {
     double* d_map; double* out_map;
 };
 bool dm_fused_supported(int t0, int t1, int kpad);
+bool dm_fused_supported_ws(int ws);
 size_t dm_fused_workspace(char* base, int n_tiles, int t0, int t1, int kpad, int levels, void* buffers_out);
 int dm_fused_solve_chunk(dm_ctx* ctx, const dm_fused_args* a, int chunk_index);

@@ -114,42 +114,32 @@ struct FinalArgs {
     const int32_t* origin; const dm_stat* stat1; const dm_stat* stat2;
     const float* rowmin; const float* rowmax;
     const int32_t* parent;      // level-1 matches [n][2][t0/2][t1/2]
-    int t0, t1, ws, normed, sub_pix;
+    int t0, t1, ws, normed, sub_pix, scene_h;
     int n_modes, modes[4];
     int s0, s1, len0, len1, out_h, out_w, first_tile;
     double* d_map; double* out_map;
 };
 
-constexpr int MAXK_REG = 8;     // window pixels per lane kept in registers (ws <= 15)
+// The 3x3 candidate windows around p_dot and the parabola neighbours of the match all lie
+// in the (ws+4)^2 pixel region of image 2 that starts two pixels up/left of window p_dot.
+// The warp stages that region in shared memory once; every lane keeps its <= 8 centred
+// patch pixels in registers and walks the region with compile-time shifts.  Dot products
+// are exact int32:  sum a'_k * (b_k - m2) = sum a'_k * b_k  -  m2 * S1'.
+constexpr int RS = 20;                  // region row stride in bytes (ws + 4 <= 19)
+constexpr int RBYTES = 19 * RS + 4;
 
-// sum over the window of (a_k - m1) * (b_k(q) - m2(q)) for up to NQ positions q, exact int32
-template <int NQ>
-__device__ __forceinline__ void window_dots(const uint8_t* __restrict__ a_base, const uint8_t* __restrict__ b_img,
-                                            int pitch, int ws, int K, int lane, int m1,
-                                            const int (&qy)[NQ], const int (&qx)[NQ], const int (&m2)[NQ],
-                                            const bool (&ok)[NQ], int (&dot)[NQ]) {
-#pragma unroll
-    for (int s = 0; s < NQ; ++s) dot[s] = 0;
-    for (int k = lane; k < K; k += 32) {
-        const int ky = k / ws, kx = k - ky * ws;
-        const int a = (int)a_base[ky * pitch + kx] - m1;
-#pragma unroll
-        for (int s = 0; s < NQ; ++s)
-            if (ok[s]) dot[s] += a * ((int)b_img[(size_t)(qy[s] + ky) * pitch + qx[s] + kx] - m2[s]);
-    }
-#pragma unroll
-    for (int s = 0; s < NQ; ++s) {
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) dot[s] += __shfl_xor_sync(0xffffffffu, dot[s], o);
-    }
-}
-
+template <int WS>
 __global__ void __launch_bounds__(256)
 dm_final_level_kernel(const FinalArgs a, long long n_patches) {
+    constexpr int K = WS * WS;
+    constexpr int KT = (K + 31) / 32;   // window pixels per lane
+    constexpr int RW = WS + 4;
+    __shared__ uint8_t region_all[8][RBYTES];
     const int lane = threadIdx.x & 31;
+    uint8_t* region = region_all[threadIdx.x >> 5];
     const long long w = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (w >= n_patches) return;
-    const int T0 = a.t0, T1 = a.t1, P = T0 * T1, K = a.ws * a.ws;
+    const int T0 = a.t0, T1 = a.t1, P = T0 * T1;
     const long long n = w / P;
     const int p = (int)(w - n * P);
     const int i = p / T1, j = p - i * T1;
@@ -165,35 +155,65 @@ dm_final_level_kernel(const FinalArgs a, long long n_patches) {
     const dm_stat s1 = a.stat1[(size_t)n * P + p];
     const bool flat1 = (s1.y == 0.0f);
     const float mn = a.rowmin[(size_t)n * P + p], mx = a.rowmax[(size_t)n * P + p];
-    const uint8_t* a_base = a.img1 + (size_t)(oy + i) * a.pitch + ox + j;
-    const uint8_t* b_img = a.img2 + (size_t)oy * a.pitch + ox;          // window q=(y,x) starts at b_img[y*pitch + x]
     const dm_stat* st2 = a.stat2 + (size_t)n * P;
-    const int m1 = (int)s1.w;
+    const int m1 = (int)s1.w, S1 = (int)s1.x;
 
-    // level-0 value of position (y,x) from its exact dot product
-    auto value = [&](int dot, const dm_stat& sq) -> float {
+    // stage the region: rows oy+d0-2 .. +RW, cols ox+d1-2 .. +RW (zeros outside the scene)
+    {
+        const int gy0 = oy + d0 - 2, gx = ox + d1 - 2 + lane;
+        const bool colok = lane < RW && gx >= 0 && gx < a.pitch;
+#pragma unroll 1
+        for (int ry = 0; ry < RW; ++ry) {
+            const int gy = gy0 + ry;
+            uint8_t v = 0;
+            if (colok && gy >= 0 && gy < a.scene_h) v = a.img2[(size_t)gy * a.pitch + gx];
+            if (lane < RW) region[ry * RS + lane] = v;
+        }
+    }
+    // this lane's centred patch pixels and their offsets inside a window
+    int av[KT], koff[KT];
+    {
+        const uint8_t* a_base = a.img1 + (size_t)(oy + i) * a.pitch + ox + j;
+#pragma unroll
+        for (int t = 0; t < KT; ++t) {
+            const int k = lane + 32 * t;
+            const int ky = k / WS, kx = k - ky * WS;
+            av[t] = (k < K) ? (int)a_base[ky * a.pitch + kx] - m1 : 0;
+            koff[t] = (k < K) ? ky * RS + kx : 0;
+        }
+    }
+    __syncwarp();
+
+    auto value = [&](int dot_ab, const dm_stat& sq) -> float {      // level-0 value from sum a'*b
+        const int dot = dot_ab - (int)sq.w * S1;
         const float z = dm_zncc_partial((float)dot, s1.x, sq.z, normed ? sq.y : 1.0f);
         return dm_rectify(dm_normalize(dm_zncc_finish(z, s1.y, flat1, normed), mn, mx));
     };
+    auto warp_sum = [](int v) -> int {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        return v;
+    };
 
     // ---- misc/Matching.py:58-78 on the recomputed 3x3 window (zero padding outside)
-    int qy[9], qx[9], m2[9], dot[9];
-    bool ok[9];
-    dm_stat sq[9];
+    int acc[9];
 #pragma unroll
-    for (int s = 0; s < 9; ++s) {
-        qy[s] = d0 + s / 3 - 1; qx[s] = d1 + s % 3 - 1;
-        ok[s] = qy[s] >= 0 && qy[s] < T0 && qx[s] >= 0 && qx[s] < T1;
-        sq[s] = ok[s] ? st2[qy[s] * T1 + qx[s]] : make_float4(0.f, 0.f, 0.f, 0.f);
-        m2[s] = (int)sq[s].w;
+    for (int s = 0; s < 9; ++s) acc[s] = 0;
+#pragma unroll
+    for (int t = 0; t < KT; ++t) {
+        const uint8_t* r = region + koff[t];
+#pragma unroll
+        for (int s = 0; s < 9; ++s) acc[s] += av[t] * (int)r[(s / 3 + 1) * RS + (s % 3 + 1)];
     }
-    window_dots<9>(a_base, b_img, a.pitch, a.ws, K, lane, m1, qy, qx, m2, ok, dot);
     float best = 0.f, centre = 0.f;
     int bi = 0;
     bool best_nan = false;
 #pragma unroll
     for (int s = 0; s < 9; ++s) {
-        const float v = ok[s] ? value(dot[s], sq[s]) : 0.0f;
+        const int qy = d0 + s / 3 - 1, qx = d1 + s % 3 - 1;
+        const bool ok = qy >= 0 && qy < T0 && qx >= 0 && qx < T1;
+        const int dot = warp_sum(acc[s]);
+        const float v = ok ? value(dot, st2[qy * T1 + qx]) : 0.0f;
         if (s == 4) centre = v;
         if (s == 0) { best = v; best_nan = (v != v); }
         else if (!best_nan && (v > best || v != v)) { best = v; bi = s; best_nan = (v != v); }
@@ -204,28 +224,37 @@ dm_final_level_kernel(const FinalArgs a, long long n_patches) {
 
     // ---- misc/Matching.py:165-209 parabola fit (index -1 wraps, upper edge skipped)
     double mrow = (double)c0, mcol = (double)c1;
-    if (a.sub_pix) {
-        int ny[4], nx[4], nm[4], nd[4];
-        bool nok[4];
-        dm_stat ns[4];
-        ny[0] = c0 + 1; nx[0] = c1; ny[1] = (c0 == 0 ? T0 - 1 : c0 - 1); nx[1] = c1;
-        ny[2] = c0; nx[2] = c1 + 1; ny[3] = c0; nx[3] = (c1 == 0 ? T1 - 1 : c1 - 1);
-        const bool in = c0 >= 0 && c0 < T0 && c1 >= 0 && c1 < T1;      // always true when filtering is off
-        nok[0] = nok[1] = in && (c0 + 1 < T0);
-        nok[2] = nok[3] = in && (c1 + 1 < T1);
+    if (a.sub_pix && c0 >= 0 && c0 < T0 && c1 >= 0 && c1 < T1) {
+        // sum a'*b for an arbitrary position: from the staged region when it is inside, else from global memory
+        auto dot_at = [&](int qy, int qx) -> int {
+            const int ry = qy - (d0 - 2), rx = qx - (d1 - 2);
+            int sacc = 0;
+            if (ry >= 0 && ry <= 4 && rx >= 0 && rx <= 4) {
+                const uint8_t* r = region + ry * RS + rx;
 #pragma unroll
-        for (int s = 0; s < 4; ++s) {
-            ns[s] = nok[s] ? st2[ny[s] * T1 + nx[s]] : make_float4(0.f, 0.f, 0.f, 0.f);
-            nm[s] = (int)ns[s].w;
-        }
-        window_dots<4>(a_base, b_img, a.pitch, a.ws, K, lane, m1, ny, nx, nm, nok, nd);
+                for (int t = 0; t < KT; ++t) sacc += av[t] * (int)r[koff[t]];
+            } else {
+                const uint8_t* b = a.img2 + (size_t)(oy + qy) * a.pitch + ox + qx;
+#pragma unroll
+                for (int t = 0; t < KT; ++t) {
+                    const int k = lane + 32 * t;
+                    const int ky = k / WS, kx = k - ky * WS;
+                    if (k < K) sacc += av[t] * (int)b[ky * a.pitch + kx];
+                }
+            }
+            return warp_sum(sacc);
+        };
         const float r0 = best;                      // level-0 value at the match itself
-        if (nok[0]) {
-            const float r1 = value(nd[0], ns[0]), rm = value(nd[1], ns[1]);
+        if (c0 + 1 < T0) {
+            const int ym = (c0 == 0 ? T0 - 1 : c0 - 1);
+            const float r1 = value(dot_at(c0 + 1, c1), st2[(c0 + 1) * T1 + c1]);
+            const float rm = value(dot_at(ym, c1), st2[ym * T1 + c1]);
             if (r0 > r1 && r0 > rm) mrow += (double)(-(r1 - rm) / (2.0f * (r1 + rm - 2.0f * r0)));
         }
-        if (nok[2]) {
-            const float r1 = value(nd[2], ns[2]), rm = value(nd[3], ns[3]);
+        if (c1 + 1 < T1) {
+            const int xm = (c1 == 0 ? T1 - 1 : c1 - 1);
+            const float r1 = value(dot_at(c0, c1 + 1), st2[c0 * T1 + c1 + 1]);
+            const float rm = value(dot_at(c0, xm), st2[c0 * T1 + xm]);
             if (r0 > r1 && r0 > rm) mcol += (double)(-(r1 - rm) / (2.0f * (r1 + rm - 2.0f * r0)));
         }
     }
@@ -247,11 +276,17 @@ dm_final_level_kernel(const FinalArgs a, long long n_patches) {
     a.out_map[pix] = (double)score;
 }
 
+template <int WS>
+static void launch_final(const FinalArgs& fa, long long n_patches, cudaStream_t st) {
+    dm_final_level_kernel<WS><<<dm_div_up(n_patches, 8), 256, 0, st>>>(fa, n_patches);
+}
+
 }  // namespace
 
 bool dm_fused_supported(int t0, int t1, int kpad) {
     return dm_correlation_umma_pool_supported(t0, t1, kpad) && t0 >= 4 && t1 >= 4;
 }
+bool dm_fused_supported_ws(int ws) { return ws >= 3 && ws <= 15 && (ws & 1); }
 
 size_t dm_fused_workspace(char* base, int n_tiles, int t0, int t1, int kpad, int levels, void* buffers_out) {
     FusedBuffers fb;
@@ -327,7 +362,17 @@ int dm_fused_solve_chunk(dm_ctx* ctx, const dm_fused_args* a, int ck) {
         fa.s0 = a->s0; fa.s1 = a->s1; fa.len0 = a->len0; fa.len1 = a->len1; fa.out_h = a->out_h; fa.out_w = a->out_w;
         fa.first_tile = a->first_tile; fa.d_map = a->d_map; fa.out_map = a->out_map;
         const long long n_patches = (long long)nt * P;
-        dm_final_level_kernel<<<dm_div_up(n_patches, 8), 256, 0, st>>>(fa, n_patches);
+        fa.scene_h = a->scene_h;
+        switch (a->ws) {
+            case 3: launch_final<3>(fa, n_patches, st); break;
+            case 5: launch_final<5>(fa, n_patches, st); break;
+            case 7: launch_final<7>(fa, n_patches, st); break;
+            case 9: launch_final<9>(fa, n_patches, st); break;
+            case 11: launch_final<11>(fa, n_patches, st); break;
+            case 13: launch_final<13>(fa, n_patches, st); break;
+            case 15: launch_final<15>(fa, n_patches, st); break;
+            default: DM_REQUIRE(false, DM_ERR_UNSUPPORTED, "fused path supports odd window sizes 3..15 (got %d)", a->ws);
+        }
         DM_LAUNCH_CHECK();
         ctx->launches[DM_STAGE_PLANES] += 1;
         if ((rc = tm.end()) != DM_OK) return rc;
