@@ -34,13 +34,16 @@ constexpr int HALVES = 2;
 constexpr int BN = 128;                 // positions per N-tile
 constexpr int BK = 64;                  // bf16 per 128-byte swizzle row
 constexpr int UMMA_K = 16;
-constexpr int STAGES = 5;
+constexpr int STAGES = 4;
 constexpr int MAX_KB = 4;               // kpad <= 256
 constexpr int BOX_BYTES = BM * BK * 2;  // 16 KiB: one [128 rows x 64] bf16 box
 constexpr int EPI_WARPS = 8;
 constexpr int THREADS = 32 * (2 + EPI_WARPS);
 constexpr int TMEM_COLS = 512;
-constexpr size_t SMEM_BYTES = 1024 /*align slack*/ + (size_t)(HALVES * MAX_KB + STAGES) * BOX_BYTES + 256;
+constexpr int STG_STRIDE = 20;          // floats per staged row (16 + 4 pad: conflict-free float4 rows)
+constexpr int STG_BYTES = 32 * STG_STRIDE * 4;      // per epilogue warp
+constexpr size_t SMEM_BYTES = 1024 /*align slack*/ + (size_t)(HALVES * MAX_KB + STAGES) * BOX_BYTES
+                              + (size_t)EPI_WARPS * STG_BYTES + 256;
 
 struct Params {
     const dm_stat* stat1;       // [n*P] float4 {S', inv, S'/K, mean}
@@ -60,7 +63,8 @@ dm_correlation_umma_kernel(const __grid_constant__ CUtensorMap mapA, const __gri
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint8_t* smemA = smem;
     uint8_t* smemB = smem + (size_t)HALVES * MAX_KB * BOX_BYTES;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smemB + (size_t)STAGES * BOX_BYTES);
+    float* smemStg = reinterpret_cast<float*>(smemB + (size_t)STAGES * BOX_BYTES);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smemB + (size_t)STAGES * BOX_BYTES + (size_t)EPI_WARPS * STG_BYTES);
     uint64_t* a_full = bars;
     uint64_t* a_empty = bars + 1;
     uint64_t* b_full = bars + 2;
@@ -149,15 +153,18 @@ dm_correlation_umma_kernel(const __grid_constant__ CUtensorMap mapA, const __gri
         const int e = warp - 2;
         const int half = e >> 2;
         const int quarter = warp & 3;                   // TMEM lanes a warp may touch: 32*(warp_id % 4)..+31
-        const int row_local = half * BM + quarter * 32 + lane;
+        const int row_local = half * BM + quarter * 32;  // first of this warp's 32 consecutive patches
         const bool normed = prm.normed != 0;
+        float* stg = smemStg + (size_t)e * (32 * STG_STRIDE);
         int acc = 0; uint32_t accph = 0;
         for (int item = blockIdx.x; item < prm.n_items; item += gridDim.x) {
             const int tile = item / prm.items_per_tile;
-            const size_t prow = (size_t)tile * P + (size_t)(item - tile * prm.items_per_tile) * (HALVES * BM) + row_local;
+            const size_t wrow = (size_t)tile * P + (size_t)(item - tile * prm.items_per_tile) * (HALVES * BM) + row_local;
+            const size_t prow = wrow + lane;
             const dm_stat s1 = prm.stat1[prow];
             const bool flat1 = (s1.y == 0.0f);
-            const float2* cs = prm.cstat2 + (size_t)tile * P;
+            const float ns1 = -s1.x;
+            const float4* cs = reinterpret_cast<const float4*>(prm.cstat2) + (size_t)tile * (P / 2);
             // MODE_POOL state: st[] = horizontally pooled previous row (odd rows) / running
             // vertical max (even rows); rmin = running row minimum of the raw values
             constexpr int HW = (MODE == MODE_POOL) ? D / 2 : 1;
@@ -167,38 +174,55 @@ dm_correlation_umma_kernel(const __grid_constant__ CUtensorMap mapA, const __gri
 #pragma unroll
                 for (int i = 0; i < HW; ++i) st[i] = -CUDART_INF_F;
             }
-            float* out_raw = (MODE == MODE_RAW) ? prm.raw + prow * (size_t)P : nullptr;
-            float* out_pool = (MODE == MODE_POOL) ? prm.pooled + prow * (size_t)(P / 4) : nullptr;
+            // output rows of this warp are `ostride` floats apart; 16 floats per row and round
+            const size_t ostride = (MODE == MODE_RAW) ? (size_t)P : (size_t)(P / 4);
+            float* wout = ((MODE == MODE_RAW) ? prm.raw : prm.pooled) + wrow * ostride;
+            float o16[16];
+            // stage this lane's 16 floats, then the warp writes 8 rows x 64 B per instruction
+            auto flush16 = [&](size_t col) {
+                float4* mine = reinterpret_cast<float4*>(stg + lane * STG_STRIDE);
+                mine[0] = make_float4(o16[0], o16[1], o16[2], o16[3]);
+                mine[1] = make_float4(o16[4], o16[5], o16[6], o16[7]);
+                mine[2] = make_float4(o16[8], o16[9], o16[10], o16[11]);
+                mine[3] = make_float4(o16[12], o16[13], o16[14], o16[15]);
+                __syncwarp();
+#pragma unroll
+                for (int it = 0; it < 4; ++it) {
+                    const int r = it * 8 + (lane >> 2), ch = lane & 3;
+                    const float4 v = *reinterpret_cast<const float4*>(stg + r * STG_STRIDE + ch * 4);
+                    *reinterpret_cast<float4*>(wout + (size_t)r * ostride + col + ch * 4) = v;
+                }
+                __syncwarp();
+            };
             for (int j = 0; j < NT; ++j) {
                 umma::mbar_wait(t_full + acc, accph);
                 umma::tc_fence_after();
                 const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)((half * 2 + acc) * BN);
                 float zprev = -CUDART_INF_F;            // last raw value of the previous 32-column chunk
-                float4 ob;                              // MODE_POOL: 4 pooled outputs being assembled
+                float va[32], vb[32];
+                umma::tmem_ld_32x32_issue(taddr, va);
 #pragma unroll
                 for (int c = 0; c < BN / 32; ++c) {
-                    float v[32];
-                    umma::tmem_ld_32x32(taddr + (uint32_t)(c * 32), v);
-                    if (c == BN / 32 - 1) {             // whole accumulator stage is in registers
+                    float (&v)[32] = (c & 1) ? vb : va;
+                    float (&vn)[32] = (c & 1) ? va : vb;
+                    umma::tmem_wait_ld();               // chunk c is in registers
+                    if (c + 1 < BN / 32) {
+                        umma::tmem_ld_32x32_issue(taddr + (uint32_t)((c + 1) * 32), vn);   // overlaps the math below
+                    } else {                            // whole accumulator stage consumed
                         umma::tc_fence_before();
                         if (lane == 0) umma::mbar_arrive(t_empty + acc);
                     }
-                    const float4* cs4 = reinterpret_cast<const float4*>(cs + (size_t)j * BN + c * 32);
+                    const float4* cs4 = cs + (size_t)j * (BN / 2) + c * 16;
 #pragma unroll
                     for (int i = 0; i < 32; i += 2) {
-                        const float4 cp = __ldg(cs4 + (i >> 1));         // {s2k, inv2} of two columns
-                        v[i] = dm_zncc_partial(v[i], s1.x, cp.x, normed ? cp.y : 1.0f);
-                        v[i + 1] = dm_zncc_partial(v[i + 1], s1.x, cp.z, normed ? cp.w : 1.0f);
+                        const float4 cp = __ldg(cs4 + (i >> 1));         // {s2k0, s2k1, inv0, inv1} of two columns
+                        umma::zncc_partial2(v[i], v[i + 1], ns1, cp.x, cp.y, normed ? cp.z : 1.0f, normed ? cp.w : 1.0f);
                     }
                     if (MODE == MODE_RAW) {
 #pragma unroll
-                        for (int i = 0; i < 32; i += 4) {
-                            float4 o;
-                            o.x = dm_zncc_finish(v[i], s1.y, flat1, normed);
-                            o.y = dm_zncc_finish(v[i + 1], s1.y, flat1, normed);
-                            o.z = dm_zncc_finish(v[i + 2], s1.y, flat1, normed);
-                            o.w = dm_zncc_finish(v[i + 3], s1.y, flat1, normed);
-                            *reinterpret_cast<float4*>(out_raw + (size_t)j * BN + c * 32 + i) = o;
+                        for (int i = 0; i < 32; ++i) {
+                            o16[i & 15] = dm_zncc_finish(v[i], s1.y, flat1, normed);
+                            if ((i & 15) == 15) flush16((size_t)j * BN + c * 32 + (i - 15));
                         }
                     } else {
                         constexpr int R = BN / D;               // map rows per N-tile (even)
@@ -208,19 +232,17 @@ dm_correlation_umma_kernel(const __grid_constant__ CUtensorMap mapA, const __gri
                             const int x = n % D, r = n / D;     // position inside the map row / row inside the N-tile
                             const int xh = x >> 1;
                             const float left = (x == 0) ? -CUDART_INF_F : (i == 0 ? zprev : v[i - 1]);
-                            const float h = fmaxf(fmaxf(left, v[i]), v[i + 1]);
-                            rmin = fminf(rmin, fminf(v[i], v[i + 1]));
+                            const float h = umma::max3(left, v[i], v[i + 1]);
+                            rmin = umma::min3(rmin, v[i], v[i + 1]);
                             if ((r & 1) == 0) {
                                 st[xh] = fmaxf(st[xh], h);      // rows 2y-1 (carried) and 2y
                             } else {
                                 const float o = dm_zncc_finish(fmaxf(st[xh], h), s1.y, flat1, normed);
                                 st[xh] = h;                     // becomes row 2(y+1)-1 of the next pooled row
                                 rmax = fmaxf(rmax, o);
-                                if ((xh & 3) == 0) ob.x = o; else if ((xh & 3) == 1) ob.y = o; else if ((xh & 3) == 2) ob.z = o; else ob.w = o;
-                                if ((xh & 3) == 3) {
-                                    const int yo = (j * R + r) >> 1;        // pooled row
-                                    *reinterpret_cast<float4*>(out_pool + (size_t)yo * (D / 2) + (xh - 3)) = ob;
-                                }
+                                const int oi = (r >> 1) * (D / 2) + xh;     // output index inside the N-tile, 0..31
+                                o16[oi & 15] = o;
+                                if ((oi & 15) == 15) flush16((size_t)j * (BN / 4) + (oi - 15));
                             }
                         }
                         zprev = v[31];

@@ -64,8 +64,9 @@ dm_descriptor_kernel(const uint8_t* __restrict__ scene, int pitch,
         const bool flat = (rq == 0);
         const float inv = flat ? 0.0f : __frcp_rn(__fsqrt_rn(var));
         stat[warp] = make_float4(s, inv, sk, (float)mean);
-        // compact column parameters for the tcgen05 epilogue: {S'/K, inv}
-        reinterpret_cast<float2*>(stat + n_patches)[warp] = make_float2(sk, inv);
+        // compact column table of the tcgen05 epilogue: per pair of patches {sk0, sk1, inv0, inv1}
+        float* ct = reinterpret_cast<float*>(stat + n_patches) + (warp >> 1) * 4 + (warp & 1);
+        ct[0] = sk; ct[2] = inv;
     }
 }
 
@@ -138,7 +139,8 @@ dm_descriptor_fast_kernel(const uint8_t* __restrict__ scene, int pitch,
         const bool flat = (rq == 0);
         const float inv = flat ? 0.0f : __frcp_rn(__fsqrt_rn(var));
         stat[pidx] = make_float4(s, inv, sk, (float)mean);
-        reinterpret_cast<float2*>(stat + n_patches)[pidx] = make_float2(sk, inv);
+        float* ct = reinterpret_cast<float*>(stat + n_patches) + (pidx >> 1) * 4 + (pidx & 1);
+        ct[0] = sk; ct[2] = inv;                                      // {sk0, sk1, inv0, inv1} per pair of patches
     }
 }
 

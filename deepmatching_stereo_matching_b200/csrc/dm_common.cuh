@@ -69,14 +69,25 @@ __device__ __forceinline__ float dm_zncc_finish(float z, float inv1, bool flat1,
     return fminf(fmaxf(r, -1.0f), 1.0f);
 }
 
-// (x - min) / (max - min), then ** 1.4   (misc/Feature_value.py:36, Correlation_map.py:159)
-__device__ __forceinline__ float dm_normalize(float x, float mn, float mx) {
-    return __fdiv_rn(__fsub_rn(x, mn), __fsub_rn(mx, mn));
+// (x - min) / (max - min)  (misc/Feature_value.py:36) evaluated as (x - min) * rinv with
+// rinv = 1/(max - min) rounded once per slice: within 1 ulp of the float32 division, and
+// 0 * inf = NaN keeps the reference's NaN slice for a flat patch (max == min).
+__device__ __forceinline__ float dm_range_inv(float mn, float mx) { return __frcp_rn(__fsub_rn(mx, mn)); }
+__device__ __forceinline__ float dm_normalize(float x, float mn, float mx, float rinv) {
+    const float r = __fmul_rn(__fsub_rn(x, mn), rinv);
+    return x == mx ? (mx > mn ? 1.0f : r) : r;        // the slice maximum maps to exactly 1, as with a division
 }
-// x ** 1.4 for x in [0,1] as exp2(1.4 * log2 x) on the special-function unit: 0 -> 0 and
-// 1 -> 1 exactly, NaN propagates, absolute error < 2e-7 (relative < 3e-6 down to 1e-3).
-// libdevice powf costs ~10x more and made the pyramid kernels ALU-bound instead of HBM-bound.
-__device__ __forceinline__ float dm_rectify(float x) { return exp2f(__fmul_rn(DM_LAM, __log2f(x))); }
+// x ** 1.4 (misc/Correlation_map.py:159) for x in [0,1] as ex2(1.4 * lg2 x) on the
+// special-function unit: 0 -> 0 and 1 -> 1 exactly, NaN propagates, absolute error < 2e-7
+// (relative < 3e-6 down to x = 1e-3).  libdevice powf costs ~10x more and made the pyramid
+// kernels ALU-bound instead of HBM-bound.
+__device__ __forceinline__ float dm_rectify(float x) {
+    float l, r;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l) : "f"(x));
+    l = __fmul_rn(DM_LAM, l);
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(l));
+    return r;
+}
 
 __device__ __forceinline__ int dm_round_mean(int sum, int k) {
     // nearest integer to sum/k for sum >= 0 (pixels are unsigned)

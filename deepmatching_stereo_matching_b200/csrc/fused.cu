@@ -91,12 +91,12 @@ dm_aggregate_first_kernel(const float* __restrict__ pooled, const float* __restr
 #pragma unroll
     for (int ch = 0; ch < 4; ++ch) {
         const size_t p = (size_t)n * P + (size_t)(2 * I + (ch >> 1)) * t1 + (2 * J + (ch & 1));
-        const float mn = __ldg(rowmin + p), mx = __ldg(rowmax + p);
+        const float mn = __ldg(rowmin + p), mx = __ldg(rowmax + p), rinv = dm_range_inv(mn, mx);
         float4 v = __ldg(reinterpret_cast<const float4*>(pooled + p * (size_t)(P / 4)) + m4);
-        v.x = dm_rectify(dm_normalize(v.x, mn, mx));
-        v.y = dm_rectify(dm_normalize(v.y, mn, mx));
-        v.z = dm_rectify(dm_normalize(v.z, mn, mx));
-        v.w = dm_rectify(dm_normalize(v.w, mn, mx));
+        v.x = dm_rectify(dm_normalize(v.x, mn, mx, rinv));
+        v.y = dm_rectify(dm_normalize(v.y, mn, mx, rinv));
+        v.z = dm_rectify(dm_normalize(v.z, mn, mx, rinv));
+        v.w = dm_rectify(dm_normalize(v.w, mn, mx, rinv));
         if (ch == 0) sum = v;
         else { sum.x = __fadd_rn(sum.x, v.x); sum.y = __fadd_rn(sum.y, v.y); sum.z = __fadd_rn(sum.z, v.z); sum.w = __fadd_rn(sum.w, v.w); }
     }
@@ -154,7 +154,7 @@ dm_final_level_kernel(const FinalArgs a, long long n_patches) {
 
     const dm_stat s1 = a.stat1[(size_t)n * P + p];
     const bool flat1 = (s1.y == 0.0f);
-    const float mn = a.rowmin[(size_t)n * P + p], mx = a.rowmax[(size_t)n * P + p];
+    const float mn = a.rowmin[(size_t)n * P + p], mx = a.rowmax[(size_t)n * P + p], rinv = dm_range_inv(mn, mx);
     const dm_stat* st2 = a.stat2 + (size_t)n * P;
     const int m1 = (int)s1.w, S1 = (int)s1.x;
 
@@ -184,36 +184,52 @@ dm_final_level_kernel(const FinalArgs a, long long n_patches) {
     }
     __syncwarp();
 
-    auto value = [&](int dot_ab, const dm_stat& sq) -> float {      // level-0 value from sum a'*b
+    // level-0 value of position (qy,qx) from sum a'*b (each lane evaluates ONE candidate)
+    auto value_at = [&](int dot_ab, int qy, int qx) -> float {
+        const dm_stat sq = st2[qy * T1 + qx];
         const int dot = dot_ab - (int)sq.w * S1;
         const float z = dm_zncc_partial((float)dot, s1.x, sq.z, normed ? sq.y : 1.0f);
-        return dm_rectify(dm_normalize(dm_zncc_finish(z, s1.y, flat1, normed), mn, mx));
-    };
-    auto warp_sum = [](int v) -> int {
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-        return v;
+        return dm_rectify(dm_normalize(dm_zncc_finish(z, s1.y, flat1, normed), mn, mx, rinv));
     };
 
     // ---- misc/Matching.py:58-78 on the recomputed 3x3 window (zero padding outside)
-    int acc[9];
+    int acc[16];
 #pragma unroll
-    for (int s = 0; s < 9; ++s) acc[s] = 0;
+    for (int s = 0; s < 16; ++s) acc[s] = 0;
 #pragma unroll
     for (int t = 0; t < KT; ++t) {
         const uint8_t* r = region + koff[t];
 #pragma unroll
         for (int s = 0; s < 9; ++s) acc[s] += av[t] * (int)r[(s / 3 + 1) * RS + (s % 3 + 1)];
     }
+    // butterfly reduction of 16 partial sums in 16 shuffles: afterwards this lane holds the
+    // warp total of candidate my_s = b4*8 + b3*4 + b2*2 + b1 (b_k = bit k of the lane id)
+    int part = 0;
+    {
+        int w8[8], w4[4], w2[2];
+        const bool h16 = lane & 16, h8 = lane & 8, h4 = lane & 4, h2 = lane & 2;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) w8[q] = (h16 ? acc[q + 8] : acc[q]) + __shfl_xor_sync(0xffffffffu, h16 ? acc[q] : acc[q + 8], 16);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) w4[q] = (h8 ? w8[q + 4] : w8[q]) + __shfl_xor_sync(0xffffffffu, h8 ? w8[q] : w8[q + 4], 8);
+#pragma unroll
+        for (int q = 0; q < 2; ++q) w2[q] = (h4 ? w4[q + 2] : w4[q]) + __shfl_xor_sync(0xffffffffu, h4 ? w4[q] : w4[q + 2], 4);
+        part = (h2 ? w2[1] : w2[0]) + __shfl_xor_sync(0xffffffffu, h2 ? w2[0] : w2[1], 2);
+        part += __shfl_xor_sync(0xffffffffu, part, 1);
+    }
+    const int my_s = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
+    float myval = 0.0f;
+    {
+        const int qy = d0 + my_s / 3 - 1, qx = d1 + my_s % 3 - 1;
+        if (my_s < 9 && qy >= 0 && qy < T0 && qx >= 0 && qx < T1) myval = value_at(part, qy, qx);
+    }
     float best = 0.f, centre = 0.f;
     int bi = 0;
     bool best_nan = false;
 #pragma unroll
     for (int s = 0; s < 9; ++s) {
-        const int qy = d0 + s / 3 - 1, qx = d1 + s % 3 - 1;
-        const bool ok = qy >= 0 && qy < T0 && qx >= 0 && qx < T1;
-        const int dot = warp_sum(acc[s]);
-        const float v = ok ? value(dot, st2[qy * T1 + qx]) : 0.0f;
+        const int src = ((s >> 3) & 1) * 16 + ((s >> 2) & 1) * 8 + ((s >> 1) & 1) * 4 + (s & 1) * 2;
+        const float v = __shfl_sync(0xffffffffu, myval, src);
         if (s == 4) centre = v;
         if (s == 0) { best = v; best_nan = (v != v); }
         else if (!best_nan && (v > best || v != v)) { best = v; bi = s; best_nan = (v != v); }
@@ -225,38 +241,49 @@ dm_final_level_kernel(const FinalArgs a, long long n_patches) {
     // ---- misc/Matching.py:165-209 parabola fit (index -1 wraps, upper edge skipped)
     double mrow = (double)c0, mcol = (double)c1;
     if (a.sub_pix && c0 >= 0 && c0 < T0 && c1 >= 0 && c1 < T1) {
-        // sum a'*b for an arbitrary position: from the staged region when it is inside, else from global memory
-        auto dot_at = [&](int qy, int qx) -> int {
-            const int ry = qy - (d0 - 2), rx = qx - (d1 - 2);
-            int sacc = 0;
-            if (ry >= 0 && ry <= 4 && rx >= 0 && rx <= 4) {
+        // neighbours: 0 = (c0+1,c1)  1 = (c0-1 | wrap, c1)  2 = (c0,c1+1)  3 = (c0, c1-1 | wrap)
+        const int ny[4] = {c0 + 1, (c0 == 0 ? T0 - 1 : c0 - 1), c0, c0};
+        const int nx[4] = {c1, c1, c1 + 1, (c1 == 0 ? T1 - 1 : c1 - 1)};
+        const bool nok[4] = {c0 + 1 < T0, c0 + 1 < T0, c1 + 1 < T1, c1 + 1 < T1};
+        int nacc[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            nacc[q] = 0;
+            if (!nok[q]) continue;                                  // warp-uniform
+            const int ry = ny[q] - (d0 - 2), rx = nx[q] - (d1 - 2);
+            if (ry >= 0 && ry <= 4 && rx >= 0 && rx <= 4) {         // inside the staged region
                 const uint8_t* r = region + ry * RS + rx;
 #pragma unroll
-                for (int t = 0; t < KT; ++t) sacc += av[t] * (int)r[koff[t]];
-            } else {
-                const uint8_t* b = a.img2 + (size_t)(oy + qy) * a.pitch + ox + qx;
+                for (int t = 0; t < KT; ++t) nacc[q] += av[t] * (int)r[koff[t]];
+            } else {                                                // wrapped index: far away, read global memory
+                const uint8_t* b = a.img2 + (size_t)(oy + ny[q]) * a.pitch + ox + nx[q];
 #pragma unroll
                 for (int t = 0; t < KT; ++t) {
                     const int k = lane + 32 * t;
                     const int ky = k / WS, kx = k - ky * WS;
-                    if (k < K) sacc += av[t] * (int)b[ky * a.pitch + kx];
+                    if (k < K) nacc[q] += av[t] * (int)b[ky * a.pitch + kx];
                 }
             }
-            return warp_sum(sacc);
-        };
+        }
+        // 4 partial sums -> lane holds the total of neighbour my_n = b4*2 + b3 (6 shuffles)
+        const bool h16 = lane & 16, h8 = lane & 8;
+        int u0 = (h16 ? nacc[2] : nacc[0]) + __shfl_xor_sync(0xffffffffu, h16 ? nacc[0] : nacc[2], 16);
+        int u1 = (h16 ? nacc[3] : nacc[1]) + __shfl_xor_sync(0xffffffffu, h16 ? nacc[1] : nacc[3], 16);
+        int tot = (h8 ? u1 : u0) + __shfl_xor_sync(0xffffffffu, h8 ? u0 : u1, 8);
+        tot += __shfl_xor_sync(0xffffffffu, tot, 4);
+        tot += __shfl_xor_sync(0xffffffffu, tot, 2);
+        tot += __shfl_xor_sync(0xffffffffu, tot, 1);
+        const int my_n = ((lane >> 4) & 1) * 2 + ((lane >> 3) & 1);
+        const int sy = my_n == 0 ? ny[0] : (my_n == 1 ? ny[1] : c0);
+        const int sx = my_n == 2 ? nx[2] : (my_n == 3 ? nx[3] : c1);
+        const bool sok = my_n < 2 ? nok[0] : nok[2];
+        float nval = 0.0f;
+        if (sok) nval = value_at(tot, sy, sx);
         const float r0 = best;                      // level-0 value at the match itself
-        if (c0 + 1 < T0) {
-            const int ym = (c0 == 0 ? T0 - 1 : c0 - 1);
-            const float r1 = value(dot_at(c0 + 1, c1), st2[(c0 + 1) * T1 + c1]);
-            const float rm = value(dot_at(ym, c1), st2[ym * T1 + c1]);
-            if (r0 > r1 && r0 > rm) mrow += (double)(-(r1 - rm) / (2.0f * (r1 + rm - 2.0f * r0)));
-        }
-        if (c1 + 1 < T1) {
-            const int xm = (c1 == 0 ? T1 - 1 : c1 - 1);
-            const float r1 = value(dot_at(c0, c1 + 1), st2[c0 * T1 + c1 + 1]);
-            const float rm = value(dot_at(c0, xm), st2[c0 * T1 + xm]);
-            if (r0 > r1 && r0 > rm) mcol += (double)(-(r1 - rm) / (2.0f * (r1 + rm - 2.0f * r0)));
-        }
+        const float v0 = __shfl_sync(0xffffffffu, nval, 0), v1 = __shfl_sync(0xffffffffu, nval, 8);
+        const float v2 = __shfl_sync(0xffffffffu, nval, 16), v3 = __shfl_sync(0xffffffffu, nval, 24);
+        if (nok[0] && r0 > v0 && r0 > v1) mrow += (double)(-(v0 - v1) / (2.0f * (v0 + v1 - 2.0f * r0)));
+        if (nok[2] && r0 > v2 && r0 > v3) mcol += (double)(-(v2 - v3) / (2.0f * (v2 + v3 - 2.0f * r0)));
     }
     if (lane != 0) return;
 

@@ -56,6 +56,7 @@ dm_minmax_rectify_kernel(const float* raw, int q, float* norm,
         if (rowmin) rowmin[row] = mn;
         if (rowmax) rowmax[row] = mx;
     }
+    const float rinv = dm_range_inv(mn, mx);
     float* dn = norm ? norm + row * (size_t)q : nullptr;
     float* dr = rect ? rect + row * (size_t)q : nullptr;
     if (CACHE > 0) {
@@ -65,8 +66,8 @@ dm_minmax_rectify_kernel(const float* raw, int q, float* norm,
             int i = c * 256 + threadIdx.x;
             if (i < q4) {
                 float4 v = buf[c];
-                v.x = dm_normalize(v.x, mn, mx); v.y = dm_normalize(v.y, mn, mx);
-                v.z = dm_normalize(v.z, mn, mx); v.w = dm_normalize(v.w, mn, mx);
+                v.x = dm_normalize(v.x, mn, mx, rinv); v.y = dm_normalize(v.y, mn, mx, rinv);
+                v.z = dm_normalize(v.z, mn, mx, rinv); v.w = dm_normalize(v.w, mn, mx, rinv);
                 if (dn) reinterpret_cast<float4*>(dn)[i] = v;
                 if (dr) {
                     v.x = dm_rectify(v.x); v.y = dm_rectify(v.y); v.z = dm_rectify(v.z); v.w = dm_rectify(v.w);
@@ -76,7 +77,7 @@ dm_minmax_rectify_kernel(const float* raw, int q, float* norm,
         }
     } else {
         for (int i = threadIdx.x; i < q; i += 256) {
-            float v = dm_normalize(src[i], mn, mx);      // plain load: src may alias norm
+            float v = dm_normalize(src[i], mn, mx, rinv);      // plain load: src may alias norm
             if (dn) dn[i] = v;
             if (dr) dr[i] = dm_rectify(v);
         }

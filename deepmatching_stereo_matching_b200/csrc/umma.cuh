@@ -85,6 +85,44 @@ __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, float (&v)[32]) {
     for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// split form: issue the load, overlap independent work, then tmem_wait_ld() before using v
+__device__ __forceinline__ void tmem_ld_32x32_issue(uint32_t taddr, float (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7]),
+          "=f"(v[8]), "=f"(v[9]), "=f"(v[10]), "=f"(v[11]), "=f"(v[12]), "=f"(v[13]), "=f"(v[14]), "=f"(v[15]),
+          "=f"(v[16]), "=f"(v[17]), "=f"(v[18]), "=f"(v[19]), "=f"(v[20]), "=f"(v[21]), "=f"(v[22]), "=f"(v[23]),
+          "=f"(v[24]), "=f"(v[25]), "=f"(v[26]), "=f"(v[27]), "=f"(v[28]), "=f"(v[29]), "=f"(v[30]), "=f"(v[31])
+        : "r"(taddr) : "memory");
+}
+
+// ---------------------------------------------------------------- packed / 3-input fp32 (sm_100)
+// (v0,v1) = (fma(ns1, s2k, v) * inv) for two columns at once: FFMA2 + FMUL2, each lane IEEE-rn,
+// bit-identical to dm_zncc_partial.
+__device__ __forceinline__ void zncc_partial2(float& v0, float& v1, float ns1, float s2k0, float s2k1, float inv0, float inv1) {
+    asm("{ .reg .b64 ra, rb, rc;\n\t"
+        "mov.b64 ra, {%2, %2};\n\t"
+        "mov.b64 rb, {%3, %4};\n\t"
+        "mov.b64 rc, {%0, %1};\n\t"
+        "fma.rn.f32x2 rc, ra, rb, rc;\n\t"
+        "mov.b64 rb, {%5, %6};\n\t"
+        "mul.rn.f32x2 rc, rc, rb;\n\t"
+        "mov.b64 {%0, %1}, rc; }"
+        : "+f"(v0), "+f"(v1) : "f"(ns1), "f"(s2k0), "f"(s2k1), "f"(inv0), "f"(inv1));
+}
+__device__ __forceinline__ float max3(float a, float b, float c) {
+    float r;
+    asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+    return r;
+}
+__device__ __forceinline__ float min3(float a, float b, float c) {
+    float r;
+    asm("min.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+    return r;
+}
+
 // ---------------------------------------------------------------- MMA
 // Shared-memory matrix descriptor, K-major operand, 128-byte swizzle: rows of 64 bf16
 // (128 B), 8-row groups 1024 B apart (SBO), LBO unused (=1), descriptor version 1.

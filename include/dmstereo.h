@@ -62,8 +62,8 @@ int         dm_device_cc(void);
  * the patch's rounded mean, exact), zero padded to kpad, plus the window statistics:
  * stat_dev holds DM_STAT_FLOATS (6) floats per patch -- first n*P float4 {S', inv, S'/K,
  * mean} with S' the residual sum and inv = 1/sqrt(sum a'^2 - S'^2/K) (0 for a flat
- * window), then n*P float2 {S'/K, inv} (the compact column table of the tcgen05
- * epilogue).  kpad = dm_kpad(ws).
+ * window), then n*P/2 float4 {S'/K (even), S'/K (odd), inv (even), inv (odd)} per pair
+ * of patches (the compact column table of the tcgen05 epilogue).  kpad = dm_kpad(ws).
  */
 #define DM_STAT_FLOATS 6
 int dm_kpad(int ws);
