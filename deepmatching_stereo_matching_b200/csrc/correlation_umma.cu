@@ -15,12 +15,19 @@
 //
 // Work item = 256 patches of one tile (two M=128 accumulator halves) x all P positions,
 // swept in N-tiles of 128 positions.  Persistent grid, one CTA per SM, 10 warps:
-//   warp 0      TMA producer   A (2 halves x KB boxes, once per item), B ring of STAGES
+//   warp 0      TMA producer   A (2 halves x KB boxes, once per item), B ring of STAGES,
+//                              and the N-tile's 1 KiB column table (bulk copy) into a
+//                              2-deep shared-memory ring
 //   warp 1      MMA issuer     tcgen05.mma cta_group::1 kind::f16, M=128 N=128 K=16;
 //                              TMEM: 2 halves x 2 accumulator stages x 128 columns = 512
 //   warps 2..9  epilogue       tcgen05.ld 32x32b, thread == patch row, so the 3x3 pooling,
 //                              the running row minimum and the halo row carried between
-//                              N-tiles are all thread-local registers.
+//                              N-tiles are all thread-local registers.  Software pipelined
+//                              in steps of 16 columns: the TMEM load and the column
+//                              parameters of step s+1 are in flight while step s is
+//                              computed (FFMA2/FMUL2 packed math, 3-input min/max).
+//                              Results leave through a per-warp shared-memory transpose so
+//                              that every store instruction writes 8 rows x 64 B.
 // B traffic: every CTA streams the tile's whole position matrix once per item; with
 // M = 256 rows per item that is 32 B/clk/SM from L2 at the MMA's full rate.
 #include "dm_common.cuh"
@@ -40,15 +47,24 @@ constexpr int BOX_BYTES = BM * BK * 2;  // 16 KiB: one [128 rows x 64] bf16 box
 constexpr int EPI_WARPS = 8;
 constexpr int THREADS = 32 * (2 + EPI_WARPS);
 constexpr int TMEM_COLS = 512;
+constexpr int STEP = 16;                // columns per epilogue pipeline step
+constexpr int NSTEP = BN / STEP;
 constexpr int STG_STRIDE = 20;          // floats per staged row (16 + 4 pad: conflict-free float4 rows)
 constexpr int STG_BYTES = 32 * STG_STRIDE * 4;      // per epilogue warp
-constexpr size_t SMEM_BYTES = 1024 /*align slack*/ + (size_t)(HALVES * MAX_KB + STAGES) * BOX_BYTES
-                              + (size_t)EPI_WARPS * STG_BYTES + 256;
+constexpr int CS_BYTES = (BN / 2) * 16; // column table of one N-tile: 64 x {sk0, sk1, inv0, inv1}
+
+// shared memory carve-up (offsets from the 1024-aligned base)
+constexpr size_t OFF_A = 0;
+constexpr size_t OFF_B = OFF_A + (size_t)HALVES * MAX_KB * BOX_BYTES;
+constexpr size_t OFF_STG = OFF_B + (size_t)STAGES * BOX_BYTES;
+constexpr size_t OFF_CS = OFF_STG + (size_t)EPI_WARPS * STG_BYTES;
+constexpr size_t OFF_BAR = OFF_CS + 2 * CS_BYTES;
+constexpr size_t SMEM_BYTES = 1024 /*align slack*/ + OFF_BAR + 256;
 
 struct Params {
     const dm_stat* stat1;       // [n*P] float4 {S', inv, S'/K, mean}
-    const float2* cstat2;       // [n*P] {S'/K, inv} of image 2
-    int n_items, P, KB, items_per_tile, normed;
+    const float4* cstat2;       // [n*P/2] {S'/K even, S'/K odd, inv even, inv odd} of image 2
+    int n_items, P, KB, items_per_tile;
     float* raw;                 // MODE_RAW : [n][P][P]
     float* pooled;              // MODE_POOL: [n][P][P/4]
     float* rowmin; float* rowmax;   // MODE_POOL: [n][P]
@@ -56,22 +72,26 @@ struct Params {
 
 enum { MODE_RAW = 0, MODE_POOL = 1 };
 
-template <int MODE, int D>      // D = positions per map row (T1); only used by MODE_POOL
+template <int MODE, int D, bool NORMED>      // D = positions per map row (T1); only used by MODE_POOL
 __global__ void __launch_bounds__(THREADS, 1)
 dm_correlation_umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const Params prm) {
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    uint8_t* smemA = smem;
-    uint8_t* smemB = smem + (size_t)HALVES * MAX_KB * BOX_BYTES;
-    float* smemStg = reinterpret_cast<float*>(smemB + (size_t)STAGES * BOX_BYTES);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smemB + (size_t)STAGES * BOX_BYTES + (size_t)EPI_WARPS * STG_BYTES);
+    // keep shared-space provenance: offset the array instead of round-tripping through integers
+    uint8_t* smem = smem_raw + ((1024u - (umma::smem_u32(smem_raw) & 1023u)) & 1023u);
+    uint8_t* smemA = smem + OFF_A;
+    uint8_t* smemB = smem + OFF_B;
+    float* smemStg = reinterpret_cast<float*>(smem + OFF_STG);
+    uint8_t* smemCs = smem + OFF_CS;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
     uint64_t* a_full = bars;
     uint64_t* a_empty = bars + 1;
     uint64_t* b_full = bars + 2;
     uint64_t* b_empty = bars + 2 + STAGES;
     uint64_t* t_full = bars + 2 + 2 * STAGES;
     uint64_t* t_empty = bars + 4 + 2 * STAGES;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 6 + 2 * STAGES);
+    uint64_t* c_full = bars + 6 + 2 * STAGES;
+    uint64_t* c_empty = bars + 8 + 2 * STAGES;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10 + 2 * STAGES);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int P = prm.P, KB = prm.KB, NT = P / BN;
@@ -80,7 +100,10 @@ dm_correlation_umma_kernel(const __grid_constant__ CUtensorMap mapA, const __gri
         umma::mbar_init(a_full, 1);
         umma::mbar_init(a_empty, 1);
         for (int s = 0; s < STAGES; ++s) { umma::mbar_init(b_full + s, 1); umma::mbar_init(b_empty + s, 1); }
-        for (int s = 0; s < 2; ++s) { umma::mbar_init(t_full + s, 1); umma::mbar_init(t_empty + s, EPI_WARPS); }
+        for (int s = 0; s < 2; ++s) {
+            umma::mbar_init(t_full + s, 1); umma::mbar_init(t_empty + s, EPI_WARPS);
+            umma::mbar_init(c_full + s, 1); umma::mbar_init(c_empty + s, EPI_WARPS);
+        }
         umma::fence_barrier_init();
         umma::tma_prefetch_desc(&mapA);
         umma::tma_prefetch_desc(&mapB);
@@ -97,7 +120,7 @@ dm_correlation_umma_kernel(const __grid_constant__ CUtensorMap mapA, const __gri
     if (warp == 0) {
         // ------------------------------------------------------------ TMA producer
         if (lane == 0) {
-            int bs = 0; uint32_t bph = 0, aph = 0;
+            int bs = 0; uint32_t bph = 0, aph = 0; int cst = 0; uint32_t cph = 0;
             for (int item = blockIdx.x; item < prm.n_items; item += gridDim.x) {
                 const int tile = item / prm.items_per_tile;
                 const int row0 = tile * P + (item - tile * prm.items_per_tile) * (HALVES * BM);
@@ -107,13 +130,18 @@ dm_correlation_umma_kernel(const __grid_constant__ CUtensorMap mapA, const __gri
                     for (int kb = 0; kb < KB; ++kb)
                         umma::tma_load_2d(smemA + (size_t)(h * MAX_KB + kb) * BOX_BYTES, &mapA, kb * BK, row0 + h * BM, a_full);
                 aph ^= 1;
-                for (int j = 0; j < NT; ++j)
+                for (int j = 0; j < NT; ++j) {
+                    umma::mbar_wait(c_empty + cst, cph ^ 1);
+                    umma::mbar_expect_tx(c_full + cst, (uint32_t)CS_BYTES);
+                    umma::bulk_g2s(smemCs + (size_t)cst * CS_BYTES, prm.cstat2 + ((size_t)tile * P + (size_t)j * BN) / 2, CS_BYTES, c_full + cst);
+                    if (++cst == 2) { cst = 0; cph ^= 1; }
                     for (int kb = 0; kb < KB; ++kb) {
                         umma::mbar_wait(b_empty + bs, bph ^ 1);
                         umma::mbar_expect_tx(b_full + bs, (uint32_t)BOX_BYTES);
                         umma::tma_load_2d(smemB + (size_t)bs * BOX_BYTES, &mapB, kb * BK, tile * P + j * BN, b_full + bs);
                         if (++bs == STAGES) { bs = 0; bph ^= 1; }
                     }
+                }
             }
         }
     } else if (warp == 1) {
@@ -154,9 +182,9 @@ dm_correlation_umma_kernel(const __grid_constant__ CUtensorMap mapA, const __gri
         const int half = e >> 2;
         const int quarter = warp & 3;                   // TMEM lanes a warp may touch: 32*(warp_id % 4)..+31
         const int row_local = half * BM + quarter * 32;  // first of this warp's 32 consecutive patches
-        const bool normed = prm.normed != 0;
         float* stg = smemStg + (size_t)e * (32 * STG_STRIDE);
-        int acc = 0; uint32_t accph = 0;
+        float4* stg_mine = reinterpret_cast<float4*>(stg + lane * STG_STRIDE);
+        int acc = 0; uint32_t accph = 0; int cst = 0; uint32_t cph = 0;
         for (int item = blockIdx.x; item < prm.n_items; item += gridDim.x) {
             const int tile = item / prm.items_per_tile;
             const size_t wrow = (size_t)tile * P + (size_t)(item - tile * prm.items_per_tile) * (HALVES * BM) + row_local;
@@ -164,7 +192,6 @@ dm_correlation_umma_kernel(const __grid_constant__ CUtensorMap mapA, const __gri
             const dm_stat s1 = prm.stat1[prow];
             const bool flat1 = (s1.y == 0.0f);
             const float ns1 = -s1.x;
-            const float4* cs = reinterpret_cast<const float4*>(prm.cstat2) + (size_t)tile * (P / 2);
             // MODE_POOL state: st[] = horizontally pooled previous row (odd rows) / running
             // vertical max (even rows); rmin = running row minimum of the raw values
             constexpr int HW = (MODE == MODE_POOL) ? D / 2 : 1;
@@ -174,17 +201,12 @@ dm_correlation_umma_kernel(const __grid_constant__ CUtensorMap mapA, const __gri
 #pragma unroll
                 for (int i = 0; i < HW; ++i) st[i] = -CUDART_INF_F;
             }
-            // output rows of this warp are `ostride` floats apart; 16 floats per row and round
+            // output rows of this warp are `ostride` floats apart
             const size_t ostride = (MODE == MODE_RAW) ? (size_t)P : (size_t)(P / 4);
             float* wout = ((MODE == MODE_RAW) ? prm.raw : prm.pooled) + wrow * ostride;
-            float o16[16];
-            // stage this lane's 16 floats, then the warp writes 8 rows x 64 B per instruction
+            // 16 floats per lane are staged in shared memory, then the warp writes 8 rows x 64 B
+            // per store instruction
             auto flush16 = [&](size_t col) {
-                float4* mine = reinterpret_cast<float4*>(stg + lane * STG_STRIDE);
-                mine[0] = make_float4(o16[0], o16[1], o16[2], o16[3]);
-                mine[1] = make_float4(o16[4], o16[5], o16[6], o16[7]);
-                mine[2] = make_float4(o16[8], o16[9], o16[10], o16[11]);
-                mine[3] = make_float4(o16[12], o16[13], o16[14], o16[15]);
                 __syncwarp();
 #pragma unroll
                 for (int it = 0; it < 4; ++it) {
@@ -195,40 +217,56 @@ dm_correlation_umma_kernel(const __grid_constant__ CUtensorMap mapA, const __gri
                 __syncwarp();
             };
             for (int j = 0; j < NT; ++j) {
+                umma::mbar_wait(c_full + cst, cph);
                 umma::mbar_wait(t_full + acc, accph);
                 umma::tc_fence_after();
                 const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)((half * 2 + acc) * BN);
-                float zprev = -CUDART_INF_F;            // last raw value of the previous 32-column chunk
-                float va[32], vb[32];
-                umma::tmem_ld_32x32_issue(taddr, va);
+                const float4* csm = reinterpret_cast<const float4*>(smemCs + (size_t)cst * CS_BYTES);
+                float zprev = -CUDART_INF_F;            // last raw value of the previous step
+                float v0[STEP], v1[STEP];
+                float4 c0[STEP / 2], c1[STEP / 2];
+                float4 ob;                              // 4 outputs being assembled
+                umma::tmem_ld_32x16_issue(taddr, v0);
 #pragma unroll
-                for (int c = 0; c < BN / 32; ++c) {
-                    float (&v)[32] = (c & 1) ? vb : va;
-                    float (&vn)[32] = (c & 1) ? va : vb;
-                    umma::tmem_wait_ld();               // chunk c is in registers
-                    if (c + 1 < BN / 32) {
-                        umma::tmem_ld_32x32_issue(taddr + (uint32_t)((c + 1) * 32), vn);   // overlaps the math below
-                    } else {                            // whole accumulator stage consumed
-                        umma::tc_fence_before();
-                        if (lane == 0) umma::mbar_arrive(t_empty + acc);
+                for (int i = 0; i < STEP / 2; ++i) c0[i] = csm[i];
+#pragma unroll
+                for (int s = 0; s < NSTEP; ++s) {
+                    float (&v)[STEP] = (s & 1) ? v1 : v0;
+                    float (&vn)[STEP] = (s & 1) ? v0 : v1;
+                    float4 (&cc)[STEP / 2] = (s & 1) ? c1 : c0;
+                    float4 (&cn)[STEP / 2] = (s & 1) ? c0 : c1;
+                    umma::tmem_wait_ld();               // step s is in registers
+                    if (s + 1 < NSTEP) {                // step s+1 in flight during the math below
+                        umma::tmem_ld_32x16_issue(taddr + (uint32_t)((s + 1) * STEP), vn);
+#pragma unroll
+                        for (int i = 0; i < STEP / 2; ++i) cn[i] = csm[(s + 1) * (STEP / 2) + i];
                     }
-                    const float4* cs4 = cs + (size_t)j * (BN / 2) + c * 16;
 #pragma unroll
-                    for (int i = 0; i < 32; i += 2) {
-                        const float4 cp = __ldg(cs4 + (i >> 1));         // {s2k0, s2k1, inv0, inv1} of two columns
-                        umma::zncc_partial2(v[i], v[i + 1], ns1, cp.x, cp.y, normed ? cp.z : 1.0f, normed ? cp.w : 1.0f);
+                    for (int i = 0; i < STEP; i += 2) {
+                        const float4 cp = cc[i >> 1];       // {s2k0, s2k1, inv0, inv1} of two columns
+                        if (NORMED) umma::zncc_partial2(v[i], v[i + 1], ns1, cp.x, cp.y, cp.z, cp.w);
+                        else umma::zncc_partial2(v[i], v[i + 1], ns1, cp.x, cp.y, 1.0f, 1.0f);
+                    }
+                    if (s + 1 == NSTEP) {               // accumulator stage and column table consumed
+                        umma::tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) { umma::mbar_arrive(t_empty + acc); umma::mbar_arrive(c_empty + cst); }
                     }
                     if (MODE == MODE_RAW) {
 #pragma unroll
-                        for (int i = 0; i < 32; ++i) {
-                            o16[i & 15] = dm_zncc_finish(v[i], s1.y, flat1, normed);
-                            if ((i & 15) == 15) flush16((size_t)j * BN + c * 32 + (i - 15));
+                        for (int i = 0; i < STEP; i += 4) {
+                            ob.x = dm_zncc_finish(v[i], s1.y, flat1, NORMED);
+                            ob.y = dm_zncc_finish(v[i + 1], s1.y, flat1, NORMED);
+                            ob.z = dm_zncc_finish(v[i + 2], s1.y, flat1, NORMED);
+                            ob.w = dm_zncc_finish(v[i + 3], s1.y, flat1, NORMED);
+                            stg_mine[i >> 2] = ob;
                         }
+                        flush16((size_t)j * BN + s * STEP);
                     } else {
                         constexpr int R = BN / D;               // map rows per N-tile (even)
 #pragma unroll
-                        for (int i = 0; i < 32; i += 2) {
-                            const int n = c * 32 + i;           // column inside the N-tile
+                        for (int i = 0; i < STEP; i += 2) {
+                            const int n = s * STEP + i;         // column inside the N-tile
                             const int x = n % D, r = n / D;     // position inside the map row / row inside the N-tile
                             const int xh = x >> 1;
                             const float left = (x == 0) ? -CUDART_INF_F : (i == 0 ? zprev : v[i - 1]);
@@ -237,21 +275,24 @@ dm_correlation_umma_kernel(const __grid_constant__ CUtensorMap mapA, const __gri
                             if ((r & 1) == 0) {
                                 st[xh] = fmaxf(st[xh], h);      // rows 2y-1 (carried) and 2y
                             } else {
-                                const float o = dm_zncc_finish(fmaxf(st[xh], h), s1.y, flat1, normed);
+                                const float o = dm_zncc_finish(fmaxf(st[xh], h), s1.y, flat1, NORMED);
                                 st[xh] = h;                     // becomes row 2(y+1)-1 of the next pooled row
                                 rmax = fmaxf(rmax, o);
                                 const int oi = (r >> 1) * (D / 2) + xh;     // output index inside the N-tile, 0..31
-                                o16[oi & 15] = o;
+                                if ((oi & 3) == 0) ob.x = o; else if ((oi & 3) == 1) ob.y = o; else if ((oi & 3) == 2) ob.z = o; else ob.w = o;
+                                if ((oi & 3) == 3) stg_mine[(oi & 15) >> 2] = ob;
                                 if ((oi & 15) == 15) flush16((size_t)j * (BN / 4) + (oi - 15));
                             }
                         }
-                        zprev = v[31];
+                        zprev = v[STEP - 1];
+                        (void)R;
                     }
                 }
                 if (++acc == 2) { acc = 0; accph ^= 1; }
+                if (++cst == 2) { cst = 0; cph ^= 1; }
             }
             if (MODE == MODE_POOL) {
-                prm.rowmin[prow] = dm_zncc_finish(rmin, s1.y, flat1, normed);
+                prm.rowmin[prow] = dm_zncc_finish(rmin, s1.y, flat1, NORMED);
                 prm.rowmax[prow] = rmax;
             }
         }
@@ -276,10 +317,10 @@ dm_encode_tiled_fn get_encode_fn() {
     return fn;
 }
 
-template <int MODE, int D>
-int launch(const CUtensorMap& mapA, const CUtensorMap& mapB, const Params& prm, cudaStream_t stream) {
+template <int MODE, int D, bool NORMED>
+int launch2(const CUtensorMap& mapA, const CUtensorMap& mapB, const Params& prm, cudaStream_t stream) {
     static bool configured = false;
-    auto kern = dm_correlation_umma_kernel<MODE, D>;
+    auto kern = dm_correlation_umma_kernel<MODE, D, NORMED>;
     if (!configured) {
         DM_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
         configured = true;
@@ -291,6 +332,11 @@ int launch(const CUtensorMap& mapA, const CUtensorMap& mapB, const Params& prm, 
     kern<<<grid, THREADS, SMEM_BYTES, stream>>>(mapA, mapB, prm);
     DM_LAUNCH_CHECK();
     return DM_OK;
+}
+
+template <int MODE, int D>
+int launch(const CUtensorMap& mapA, const CUtensorMap& mapB, const Params& prm, bool normed, cudaStream_t stream) {
+    return normed ? launch2<MODE, D, true>(mapA, mapB, prm, stream) : launch2<MODE, D, false>(mapA, mapB, prm, stream);
 }
 
 }  // namespace
@@ -318,17 +364,16 @@ bool dm_correlation_umma_pool_supported(int t0, int t1, int kpad) {
 }
 
 static int fill_params(Params& prm, CUtensorMap& mapA, CUtensorMap& mapB, const void* desc1, const float* stat1,
-                       const void* desc2, const float* stat2, int n_tiles, int p, int kpad, int method) {
+                       const void* desc2, const float* stat2, int n_tiles, int p, int kpad) {
     const uint64_t rows = (uint64_t)n_tiles * p;
     int rc = dm_make_desc_tensor_map(&mapA, desc1, rows, kpad, BM);
     if (rc != DM_OK) return rc;
     rc = dm_make_desc_tensor_map(&mapB, desc2, rows, kpad, BN);
     if (rc != DM_OK) return rc;
     prm.stat1 = (const dm_stat*)stat1;
-    prm.cstat2 = reinterpret_cast<const float2*>((const dm_stat*)stat2 + rows);
+    prm.cstat2 = reinterpret_cast<const float4*>((const dm_stat*)stat2 + rows);
     prm.P = p; prm.KB = kpad / BK; prm.items_per_tile = p / (HALVES * BM);
     prm.n_items = n_tiles * prm.items_per_tile;
-    prm.normed = method == DM_TM_CCOEFF_NORMED;
     prm.raw = prm.pooled = prm.rowmin = prm.rowmax = nullptr;
     return DM_OK;
 }
@@ -336,10 +381,10 @@ static int fill_params(Params& prm, CUtensorMap& mapA, CUtensorMap& mapB, const 
 int dm_correlation_umma(const void* desc1, const float* stat1, const void* desc2, const float* stat2,
                         int n_tiles, int p, int kpad, int method, float* raw, cudaStream_t stream) {
     Params prm; CUtensorMap mapA, mapB;
-    int rc = fill_params(prm, mapA, mapB, desc1, stat1, desc2, stat2, n_tiles, p, kpad, method);
+    int rc = fill_params(prm, mapA, mapB, desc1, stat1, desc2, stat2, n_tiles, p, kpad);
     if (rc != DM_OK) return rc;
     prm.raw = raw;
-    return launch<MODE_RAW, 64>(mapA, mapB, prm, stream);
+    return launch<MODE_RAW, 64>(mapA, mapB, prm, method == DM_TM_CCOEFF_NORMED, stream);
 }
 
 int dm_correlation_umma_pool(const void* desc1, const float* stat1, const void* desc2, const float* stat2,
@@ -347,10 +392,11 @@ int dm_correlation_umma_pool(const void* desc1, const float* stat1, const void* 
                              float* pooled, float* rowmin, float* rowmax, cudaStream_t stream) {
     DM_REQUIRE(dm_correlation_umma_pool_supported(t0, t1, kpad), DM_ERR_UNSUPPORTED, "pooled tcgen05 correlation: unsupported grid (%d,%d)", t0, t1);
     Params prm; CUtensorMap mapA, mapB;
-    int rc = fill_params(prm, mapA, mapB, desc1, stat1, desc2, stat2, n_tiles, t0 * t1, kpad, method);
+    int rc = fill_params(prm, mapA, mapB, desc1, stat1, desc2, stat2, n_tiles, t0 * t1, kpad);
     if (rc != DM_OK) return rc;
     prm.pooled = pooled; prm.rowmin = rowmin; prm.rowmax = rowmax;
-    if (t1 == 64) return launch<MODE_POOL, 64>(mapA, mapB, prm, stream);
-    if (t1 == 32) return launch<MODE_POOL, 32>(mapA, mapB, prm, stream);
-    return launch<MODE_POOL, 16>(mapA, mapB, prm, stream);
+    const bool normed = method == DM_TM_CCOEFF_NORMED;
+    if (t1 == 64) return launch<MODE_POOL, 64>(mapA, mapB, prm, normed, stream);
+    if (t1 == 32) return launch<MODE_POOL, 32>(mapA, mapB, prm, normed, stream);
+    return launch<MODE_POOL, 16>(mapA, mapB, prm, normed, stream);
 }

@@ -98,6 +98,15 @@ __device__ __forceinline__ void tmem_ld_32x32_issue(uint32_t taddr, float (&v)[3
         : "r"(taddr) : "memory");
 }
 
+__device__ __forceinline__ void tmem_ld_32x16_issue(uint32_t taddr, float (&v)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7]),
+          "=f"(v[8]), "=f"(v[9]), "=f"(v[10]), "=f"(v[11]), "=f"(v[12]), "=f"(v[13]), "=f"(v[14]), "=f"(v[15])
+        : "r"(taddr) : "memory");
+}
+
 // ---------------------------------------------------------------- packed / 3-input fp32 (sm_100)
 // (v0,v1) = (fma(ns1, s2k, v) * inv) for two columns at once: FFMA2 + FMUL2, each lane IEEE-rn,
 // bit-identical to dm_zncc_partial.
