@@ -52,13 +52,14 @@ constexpr int NSTEP = BN / STEP;
 constexpr int STG_STRIDE = 20;          // floats per staged row (16 + 4 pad: conflict-free float4 rows)
 constexpr int STG_BYTES = 32 * STG_STRIDE * 4;      // per epilogue warp
 constexpr int CS_BYTES = (BN / 2) * 16; // column table of one N-tile: 64 x {sk0, sk1, inv0, inv1}
+constexpr int CS_STAGES = 4;
 
 // shared memory carve-up (offsets from the 1024-aligned base)
 constexpr size_t OFF_A = 0;
 constexpr size_t OFF_B = OFF_A + (size_t)HALVES * MAX_KB * BOX_BYTES;
 constexpr size_t OFF_STG = OFF_B + (size_t)STAGES * BOX_BYTES;
 constexpr size_t OFF_CS = OFF_STG + (size_t)EPI_WARPS * STG_BYTES;
-constexpr size_t OFF_BAR = OFF_CS + 2 * CS_BYTES;
+constexpr size_t OFF_BAR = OFF_CS + CS_STAGES * CS_BYTES;
 constexpr size_t SMEM_BYTES = 1024 /*align slack*/ + OFF_BAR + 256;
 
 struct Params {
@@ -90,8 +91,8 @@ dm_correlation_umma_kernel(const __grid_constant__ CUtensorMap mapA, const __gri
     uint64_t* t_full = bars + 2 + 2 * STAGES;
     uint64_t* t_empty = bars + 4 + 2 * STAGES;
     uint64_t* c_full = bars + 6 + 2 * STAGES;
-    uint64_t* c_empty = bars + 8 + 2 * STAGES;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10 + 2 * STAGES);
+    uint64_t* c_empty = bars + 6 + 2 * STAGES + CS_STAGES;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 6 + 2 * STAGES + 2 * CS_STAGES);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int P = prm.P, KB = prm.KB, NT = P / BN;
@@ -100,10 +101,8 @@ dm_correlation_umma_kernel(const __grid_constant__ CUtensorMap mapA, const __gri
         umma::mbar_init(a_full, 1);
         umma::mbar_init(a_empty, 1);
         for (int s = 0; s < STAGES; ++s) { umma::mbar_init(b_full + s, 1); umma::mbar_init(b_empty + s, 1); }
-        for (int s = 0; s < 2; ++s) {
-            umma::mbar_init(t_full + s, 1); umma::mbar_init(t_empty + s, EPI_WARPS);
-            umma::mbar_init(c_full + s, 1); umma::mbar_init(c_empty + s, EPI_WARPS);
-        }
+        for (int s = 0; s < 2; ++s) { umma::mbar_init(t_full + s, 1); umma::mbar_init(t_empty + s, EPI_WARPS); }
+        for (int s = 0; s < CS_STAGES; ++s) { umma::mbar_init(c_full + s, 1); umma::mbar_init(c_empty + s, EPI_WARPS); }
         umma::fence_barrier_init();
         umma::tma_prefetch_desc(&mapA);
         umma::tma_prefetch_desc(&mapB);
@@ -131,16 +130,17 @@ dm_correlation_umma_kernel(const __grid_constant__ CUtensorMap mapA, const __gri
                         umma::tma_load_2d(smemA + (size_t)(h * MAX_KB + kb) * BOX_BYTES, &mapA, kb * BK, row0 + h * BM, a_full);
                 aph ^= 1;
                 for (int j = 0; j < NT; ++j) {
-                    umma::mbar_wait(c_empty + cst, cph ^ 1);
-                    umma::mbar_expect_tx(c_full + cst, (uint32_t)CS_BYTES);
-                    umma::bulk_g2s(smemCs + (size_t)cst * CS_BYTES, prm.cstat2 + ((size_t)tile * P + (size_t)j * BN) / 2, CS_BYTES, c_full + cst);
-                    if (++cst == 2) { cst = 0; cph ^= 1; }
                     for (int kb = 0; kb < KB; ++kb) {
                         umma::mbar_wait(b_empty + bs, bph ^ 1);
                         umma::mbar_expect_tx(b_full + bs, (uint32_t)BOX_BYTES);
                         umma::tma_load_2d(smemB + (size_t)bs * BOX_BYTES, &mapB, kb * BK, tile * P + j * BN, b_full + bs);
                         if (++bs == STAGES) { bs = 0; bph ^= 1; }
                     }
+                    // column table of this N-tile (needed only by the epilogue, after the MMAs)
+                    umma::mbar_wait(c_empty + cst, cph ^ 1);
+                    umma::mbar_expect_tx(c_full + cst, (uint32_t)CS_BYTES);
+                    umma::bulk_g2s(smemCs + (size_t)cst * CS_BYTES, prm.cstat2 + ((size_t)tile * P + (size_t)j * BN) / 2, CS_BYTES, c_full + cst);
+                    if (++cst == CS_STAGES) { cst = 0; cph ^= 1; }
                 }
             }
         }
@@ -221,14 +221,14 @@ dm_correlation_umma_kernel(const __grid_constant__ CUtensorMap mapA, const __gri
                 umma::mbar_wait(t_full + acc, accph);
                 umma::tc_fence_after();
                 const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)((half * 2 + acc) * BN);
-                const float4* csm = reinterpret_cast<const float4*>(smemCs + (size_t)cst * CS_BYTES);
+                const uint32_t csm = umma::smem_u32(smemCs + (size_t)cst * CS_BYTES);
                 float zprev = -CUDART_INF_F;            // last raw value of the previous step
                 float v0[STEP], v1[STEP];
                 float4 c0[STEP / 2], c1[STEP / 2];
                 float4 ob;                              // 4 outputs being assembled
                 umma::tmem_ld_32x16_issue(taddr, v0);
 #pragma unroll
-                for (int i = 0; i < STEP / 2; ++i) c0[i] = csm[i];
+                for (int i = 0; i < STEP / 2; ++i) c0[i] = umma::lds128(csm + 16 * i);
 #pragma unroll
                 for (int s = 0; s < NSTEP; ++s) {
                     float (&v)[STEP] = (s & 1) ? v1 : v0;
@@ -239,7 +239,7 @@ dm_correlation_umma_kernel(const __grid_constant__ CUtensorMap mapA, const __gri
                     if (s + 1 < NSTEP) {                // step s+1 in flight during the math below
                         umma::tmem_ld_32x16_issue(taddr + (uint32_t)((s + 1) * STEP), vn);
 #pragma unroll
-                        for (int i = 0; i < STEP / 2; ++i) cn[i] = csm[(s + 1) * (STEP / 2) + i];
+                        for (int i = 0; i < STEP / 2; ++i) cn[i] = umma::lds128(csm + 16 * ((s + 1) * (STEP / 2) + i));
                     }
 #pragma unroll
                     for (int i = 0; i < STEP; i += 2) {
@@ -289,7 +289,7 @@ dm_correlation_umma_kernel(const __grid_constant__ CUtensorMap mapA, const __gri
                     }
                 }
                 if (++acc == 2) { acc = 0; accph ^= 1; }
-                if (++cst == 2) { cst = 0; cph ^= 1; }
+                if (++cst == CS_STAGES) { cst = 0; cph ^= 1; }
             }
             if (MODE == MODE_POOL) {
                 prm.rowmin[prow] = dm_zncc_finish(rmin, s1.y, flat1, NORMED);

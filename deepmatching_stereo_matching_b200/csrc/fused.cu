@@ -76,34 +76,44 @@ __global__ void dm_tile_origin_kernel2(int32_t* origin, int n, int first_tile, i
 // ---------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 dm_aggregate_first_kernel(const float* __restrict__ pooled, const float* __restrict__ rowmin,
-                          const float* __restrict__ rowmax, long long total4, int t0, int t1,
-                          float* __restrict__ out) {
-    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= total4) return;
-    const int P = t0 * t1, Q4 = P / 16;                 // float4 per pooled map
+                          const float* __restrict__ rowmax, int t0, int t1, float* __restrict__ out) {
+    // blockIdx.x = parent (n, I, J) flattened; threads cover the P/16 float4 of its map
+    const int P = t0 * t1, Q4 = P >> 4;
     const int hA = t0 >> 1, hB = t1 >> 1;
-    const int m4 = (int)(idx % Q4);
-    long long t = idx / Q4;
-    const int J = (int)(t % hB); t /= hB;
-    const int I = (int)(t % hA);
-    const long long n = t / hA;
-    float4 sum;
+    const unsigned par = blockIdx.x;
+    const int J = par % hB;
+    const unsigned t = par / hB;
+    const int I = t % hA;
+    const size_t n = t / hA;
+    const float4* src[4];
+    float mn[4], mx[4], rinv[4];
 #pragma unroll
     for (int ch = 0; ch < 4; ++ch) {
-        const size_t p = (size_t)n * P + (size_t)(2 * I + (ch >> 1)) * t1 + (2 * J + (ch & 1));
-        const float mn = __ldg(rowmin + p), mx = __ldg(rowmax + p), rinv = dm_range_inv(mn, mx);
-        float4 v = __ldg(reinterpret_cast<const float4*>(pooled + p * (size_t)(P / 4)) + m4);
-        v.x = dm_rectify(dm_normalize(v.x, mn, mx, rinv));
-        v.y = dm_rectify(dm_normalize(v.y, mn, mx, rinv));
-        v.z = dm_rectify(dm_normalize(v.z, mn, mx, rinv));
-        v.w = dm_rectify(dm_normalize(v.w, mn, mx, rinv));
-        if (ch == 0) sum = v;
-        else { sum.x = __fadd_rn(sum.x, v.x); sum.y = __fadd_rn(sum.y, v.y); sum.z = __fadd_rn(sum.z, v.z); sum.w = __fadd_rn(sum.w, v.w); }
+        const size_t p = n * P + (size_t)(2 * I + (ch >> 1)) * t1 + (2 * J + (ch & 1));
+        mn[ch] = __ldg(rowmin + p); mx[ch] = __ldg(rowmax + p); rinv[ch] = dm_range_inv(mn[ch], mx[ch]);
+        src[ch] = reinterpret_cast<const float4*>(pooled + p * (size_t)(P / 4));
     }
-    float4 o;
-    o.x = dm_rectify(__fmul_rn(sum.x, 0.25f)); o.y = dm_rectify(__fmul_rn(sum.y, 0.25f));
-    o.z = dm_rectify(__fmul_rn(sum.z, 0.25f)); o.w = dm_rectify(__fmul_rn(sum.w, 0.25f));
-    reinterpret_cast<float4*>(out)[idx] = o;
+    float4* dst = reinterpret_cast<float4*>(out) + (size_t)par * Q4;
+    for (int m4 = threadIdx.x; m4 < Q4; m4 += blockDim.x) {
+        float4 v[4];
+#pragma unroll
+        for (int ch = 0; ch < 4; ++ch) v[ch] = __ldg(src[ch] + m4);
+        float4 sum;
+#pragma unroll
+        for (int ch = 0; ch < 4; ++ch) {
+            float4 r;
+            r.x = dm_rectify(dm_normalize(v[ch].x, mn[ch], mx[ch], rinv[ch]));
+            r.y = dm_rectify(dm_normalize(v[ch].y, mn[ch], mx[ch], rinv[ch]));
+            r.z = dm_rectify(dm_normalize(v[ch].z, mn[ch], mx[ch], rinv[ch]));
+            r.w = dm_rectify(dm_normalize(v[ch].w, mn[ch], mx[ch], rinv[ch]));
+            if (ch == 0) sum = r;
+            else { sum.x = __fadd_rn(sum.x, r.x); sum.y = __fadd_rn(sum.y, r.y); sum.z = __fadd_rn(sum.z, r.z); sum.w = __fadd_rn(sum.w, r.w); }
+        }
+        float4 o;
+        o.x = dm_rectify(__fmul_rn(sum.x, 0.25f)); o.y = dm_rectify(__fmul_rn(sum.y, 0.25f));
+        o.z = dm_rectify(__fmul_rn(sum.z, 0.25f)); o.w = dm_rectify(__fmul_rn(sum.w, 0.25f));
+        dst[m4] = o;
+    }
 }
 
 // ---------------------------------------------------------------------------------------
@@ -140,8 +150,8 @@ dm_final_level_kernel(const FinalArgs a, long long n_patches) {
     const long long w = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (w >= n_patches) return;
     const int T0 = a.t0, T1 = a.t1, P = T0 * T1;
-    const long long n = w / P;
-    const int p = (int)(w - n * P);
+    const int n = (int)(w / P);                          // tile inside the chunk
+    const int p = (int)(w - (long long)n * P);
     const int i = p / T1, j = p - i * T1;
     const int oy = a.origin[2 * n], ox = a.origin[2 * n + 1];
     const bool normed = a.normed != 0;
@@ -158,16 +168,21 @@ dm_final_level_kernel(const FinalArgs a, long long n_patches) {
     const dm_stat* st2 = a.stat2 + (size_t)n * P;
     const int m1 = (int)s1.w, S1 = (int)s1.x;
 
-    // stage the region: rows oy+d0-2 .. +RW, cols ox+d1-2 .. +RW (zeros outside the scene)
+    // stage the region: rows oy+d0-2 .. +RW, cols ox+d1-2 .. +RW (zeros outside the scene).
+    // Fully unrolled so that all RW row loads of a lane are in flight together.
     {
         const int gy0 = oy + d0 - 2, gx = ox + d1 - 2 + lane;
         const bool colok = lane < RW && gx >= 0 && gx < a.pitch;
-#pragma unroll 1
+        const uint8_t* src = a.img2 + (ptrdiff_t)gy0 * a.pitch + gx;
+        uint8_t vals[RW];
+#pragma unroll
         for (int ry = 0; ry < RW; ++ry) {
             const int gy = gy0 + ry;
-            uint8_t v = 0;
-            if (colok && gy >= 0 && gy < a.scene_h) v = a.img2[(size_t)gy * a.pitch + gx];
-            if (lane < RW) region[ry * RS + lane] = v;
+            vals[ry] = (colok && gy >= 0 && gy < a.scene_h) ? __ldg(src + ry * a.pitch) : (uint8_t)0;
+        }
+        if (lane < RW) {
+#pragma unroll
+            for (int ry = 0; ry < RW; ++ry) region[ry * RS + lane] = vals[ry];
         }
     }
     // this lane's centred patch pixels and their offsets inside a window
@@ -349,8 +364,10 @@ int dm_fused_solve_chunk(dm_ctx* ctx, const dm_fused_args* a, int ck) {
     {
         StageTimer tm(ctx, DM_STAGE_NORMALIZE);        // min-max + rectify + first child average
         if ((rc = tm.begin(ck)) != DM_OK) return rc;
-        const long long total4 = (long long)nt * (P / 4) * (P / 16);
-        dm_aggregate_first_kernel<<<dm_div_up(total4, 256), 256, 0, st>>>(fb.pooled, fb.rowmin, fb.rowmax, total4, t0, t1, fb.level[1]);
+        const long long parents = (long long)nt * (P / 4);
+        const int q4 = P / 16;
+        const int threads = q4 >= 256 ? 256 : (q4 < 32 ? 32 : q4);
+        dm_aggregate_first_kernel<<<(unsigned)parents, threads, 0, st>>>(fb.pooled, fb.rowmin, fb.rowmax, t0, t1, fb.level[1]);
         DM_LAUNCH_CHECK();
         ctx->launches[DM_STAGE_NORMALIZE] += 1;
         if ((rc = tm.end()) != DM_OK) return rc;

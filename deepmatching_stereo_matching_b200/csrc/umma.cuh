@@ -107,6 +107,14 @@ __device__ __forceinline__ void tmem_ld_32x16_issue(uint32_t taddr, float (&v)[1
         : "r"(taddr) : "memory");
 }
 
+// 16-byte shared load pinned in program order (volatile): keeps the software pipeline's
+// prefetches where they were written instead of letting the scheduler sink them to the use
+__device__ __forceinline__ float4 lds128(uint32_t saddr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(saddr));
+    return v;
+}
+
 // ---------------------------------------------------------------- packed / 3-input fp32 (sm_100)
 // (v0,v1) = (fma(ns1, s2k, v) * inv) for two columns at once: FFMA2 + FMUL2, each lane IEEE-rn,
 // bit-identical to dm_zncc_partial.
