@@ -253,40 +253,76 @@ def run_ours(args):
     roofline = None
     if rank == 0:
         peaks = load_peaks()
-        tctx = _native.Context(timing=True)
-        prm = solver.prm
-        for _ in range(2):
-            tctx.solve_device(prm, d1, d2, planes[:-1], planes[-1])
-        acc = {}
-        reps = 3
-        for _ in range(reps):
-            tinfo = tctx.solve_device(prm, d1, d2, planes[:-1], planes[-1])
-            st_ms, st_launch = tctx.stage_ms()
-            for k, v in st_ms.items():
-                acc[k] = acc.get(k, 0.0) + v / reps
+
+        def stage_times(prm_, reps=3):
+            tctx = _native.Context(timing=True)
+            for _ in range(2):
+                tctx.solve_device(prm_, d1, d2, planes[:-1], planes[-1])
+            acc_, launch_, tinfo_ = {}, {}, None
+            for _ in range(reps):
+                tinfo_ = tctx.solve_device(prm_, d1, d2, planes[:-1], planes[-1])
+                st_ms, launch_ = tctx.stage_ms()
+                for k, v in st_ms.items():
+                    acc_[k] = acc_.get(k, 0.0) + v / reps
+            tctx.close()
+            return acc_, launch_, tinfo_
+
+        acc, st_launch, tinfo = stage_times(solver.prm)
         tiles = tinfo.n_tiles
         P = T * T
-        flops = 2.0 * WS * WS * P * P * tiles
-        lv_bytes = sum(4.0 * (P * P / 16.0 ** k + P * P / 16.0 ** (k + 1)) for k in range(info.levels - 1)) * tiles
-        top = max(acc, key=acc.get)
+        kpad = ((WS * WS + 63) // 64) * 64
+        fused = bool(tinfo.used_fused)
+        # algorithmic work per step (DESIGN.md "Kernels")
+        flops = 2.0 * WS * WS * P * P * tiles                                  # unpadded K
+        lvl = lambda k: P * P / 16.0 ** k                                       # entries of level k per tile
+        first = 1 if fused else 0
+        agg_bytes = sum(4.0 * (lvl(k) + lvl(k + 1)) for k in range(first, info.levels - 1)) * tiles
+        work = {
+            'descriptors': ('hbm', 2.0 * (P * kpad * 2 + (T + WS - 1) ** 2) * tiles),
+            'correlation': ('tensor', flops),
+            # fused: pooled raw map read + level 1 written; materialising: level 0 read + written
+            'normalize': ('hbm', (4.0 * (lvl(0) / 4 + lvl(1)) if fused else 8.0 * lvl(0)) * tiles),
+            'aggregate': ('hbm', agg_bytes),
+        }
+        kern_name = {'descriptors': 'dm_descriptor_fast_kernel', 'correlation': 'dm_correlation_umma_kernel',
+                     'normalize': 'dm_aggregate_first_kernel' if fused else 'dm_minmax_rectify_kernel',
+                     'aggregate': 'dm_aggregate_kernel', 'backtrack': 'dm_backtrack_kernel',
+                     'planes': 'dm_final_level_kernel' if fused else 'dm_planes_kernel'}
+        traffic = {}
+        tp = os.path.join(REPO, 'profiles', 'ncu_traffic.json')       # dram bytes per launch from ncu --set full
+        if os.path.exists(tp):
+            traffic = json.load(open(tp)).get('fused' if fused else 'materialising', {})
+        kernels = {}
+        for k, (bound, w) in work.items():
+            if acc.get(k, 0) <= 0:
+                continue
+            if bound == 'tensor':
+                ach, pk, unit = w / (acc[k] * 1e-3) / 1e12, peaks['tensor'], 'TFLOP/s'
+            else:
+                ach, pk, unit = w / (acc[k] * 1e-3) / 1e9, peaks['hbm'], 'GB/s'
+            kernels[k] = {'kernel': kern_name[k], 'bound': bound, 'achieved': ach, 'peak': pk, 'unit': unit, 'frac': ach / pk,
+                          'ms': acc[k], 'launches': st_launch[k], 'traffic': traffic.get(kern_name[k])}
         total = sum(acc.values())
-        if top == 'correlation':
-            ach = flops / (acc[top] * 1e-3) / 1e12
-            roofline = {'kernel': 'correlation', 'bound': 'tensor', 'achieved': ach, 'peak': peaks['tensor'], 'unit': 'TFLOP/s',
-                        'frac': ach / peaks['tensor'], 'traffic': None}
-        else:
-            nbytes = lv_bytes if top == 'aggregate' else 4.0 * 2 * P * P * tiles
-            ach = nbytes / (acc[top] * 1e-3) / 1e9
-            roofline = {'kernel': top, 'bound': 'hbm', 'achieved': ach, 'peak': peaks['hbm'], 'unit': 'GB/s',
-                        'frac': ach / peaks['hbm'], 'traffic': None}
-        roofline['peak_source'] = peaks['source']
-        roofline['share_of_step'] = acc[top] / total if total > 0 else None
-        roofline['stage_ms'] = {k: round(v, 4) for k, v in acc.items()}
-        roofline['stage_launches'] = st_launch
-        roofline['correlation_tflops'] = flops / (acc['correlation'] * 1e-3) / 1e12 if acc.get('correlation') else None
-        roofline['aggregate_gbs'] = lv_bytes / (acc['aggregate'] * 1e-3) / 1e9 if acc.get('aggregate') else None
-        roofline['used_fused'] = bool(tinfo.used_fused)
-        tctx.close()
+        top = max(kernels, key=lambda k: kernels[k]['ms'])
+        roofline = dict(kernels[top])
+        roofline.pop('ms'); roofline.pop('launches')
+        roofline.update({'peak_source': peaks['source'] + ' (sustained bf16 / copy bandwidth of MEASURED_PEAKS.json)',
+                         'share_of_step': acc[top] / total if total > 0 else None,
+                         'stage_ms': {k: round(v, 4) for k, v in acc.items()}, 'stage_launches': st_launch,
+                         'kernels': kernels, 'used_fused': fused})
+        if fused and not args.no_materialising:
+            # the stand-alone aggregation kernel on level 0 -> 1 only runs on the materialising path
+            import ctypes
+            prm0 = type(solver.prm)()
+            ctypes.memmove(ctypes.byref(prm0), ctypes.byref(solver.prm), ctypes.sizeof(prm0))
+            prm0.fused = 0
+            acc0, launch0, _ = stage_times(prm0, reps=2)
+            b0 = sum(4.0 * (lvl(k) + lvl(k + 1)) for k in range(0, info.levels - 1)) * tiles
+            roofline['materialising_path'] = {
+                'stage_ms': {k: round(v, 4) for k, v in acc0.items()},
+                'aggregate': {'kernel': 'dm_aggregate_kernel', 'bound': 'hbm', 'achieved': b0 / (acc0['aggregate'] * 1e-3) / 1e9,
+                              'peak': peaks['hbm'], 'unit': 'GB/s', 'frac': b0 / (acc0['aggregate'] * 1e-3) / 1e9 / peaks['hbm'],
+                              'launches': launch0['aggregate']}}
 
     if rank == 0:
         value = out_px * args.steps / 1e6 / (ms * 1e-3)
@@ -324,6 +360,7 @@ def main():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--fused', type=int, default=-1, help='-1 auto, 0 materialising path, 1 fused tcgen05 path')
     ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
+    ap.add_argument('--no-materialising', action='store_true', help='skip the extra stage timing of the materialising path')
     args = ap.parse_args()
     if args.impl == 'reference':
         return run_reference(args)

@@ -39,6 +39,10 @@ extern "C" int dm_correlation(const void* desc1_dev, const float* stat1_dev,
     DM_REQUIRE(n_tiles > 0 && p > 0 && kpad == dm_kpad(ws), DM_ERR_INVALID, "dm_correlation: bad shape (kpad %d for ws %d)", kpad, ws);
     cudaStream_t st = (cudaStream_t)stream;
     const bool umma_ok = dm_correlation_umma_supported(p, kpad);
+    if (engine == 3) {      // undocumented measurement aid: MMA + TMEM drain only
+        DM_REQUIRE(umma_ok, DM_ERR_UNSUPPORTED, "dm_correlation: unsupported shape");
+        return dm_correlation_umma_null(desc1_dev, stat1_dev, desc2_dev, stat2_dev, n_tiles, p, kpad, raw_dev, st);
+    }
     if (engine == DM_CORR_UMMA) {
         DM_REQUIRE(umma_ok, DM_ERR_UNSUPPORTED, "dm_correlation: tcgen05 engine needs P %% 128 == 0 and kpad <= 256 (P=%d kpad=%d)", p, kpad);
         return dm_correlation_umma(desc1_dev, stat1_dev, desc2_dev, stat2_dev, n_tiles, p, kpad, method, raw_dev, st);

@@ -71,7 +71,7 @@ struct Params {
     float* rowmin; float* rowmax;   // MODE_POOL: [n][P]
 };
 
-enum { MODE_RAW = 0, MODE_POOL = 1 };
+enum { MODE_RAW = 0, MODE_POOL = 1, MODE_NULL = 2 };   // MODE_NULL: drain TMEM only (measurement aid)
 
 template <int MODE, int D, bool NORMED>      // D = positions per map row (T1); only used by MODE_POOL
 __global__ void __launch_bounds__(THREADS, 1)
@@ -241,6 +241,15 @@ dm_correlation_umma_kernel(const __grid_constant__ CUtensorMap mapA, const __gri
 #pragma unroll
                         for (int i = 0; i < STEP / 2; ++i) cn[i] = umma::lds128(csm + 16 * ((s + 1) * (STEP / 2) + i));
                     }
+                    if (MODE == MODE_NULL) {            // measurement aid: TMEM drain + barriers only
+                        rmax = fmaxf(rmax, v[0]);
+                        if (s + 1 == NSTEP) {
+                            umma::tc_fence_before();
+                            __syncwarp();
+                            if (lane == 0) { umma::mbar_arrive(t_empty + acc); umma::mbar_arrive(c_empty + cst); }
+                        }
+                        continue;
+                    }
 #pragma unroll
                     for (int i = 0; i < STEP; i += 2) {
                         const float4 cp = cc[i >> 1];       // {s2k0, s2k1, inv0, inv1} of two columns
@@ -295,6 +304,7 @@ dm_correlation_umma_kernel(const __grid_constant__ CUtensorMap mapA, const __gri
                 prm.rowmin[prow] = dm_zncc_finish(rmin, s1.y, flat1, NORMED);
                 prm.rowmax[prow] = rmax;
             }
+            if (MODE == MODE_NULL && rmax == 12345.678f) prm.raw[prow] = rmax;     // keep the loads alive
         }
     }
 
@@ -385,6 +395,16 @@ int dm_correlation_umma(const void* desc1, const float* stat1, const void* desc2
     if (rc != DM_OK) return rc;
     prm.raw = raw;
     return launch<MODE_RAW, 64>(mapA, mapB, prm, method == DM_TM_CCOEFF_NORMED, stream);
+}
+
+// measurement aid (DM_CORR_UMMA_NULL): MMAs + TMEM drain, no epilogue math, no output
+int dm_correlation_umma_null(const void* desc1, const float* stat1, const void* desc2, const float* stat2,
+                             int n_tiles, int p, int kpad, float* raw, cudaStream_t stream) {
+    Params prm; CUtensorMap mapA, mapB;
+    int rc = fill_params(prm, mapA, mapB, desc1, stat1, desc2, stat2, n_tiles, p, kpad);
+    if (rc != DM_OK) return rc;
+    prm.raw = raw;
+    return launch<MODE_NULL, 64>(mapA, mapB, prm, true, stream);
 }
 
 int dm_correlation_umma_pool(const void* desc1, const float* stat1, const void* desc2, const float* stat2,

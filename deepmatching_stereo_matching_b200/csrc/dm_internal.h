@@ -16,6 +16,8 @@ bool dm_correlation_umma_supported(int p, int kpad);
 int dm_correlation_umma(const void* desc1, const float* stat1, const void* desc2, const float* stat2,
                         int n_tiles, int p, int kpad, int method, float* raw, cudaStream_t stream);
 
+int dm_correlation_umma_null(const void* desc1, const float* stat1, const void* desc2, const float* stat2,
+                             int n_tiles, int p, int kpad, float* raw, cudaStream_t stream);
 // pooled epilogue: level 0 is max-pooled on the fly, only [n][P][P/4] + row min/max reach HBM
 bool dm_correlation_umma_pool_supported(int t0, int t1, int kpad);
 int dm_correlation_umma_pool(const void* desc1, const float* stat1, const void* desc2, const float* stat2,

@@ -132,19 +132,19 @@ struct FinalArgs {
 
 // The 3x3 candidate windows around p_dot and the parabola neighbours of the match all lie
 // in the (ws+4)^2 pixel region of image 2 that starts two pixels up/left of window p_dot.
-// The warp stages that region in shared memory once; every lane keeps its <= 8 centred
-// patch pixels in registers and walks the region with compile-time shifts.  Dot products
-// are exact int32:  sum a'_k * (b_k - m2) = sum a'_k * b_k  -  m2 * S1'.
-constexpr int RS = 20;                  // region row stride in bytes (ws + 4 <= 19)
-constexpr int RBYTES = 19 * RS + 4;
+// The warp stages that region in shared memory once (word-aligned rows).  Lane (ky, hf)
+// owns bytes [8*hf, 8*hf+8) of patch row ky as two packed words and sweeps the shifted
+// windows with funnel shifts + DP4A (4 byte-MACs per instruction).  All sums are exact:
+//   sum (a-m1)(b-m2) = sum a*b - m2*S1' - m1*S2' - K*m1*m2     (S' = residual sums of the stats)
+constexpr int RSB = 24;                 // region row stride in bytes (ws + 4 <= 19, word aligned)
+constexpr int RBYTES = 19 * RSB + 8;
 
 template <int WS>
 __global__ void __launch_bounds__(256)
 dm_final_level_kernel(const FinalArgs a, long long n_patches) {
     constexpr int K = WS * WS;
-    constexpr int KT = (K + 31) / 32;   // window pixels per lane
     constexpr int RW = WS + 4;
-    __shared__ uint8_t region_all[8][RBYTES];
+    __shared__ __align__(16) uint8_t region_all[8][RBYTES];
     const int lane = threadIdx.x & 31;
     uint8_t* region = region_all[threadIdx.x >> 5];
     const long long w = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -169,59 +169,77 @@ dm_final_level_kernel(const FinalArgs a, long long n_patches) {
     const int m1 = (int)s1.w, S1 = (int)s1.x;
 
     // stage the region: rows oy+d0-2 .. +RW, cols ox+d1-2 .. +RW (zeros outside the scene).
-    // Fully unrolled so that all RW row loads of a lane are in flight together.
+    // Fully unrolled so that all RW row loads of a lane are in flight together; the common
+    // case (region entirely inside the scene) runs without per-row guards.
     {
-        const int gy0 = oy + d0 - 2, gx = ox + d1 - 2 + lane;
-        const bool colok = lane < RW && gx >= 0 && gx < a.pitch;
-        const uint8_t* src = a.img2 + (ptrdiff_t)gy0 * a.pitch + gx;
+        const int gy0 = oy + d0 - 2, gx0 = ox + d1 - 2;
+        const int gx = gx0 + lane;
         uint8_t vals[RW];
+        if (gy0 >= 0 && gy0 + RW <= a.scene_h && gx0 >= 0 && gx0 + RW <= a.pitch) {     // warp-uniform
+            const uint8_t* src = a.img2 + (size_t)gy0 * a.pitch + gx0 + (lane < RW ? lane : 0);
 #pragma unroll
-        for (int ry = 0; ry < RW; ++ry) {
-            const int gy = gy0 + ry;
-            vals[ry] = (colok && gy >= 0 && gy < a.scene_h) ? __ldg(src + ry * a.pitch) : (uint8_t)0;
+            for (int ry = 0; ry < RW; ++ry) { vals[ry] = __ldg(src); src += a.pitch; }
+        } else {
+            const bool colok = lane < RW && gx >= 0 && gx < a.pitch;
+#pragma unroll
+            for (int ry = 0; ry < RW; ++ry) {
+                const int gy = gy0 + ry;
+                vals[ry] = (colok && gy >= 0 && gy < a.scene_h) ? __ldg(a.img2 + (size_t)gy * a.pitch + gx) : (uint8_t)0;
+            }
         }
-        if (lane < RW) {
+        if (lane < RSB) {
+            uint8_t* dst = region + lane;
 #pragma unroll
-            for (int ry = 0; ry < RW; ++ry) region[ry * RS + lane] = vals[ry];
+            for (int ry = 0; ry < RW; ++ry) dst[ry * RSB] = (lane < RW) ? vals[ry] : (uint8_t)0;
         }
     }
-    // this lane's centred patch pixels and their offsets inside a window
-    int av[KT], koff[KT];
+    // this lane's 8 patch bytes (row ky, columns 8*hf .. 8*hf+7; zero beyond the window)
+    const int ky = lane >> 1, hf = lane & 1;
+    const bool rowlive = ky < WS;
+    uint32_t a0 = 0, a1 = 0;
     {
-        const uint8_t* a_base = a.img1 + (size_t)(oy + i) * a.pitch + ox + j;
+        const uint8_t* a_row = a.img1 + (size_t)(oy + i + (rowlive ? ky : 0)) * a.pitch + ox + j + hf * 8;
+        const int nvalid = rowlive ? (hf ? WS - 8 : (WS < 8 ? WS : 8)) : 0;
 #pragma unroll
-        for (int t = 0; t < KT; ++t) {
-            const int k = lane + 32 * t;
-            const int ky = k / WS, kx = k - ky * WS;
-            av[t] = (k < K) ? (int)a_base[ky * a.pitch + kx] - m1 : 0;
-            koff[t] = (k < K) ? ky * RS + kx : 0;
+        for (int u = 0; u < 8; ++u) {
+            const uint32_t v = (u < nvalid) ? (uint32_t)__ldg(a_row + u) : 0u;
+            if (u < 4) a0 |= v << (8 * u); else a1 |= v << (8 * (u - 4));
         }
     }
     __syncwarp();
+    const uint32_t* rwords = reinterpret_cast<const uint32_t*>(region) + hf * 2;    // lane's first word in a region row
 
-    // level-0 value of position (qy,qx) from sum a'*b (each lane evaluates ONE candidate)
-    auto value_at = [&](int dot_ab, int qy, int qx) -> float {
+    // level-0 value of position (qy,qx) from sum a*b (each lane evaluates ONE candidate)
+    auto value_at = [&](int sum_ab, int qy, int qx) -> float {
         const dm_stat sq = st2[qy * T1 + qx];
-        const int dot = dot_ab - (int)sq.w * S1;
+        const int m2 = (int)sq.w, S2 = (int)sq.x;
+        const int dot = sum_ab - m2 * S1 - m1 * S2 - K * m1 * m2;
         const float z = dm_zncc_partial((float)dot, s1.x, sq.z, normed ? sq.y : 1.0f);
         return dm_rectify(dm_normalize(dm_zncc_finish(z, s1.y, flat1, normed), mn, mx, rinv));
     };
 
     // ---- misc/Matching.py:58-78 on the recomputed 3x3 window (zero padding outside)
-    int acc[16];
+    uint32_t acc[16];
 #pragma unroll
     for (int s = 0; s < 16; ++s) acc[s] = 0;
+    if (rowlive) {
 #pragma unroll
-    for (int t = 0; t < KT; ++t) {
-        const uint8_t* r = region + koff[t];
+        for (int dy = 0; dy < 3; ++dy) {                 // candidate rows d0-1 .. d0+1 = region rows ky+1 .. ky+3
+            const uint32_t* rr = rwords + (ky + dy + 1) * (RSB / 4);
+            const uint32_t w0 = rr[0], w1 = rr[1], w2 = rr[2];
 #pragma unroll
-        for (int s = 0; s < 9; ++s) acc[s] += av[t] * (int)r[(s / 3 + 1) * RS + (s % 3 + 1)];
+            for (int dx = 0; dx < 3; ++dx) {             // candidate cols d1-1 .. d1+1 = region cols +1 .. +3
+                const uint32_t b0 = __funnelshift_r(w0, w1, 8 * (dx + 1));
+                const uint32_t b1 = __funnelshift_r(w1, w2, 8 * (dx + 1));
+                acc[dy * 3 + dx] = __dp4a(a1, b1, __dp4a(a0, b0, acc[dy * 3 + dx]));
+            }
+        }
     }
     // butterfly reduction of 16 partial sums in 16 shuffles: afterwards this lane holds the
     // warp total of candidate my_s = b4*8 + b3*4 + b2*2 + b1 (b_k = bit k of the lane id)
-    int part = 0;
+    uint32_t part = 0;
     {
-        int w8[8], w4[4], w2[2];
+        uint32_t w8[8], w4[4], w2[2];
         const bool h16 = lane & 16, h8 = lane & 8, h4 = lane & 4, h2 = lane & 2;
 #pragma unroll
         for (int q = 0; q < 8; ++q) w8[q] = (h16 ? acc[q + 8] : acc[q]) + __shfl_xor_sync(0xffffffffu, h16 ? acc[q] : acc[q + 8], 16);
@@ -236,7 +254,7 @@ dm_final_level_kernel(const FinalArgs a, long long n_patches) {
     float myval = 0.0f;
     {
         const int qy = d0 + my_s / 3 - 1, qx = d1 + my_s % 3 - 1;
-        if (my_s < 9 && qy >= 0 && qy < T0 && qx >= 0 && qx < T1) myval = value_at(part, qy, qx);
+        if (my_s < 9 && qy >= 0 && qy < T0 && qx >= 0 && qx < T1) myval = value_at((int)part, qy, qx);
     }
     float best = 0.f, centre = 0.f;
     int bi = 0;
@@ -260,31 +278,34 @@ dm_final_level_kernel(const FinalArgs a, long long n_patches) {
         const int ny[4] = {c0 + 1, (c0 == 0 ? T0 - 1 : c0 - 1), c0, c0};
         const int nx[4] = {c1, c1, c1 + 1, (c1 == 0 ? T1 - 1 : c1 - 1)};
         const bool nok[4] = {c0 + 1 < T0, c0 + 1 < T0, c1 + 1 < T1, c1 + 1 < T1};
-        int nacc[4];
+        uint32_t nacc[4];
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
             nacc[q] = 0;
-            if (!nok[q]) continue;                                  // warp-uniform
+            if (!nok[q] || !rowlive) continue;
             const int ry = ny[q] - (d0 - 2), rx = nx[q] - (d1 - 2);
-            if (ry >= 0 && ry <= 4 && rx >= 0 && rx <= 4) {         // inside the staged region
-                const uint8_t* r = region + ry * RS + rx;
-#pragma unroll
-                for (int t = 0; t < KT; ++t) nacc[q] += av[t] * (int)r[koff[t]];
+            if (ry >= 0 && ry <= 4 && rx >= 0 && rx <= 4) {         // inside the staged region (warp-uniform)
+                const int bo = hf * 8 + rx;
+                const uint32_t* rr = reinterpret_cast<const uint32_t*>(region) + (ky + ry) * (RSB / 4) + (bo >> 2);
+                const uint32_t w0 = rr[0], w1 = rr[1], w2 = rr[2];
+                const int sh = (bo & 3) * 8;
+                nacc[q] = __dp4a(a1, __funnelshift_r(w1, w2, sh), __dp4a(a0, __funnelshift_r(w0, w1, sh), 0u));
             } else {                                                // wrapped index: far away, read global memory
-                const uint8_t* b = a.img2 + (size_t)(oy + ny[q]) * a.pitch + ox + nx[q];
+                const uint8_t* b = a.img2 + (size_t)(oy + ny[q] + ky) * a.pitch + ox + nx[q] + hf * 8;
+                uint32_t b0 = 0, b1 = 0;
 #pragma unroll
-                for (int t = 0; t < KT; ++t) {
-                    const int k = lane + 32 * t;
-                    const int ky = k / WS, kx = k - ky * WS;
-                    if (k < K) nacc[q] += av[t] * (int)b[ky * a.pitch + kx];
+                for (int u = 0; u < 8; ++u) {
+                    const uint32_t v = (hf * 8 + u < WS) ? (uint32_t)__ldg(b + u) : 0u;
+                    if (u < 4) b0 |= v << (8 * u); else b1 |= v << (8 * (u - 4));
                 }
+                nacc[q] = __dp4a(a1, b1, __dp4a(a0, b0, 0u));
             }
         }
         // 4 partial sums -> lane holds the total of neighbour my_n = b4*2 + b3 (6 shuffles)
         const bool h16 = lane & 16, h8 = lane & 8;
-        int u0 = (h16 ? nacc[2] : nacc[0]) + __shfl_xor_sync(0xffffffffu, h16 ? nacc[0] : nacc[2], 16);
-        int u1 = (h16 ? nacc[3] : nacc[1]) + __shfl_xor_sync(0xffffffffu, h16 ? nacc[1] : nacc[3], 16);
-        int tot = (h8 ? u1 : u0) + __shfl_xor_sync(0xffffffffu, h8 ? u0 : u1, 8);
+        uint32_t u0 = (h16 ? nacc[2] : nacc[0]) + __shfl_xor_sync(0xffffffffu, h16 ? nacc[0] : nacc[2], 16);
+        uint32_t u1 = (h16 ? nacc[3] : nacc[1]) + __shfl_xor_sync(0xffffffffu, h16 ? nacc[1] : nacc[3], 16);
+        uint32_t tot = (h8 ? u1 : u0) + __shfl_xor_sync(0xffffffffu, h8 ? u0 : u1, 8);
         tot += __shfl_xor_sync(0xffffffffu, tot, 4);
         tot += __shfl_xor_sync(0xffffffffu, tot, 2);
         tot += __shfl_xor_sync(0xffffffffu, tot, 1);
@@ -293,7 +314,7 @@ dm_final_level_kernel(const FinalArgs a, long long n_patches) {
         const int sx = my_n == 2 ? nx[2] : (my_n == 3 ? nx[3] : c1);
         const bool sok = my_n < 2 ? nok[0] : nok[2];
         float nval = 0.0f;
-        if (sok) nval = value_at(tot, sy, sx);
+        if (sok) nval = value_at((int)tot, sy, sx);
         const float r0 = best;                      // level-0 value at the match itself
         const float v0 = __shfl_sync(0xffffffffu, nval, 0), v1 = __shfl_sync(0xffffffffu, nval, 8);
         const float v2 = __shfl_sync(0xffffffffu, nval, 16), v3 = __shfl_sync(0xffffffffu, nval, 24);
@@ -303,7 +324,7 @@ dm_final_level_kernel(const FinalArgs a, long long n_patches) {
     if (lane != 0) return;
 
     // ---- planes + paste (misc/Calc_difference.py:36-48, misc/image_cut_solver.py:165-175)
-    const int g = a.first_tile + (int)n;
+    const int g = a.first_tile + n;
     const int gi = g / a.len1, gj = g - gi * a.len1;
     const int Y = a.s0 * gi + i, X = a.s1 * gj + j;
     if (min(Y / a.s0, a.len0 - 1) != gi || min(X / a.s1, a.len1 - 1) != gj) return;   // a later tile owns this pixel
