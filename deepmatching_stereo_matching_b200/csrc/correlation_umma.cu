@@ -284,7 +284,11 @@ dm_correlation_umma_kernel(const __grid_constant__ CUtensorMap mapA, const __gri
                             if ((r & 1) == 0) {
                                 st[xh] = fmaxf(st[xh], h);      // rows 2y-1 (carried) and 2y
                             } else {
-                                const float o = dm_zncc_finish(fmaxf(st[xh], h), s1.y, flat1, NORMED);
+                                // pooled output: row factor and upper clamp only.  A flat patch has
+                                // inv1 = 0 -> the whole row is 0 -> min == max -> NaN downstream, exactly
+                                // like OpenCV's all-ones map; a pooled maximum below -1 cannot occur.
+                                float o = fmaxf(st[xh], h);
+                                if (NORMED) o = fminf(__fmul_rn(o, s1.y), 1.0f);
                                 st[xh] = h;                     // becomes row 2(y+1)-1 of the next pooled row
                                 rmax = fmaxf(rmax, o);
                                 const int oi = (r >> 1) * (D / 2) + xh;     // output index inside the N-tile, 0..31
@@ -301,8 +305,9 @@ dm_correlation_umma_kernel(const __grid_constant__ CUtensorMap mapA, const __gri
                 if (++cst == CS_STAGES) { cst = 0; cph ^= 1; }
             }
             if (MODE == MODE_POOL) {
-                prm.rowmin[prow] = dm_zncc_finish(rmin, s1.y, flat1, NORMED);
-                prm.rowmax[prow] = rmax;
+                // flat patch: OpenCV's map is all ones -> min == max == 1 -> NaN slice downstream
+                prm.rowmin[prow] = NORMED ? (flat1 ? 1.0f : fminf(fmaxf(__fmul_rn(rmin, s1.y), -1.0f), 1.0f)) : rmin;
+                prm.rowmax[prow] = (NORMED && flat1) ? 1.0f : rmax;
             }
             if (MODE == MODE_NULL && rmax == 12345.678f) prm.raw[prow] = rmax;     // keep the loads alive
         }

@@ -9,12 +9,32 @@
 // the layout TMA loads straight into 128B-swizzled shared memory for tcgen05.mma.
 #include "dm_common.cuh"
 
+// K layout of a descriptor row: k = ky * rstride + kx with rstride = 8 / 16 / 32 (window rows
+// padded to a power of two, so a lane owns 8 consecutive entries of ONE window row); both
+// images use the same order, the contraction does not care.
+static __host__ __device__ inline int dm_row_stride(int ws) { return ws <= 8 ? 8 : (ws <= 16 ? 16 : 32); }
+
 extern "C" int dm_kpad(int ws) {
-    int k = ws * ws;
+    int k = ws * dm_row_stride(ws);
     return ((k + 63) / 64) * 64;       // multiple of 64 bf16 = one 128-byte swizzle row
 }
 
-// Generic kernel (any odd ws <= 31): one warp per patch, two passes over the window.
+__device__ __forceinline__ void dm_write_stats(dm_stat* stat, long long n_patches, long long pidx, int K, int S, int Q, int mean) {
+    // S, Q = sum and sum of squares of the raw window; residuals after centring on `mean`
+    const int rs = S - K * mean;                                  // S'
+    const int rq = Q - 2 * mean * S + K * mean * mean;            // sum (a - mean)^2
+    const float s = (float)rs;
+    const float sk = __fdiv_rn(s, (float)K);
+    const float var = __fsub_rn((float)rq, __fmul_rn(s, sk));     // sum a'^2 - S'^2/K
+    const bool flat = (rq == 0);
+    const float inv = flat ? 0.0f : __frcp_rn(__fsqrt_rn(var));
+    stat[pidx] = make_float4(s, inv, sk, (float)mean);
+    // compact column table of the tcgen05 epilogue: per pair of patches {sk0, sk1, inv0, inv1}
+    float* ct = reinterpret_cast<float*>(stat + n_patches) + (pidx >> 1) * 4 + (pidx & 1);
+    ct[0] = sk; ct[2] = inv;
+}
+
+// Generic kernel (any odd ws <= 31, any grid): one warp per patch, two passes over the window.
 __global__ void __launch_bounds__(256)
 dm_descriptor_kernel(const uint8_t* __restrict__ scene, int pitch,
                      const int32_t* __restrict__ origin_yx, long long n_patches,
@@ -27,133 +47,114 @@ dm_descriptor_kernel(const uint8_t* __restrict__ scene, int pitch,
     const int tile = (int)(warp / P);
     const int p = (int)(warp - (long long)tile * P);
     const int i = p / t1, j = p - i * t1;
-    const int K = ws * ws;
+    const int K = ws * ws, rstr = dm_row_stride(ws);
     const uint8_t* base = scene + (size_t)(origin_yx[2 * tile] + i) * pitch + origin_yx[2 * tile + 1] + j;
 
-    int sum = 0;
+    int sum = 0, sq = 0;
     for (int k = lane; k < K; k += 32) {
         int ky = k / ws, kx = k - ky * ws;
-        sum += base[ky * pitch + kx];
+        int v = base[ky * pitch + kx];
+        sum += v; sq += v * v;
     }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    for (int o = 16; o > 0; o >>= 1) { sum += __shfl_xor_sync(0xffffffffu, sum, o); sq += __shfl_xor_sync(0xffffffffu, sq, o); }
     const int mean = dm_round_mean(sum, K);
-
     __nv_bfloat16* row = desc + (size_t)warp * kpad;
-    int rs = 0, rq = 0;
     for (int k = lane; k < kpad; k += 32) {
+        const int ky = k / rstr, kx = k - ky * rstr;
         int v = 0;
-        if (k < K) {
-            int ky = k / ws, kx = k - ky * ws;
-            v = (int)base[ky * pitch + kx] - mean;
-        }
-        rs += v;
-        rq += v * v;
+        if (ky < ws && kx < ws) v = (int)base[ky * pitch + kx] - mean;
         row[k] = __float2bfloat16((float)v);
     }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        rs += __shfl_xor_sync(0xffffffffu, rs, o);
-        rq += __shfl_xor_sync(0xffffffffu, rq, o);
-    }
-    if (lane == 0) {
-        const float fk = (float)K;
-        const float s = (float)rs;
-        const float sk = __fdiv_rn(s, fk);
-        const float var = __fsub_rn((float)rq, __fmul_rn(s, sk));     // sum a'^2 - S'^2/K
-        const bool flat = (rq == 0);
-        const float inv = flat ? 0.0f : __frcp_rn(__fsqrt_rn(var));
-        stat[warp] = make_float4(s, inv, sk, (float)mean);
-        // compact column table of the tcgen05 epilogue: per pair of patches {sk0, sk1, inv0, inv1}
-        float* ct = reinterpret_cast<float*>(stat + n_patches) + (warp >> 1) * 4 + (warp & 1);
-        ct[0] = sk; ct[2] = inv;
-    }
+    if (lane == 0) dm_write_stats(stat, n_patches, warp, K, sum, sq, mean);
 }
 
-// Fast kernel for the window sizes the repo uses (ws <= 15): the window is read once, every
-// lane owns 8 consecutive K entries of its patch and writes them as one 16-byte store, so a
-// descriptor row leaves the warp as coalesced 128..512-byte segments.  G = lanes per patch.
+// Fast kernel for ws <= 15 and T1 % 8 == 0.  A group of lanes produces the descriptors of 8
+// consecutive patches of one grid row: lane (ky, hf) reads the 15 scene bytes of window row
+// ky that those 8 windows share, keeps them packed in 4 words, and slides over them with
+// funnel shifts.  Sums come from DP4A + REDUX, the centred values are formed with the
+// 0x4B000000 byte-to-float trick, and every lane writes its 8 entries of each patch as one
+// 16-byte store (a descriptor row leaves the group as one contiguous segment).
 template <int WS>
 __global__ void __launch_bounds__(256)
-dm_descriptor_fast_kernel(const uint8_t* __restrict__ scene, int pitch,
-                          const int32_t* __restrict__ origin_yx, long long n_patches, int t0, int t1,
-                          __nv_bfloat16* __restrict__ desc, dm_stat* __restrict__ stat) {
+dm_descriptor_row_kernel(const uint8_t* __restrict__ scene, int pitch,
+                         const int32_t* __restrict__ origin_yx, long long n_groups, long long n_patches,
+                         int t0, int t1, __nv_bfloat16* __restrict__ desc, dm_stat* __restrict__ stat) {
     constexpr int K = WS * WS;
-    constexpr int KPAD = ((K + 63) / 64) * 64;
-    constexpr int LANES = KPAD / 8;                                   // lanes that store
-    constexpr int G = LANES <= 8 ? 8 : (LANES <= 16 ? 16 : 32);       // lanes per patch
-    constexpr int PER_WARP = 32 / G;
-    const int lane = threadIdx.x & 31, gl = lane % G;
-    const long long warp = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    long long pidx = warp * PER_WARP + lane / G;
-    const bool live = pidx < n_patches;
-    if (!live) pidx = n_patches - 1;                                  // keep the warp converged for the shuffles
-    const int P = t0 * t1;
-    const int tile = (int)(pidx / P);
-    const int p = (int)(pidx - (long long)tile * P);
-    const int i = p / t1, j = p - i * t1;
-    const uint8_t* base = scene + (size_t)(origin_yx[2 * tile] + i) * pitch + origin_yx[2 * tile + 1] + j;
-    int px[8];
-    int sum = 0;
+    constexpr int RSTR = WS <= 8 ? 8 : 16;
+    constexpr int KPAD = ((WS * RSTR + 63) / 64) * 64;
+    constexpr int LPG = RSTR == 16 ? 32 : 8;                          // lanes per group
+    constexpr int GPW = 32 / LPG;                                     // groups per warp
+    const int lane = threadIdx.x & 31, gl = lane % LPG;
+    const unsigned gmask = LPG == 32 ? 0xffffffffu : (0xffu << (lane & ~7));
+    long long g = ((long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * GPW + lane / LPG;
+    const bool live = g < n_groups;
+    if (!live) g = n_groups - 1;                                      // keep the group converged for REDUX
+    const int jb_n = t1 >> 3;
+    const int jb = (int)(g % jb_n);
+    const long long t = g / jb_n;
+    const int i = (int)(t % t0);
+    const int tile = (int)(t / t0);
+    const int j0 = jb * 8;
+    const int ky = RSTR == 16 ? (gl >> 1) : gl, hf = RSTR == 16 ? (gl & 1) : 0;
+    const bool rowlive = ky < WS;
+    // bytes of scene row (i + ky) this lane needs: columns j0 + 8*hf + [0, nb)
+    const int nb = !rowlive ? 0 : (hf == 0 ? (7 + WS < 15 ? 7 + WS : 15) : WS - 8 + 7);
+    const uint8_t* src = scene + (size_t)(origin_yx[2 * tile] + i + (rowlive ? ky : 0)) * pitch + origin_yx[2 * tile + 1] + j0 + hf * 8;
+    uint32_t w[4] = {0u, 0u, 0u, 0u};
 #pragma unroll
-    for (int u = 0; u < 8; ++u) {
-        const int k = gl * 8 + u;
-        px[u] = 0;
-        if (k < K) {
-            const int ky = k / WS, kx = k - ky * WS;
-            px[u] = base[ky * pitch + kx];
-            sum += px[u];
+    for (int c = 0; c < 15; ++c) {
+        const uint32_t v = (c < nb) ? (uint32_t)__ldg(src + c) : 0u;
+        w[c >> 2] |= v << (8 * (c & 3));
+    }
+    // valid bytes of an 8-byte window slice: window columns 8*hf + u < WS
+    const int nv = !rowlive ? 0 : (WS - hf * 8 > 8 ? 8 : WS - hf * 8);
+    const uint32_t mlo = nv >= 4 ? 0xffffffffu : ((1u << (8 * nv)) - 1u);
+    const uint32_t mhi = nv <= 4 ? 0u : (nv >= 8 ? 0xffffffffu : ((1u << (8 * (nv - 4))) - 1u));
+    const long long p0 = ((long long)tile * t0 + i) * t1 + j0;        // first patch of the group
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+        const uint32_t lo = __funnelshift_r(w[q >> 2], w[(q >> 2) + 1], 8 * (q & 3)) & mlo;
+        const uint32_t hi = __funnelshift_r(w[(q >> 2) + 1], w[(q >> 2) + 2], 8 * (q & 3)) & mhi;
+        const int s = (int)__dp4a(lo, 0x01010101u, __dp4a(hi, 0x01010101u, 0u));
+        const int sq = (int)__dp4a(lo, lo, __dp4a(hi, hi, 0u));
+        const int S = __reduce_add_sync(gmask, s), Q = __reduce_add_sync(gmask, sq);
+        const int mean = dm_round_mean(S, K);
+        if (!live) continue;
+        if (gl * 8 < KPAD) {
+            // invalid positions take the value `mean` so that they centre to exactly 0
+            const uint32_t mw = (uint32_t)mean * 0x01010101u;
+            const uint32_t l2 = lo | (mw & ~mlo), h2 = hi | (mw & ~mhi);
+            const float off = 8388608.0f + (float)mean;              // 2^23 + mean
+            float f[8];
+            f[0] = __uint_as_float(__byte_perm(l2, 0x4B000000u, 0x7650)) - off;
+            f[1] = __uint_as_float(__byte_perm(l2, 0x4B000000u, 0x7651)) - off;
+            f[2] = __uint_as_float(__byte_perm(l2, 0x4B000000u, 0x7652)) - off;
+            f[3] = __uint_as_float(__byte_perm(l2, 0x4B000000u, 0x7653)) - off;
+            f[4] = __uint_as_float(__byte_perm(h2, 0x4B000000u, 0x7650)) - off;
+            f[5] = __uint_as_float(__byte_perm(h2, 0x4B000000u, 0x7651)) - off;
+            f[6] = __uint_as_float(__byte_perm(h2, 0x4B000000u, 0x7652)) - off;
+            f[7] = __uint_as_float(__byte_perm(h2, 0x4B000000u, 0x7653)) - off;
+            __nv_bfloat162 b0 = __floats2bfloat162_rn(f[0], f[1]), b1 = __floats2bfloat162_rn(f[2], f[3]);
+            __nv_bfloat162 b2 = __floats2bfloat162_rn(f[4], f[5]), b3 = __floats2bfloat162_rn(f[6], f[7]);
+            uint4 pk;
+            pk.x = *reinterpret_cast<uint32_t*>(&b0); pk.y = *reinterpret_cast<uint32_t*>(&b1);
+            pk.z = *reinterpret_cast<uint32_t*>(&b2); pk.w = *reinterpret_cast<uint32_t*>(&b3);
+            *reinterpret_cast<uint4*>(desc + (size_t)(p0 + q) * KPAD + gl * 8) = pk;
         }
-    }
-#pragma unroll
-    for (int o = G / 2; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-    const int mean = dm_round_mean(sum, K);
-    int rs = 0, rq = 0;
-    float f[8];
-#pragma unroll
-    for (int u = 0; u < 8; ++u) {
-        const int k = gl * 8 + u;
-        const int v = (k < K) ? px[u] - mean : 0;
-        rs += v;
-        rq += v * v;
-        f[u] = (float)v;
-    }
-#pragma unroll
-    for (int o = G / 2; o > 0; o >>= 1) {
-        rs += __shfl_xor_sync(0xffffffffu, rs, o);
-        rq += __shfl_xor_sync(0xffffffffu, rq, o);
-    }
-    if (!live) return;
-    if (gl < LANES) {
-        __nv_bfloat162 h0 = __floats2bfloat162_rn(f[0], f[1]), h1 = __floats2bfloat162_rn(f[2], f[3]);
-        __nv_bfloat162 h2 = __floats2bfloat162_rn(f[4], f[5]), h3 = __floats2bfloat162_rn(f[6], f[7]);
-        uint4 pk;
-        pk.x = *reinterpret_cast<uint32_t*>(&h0); pk.y = *reinterpret_cast<uint32_t*>(&h1);
-        pk.z = *reinterpret_cast<uint32_t*>(&h2); pk.w = *reinterpret_cast<uint32_t*>(&h3);
-        *reinterpret_cast<uint4*>(desc + (size_t)pidx * KPAD + gl * 8) = pk;
-    }
-    if (gl == 0) {
-        const float s = (float)rs;
-        const float sk = __fdiv_rn(s, (float)K);
-        const float var = __fsub_rn((float)rq, __fmul_rn(s, sk));
-        const bool flat = (rq == 0);
-        const float inv = flat ? 0.0f : __frcp_rn(__fsqrt_rn(var));
-        stat[pidx] = make_float4(s, inv, sk, (float)mean);
-        float* ct = reinterpret_cast<float*>(stat + n_patches) + (pidx >> 1) * 4 + (pidx & 1);
-        ct[0] = sk; ct[2] = inv;                                      // {sk0, sk1, inv0, inv1} per pair of patches
+        if (gl == q) dm_write_stats(stat, n_patches, p0 + q, K, S, Q, mean);
     }
 }
 
 template <int WS>
-static void launch_descriptor_fast(const uint8_t* scene, int pitch, const int32_t* origin, long long n_patches,
-                                   int t0, int t1, void* desc, float* stat, cudaStream_t st) {
-    constexpr int K = WS * WS;
-    constexpr int KPAD = ((K + 63) / 64) * 64;
-    constexpr int LANES = KPAD / 8;
-    constexpr int G = LANES <= 8 ? 8 : (LANES <= 16 ? 16 : 32);
-    const long long warps = (n_patches + (32 / G) - 1) / (32 / G);
-    dm_descriptor_fast_kernel<WS><<<dm_div_up(warps, 8), 256, 0, st>>>(scene, pitch, origin, n_patches, t0, t1,
-                                                                        (__nv_bfloat16*)desc, (dm_stat*)stat);
+static void launch_descriptor_row(const uint8_t* scene, int pitch, const int32_t* origin, long long n_patches,
+                                  int t0, int t1, void* desc, float* stat, cudaStream_t st) {
+    constexpr int RSTR = WS <= 8 ? 8 : 16;
+    constexpr int GPW = RSTR == 16 ? 1 : 4;
+    const long long n_groups = n_patches / 8;
+    const long long warps = (n_groups + GPW - 1) / GPW;
+    dm_descriptor_row_kernel<WS><<<dm_div_up(warps, 8), 256, 0, st>>>(scene, pitch, origin, n_groups, n_patches, t0, t1,
+                                                                       (__nv_bfloat16*)desc, (dm_stat*)stat);
 }
 
 extern "C" int dm_descriptors(const uint8_t* scene_dev, int scene_h, int scene_w, int pitch,
@@ -165,14 +166,15 @@ extern "C" int dm_descriptors(const uint8_t* scene_dev, int scene_h, int scene_w
                "dm_descriptors: scene %dx%d smaller than a tile", scene_h, scene_w);
     const long long n_patches = (long long)n_tiles * t0 * t1;
     cudaStream_t st = (cudaStream_t)stream;
-    switch (ws) {
-        case 3:  launch_descriptor_fast<3>(scene_dev, pitch, origin_yx_dev, n_patches, t0, t1, desc_bf16_dev, stat_dev, st); break;
-        case 5:  launch_descriptor_fast<5>(scene_dev, pitch, origin_yx_dev, n_patches, t0, t1, desc_bf16_dev, stat_dev, st); break;
-        case 7:  launch_descriptor_fast<7>(scene_dev, pitch, origin_yx_dev, n_patches, t0, t1, desc_bf16_dev, stat_dev, st); break;
-        case 9:  launch_descriptor_fast<9>(scene_dev, pitch, origin_yx_dev, n_patches, t0, t1, desc_bf16_dev, stat_dev, st); break;
-        case 11: launch_descriptor_fast<11>(scene_dev, pitch, origin_yx_dev, n_patches, t0, t1, desc_bf16_dev, stat_dev, st); break;
-        case 13: launch_descriptor_fast<13>(scene_dev, pitch, origin_yx_dev, n_patches, t0, t1, desc_bf16_dev, stat_dev, st); break;
-        case 15: launch_descriptor_fast<15>(scene_dev, pitch, origin_yx_dev, n_patches, t0, t1, desc_bf16_dev, stat_dev, st); break;
+    const bool rowk = (t1 % 8 == 0);
+    switch (rowk ? ws : 0) {
+        case 3:  launch_descriptor_row<3>(scene_dev, pitch, origin_yx_dev, n_patches, t0, t1, desc_bf16_dev, stat_dev, st); break;
+        case 5:  launch_descriptor_row<5>(scene_dev, pitch, origin_yx_dev, n_patches, t0, t1, desc_bf16_dev, stat_dev, st); break;
+        case 7:  launch_descriptor_row<7>(scene_dev, pitch, origin_yx_dev, n_patches, t0, t1, desc_bf16_dev, stat_dev, st); break;
+        case 9:  launch_descriptor_row<9>(scene_dev, pitch, origin_yx_dev, n_patches, t0, t1, desc_bf16_dev, stat_dev, st); break;
+        case 11: launch_descriptor_row<11>(scene_dev, pitch, origin_yx_dev, n_patches, t0, t1, desc_bf16_dev, stat_dev, st); break;
+        case 13: launch_descriptor_row<13>(scene_dev, pitch, origin_yx_dev, n_patches, t0, t1, desc_bf16_dev, stat_dev, st); break;
+        case 15: launch_descriptor_row<15>(scene_dev, pitch, origin_yx_dev, n_patches, t0, t1, desc_bf16_dev, stat_dev, st); break;
         default: {
             const int warps = 8;
             dm_descriptor_kernel<<<dm_div_up(n_patches, warps), warps * 32, 0, st>>>(

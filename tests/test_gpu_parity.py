@@ -256,6 +256,63 @@ def test_fused_path_equals_materialising_path(dm, shape, size, stride, ws, sub):
     assert np.mean(np.abs(s0 - s1) > 1e-5) <= 2e-4
 
 
+def test_fused_path_flat_patch_nan(dm):
+    """A flat patch poisons its ancestors with NaN in the reference; both GPU paths must
+    put the NaNs in the same pixels."""
+    from deepmatching_stereo_matching_b200.synth import stereo_pair
+    i1, i2 = stereo_pair((96, 96), seed=8, mode='shift', amp=2, plain_noise=True)
+    i1 = i1.copy()
+    i1[30:35, 40:45] = 77
+    res = []
+    for fused in (0, 1):
+        s = dm.ImageCutSolver(i1, i2, image_size=[16, 16], stride=[12, 12], window_size=5, degree_map_mode=['elevation'], sub_pix=True)
+        s.log_flg = False
+        s.fused = fused
+        res.append(s())
+    (d0, s0), (d1, s1) = res
+    assert np.isnan(s0).any()
+    assert np.array_equal(np.isnan(d0), np.isnan(d1)) and np.array_equal(np.isnan(s0), np.isnan(s1))
+    ref_d, ref_s = O.image_cut_solver(i1, i2, (16, 16), (12, 12), 5, ('elevation',), True)
+    assert np.array_equal(np.isnan(ref_s), np.isnan(s1))
+
+
+def test_descriptor_kernels_agree(dm):
+    """The 8-patches-per-group descriptor kernel and the generic one write identical rows/stats."""
+    import torch
+    from deepmatching_stereo_matching_b200 import _native
+    from deepmatching_stereo_matching_b200.synth import texture
+    lib = _native.lib()
+    for ws in (3, 5, 7, 9, 11, 13, 15):
+        e2 = ws - 1
+        for (t0, t1) in ((8, 16), (4, 12)):           # t1 % 8 == 0 -> row kernel, else generic
+            pass
+        sc = torch.from_numpy(texture((40 + e2, 60 + e2), seed=ws)).cuda()
+        H, W = sc.shape
+        origin = torch.tensor([[3, 5], [7, 20]], dtype=torch.int32, device='cuda')
+        kpad = lib.dm_kpad(ws)
+        out = []
+        for (t0, t1, ox) in ((8, 16, 0), (8, 12, 0)):
+            desc = torch.zeros((2 * t0 * t1, kpad), dtype=torch.bfloat16, device='cuda')
+            stat = torch.zeros((2 * t0 * t1 * 6,), dtype=torch.float32, device='cuda')
+            _native.check(lib.dm_descriptors(_native.ptr(sc), H, W, W, _native.ptr(origin), 2, t0, t1, ws,
+                                             _native.ptr(desc), _native.ptr(stat), _native.stream_ptr()))
+            out.append((desc.float().cpu().numpy().reshape(2, t0, t1, kpad), stat[:2 * t0 * t1 * 4].cpu().numpy().reshape(2, t0, t1, 4)))
+        (da, sa), (db, sb) = out
+        assert np.array_equal(da[:, :, :12], db) and np.array_equal(sa[:, :, :12], sb)
+        # and against numpy: centred window values in the k = ky*rstride + kx layout
+        img = sc.cpu().numpy().astype(np.int64)
+        rstr = 8 if ws <= 8 else 16
+        for (n, i, j) in ((0, 0, 0), (1, 7, 11), (0, 3, 9)):
+            oy, ox = origin[n].tolist()
+            win = img[oy + i:oy + i + ws, ox + j:ox + j + ws]
+            mean = (2 * win.sum() + ws * ws) // (2 * ws * ws)
+            exp = np.zeros(kpad)
+            for ky in range(ws):
+                exp[ky * rstr:ky * rstr + ws] = win[ky] - mean
+            assert np.array_equal(db[n, i, j], exp)
+            assert sb[n, i, j, 3] == mean and sb[n, i, j, 0] == (win - mean).sum()
+
+
 def test_oracle_tile_t64_ws15(dm):
     """One tile at the C2/C3 geometry (T=64, ws=15) against the numpy oracle."""
     from deepmatching_stereo_matching_b200.synth import stereo_pair
