@@ -287,7 +287,7 @@ def run_ours(args):
         kern_name = {'descriptors': 'dm_descriptor_fast_kernel', 'correlation': 'dm_correlation_umma_kernel',
                      'normalize': 'dm_aggregate_first_kernel' if fused else 'dm_minmax_rectify_kernel',
                      'aggregate': 'dm_aggregate_kernel', 'backtrack': 'dm_backtrack_kernel',
-                     'planes': 'dm_final_level_kernel' if fused else 'dm_planes_kernel'}
+                     'planes': 'dm_final_quad_kernel' if fused else 'dm_planes_kernel'}
         traffic = {}
         tp = os.path.join(REPO, 'profiles', 'ncu_traffic.json')       # dram bytes per launch from ncu --set full
         if os.path.exists(tp):

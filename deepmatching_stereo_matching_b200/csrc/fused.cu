@@ -117,7 +117,7 @@ dm_aggregate_first_kernel(const float* __restrict__ pooled, const float* __restr
 }
 
 // ---------------------------------------------------------------------------------------
-// Final level.  One warp per patch p = (i,j) of a tile.
+// Final level: arguments.
 // ---------------------------------------------------------------------------------------
 struct FinalArgs {
     const uint8_t* img1; const uint8_t* img2; int pitch;
@@ -130,37 +130,43 @@ struct FinalArgs {
     double* d_map; double* out_map;
 };
 
-// The 3x3 candidate windows around p_dot and the parabola neighbours of the match all lie
-// in the (ws+4)^2 pixel region of image 2 that starts two pixels up/left of window p_dot.
-// The warp stages that region in shared memory once (word-aligned rows).  Lane (ky, hf)
-// owns bytes [8*hf, 8*hf+8) of patch row ky as two packed words and sweeps the shifted
-// windows with funnel shifts + DP4A (4 byte-MACs per instruction).  All sums are exact:
-//   sum (a-m1)(b-m2) = sum a*b - m2*S1' - m1*S2' - K*m1*m2     (S' = residual sums of the stats)
-constexpr int RSB = 24;                 // region row stride in bytes (ws + 4 <= 19, word aligned)
-constexpr int RBYTES = 19 * RSB + 8;
+// ---------------------------------------------------------------------------------------
+// Final level, one warp per PARENT: its four children (2I+ci, 2J+cj) share the parent's
+// match, so their candidate windows lie in one (ws+5)^2 region of image 2.  The warp stages
+// that region once (two copies, the second shifted by one byte so that both cj = 0 and
+// cj = 1 see compile-time funnel shifts); 8 lanes serve one child, lane l owns patch rows
+// l and l+8 as 4 packed words each.  Reductions, candidate evaluation, argmax, parabola
+// fit and the plane writes are shared by the four children.
+// ---------------------------------------------------------------------------------------
+constexpr int QRS = 32;                 // region row stride in bytes (16-byte aligned rows)
+constexpr int QROWS = 20;               // ws + 5 <= 20
 
 template <int WS>
 __global__ void __launch_bounds__(256)
-dm_final_level_kernel(const FinalArgs a, long long n_patches) {
+dm_final_quad_kernel(const FinalArgs a, long long n_quads) {
     constexpr int K = WS * WS;
-    constexpr int RW = WS + 4;
-    __shared__ __align__(16) uint8_t region_all[8][RBYTES];
+    constexpr int RWQ = WS + 5;
+    __shared__ __align__(16) uint8_t region_all[8][2][QROWS * QRS];
     const int lane = threadIdx.x & 31;
-    uint8_t* region = region_all[threadIdx.x >> 5];
+    uint8_t* reg0 = region_all[threadIdx.x >> 5][0];
+    uint8_t* reg1 = region_all[threadIdx.x >> 5][1];
     const long long w = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (w >= n_patches) return;
+    if (w >= n_quads) return;
     const int T0 = a.t0, T1 = a.t1, P = T0 * T1;
-    const int n = (int)(w / P);                          // tile inside the chunk
-    const int p = (int)(w - (long long)n * P);
-    const int i = p / T1, j = p - i * T1;
+    const int hA = T0 >> 1, hB = T1 >> 1, PQ = hA * hB;
+    const int n = (int)(w / PQ);                         // tile inside the chunk
+    const int pq = (int)(w - (long long)n * PQ);
+    const int I = pq / hB, J = pq - I * hB;
     const int oy = a.origin[2 * n], ox = a.origin[2 * n + 1];
     const bool normed = a.normed != 0;
+    const int c = lane >> 3, l = lane & 7, ci = c >> 1, cj = c & 1;
+    const unsigned gbase = lane & 24;                    // first lane of this child's group
+    const int i = 2 * I + ci, j = 2 * J + cj, p = i * T1 + j;
 
     // misc/Matching.py:116-124: p_dot = 2 * parent match + o
-    const int hA = T0 >> 1, hB = T1 >> 1;
-    const size_t pb = (size_t)n * 2 * hA * hB, pi = (size_t)(i >> 1) * hB + (j >> 1);
-    const int d0 = 2 * a.parent[pb + pi] + (i & 1);
-    const int d1 = 2 * a.parent[pb + (size_t)hA * hB + pi] + (j & 1);
+    const size_t pb = (size_t)n * 2 * PQ;
+    const int pm0 = a.parent[pb + pq], pm1 = a.parent[pb + PQ + pq];
+    const int d0 = 2 * pm0 + ci, d1 = 2 * pm1 + cj;
 
     const dm_stat s1 = a.stat1[(size_t)n * P + p];
     const bool flat1 = (s1.y == 0.0f);
@@ -168,48 +174,55 @@ dm_final_level_kernel(const FinalArgs a, long long n_patches) {
     const dm_stat* st2 = a.stat2 + (size_t)n * P;
     const int m1 = (int)s1.w, S1 = (int)s1.x;
 
-    // stage the region: rows oy+d0-2 .. +RW, cols ox+d1-2 .. +RW (zeros outside the scene).
-    // Fully unrolled so that all RW row loads of a lane are in flight together; the common
-    // case (region entirely inside the scene) runs without per-row guards.
+    // ---- stage the shared region: scene rows oy+2*pm0-2 .. +RWQ, cols ox+2*pm1-2 .. +RWQ
     {
-        const int gy0 = oy + d0 - 2, gx0 = ox + d1 - 2;
-        const int gx = gx0 + lane;
-        uint8_t vals[RW];
-        if (gy0 >= 0 && gy0 + RW <= a.scene_h && gx0 >= 0 && gx0 + RW <= a.pitch) {     // warp-uniform
-            const uint8_t* src = a.img2 + (size_t)gy0 * a.pitch + gx0 + (lane < RW ? lane : 0);
+        const int gy0 = oy + 2 * pm0 - 2, gx0 = ox + 2 * pm1 - 2;
+        uint8_t vals[RWQ];
+        if (gy0 >= 0 && gy0 + RWQ <= a.scene_h && gx0 >= 0 && gx0 + RWQ <= a.pitch) {     // warp-uniform
+            const uint8_t* src = a.img2 + (size_t)gy0 * a.pitch + gx0 + (lane < RWQ ? lane : 0);
 #pragma unroll
-            for (int ry = 0; ry < RW; ++ry) { vals[ry] = __ldg(src); src += a.pitch; }
+            for (int ry = 0; ry < RWQ; ++ry) { vals[ry] = __ldg(src); src += a.pitch; }
         } else {
-            const bool colok = lane < RW && gx >= 0 && gx < a.pitch;
+            const int gx = gx0 + lane;
+            const bool colok = lane < RWQ && gx >= 0 && gx < a.pitch;
 #pragma unroll
-            for (int ry = 0; ry < RW; ++ry) {
+            for (int ry = 0; ry < RWQ; ++ry) {
                 const int gy = gy0 + ry;
                 vals[ry] = (colok && gy >= 0 && gy < a.scene_h) ? __ldg(a.img2 + (size_t)gy * a.pitch + gx) : (uint8_t)0;
             }
         }
-        if (lane < RSB) {
-            uint8_t* dst = region + lane;
 #pragma unroll
-            for (int ry = 0; ry < RW; ++ry) dst[ry * RSB] = (lane < RW) ? vals[ry] : (uint8_t)0;
+        for (int ry = 0; ry < RWQ; ++ry) {
+            const uint8_t v = (lane < RWQ) ? vals[ry] : (uint8_t)0;
+            reg0[ry * QRS + lane] = v;                   // copy 0: column x at byte x
+            if (lane >= 1) reg1[ry * QRS + lane - 1] = v;    // copy 1: column x at byte x - 1
+        }
+        if (lane == 0) {
+#pragma unroll
+            for (int ry = 0; ry < RWQ; ++ry) reg1[ry * QRS + 31] = 0;
         }
     }
-    // this lane's 8 patch bytes (row ky, columns 8*hf .. 8*hf+7; zero beyond the window)
-    const int ky = lane >> 1, hf = lane & 1;
-    const bool rowlive = ky < WS;
-    uint32_t a0 = 0, a1 = 0;
-    {
-        const uint8_t* a_row = a.img1 + (size_t)(oy + i + (rowlive ? ky : 0)) * a.pitch + ox + j + hf * 8;
-        const int nvalid = rowlive ? (hf ? WS - 8 : (WS < 8 ? WS : 8)) : 0;
+    // ---- this lane's patch rows ky = l and l + 8, 16 bytes each (zero beyond the window)
+    uint32_t aw[2][4];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
-            const uint32_t v = (u < nvalid) ? (uint32_t)__ldg(a_row + u) : 0u;
-            if (u < 4) a0 |= v << (8 * u); else a1 |= v << (8 * (u - 4));
+    for (int r = 0; r < 2; ++r) {
+        const int ky = l + 8 * r;
+        const bool live = ky < WS;
+        const uint8_t* a_row = a.img1 + (size_t)(oy + i + (live ? ky : 0)) * a.pitch + ox + j;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) aw[r][q] = 0;
+#pragma unroll
+        for (int u = 0; u < 16; ++u) {
+            if (u < WS) {
+                const uint32_t v = live ? (uint32_t)__ldg(a_row + u) : 0u;
+                aw[r][u >> 2] |= v << (8 * (u & 3));
+            }
         }
     }
     __syncwarp();
-    const uint32_t* rwords = reinterpret_cast<const uint32_t*>(region) + hf * 2;    // lane's first word in a region row
+    const uint8_t* regc = cj ? reg1 : reg0;              // this child's view: window column x at byte x
 
-    // level-0 value of position (qy,qx) from sum a*b (each lane evaluates ONE candidate)
+    // level-0 value of position (qy,qx) from sum a*b
     auto value_at = [&](int sum_ab, int qy, int qx) -> float {
         const dm_stat sq = st2[qy * T1 + qx];
         const int m2 = (int)sq.w, S2 = (int)sq.x;
@@ -217,52 +230,69 @@ dm_final_level_kernel(const FinalArgs a, long long n_patches) {
         const float z = dm_zncc_partial((float)dot, s1.x, sq.z, normed ? sq.y : 1.0f);
         return dm_rectify(dm_normalize(dm_zncc_finish(z, s1.y, flat1, normed), mn, mx, rinv));
     };
+    // 16 bytes of a against region row `row`, window starting at byte `bo` (dynamic)
+    auto row_dot = [&](const uint32_t (&aq)[4], int row, int bo) -> uint32_t {
+        const uint32_t* rr = reinterpret_cast<const uint32_t*>(regc + row * QRS) + (bo >> 2);
+        const int sh = (bo & 3) * 8;
+        const uint32_t w0 = rr[0], w1 = rr[1], w2 = rr[2], w3 = rr[3], w4 = rr[4];
+        uint32_t acc = __dp4a(aq[0], __funnelshift_r(w0, w1, sh), 0u);
+        acc = __dp4a(aq[1], __funnelshift_r(w1, w2, sh), acc);
+        acc = __dp4a(aq[2], __funnelshift_r(w2, w3, sh), acc);
+        return __dp4a(aq[3], __funnelshift_r(w3, w4, sh), acc);
+    };
 
     // ---- misc/Matching.py:58-78 on the recomputed 3x3 window (zero padding outside)
+    // candidate (dy,dx) of this child starts at region row ci + dy + 2, byte dx + 2 of its view
     uint32_t acc[16];
 #pragma unroll
     for (int s = 0; s < 16; ++s) acc[s] = 0;
-    if (rowlive) {
 #pragma unroll
-        for (int dy = 0; dy < 3; ++dy) {                 // candidate rows d0-1 .. d0+1 = region rows ky+1 .. ky+3
-            const uint32_t* rr = rwords + (ky + dy + 1) * (RSB / 4);
-            const uint32_t w0 = rr[0], w1 = rr[1], w2 = rr[2];
+    for (int r = 0; r < 2; ++r) {
+        const int ky = l + 8 * r;
+        if (ky < WS) {
 #pragma unroll
-            for (int dx = 0; dx < 3; ++dx) {             // candidate cols d1-1 .. d1+1 = region cols +1 .. +3
-                const uint32_t b0 = __funnelshift_r(w0, w1, 8 * (dx + 1));
-                const uint32_t b1 = __funnelshift_r(w1, w2, 8 * (dx + 1));
-                acc[dy * 3 + dx] = __dp4a(a1, b1, __dp4a(a0, b0, acc[dy * 3 + dx]));
+            for (int dy = 0; dy < 3; ++dy) {
+                const uint4 lo = *reinterpret_cast<const uint4*>(regc + (ky + ci + dy + 1) * QRS);
+                const uint32_t w4 = *reinterpret_cast<const uint32_t*>(regc + (ky + ci + dy + 1) * QRS + 16);
+#pragma unroll
+                for (int dx = 0; dx < 3; ++dx) {
+                    const int sh = 8 * (dx + 1);
+                    uint32_t t = __dp4a(aw[r][0], __funnelshift_r(lo.x, lo.y, sh), acc[dy * 3 + dx]);
+                    t = __dp4a(aw[r][1], __funnelshift_r(lo.y, lo.z, sh), t);
+                    t = __dp4a(aw[r][2], __funnelshift_r(lo.z, lo.w, sh), t);
+                    acc[dy * 3 + dx] = __dp4a(aw[r][3], __funnelshift_r(lo.w, w4, sh), t);
+                }
             }
         }
     }
-    // butterfly reduction of 16 partial sums in 16 shuffles: afterwards this lane holds the
-    // warp total of candidate my_s = b4*8 + b3*4 + b2*2 + b1 (b_k = bit k of the lane id)
-    uint32_t part = 0;
+    // butterfly over the 8 lanes of the child: 16 -> 2 values per lane (14 shuffles);
+    // lane bits (b2 b1 b0) end with candidates 8*b2 + 4*b1 + 2*b0 and the next one
+    uint32_t r0v, r1v;
     {
-        uint32_t w8[8], w4[4], w2[2];
-        const bool h16 = lane & 16, h8 = lane & 8, h4 = lane & 4, h2 = lane & 2;
+        uint32_t w8[8], w4[4];
+        const bool h4 = l & 4, h2 = l & 2, h1 = l & 1;
 #pragma unroll
-        for (int q = 0; q < 8; ++q) w8[q] = (h16 ? acc[q + 8] : acc[q]) + __shfl_xor_sync(0xffffffffu, h16 ? acc[q] : acc[q + 8], 16);
+        for (int q = 0; q < 8; ++q) w8[q] = (h4 ? acc[q + 8] : acc[q]) + __shfl_xor_sync(0xffffffffu, h4 ? acc[q] : acc[q + 8], 4);
 #pragma unroll
-        for (int q = 0; q < 4; ++q) w4[q] = (h8 ? w8[q + 4] : w8[q]) + __shfl_xor_sync(0xffffffffu, h8 ? w8[q] : w8[q + 4], 8);
-#pragma unroll
-        for (int q = 0; q < 2; ++q) w2[q] = (h4 ? w4[q + 2] : w4[q]) + __shfl_xor_sync(0xffffffffu, h4 ? w4[q] : w4[q + 2], 4);
-        part = (h2 ? w2[1] : w2[0]) + __shfl_xor_sync(0xffffffffu, h2 ? w2[0] : w2[1], 2);
-        part += __shfl_xor_sync(0xffffffffu, part, 1);
+        for (int q = 0; q < 4; ++q) w4[q] = (h2 ? w8[q + 4] : w8[q]) + __shfl_xor_sync(0xffffffffu, h2 ? w8[q] : w8[q + 4], 2);
+        r0v = (h1 ? w4[2] : w4[0]) + __shfl_xor_sync(0xffffffffu, h1 ? w4[0] : w4[2], 1);
+        r1v = (h1 ? w4[3] : w4[1]) + __shfl_xor_sync(0xffffffffu, h1 ? w4[1] : w4[3], 1);
     }
-    const int my_s = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
-    float myval = 0.0f;
+    const int s_base = ((l >> 2) & 1) * 8 + ((l >> 1) & 1) * 4 + (l & 1) * 2;
+    float val0 = 0.0f, val1 = 0.0f;
     {
-        const int qy = d0 + my_s / 3 - 1, qx = d1 + my_s % 3 - 1;
-        if (my_s < 9 && qy >= 0 && qy < T0 && qx >= 0 && qx < T1) myval = value_at((int)part, qy, qx);
+        const int sA = s_base, sB = s_base + 1;
+        const int qyA = d0 + sA / 3 - 1, qxA = d1 + sA % 3 - 1, qyB = d0 + sB / 3 - 1, qxB = d1 + sB % 3 - 1;
+        if (sA < 9 && qyA >= 0 && qyA < T0 && qxA >= 0 && qxA < T1) val0 = value_at((int)r0v, qyA, qxA);
+        if (sB < 9 && qyB >= 0 && qyB < T0 && qxB >= 0 && qxB < T1) val1 = value_at((int)r1v, qyB, qxB);
     }
     float best = 0.f, centre = 0.f;
     int bi = 0;
     bool best_nan = false;
 #pragma unroll
     for (int s = 0; s < 9; ++s) {
-        const int src = ((s >> 3) & 1) * 16 + ((s >> 2) & 1) * 8 + ((s >> 1) & 1) * 4 + (s & 1) * 2;
-        const float v = __shfl_sync(0xffffffffu, myval, src);
+        const int src = ((s >> 3) & 1) * 4 + ((s >> 2) & 1) * 2 + ((s >> 1) & 1);
+        const float v = __shfl_sync(0xffffffffu, (s & 1) ? val1 : val0, gbase + src);
         if (s == 4) centre = v;
         if (s == 0) { best = v; best_nan = (v != v); }
         else if (!best_nan && (v > best || v != v)) { best = v; bi = s; best_nan = (v != v); }
@@ -273,55 +303,55 @@ dm_final_level_kernel(const FinalArgs a, long long n_patches) {
 
     // ---- misc/Matching.py:165-209 parabola fit (index -1 wraps, upper edge skipped)
     double mrow = (double)c0, mcol = (double)c1;
-    if (a.sub_pix && c0 >= 0 && c0 < T0 && c1 >= 0 && c1 < T1) {
+    if (a.sub_pix) {                                     // warp-uniform
+        const bool in = c0 >= 0 && c0 < T0 && c1 >= 0 && c1 < T1;
         // neighbours: 0 = (c0+1,c1)  1 = (c0-1 | wrap, c1)  2 = (c0,c1+1)  3 = (c0, c1-1 | wrap)
         const int ny[4] = {c0 + 1, (c0 == 0 ? T0 - 1 : c0 - 1), c0, c0};
         const int nx[4] = {c1, c1, c1 + 1, (c1 == 0 ? T1 - 1 : c1 - 1)};
-        const bool nok[4] = {c0 + 1 < T0, c0 + 1 < T0, c1 + 1 < T1, c1 + 1 < T1};
+        const bool nok[4] = {in && c0 + 1 < T0, in && c0 + 1 < T0, in && c1 + 1 < T1, in && c1 + 1 < T1};
         uint32_t nacc[4];
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
             nacc[q] = 0;
-            if (!nok[q] || !rowlive) continue;
+            if (!nok[q]) continue;
+            // window start relative to the child's candidate origin (d0 - 2, d1 - 2)
             const int ry = ny[q] - (d0 - 2), rx = nx[q] - (d1 - 2);
-            if (ry >= 0 && ry <= 4 && rx >= 0 && rx <= 4) {         // inside the staged region (warp-uniform)
-                const int bo = hf * 8 + rx;
-                const uint32_t* rr = reinterpret_cast<const uint32_t*>(region) + (ky + ry) * (RSB / 4) + (bo >> 2);
-                const uint32_t w0 = rr[0], w1 = rr[1], w2 = rr[2];
-                const int sh = (bo & 3) * 8;
-                nacc[q] = __dp4a(a1, __funnelshift_r(w1, w2, sh), __dp4a(a0, __funnelshift_r(w0, w1, sh), 0u));
-            } else {                                                // wrapped index: far away, read global memory
-                const uint8_t* b = a.img2 + (size_t)(oy + ny[q] + ky) * a.pitch + ox + nx[q] + hf * 8;
-                uint32_t b0 = 0, b1 = 0;
+            const bool inreg = ry >= 0 && ry <= 4 && rx >= 0 && rx <= 4;
 #pragma unroll
-                for (int u = 0; u < 8; ++u) {
-                    const uint32_t v = (hf * 8 + u < WS) ? (uint32_t)__ldg(b + u) : 0u;
-                    if (u < 4) b0 |= v << (8 * u); else b1 |= v << (8 * (u - 4));
+            for (int r = 0; r < 2; ++r) {
+                const int ky = l + 8 * r;
+                if (ky >= WS) continue;
+                if (inreg) {
+                    nacc[q] += row_dot(aw[r], ky + ci + ry, rx);
+                } else {                                 // wrapped index: far away, read global memory
+                    const uint8_t* b = a.img2 + (size_t)(oy + ny[q] + ky) * a.pitch + ox + nx[q];
+                    uint32_t bw[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+                    for (int u = 0; u < 16; ++u)
+                        if (u < WS) bw[u >> 2] |= (uint32_t)__ldg(b + u) << (8 * (u & 3));
+                    nacc[q] = __dp4a(aw[r][3], bw[3], __dp4a(aw[r][2], bw[2], __dp4a(aw[r][1], bw[1], __dp4a(aw[r][0], bw[0], nacc[q]))));
                 }
-                nacc[q] = __dp4a(a1, b1, __dp4a(a0, b0, 0u));
             }
         }
-        // 4 partial sums -> lane holds the total of neighbour my_n = b4*2 + b3 (6 shuffles)
-        const bool h16 = lane & 16, h8 = lane & 8;
-        uint32_t u0 = (h16 ? nacc[2] : nacc[0]) + __shfl_xor_sync(0xffffffffu, h16 ? nacc[0] : nacc[2], 16);
-        uint32_t u1 = (h16 ? nacc[3] : nacc[1]) + __shfl_xor_sync(0xffffffffu, h16 ? nacc[1] : nacc[3], 16);
-        uint32_t tot = (h8 ? u1 : u0) + __shfl_xor_sync(0xffffffffu, h8 ? u0 : u1, 8);
-        tot += __shfl_xor_sync(0xffffffffu, tot, 4);
-        tot += __shfl_xor_sync(0xffffffffu, tot, 2);
+        // 4 partial sums over 8 lanes -> lane holds neighbour 2*b2 + b1 (4 shuffles)
+        const bool h4 = l & 4, h2 = l & 2;
+        uint32_t u0 = (h4 ? nacc[2] : nacc[0]) + __shfl_xor_sync(0xffffffffu, h4 ? nacc[0] : nacc[2], 4);
+        uint32_t u1 = (h4 ? nacc[3] : nacc[1]) + __shfl_xor_sync(0xffffffffu, h4 ? nacc[1] : nacc[3], 4);
+        uint32_t tot = (h2 ? u1 : u0) + __shfl_xor_sync(0xffffffffu, h2 ? u0 : u1, 2);
         tot += __shfl_xor_sync(0xffffffffu, tot, 1);
-        const int my_n = ((lane >> 4) & 1) * 2 + ((lane >> 3) & 1);
+        const int my_n = ((l >> 2) & 1) * 2 + ((l >> 1) & 1);
         const int sy = my_n == 0 ? ny[0] : (my_n == 1 ? ny[1] : c0);
         const int sx = my_n == 2 ? nx[2] : (my_n == 3 ? nx[3] : c1);
         const bool sok = my_n < 2 ? nok[0] : nok[2];
         float nval = 0.0f;
         if (sok) nval = value_at((int)tot, sy, sx);
         const float r0 = best;                      // level-0 value at the match itself
-        const float v0 = __shfl_sync(0xffffffffu, nval, 0), v1 = __shfl_sync(0xffffffffu, nval, 8);
-        const float v2 = __shfl_sync(0xffffffffu, nval, 16), v3 = __shfl_sync(0xffffffffu, nval, 24);
+        const float v0 = __shfl_sync(0xffffffffu, nval, gbase + 0), v1 = __shfl_sync(0xffffffffu, nval, gbase + 2);
+        const float v2 = __shfl_sync(0xffffffffu, nval, gbase + 4), v3 = __shfl_sync(0xffffffffu, nval, gbase + 6);
         if (nok[0] && r0 > v0 && r0 > v1) mrow += (double)(-(v0 - v1) / (2.0f * (v0 + v1 - 2.0f * r0)));
         if (nok[2] && r0 > v2 && r0 > v3) mcol += (double)(-(v2 - v3) / (2.0f * (v2 + v3 - 2.0f * r0)));
     }
-    if (lane != 0) return;
+    if (l != 0) return;
 
     // ---- planes + paste (misc/Calc_difference.py:36-48, misc/image_cut_solver.py:165-175)
     const int g = a.first_tile + n;
@@ -340,8 +370,8 @@ dm_final_level_kernel(const FinalArgs a, long long n_patches) {
 }
 
 template <int WS>
-static void launch_final(const FinalArgs& fa, long long n_patches, cudaStream_t st) {
-    dm_final_level_kernel<WS><<<dm_div_up(n_patches, 8), 256, 0, st>>>(fa, n_patches);
+static void launch_final_quad(const FinalArgs& fa, long long n_quads, cudaStream_t st) {
+    dm_final_quad_kernel<WS><<<dm_div_up(n_quads, 8), 256, 0, st>>>(fa, n_quads);
 }
 
 }  // namespace
@@ -428,14 +458,15 @@ int dm_fused_solve_chunk(dm_ctx* ctx, const dm_fused_args* a, int ck) {
         fa.first_tile = a->first_tile; fa.d_map = a->d_map; fa.out_map = a->out_map;
         const long long n_patches = (long long)nt * P;
         fa.scene_h = a->scene_h;
+        const long long n_quads = n_patches / 4;
         switch (a->ws) {
-            case 3: launch_final<3>(fa, n_patches, st); break;
-            case 5: launch_final<5>(fa, n_patches, st); break;
-            case 7: launch_final<7>(fa, n_patches, st); break;
-            case 9: launch_final<9>(fa, n_patches, st); break;
-            case 11: launch_final<11>(fa, n_patches, st); break;
-            case 13: launch_final<13>(fa, n_patches, st); break;
-            case 15: launch_final<15>(fa, n_patches, st); break;
+            case 3: launch_final_quad<3>(fa, n_quads, st); break;
+            case 5: launch_final_quad<5>(fa, n_quads, st); break;
+            case 7: launch_final_quad<7>(fa, n_quads, st); break;
+            case 9: launch_final_quad<9>(fa, n_quads, st); break;
+            case 11: launch_final_quad<11>(fa, n_quads, st); break;
+            case 13: launch_final_quad<13>(fa, n_quads, st); break;
+            case 15: launch_final_quad<15>(fa, n_quads, st); break;
             default: DM_REQUIRE(false, DM_ERR_UNSUPPORTED, "fused path supports odd window sizes 3..15 (got %d)", a->ws);
         }
         DM_LAUNCH_CHECK();
