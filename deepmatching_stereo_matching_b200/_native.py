@@ -157,6 +157,9 @@ class Context(object):
                                         c_void_p(d_map_np.ctypes.data), c_void_p(out_map_np.ctypes.data), byref(info)))
         return info
 
+    def set_workspace_limit(self, nbytes):
+        check(lib().dm_ctx_set_workspace_limit(self._h, int(nbytes)))
+
     def stage_ms(self):
         ms = (c_float * len(STAGES))()
         ln = (c_int * len(STAGES))()

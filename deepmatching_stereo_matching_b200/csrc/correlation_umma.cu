@@ -228,7 +228,11 @@ dm_correlation_umma_kernel(const __grid_constant__ CUtensorMap mapA, const __gri
                 float4 ob;                              // 4 outputs being assembled
                 umma::tmem_ld_32x16_issue(taddr, v0);
 #pragma unroll
+#ifdef DM_EXP_NOCS
+                for (int i = 0; i < STEP / 2; ++i) c0[i] = make_float4(0.5f, 0.25f, 1.0f, 1.0f);
+#else
                 for (int i = 0; i < STEP / 2; ++i) c0[i] = umma::lds128(csm + 16 * i);
+#endif
 #pragma unroll
                 for (int s = 0; s < NSTEP; ++s) {
                     float (&v)[STEP] = (s & 1) ? v1 : v0;
@@ -239,7 +243,11 @@ dm_correlation_umma_kernel(const __grid_constant__ CUtensorMap mapA, const __gri
                     if (s + 1 < NSTEP) {                // step s+1 in flight during the math below
                         umma::tmem_ld_32x16_issue(taddr + (uint32_t)((s + 1) * STEP), vn);
 #pragma unroll
+#ifdef DM_EXP_NOCS
+                        for (int i = 0; i < STEP / 2; ++i) cn[i] = make_float4(0.5f, 0.25f, 1.0f, 1.0f);
+#else
                         for (int i = 0; i < STEP / 2; ++i) cn[i] = umma::lds128(csm + 16 * ((s + 1) * (STEP / 2) + i));
+#endif
                     }
                     if (MODE == MODE_NULL) {            // measurement aid: TMEM drain + barriers only
                         rmax = fmaxf(rmax, v[0]);

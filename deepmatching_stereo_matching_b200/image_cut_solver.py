@@ -28,6 +28,12 @@ def _context():
     return _CTX[dev]
 
 
+def set_workspace_limit(nbytes):
+    """Caps the device workspace of this process's solver context; scenes whose tiles do not
+    fit are processed in equal chunks of tiles (default limit: 48 GB)."""
+    _context().set_workspace_limit(nbytes)
+
+
 def pinned_empty(shape, dtype):
     """numpy array backed by page-locked host memory (torch owns the allocation)."""
     torch = _native.require_cuda()

@@ -327,6 +327,49 @@ def test_oracle_tile_t64_ws15(dm):
     assert bad <= MAX_INDEX_DISAGREEMENT
 
 
+def test_chunked_scene_equals_single_chunk(dm):
+    """A workspace limit that forces several chunks of tiles must not change a single bit."""
+    from deepmatching_stereo_matching_b200 import image_cut_solver as ics
+    from deepmatching_stereo_matching_b200.synth import stereo_pair
+    i1, i2 = stereo_pair((300, 420), seed=12, mode='sine', amp=4)
+    kw = dict(image_size=[32, 32], stride=[30, 30], window_size=5, degree_map_mode=['elevation', 'distance'], sub_pix=True)
+    out = {}
+    try:
+        for fused in (1, 0):
+            for limit in (48 << 30, 40 << 20):
+                ics.set_workspace_limit(limit)
+                s = dm.ImageCutSolver(i1, i2, **kw)
+                s.log_flg = False
+                s.fused = fused
+                d, sc = s()
+                out[(fused, limit)] = (d.copy(), sc.copy(), s.info.chunk_tiles, s.info.n_tiles)
+            a, b = out[(fused, 48 << 30)], out[(fused, 40 << 20)]
+            assert a[2] == a[3] and b[2] < b[3]                     # one chunk vs several
+            assert np.array_equal(a[0], b[0], equal_nan=True) and np.array_equal(a[1], b[1], equal_nan=True)
+    finally:
+        ics.set_workspace_limit(48 << 30)
+
+
+def test_t128_tiles_c5_geometry(dm):
+    """C5 geometry (image_size 128, ws 15, stride 124): constant-shift recovery through the
+    materialising path (the pooled epilogue covers T1 <= 64), plus a spot check of one tile's
+    level-0 rows against the oracle's exact ZNCC."""
+    from deepmatching_stereo_matching_b200.synth import stereo_pair
+    i1, i2 = stereo_pair((400, 400), seed=3, mode='shift', amp=5)
+    s = dm.ImageCutSolver(i1, i2, image_size=[128, 128], stride=[124, 124], window_size=15,
+                          degree_map_mode=['elevation', 'elevation2'], sub_pix=True)
+    s.log_flg = False
+    d, sc = s()
+    assert d.shape == (2, 252, 252) and list(s.len) == [2, 2] and s.info.levels == 8 and s.info.used_fused == 0
+    assert np.mean(np.abs(d[0] - 5.0) < 0.5) > 0.93 and np.mean(np.abs(d[1]) < 0.5) > 0.93
+    co = dm.Correlation_map(i1[:142, :142], i2[:142, :142], window_size=15)
+    co._create_atomic_patch()
+    co._create_simple_initial_co_map()
+    got = co._dev['co_map'][5, 7].cpu().numpy()
+    patch = i1[5:20, 7:22]
+    assert np.abs(got - O.feature_value(patch, i2[:142, :142])).max() <= 2e-6
+
+
 def test_scene_c2_properties(dm):
     """Full C2 size (1024^2, T=64, ws=15, stride 60): constant-shift recovery,
     determinism, and strip partition == whole-scene solve (bit-exact)."""

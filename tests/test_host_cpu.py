@@ -107,6 +107,16 @@ def test_reference_shaped_validation(capsys):
     assert np.array_equal(dm.image_threshold(np.array([-5., 0.5, 20.])), np.array([0., 0.5, 10.]))
 
 
+def test_no_tile_fits_raises_index_error_like_reference():
+    import deepmatching_stereo_matching_b200 as dm
+    s = dm.ImageCutSolver(np.zeros((40, 200), np.uint8), np.zeros((40, 200), np.uint8), image_size=[32, 32], stride=[32, 32], window_size=5)
+    assert s.len[0] == 0
+    with pytest.raises(IndexError):
+        s()                                   # img_index[-1] on an empty list (image_cut_solver.py:150)
+    with pytest.raises(NotImplementedError):
+        dm.ImageCutSolver(np.zeros((64, 64), np.uint8), np.zeros((64, 64), np.uint8), padding=True)
+
+
 def test_no_cpu_fallback_without_gpu():
     import torch
     if torch.cuda.is_available():

@@ -20,6 +20,7 @@ for sc in (s1, s2):
 raw = torch.empty((n, P, P), dtype=torch.float32, device='cuda')
 flops = 2.0 * ws * ws * P * P * n
 for name, engine in (('umma_raw', 2), ('umma_null', 3)):
+    if os.environ.get('DM_ONLY_POOL'): break
     for _ in range(3):
         _native.check(lib.dm_correlation(*[_native.ptr(b) for b in bufs], n, P, kpad, ws, 5, engine, _native.ptr(raw), _native.stream_ptr()))
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -29,3 +30,20 @@ for name, engine in (('umma_raw', 2), ('umma_null', 3)):
     e1.record(); torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / 5
     print('%-10s %.3f ms  %.0f TFLOP/s' % (name, ms, flops / ms / 1e9))
+
+# pooled epilogue through the scene solver's stage timer
+import numpy as np
+from deepmatching_stereo_matching_b200.synth import stereo_pair
+i1, i2 = stereo_pair((1024, 1024), seed=1, mode='sine', amp=16)
+d1 = torch.from_numpy(i1).cuda(); d2 = torch.from_numpy(i2).cuda()
+prm = _native.scene_params((1024, 1024), (64, 64), (60, 60), 15, 'cv2.TM_CCOEFF_NORMED', ['elevation', 'elevation2'], True, None, 1)
+ctx = _native.Context(timing=True)
+planes = torch.zeros((3, 904, 904), dtype=torch.float64, device='cuda')
+for _ in range(3):
+    ctx.solve_device(prm, d1, d2, planes[:-1], planes[-1])
+acc = {}
+for _ in range(5):
+    ctx.solve_device(prm, d1, d2, planes[:-1], planes[-1])
+    ms, _ = ctx.stage_ms()
+    for k, v in ms.items(): acc[k] = acc.get(k, 0) + v / 5
+print('fused stages', {k: round(v, 3) for k, v in acc.items()})
