@@ -11,7 +11,7 @@ backtracking -> sub-pixel -> planes/mosaic) over one synthetic scene:
   N = 1 : BASELINE.json configs[1] -- 1024x1024 pair, ws 15, image_size 64 (+/-64 px),
           stride 60 (ex_deepmatching_rawinput.py:28-30) -> 225 tiles, 904x904 output.
   N > 1 : weak scaling -- the scene grows by 900 rows (15 tile rows) per extra rank, each
-          rank solves its strip of tile rows, one NCCL all-gather of the finished strips.
+          rank solves its strip of tile rows, one NCCL gather of the finished strips to rank 0.
 `value`  : output megapixels / s with both scenes already resident in HBM.
 `e2e`    : the same through the public API (ImageCutSolver / dm_solve_scene_host) from
            pinned host uint8 scenes to host float64 planes, copies inside the timed region.
@@ -175,6 +175,8 @@ def run_ours(args):
     assert world == args.gpus, '--gpus %d but WORLD_SIZE=%d (launch with torch.distributed.run)' % (args.gpus, world)
     torch.cuda.set_device(local_rank)
     if world > 1:
+        if not os.environ.get('DM_KEEP_NCCL_DEBUG'):
+            os.environ['NCCL_DEBUG'] = 'WARN'       # keep stdout to the one JSON line (NCCL prints its version there)
         dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
 
     def barrier():
@@ -341,7 +343,7 @@ def run_ours(args):
             'config': {'workload': workload_name(world), 'tiles': int(solver.len0 * solver.len1), 'output': [solver.out_h, solver.out_w],
                        'l2': 'no flush: the per-step working set (%.1f GB of pyramid levels) is far larger than the 126 MB L2'
                              % (solver.ctx.workspace_bytes / 1e9),
-                       'parallelism': 'tile-row strips x%d, all_gather of finished strips' % world},
+                       'parallelism': 'tile-row strips x%d, one NCCL gather of the finished strips to rank 0' % world},
             'e2e': {'value': out_px * args.steps / 1e6 / e2e_s, 'unit': 'MP/s', 'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': int(d2h)},
             'gpu_launches': int(launches_per_step * args.steps),
             'clocks': clk, 'roofline': roofline, 'cpu_baseline': cpu,

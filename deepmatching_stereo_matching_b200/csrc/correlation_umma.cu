@@ -280,7 +280,9 @@ dm_correlation_umma_kernel(const __grid_constant__ CUtensorMap mapA, const __gri
                         }
                         flush16((size_t)j * BN + s * STEP);
                     } else {
-                        constexpr int R = BN / D;               // map rows per N-tile (even)
+                        // map rows per N-tile: BN / D (even) for D <= 64; for D == 128 one N-tile is one
+                        // map row and the row parity alternates with j (warp-uniform runtime branch)
+                        const bool odd_tile = (D == 128) && (j & 1);
 #pragma unroll
                         for (int i = 0; i < STEP; i += 2) {
                             const int n = s * STEP + i;         // column inside the N-tile
@@ -289,7 +291,7 @@ dm_correlation_umma_kernel(const __grid_constant__ CUtensorMap mapA, const __gri
                             const float left = (x == 0) ? -CUDART_INF_F : (i == 0 ? zprev : v[i - 1]);
                             const float h = umma::max3(left, v[i], v[i + 1]);
                             rmin = umma::min3(rmin, v[i], v[i + 1]);
-                            if ((r & 1) == 0) {
+                            if (D == 128 ? !odd_tile : ((r & 1) == 0)) {
                                 st[xh] = fmaxf(st[xh], h);      // rows 2y-1 (carried) and 2y
                             } else {
                                 // pooled output: row factor and upper clamp only.  A flat patch has
@@ -299,14 +301,15 @@ dm_correlation_umma_kernel(const __grid_constant__ CUtensorMap mapA, const __gri
                                 if (NORMED) o = fminf(__fmul_rn(o, s1.y), 1.0f);
                                 st[xh] = h;                     // becomes row 2(y+1)-1 of the next pooled row
                                 rmax = fmaxf(rmax, o);
-                                const int oi = (r >> 1) * (D / 2) + xh;     // output index inside the N-tile, 0..31
+                                // output index inside the pooled rows this N-tile completes
+                                const int oi = (D == 128) ? xh : (r >> 1) * (D / 2) + xh;
                                 if ((oi & 3) == 0) ob.x = o; else if ((oi & 3) == 1) ob.y = o; else if ((oi & 3) == 2) ob.z = o; else ob.w = o;
                                 if ((oi & 3) == 3) stg_mine[(oi & 15) >> 2] = ob;
-                                if ((oi & 15) == 15) flush16((size_t)j * (BN / 4) + (oi - 15));
+                                if ((oi & 15) == 15)
+                                    flush16((D == 128) ? (size_t)(j >> 1) * (D / 2) + (oi - 15) : (size_t)j * (BN / 4) + (oi - 15));
                             }
                         }
                         zprev = v[STEP - 1];
-                        (void)R;
                     }
                 }
                 if (++acc == 2) { acc = 0; accph ^= 1; }
@@ -383,7 +386,7 @@ bool dm_correlation_umma_supported(int p, int kpad) {
 }
 
 bool dm_correlation_umma_pool_supported(int t0, int t1, int kpad) {
-    return dm_correlation_umma_supported(t0 * t1, kpad) && (t1 == 16 || t1 == 32 || t1 == 64) && t0 % 2 == 0;
+    return dm_correlation_umma_supported(t0 * t1, kpad) && (t1 == 16 || t1 == 32 || t1 == 64 || t1 == 128) && t0 % 2 == 0;
 }
 
 static int fill_params(Params& prm, CUtensorMap& mapA, CUtensorMap& mapB, const void* desc1, const float* stat1,
@@ -429,6 +432,7 @@ int dm_correlation_umma_pool(const void* desc1, const float* stat1, const void* 
     if (rc != DM_OK) return rc;
     prm.pooled = pooled; prm.rowmin = rowmin; prm.rowmax = rowmax;
     const bool normed = method == DM_TM_CCOEFF_NORMED;
+    if (t1 == 128) return launch<MODE_POOL, 128>(mapA, mapB, prm, normed, stream);
     if (t1 == 64) return launch<MODE_POOL, 64>(mapA, mapB, prm, normed, stream);
     if (t1 == 32) return launch<MODE_POOL, 32>(mapA, mapB, prm, normed, stream);
     return launch<MODE_POOL, 16>(mapA, mapB, prm, normed, stream);

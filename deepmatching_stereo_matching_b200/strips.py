@@ -1,7 +1,7 @@
 # -*- coding: utf-8 -*-
 """
 Multi-GPU partition of a scene: contiguous strips of tile rows, one per rank, solved
-independently; one gather of the finished disparity strips (NCCL over NVLink on the GPU
+independently; one gather of the finished disparity strips to rank 0 (NCCL over NVLink on the GPU
 box, gloo in the CPU tests).  SURVEY.md section 8(e); tiles are independent in the
 reference (misc/image_cut_solver.py:163-175).
 
@@ -40,7 +40,7 @@ def gather_strips(local, row_ranges, group=None, dst=0):
 
     local: torch tensor (planes, out_h, out_w) on this rank's device; only
     rows row_ranges[rank] are meaningful.  Returns the assembled tensor on ``dst`` and
-    None elsewhere.  Strips are padded to the tallest one so a single all_gather moves
+    None elsewhere.  Strips are padded to the tallest one so a single gather moves
     everything (NCCL: NVLink/NVSwitch; payload is a few hundred MB at most).
     """
     import torch
@@ -53,14 +53,16 @@ def gather_strips(local, row_ranges, group=None, dst=0):
     send = torch.zeros((planes, tall, out_w), dtype=local.dtype, device=local.device)
     if hi > lo:
         send[:, :hi - lo] = local[:, lo:hi]
-    recv = torch.empty((world, planes, tall, out_w), dtype=local.dtype, device=local.device)
-    dist.all_gather([recv[r] for r in range(world)], send, group=group)
+    # only `dst` needs the strips: a gather moves (world-1) strips into one GPU instead of
+    # world*(world-1) for an all-gather
+    recv = [torch.empty_like(send) for _ in range(world)] if rank == dst else None
+    dist.gather(send, recv, dst=dst, group=group)
     if rank != dst:
         return None
     full = torch.empty((planes, out_h, out_w), dtype=local.dtype, device=local.device)
     for r, (a, b) in enumerate(row_ranges):
         if b > a:
-            full[:, a:b] = recv[r, :, :b - a]
+            full[:, a:b] = recv[r][:, :b - a]
     return full
 
 

@@ -351,17 +351,22 @@ def test_chunked_scene_equals_single_chunk(dm):
 
 
 def test_t128_tiles_c5_geometry(dm):
-    """C5 geometry (image_size 128, ws 15, stride 124): constant-shift recovery through the
-    materialising path (the pooled epilogue covers T1 <= 64), plus a spot check of one tile's
-    level-0 rows against the oracle's exact ZNCC."""
+    """C5 geometry (image_size 128, ws 15, stride 124): constant-shift recovery on both GPU
+    paths, their agreement, and a spot check of level-0 rows against the oracle's exact ZNCC."""
     from deepmatching_stereo_matching_b200.synth import stereo_pair
     i1, i2 = stereo_pair((400, 400), seed=3, mode='shift', amp=5)
-    s = dm.ImageCutSolver(i1, i2, image_size=[128, 128], stride=[124, 124], window_size=15,
-                          degree_map_mode=['elevation', 'elevation2'], sub_pix=True)
-    s.log_flg = False
-    d, sc = s()
-    assert d.shape == (2, 252, 252) and list(s.len) == [2, 2] and s.info.levels == 8 and s.info.used_fused == 0
-    assert np.mean(np.abs(d[0] - 5.0) < 0.5) > 0.93 and np.mean(np.abs(d[1]) < 0.5) > 0.93
+    res = []
+    for fused in (0, 1):
+        s = dm.ImageCutSolver(i1, i2, image_size=[128, 128], stride=[124, 124], window_size=15,
+                              degree_map_mode=['elevation', 'elevation2'], sub_pix=True)
+        s.log_flg = False
+        s.fused = fused
+        d, sc = s()
+        assert d.shape == (2, 252, 252) and list(s.len) == [2, 2] and s.info.levels == 8 and s.info.used_fused == fused
+        assert np.mean(np.abs(d[0] - 5.0) < 0.5) > 0.93 and np.mean(np.abs(d[1]) < 0.5) > 0.93
+        res.append((d, sc))
+    assert np.mean(np.abs(res[0][0] - res[1][0]) > 1e-4) <= 2e-4
+    assert np.mean(np.abs(res[0][1] - res[1][1]) > 1e-5) <= 2e-4
     co = dm.Correlation_map(i1[:142, :142], i2[:142, :142], window_size=15)
     co._create_atomic_patch()
     co._create_simple_initial_co_map()
