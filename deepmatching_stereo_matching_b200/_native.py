@@ -27,7 +27,7 @@ class SceneParams(Structure):
                 ('s0', c_int32), ('s1', c_int32), ('ws', c_int32), ('method', c_int32),
                 ('n_modes', c_int32), ('modes', c_int32 * 4), ('sub_pix', c_int32),
                 ('tile_row_lo', c_int32), ('tile_row_hi', c_int32), ('fused', c_int32),
-                ('reserved', c_int32 * 3)]
+                ('n_scenes', c_int32), ('reserved', c_int32 * 2)]
 
 
 class SceneInfo(Structure):
@@ -171,7 +171,7 @@ class Context(object):
         return int(lib().dm_ctx_workspace_bytes(self._h))
 
 
-def scene_params(shape, image_size, stride, window_size, feature_name, modes, sub_pix, tile_rows=None, fused=-1):
+def scene_params(shape, image_size, stride, window_size, feature_name, modes, sub_pix, tile_rows=None, fused=-1, n_scenes=1):
     prm = SceneParams()
     prm.scene_h, prm.scene_w = int(shape[0]), int(shape[1])
     prm.t0, prm.t1 = int(image_size[0]), int(image_size[1])
@@ -184,6 +184,7 @@ def scene_params(shape, image_size, stride, window_size, feature_name, modes, su
     prm.sub_pix = 1 if sub_pix else 0
     prm.tile_row_lo, prm.tile_row_hi = (0, 0) if tile_rows is None else (int(tile_rows[0]), int(tile_rows[1]))
     prm.fused = int(fused)
+    prm.n_scenes = int(n_scenes)
     return prm
 
 

@@ -145,7 +145,10 @@ extern "C" int dm_scene_geometry(const dm_scene_params* prm, dm_scene_info* info
     DM_REQUIRE(lo >= 0 && lo < hi && hi <= info->len0, DM_ERR_INVALID, "tile row strip [%d,%d) outside [0,%d)", lo, hi, info->len0);
     info->row_lo = prm->s0 * lo;
     info->row_hi = (hi == info->len0) ? info->out_h : prm->s0 * hi;
-    info->n_tiles = (hi - lo) * info->len1;
+    const int ns = prm->n_scenes > 1 ? prm->n_scenes : 1;
+    DM_REQUIRE(ns == 1 || (lo == 0 && hi == info->len0), DM_ERR_INVALID, "a batch of scenes cannot be combined with a tile-row strip");
+    DM_REQUIRE((long long)ns * info->len0 * info->len1 < (1LL << 31), DM_ERR_INVALID, "too many tiles");
+    info->n_tiles = (hi - lo) * info->len1 * ns;
     info->levels = lg + 1;
     info->n_map = mn;
     return DM_OK;
@@ -154,12 +157,15 @@ extern "C" int dm_scene_geometry(const dm_scene_params* prm, dm_scene_info* info
 // ------------------------------------------------------------------ scene kernels
 namespace {
 
-__global__ void dm_tile_origin_kernel(int32_t* origin, int n, int first_tile, int len1, int s0, int s1) {
+// tile g of a (batch of) scene(s): scene = g / (len0*len1), then row-major (gi, gj); scenes are
+// stacked along rows, so the origin of a tile is (scene*S0 + s0*gi, s1*gj)
+__global__ void dm_tile_origin_kernel(int32_t* origin, int n, int first_tile, int len0, int len1, int s0, int s1, int scene_h) {
     int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n) return;
-    int g = first_tile + t;
-    origin[2 * t] = s0 * (g / len1);
-    origin[2 * t + 1] = s1 * (g % len1);
+    const int g = first_tile + t, tps = len0 * len1;
+    const int sc = g / tps, r = g - sc * tps;
+    origin[2 * t] = sc * scene_h + s0 * (r / len1);
+    origin[2 * t + 1] = s1 * (r % len1);
 }
 
 struct PlaneArgs {
@@ -182,8 +188,9 @@ dm_planes_kernel(const float* __restrict__ l0, long long total, PlaneArgs a,
     const long long n = idx / P;
     const int p = (int)(idx - n * P);
     const int i = p / a.T1, j = p - i * a.T1;
-    const int g = a.first_tile + (int)n;
-    const int gi = g / a.len1, gj = g - gi * a.len1;
+    const int g = a.first_tile + (int)n, tps = a.len0 * a.len1;
+    const int sc = g / tps, gr = g - sc * tps;
+    const int gi = gr / a.len1, gj = gr - gi * a.len1;
     const int Y = a.s0 * gi + i, X = a.s1 * gj + j;
     if (min(Y / a.s0, a.len0 - 1) != gi || min(X / a.s1, a.len1 - 1) != gj) return;
     const int c0 = match[(size_t)n * 2 * P + p];
@@ -209,9 +216,9 @@ dm_planes_kernel(const float* __restrict__ l0, long long total, PlaneArgs a,
         double v = a.modes[m] == DM_MODE_ELEVATION ? e1
                  : a.modes[m] == DM_MODE_ELEVATION2 ? e0
                  : __dsqrt_rn(__fma_rn(e1, e1, __dmul_rn(e0, e0)));
-        d_map[m * plane + pix] = v;
+        d_map[((size_t)sc * a.n_modes + m) * plane + pix] = v;
     }
-    out_map[pix] = (double)score[(size_t)n * P + p];
+    out_map[(size_t)sc * plane + pix] = (double)score[(size_t)n * P + p];
 }
 
 }  // namespace
@@ -267,6 +274,7 @@ extern "C" int dm_solve_scene(dm_ctx* ctx, const dm_scene_params* prm,
     int lo = prm->tile_row_lo, hi = prm->tile_row_hi;
     if (hi <= 0) { lo = 0; hi = info.len0; }
 
+    const int ns = prm->n_scenes > 1 ? prm->n_scenes : 1;
     const bool want_fused = prm->fused != 0;
     const bool fused = want_fused && dm_fused_supported(t0, t1, kpad) && dm_fused_supported_ws(prm->ws);
     DM_REQUIRE(!(prm->fused == 1 && !fused), DM_ERR_UNSUPPORTED, "fused path does not support image_size (%d,%d) with window %d", t0, t1, prm->ws);
@@ -300,7 +308,7 @@ extern "C" int dm_solve_scene(dm_ctx* ctx, const dm_scene_params* prm,
         pa.first_tile = first;
         if (fused) {
             dm_fused_args fa;
-            fa.img1 = img1_dev; fa.img2 = img2_dev; fa.scene_h = prm->scene_h; fa.scene_w = prm->scene_w;
+            fa.img1 = img1_dev; fa.img2 = img2_dev; fa.scene_h = prm->scene_h; fa.scene_w = prm->scene_w; fa.n_scenes = ns;
             fa.t0 = t0; fa.t1 = t1; fa.ws = prm->ws; fa.kpad = kpad; fa.levels = L; fa.method = prm->method;
             fa.first_tile = first; fa.n_tiles = nt; fa.len0 = info.len0; fa.len1 = info.len1;
             fa.s0 = prm->s0; fa.s1 = prm->s1; fa.out_h = info.out_h; fa.out_w = info.out_w;
@@ -314,10 +322,10 @@ extern "C" int dm_solve_scene(dm_ctx* ctx, const dm_scene_params* prm,
         {
             StageTimer tm(ctx, DM_STAGE_DESCRIPTORS);
             if ((rc = tm.begin(ck)) != DM_OK) return rc;
-            dm_tile_origin_kernel<<<dm_div_up(nt, 128), 128, 0, st>>>(tb.origin, nt, first, info.len1, prm->s0, prm->s1);
+            dm_tile_origin_kernel<<<dm_div_up(nt, 128), 128, 0, st>>>(tb.origin, nt, first, info.len0, info.len1, prm->s0, prm->s1, prm->scene_h);
             DM_LAUNCH_CHECK();
-            if ((rc = dm_descriptors(img1_dev, prm->scene_h, prm->scene_w, prm->scene_w, tb.origin, nt, t0, t1, prm->ws, tb.desc1, tb.stat1, st)) != DM_OK) return rc;
-            if ((rc = dm_descriptors(img2_dev, prm->scene_h, prm->scene_w, prm->scene_w, tb.origin, nt, t0, t1, prm->ws, tb.desc2, tb.stat2, st)) != DM_OK) return rc;
+            if ((rc = dm_descriptors(img1_dev, prm->scene_h * ns, prm->scene_w, prm->scene_w, tb.origin, nt, t0, t1, prm->ws, tb.desc1, tb.stat1, st)) != DM_OK) return rc;
+            if ((rc = dm_descriptors(img2_dev, prm->scene_h * ns, prm->scene_w, prm->scene_w, tb.origin, nt, t0, t1, prm->ws, tb.desc2, tb.stat2, st)) != DM_OK) return rc;
             ctx->launches[DM_STAGE_DESCRIPTORS] += 3;
             if ((rc = tm.end()) != DM_OK) return rc;
         }
@@ -383,7 +391,8 @@ extern "C" int dm_solve_scene_host(dm_ctx* ctx, const dm_scene_params* prm,
     int rc = dm_scene_geometry(prm, &info);
     if (rc != DM_OK) return rc;
     cudaStream_t st = ctx->stream;
-    const size_t sb = (size_t)prm->scene_h * prm->scene_w;
+    const int ns = prm->n_scenes > 1 ? prm->n_scenes : 1;
+    const size_t sb = (size_t)prm->scene_h * prm->scene_w * ns;
     if (sb > ctx->scene_bytes) {
         DM_CUDA_CHECK(cudaStreamSynchronize(st));
         cudaFree(ctx->scene1); cudaFree(ctx->scene2); ctx->scene1 = ctx->scene2 = nullptr; ctx->scene_bytes = 0;
@@ -392,7 +401,7 @@ extern "C" int dm_solve_scene_host(dm_ctx* ctx, const dm_scene_params* prm,
         ctx->scene_bytes = sb;
     }
     const size_t plane = (size_t)info.out_h * info.out_w;
-    const size_t pb = plane * (prm->n_modes + 1) * sizeof(double);
+    const size_t pb = plane * (prm->n_modes + 1) * sizeof(double) * ns;
     if (pb > ctx->planes_bytes) {
         DM_CUDA_CHECK(cudaStreamSynchronize(st));
         cudaFree(ctx->planes); ctx->planes = nullptr; ctx->planes_bytes = 0;
@@ -402,21 +411,26 @@ extern "C" int dm_solve_scene_host(dm_ctx* ctx, const dm_scene_params* prm,
     // only the rows the strip's tiles read: [s0*lo, s0*(hi-1) + t0 + ws - 1)
     int lo = prm->tile_row_lo, hi = prm->tile_row_hi;
     if (hi <= 0) { lo = 0; hi = info.len0; }
-    const size_t in_lo = (size_t)prm->s0 * lo, in_hi = (size_t)prm->s0 * (hi - 1) + prm->t0 + prm->ws - 1;
+    const size_t in_lo = (size_t)prm->s0 * lo, in_hi = ns > 1 ? (size_t)prm->scene_h * ns : (size_t)prm->s0 * (hi - 1) + prm->t0 + prm->ws - 1;
     const size_t in_off = in_lo * prm->scene_w, in_bytes = (in_hi - in_lo) * prm->scene_w;
     DM_CUDA_CHECK(cudaMemcpyAsync(ctx->scene1 + in_off, img1_host + in_off, in_bytes, cudaMemcpyHostToDevice, st));
     DM_CUDA_CHECK(cudaMemcpyAsync(ctx->scene2 + in_off, img2_host + in_off, in_bytes, cudaMemcpyHostToDevice, st));
     double* d_map = ctx->planes;
-    double* out_map = ctx->planes + plane * prm->n_modes;
+    double* out_map = ctx->planes + plane * prm->n_modes * ns;
     if (prm->s0 > prm->t0 || prm->s1 > prm->t1)      // gaps between tiles: np.empty in the reference, zeros here
         DM_CUDA_CHECK(cudaMemsetAsync(ctx->planes, 0, pb, st));
     rc = dm_solve_scene(ctx, prm, ctx->scene1, ctx->scene2, d_map, out_map, &info);
     if (rc != DM_OK) return rc;
-    const size_t row_off = (size_t)info.row_lo * info.out_w;
-    const size_t row_bytes = (size_t)(info.row_hi - info.row_lo) * info.out_w * sizeof(double);
-    for (int m = 0; m < prm->n_modes; ++m)
-        DM_CUDA_CHECK(cudaMemcpyAsync(d_map_host + m * plane + row_off, d_map + m * plane + row_off, row_bytes, cudaMemcpyDeviceToHost, st));
-    DM_CUDA_CHECK(cudaMemcpyAsync(out_map_host + row_off, out_map + row_off, row_bytes, cudaMemcpyDeviceToHost, st));
+    if (ns > 1) {       // whole batch: both result arrays are contiguous
+        DM_CUDA_CHECK(cudaMemcpyAsync(d_map_host, d_map, plane * prm->n_modes * ns * sizeof(double), cudaMemcpyDeviceToHost, st));
+        DM_CUDA_CHECK(cudaMemcpyAsync(out_map_host, out_map, plane * ns * sizeof(double), cudaMemcpyDeviceToHost, st));
+    } else {
+        const size_t row_off = (size_t)info.row_lo * info.out_w;
+        const size_t row_bytes = (size_t)(info.row_hi - info.row_lo) * info.out_w * sizeof(double);
+        for (int m = 0; m < prm->n_modes; ++m)
+            DM_CUDA_CHECK(cudaMemcpyAsync(d_map_host + m * plane + row_off, d_map + m * plane + row_off, row_bytes, cudaMemcpyDeviceToHost, st));
+        DM_CUDA_CHECK(cudaMemcpyAsync(out_map_host + row_off, out_map + row_off, row_bytes, cudaMemcpyDeviceToHost, st));
+    }
     DM_CUDA_CHECK(cudaStreamSynchronize(st));
     if (info_out) *info_out = info;
     return DM_OK;

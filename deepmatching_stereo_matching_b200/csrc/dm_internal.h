@@ -49,7 +49,7 @@ struct StageTimer {
 
 // Fused solver (fused.cu): level 0 is never written to HBM.
 struct dm_fused_args {
-    const uint8_t* img1; const uint8_t* img2; int scene_h, scene_w;
+    const uint8_t* img1; const uint8_t* img2; int scene_h, scene_w, n_scenes;
     int t0, t1, ws, kpad, levels, method;
     int first_tile, n_tiles, len0, len1, s0, s1, out_h, out_w;
     int n_modes, modes[4], sub_pix;

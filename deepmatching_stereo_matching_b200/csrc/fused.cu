@@ -60,12 +60,14 @@ size_t carve(char* base, int nt, int t0, int t1, int kpad, int levels, FusedBuff
     return (c.off + 255) & ~(size_t)255;
 }
 
-__global__ void dm_tile_origin_kernel2(int32_t* origin, int n, int first_tile, int len1, int s0, int s1) {
+// tile g of a (batch of) scene(s) stacked along rows: origin = (scene*S0 + s0*gi, s1*gj)
+__global__ void dm_tile_origin_kernel2(int32_t* origin, int n, int first_tile, int len0, int len1, int s0, int s1, int scene_h) {
     int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n) return;
-    int g = first_tile + t;
-    origin[2 * t] = s0 * (g / len1);
-    origin[2 * t + 1] = s1 * (g % len1);
+    const int g = first_tile + t, tps = len0 * len1;
+    const int sc = g / tps, r = g - sc * tps;
+    origin[2 * t] = sc * scene_h + s0 * (r / len1);
+    origin[2 * t + 1] = s1 * (r % len1);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -354,8 +356,9 @@ dm_final_quad_kernel(const FinalArgs a, long long n_quads) {
     if (l != 0) return;
 
     // ---- planes + paste (misc/Calc_difference.py:36-48, misc/image_cut_solver.py:165-175)
-    const int g = a.first_tile + n;
-    const int gi = g / a.len1, gj = g - gi * a.len1;
+    const int g = a.first_tile + n, tps = a.len0 * a.len1;
+    const int sc = g / tps, gr = g - sc * tps;
+    const int gi = gr / a.len1, gj = gr - gi * a.len1;
     const int Y = a.s0 * gi + i, X = a.s1 * gj + j;
     if (min(Y / a.s0, a.len0 - 1) != gi || min(X / a.s1, a.len1 - 1) != gj) return;   // a later tile owns this pixel
     const double e0 = __dsub_rn((double)i, mrow), e1 = __dsub_rn((double)j, mcol);
@@ -364,9 +367,9 @@ dm_final_quad_kernel(const FinalArgs a, long long n_quads) {
         const double v = a.modes[m] == DM_MODE_ELEVATION ? e1
                        : a.modes[m] == DM_MODE_ELEVATION2 ? e0
                        : __dsqrt_rn(__fma_rn(e1, e1, __dmul_rn(e0, e0)));
-        a.d_map[m * plane + pix] = v;
+        a.d_map[((size_t)sc * a.n_modes + m) * plane + pix] = v;
     }
-    a.out_map[pix] = (double)score;
+    a.out_map[(size_t)sc * plane + pix] = (double)score;
 }
 
 template <int WS>
@@ -397,10 +400,10 @@ int dm_fused_solve_chunk(dm_ctx* ctx, const dm_fused_args* a, int ck) {
     {
         StageTimer tm(ctx, DM_STAGE_DESCRIPTORS);
         if ((rc = tm.begin(ck)) != DM_OK) return rc;
-        dm_tile_origin_kernel2<<<dm_div_up(nt, 128), 128, 0, st>>>(fb.origin, nt, a->first_tile, a->len1, a->s0, a->s1);
+        dm_tile_origin_kernel2<<<dm_div_up(nt, 128), 128, 0, st>>>(fb.origin, nt, a->first_tile, a->len0, a->len1, a->s0, a->s1, a->scene_h);
         DM_LAUNCH_CHECK();
-        if ((rc = dm_descriptors(a->img1, a->scene_h, a->scene_w, a->scene_w, fb.origin, nt, t0, t1, a->ws, fb.desc1, fb.stat1, st)) != DM_OK) return rc;
-        if ((rc = dm_descriptors(a->img2, a->scene_h, a->scene_w, a->scene_w, fb.origin, nt, t0, t1, a->ws, fb.desc2, fb.stat2, st)) != DM_OK) return rc;
+        if ((rc = dm_descriptors(a->img1, a->scene_h * a->n_scenes, a->scene_w, a->scene_w, fb.origin, nt, t0, t1, a->ws, fb.desc1, fb.stat1, st)) != DM_OK) return rc;
+        if ((rc = dm_descriptors(a->img2, a->scene_h * a->n_scenes, a->scene_w, a->scene_w, fb.origin, nt, t0, t1, a->ws, fb.desc2, fb.stat2, st)) != DM_OK) return rc;
         ctx->launches[DM_STAGE_DESCRIPTORS] += 3;
         if ((rc = tm.end()) != DM_OK) return rc;
     }
@@ -457,7 +460,7 @@ int dm_fused_solve_chunk(dm_ctx* ctx, const dm_fused_args* a, int ck) {
         fa.s0 = a->s0; fa.s1 = a->s1; fa.len0 = a->len0; fa.len1 = a->len1; fa.out_h = a->out_h; fa.out_w = a->out_w;
         fa.first_tile = a->first_tile; fa.d_map = a->d_map; fa.out_map = a->out_map;
         const long long n_patches = (long long)nt * P;
-        fa.scene_h = a->scene_h;
+        fa.scene_h = a->scene_h * a->n_scenes;       // bound of the stacked image
         const long long n_quads = n_patches / 4;
         switch (a->ws) {
             case 3: launch_final_quad<3>(fa, n_quads, st); break;

@@ -41,6 +41,25 @@ def pinned_empty(shape, dtype):
     return t.numpy()
 
 
+def solve_batch(imgs1, imgs2, image_size=[32, 32], stride=[32, 32], window_size=5,
+                feature_name='cv2.TM_CCOEFF_NORMED', degree_map_mode=['elevation'], sub_pix=True, fused=-1):
+    """ImageCutSolver(...)() for a batch of equally sized scene pairs in ONE library call
+    (BASELINE config 4: 64 pairs of 512x512).  imgs1, imgs2: uint8 (n, S0, S1).
+    Returns (d_maps float64 (n, n_modes, S0', S1'), out_maps float64 (n, S0', S1')), each
+    slice identical to what ImageCutSolver returns for that pair."""
+    a = np.ascontiguousarray(imgs1, dtype=np.uint8)
+    b = np.ascontiguousarray(imgs2, dtype=np.uint8)
+    assert a.ndim == 3 and a.shape == b.shape, 'two (n, S0, S1) uint8 stacks of the same shape'
+    n = a.shape[0]
+    prm = _native.scene_params(a.shape[1:], image_size, stride, window_size, feature_name, list(degree_map_mode),
+                               sub_pix, None, fused, n_scenes=n)
+    info = _native.scene_geometry(prm)
+    d_maps = pinned_empty((n, len(degree_map_mode), info.out_h, info.out_w), np.float64)
+    out_maps = pinned_empty((n, info.out_h, info.out_w), np.float64)
+    _context().solve_host(prm, a, b, d_maps, out_maps)
+    return d_maps, out_maps
+
+
 class ImageCutSolver():
 
     def __init__(

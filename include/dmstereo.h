@@ -149,14 +149,18 @@ typedef struct dm_scene_params {
     int32_t tile_row_lo, tile_row_hi; /* strip of tile rows [lo,hi); hi<=0 means all      */
     int32_t fused;                  /* 1: fused tcgen05 path (no level-0 in HBM) when the
                                        shape allows it, 0: materialising path, -1: auto  */
-    int32_t reserved[3];
+    int32_t n_scenes;               /* batch of equally sized scene pairs stacked along rows
+                                       ([n_scenes][S0][S1] inputs, [n_scenes][n_modes][S0'][S1']
+                                       and [n_scenes][S0'][S1'] outputs); 0 or 1 = single pair.
+                                       Not combinable with a tile-row strip.                */
+    int32_t reserved[2];
 } dm_scene_params;
 
 typedef struct dm_scene_info {
     int32_t len0, len1;             /* tile grid (misc/image_cut_solver.py:62)            */
     int32_t out_h, out_w;           /* S0', S1' of the full mosaic                        */
     int32_t row_lo, row_hi;         /* output rows owned by the strip                     */
-    int32_t n_tiles;                /* tiles in the strip                                 */
+    int32_t n_tiles;                /* tiles in the strip (all scenes of a batch)         */
     int32_t levels;                 /* pyramid depth ("iteration")                        */
     int32_t n_map;                  /* N_map                                              */
     int32_t used_fused;             /* which path ran                                     */

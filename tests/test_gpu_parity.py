@@ -327,6 +327,31 @@ def test_oracle_tile_t64_ws15(dm):
     assert bad <= MAX_INDEX_DISAGREEMENT
 
 
+def test_batch_of_pairs_equals_one_by_one(dm):
+    """Config-4 style batch (equally sized pairs, sub_pix + post-hoc sub_pix_cal): one batched
+    call must reproduce the per-pair ImageCutSolver results bit for bit, on both paths."""
+    from deepmatching_stereo_matching_b200 import image_cut_solver as ics
+    from deepmatching_stereo_matching_b200.synth import stereo_pair
+    pairs = [stereo_pair((150, 182), seed=100 + b, mode='sine', amp=4) for b in range(3)]
+    i1 = np.stack([p[0] for p in pairs]); i2 = np.stack([p[1] for p in pairs])
+    kw = dict(image_size=[32, 32], stride=[32, 32], window_size=5, degree_map_mode=['elevation', 'elevation2'], sub_pix=True)
+    for fused in (1, 0):
+        d, sc = ics.solve_batch(i1, i2, fused=fused, **kw)
+        assert d.shape == (3, 2, 96, 128) and sc.shape == (3, 96, 128)
+        for b in range(3):
+            s = dm.ImageCutSolver(pairs[b][0], pairs[b][1], **kw)
+            s.log_flg = False
+            s.fused = fused
+            db, sb = s()
+            assert np.array_equal(d[b], db, equal_nan=True) and np.array_equal(sc[b], sb, equal_nan=True)
+    # the post-hoc refinement of config 4 (direction rule of image_cut_solver.py:137) vs the oracle
+    rd, rs = O.image_cut_solver(pairs[0][0], pairs[0][1], (32, 32), (32, 32), 5, ('elevation', 'elevation2'), True)
+    got = dm.sub_pix_cal(d[0, 0], sc[0], direction=1)
+    ref = O.sub_pix_cal(rd[0], rs, direction=1)
+    ok = ~(np.isnan(got) | np.isnan(ref))
+    assert np.mean(np.abs(got[ok] - ref[ok]) > 1e-2) <= 5e-3
+
+
 def test_chunked_scene_equals_single_chunk(dm):
     """A workspace limit that forces several chunks of tiles must not change a single bit."""
     from deepmatching_stereo_matching_b200 import image_cut_solver as ics
