@@ -99,7 +99,7 @@ def kernels(tag, rep, path_name):
         w = csv.DictWriter(f, keys)
         w.writeheader(); w.writerows(res)
     with open(os.path.join(PROF, tag + '_kernels.md'), 'w') as f:
-        f.write('| kernel | ms | DRAM read GB | DRAM write GB | DRAM %% | tensor %% | SM %% | L1/TEX %% | issue %% | regs | grid x block |\n|---|---|---|---|---|---|---|---|---|---|---|\n')
+        f.write('| kernel | ms | DRAM read GB | DRAM write GB | DRAM % | tensor % | SM % | L1/TEX % | issue % | regs | grid x block |\n|---|---|---|---|---|---|---|---|---|---|---|\n')
         for d in res:
             f.write('| `%s` | %.3f | %.3f | %.3f | %.1f | %.1f | %.1f | %.1f | %.1f | %d | %d x %d |\n' % (
                 d['kernel'], d['time_ms'], d['dram_read_bytes'] / 1e9, d['dram_write_bytes'] / 1e9, d['dram_pct'], d['tensor_pct'],
