@@ -20,14 +20,19 @@
 //                              2-deep shared-memory ring
 //   warp 1      MMA issuer     tcgen05.mma cta_group::1 kind::f16, M=128 N=128 K=16;
 //                              TMEM: 2 halves x 2 accumulator stages x 128 columns = 512
-//   warps 2..9  epilogue       tcgen05.ld 32x32b, thread == patch row, so the 3x3 pooling,
-//                              the running row minimum and the halo row carried between
-//                              N-tiles are all thread-local registers.  Software pipelined
-//                              in steps of 16 columns: the TMEM load and the column
-//                              parameters of step s+1 are in flight while step s is
-//                              computed (FFMA2/FMUL2 packed math, 3-input min/max).
-//                              Results leave through a per-warp shared-memory transpose so
-//                              that every store instruction writes 8 rows x 64 B.
+//   warps 2..9  epilogue       tcgen05.ld 32x32b.  A thread owns TWO patch rows -- TMEM lane l
+//                              of both accumulator halves -- and one half of the columns
+//                              of every map row, so the 3x3 pooling, the running row
+//                              minimum and the halo row carried between N-tiles are
+//                              thread-local registers, the per-column parameters are
+//                              fetched once for two rows (the shared-memory broadcast is
+//                              what the epilogue pays most for) and two independent
+//                              dependency chains interleave.  The one halo column at the
+//                              split comes from a 1-column TMEM load.  Software pipelined
+//                              in steps of 8 columns (loads of step s+1 in flight during
+//                              step s), FFMA2/FMUL2 packed math, 3-input min/max.  Results
+//                              leave through a per-warp shared-memory transpose so that
+//                              every store instruction writes 8 rows x 64 B.
 // B traffic: every CTA streams the tile's whole position matrix once per item; with
 // M = 256 rows per item that is 32 B/clk/SM from L2 at the MMA's full rate.
 #include "dm_common.cuh"
@@ -41,16 +46,16 @@ constexpr int HALVES = 2;
 constexpr int BN = 128;                 // positions per N-tile
 constexpr int BK = 64;                  // bf16 per 128-byte swizzle row
 constexpr int UMMA_K = 16;
-constexpr int STAGES = 4;
+constexpr int STAGES = 3;
 constexpr int MAX_KB = 4;               // kpad <= 256
 constexpr int BOX_BYTES = BM * BK * 2;  // 16 KiB: one [128 rows x 64] bf16 box
 constexpr int EPI_WARPS = 8;
 constexpr int THREADS = 32 * (2 + EPI_WARPS);
 constexpr int TMEM_COLS = 512;
-constexpr int STEP = 16;                // columns per epilogue pipeline step
-constexpr int NSTEP = BN / STEP;
+constexpr int SW = 8;                   // columns per epilogue pipeline step (per accumulator half)
+constexpr int NSTEP = (BN / 2) / SW;    // a thread covers half of the N-tile's columns
 constexpr int STG_STRIDE = 20;          // floats per staged row (16 + 4 pad: conflict-free float4 rows)
-constexpr int STG_BYTES = 32 * STG_STRIDE * 4;      // per epilogue warp
+constexpr int STG_BYTES = 2 * 32 * STG_STRIDE * 4;  // per epilogue warp: one region per accumulator half
 constexpr int CS_BYTES = (BN / 2) * 16; // column table of one N-tile: 64 x {sk0, sk1, inv0, inv1}
 constexpr int CS_STAGES = 4;
 
@@ -68,7 +73,7 @@ struct Params {
     int n_items, P, KB, items_per_tile;
     float* raw;                 // MODE_RAW : [n][P][P]
     float* pooled;              // MODE_POOL: [n][P][P/4]
-    float* rowmin; float* rowmax;   // MODE_POOL: [n][P]
+    float* rowmin; float* rowmax;   // MODE_POOL: [n][P][2] partial min / max of the two column halves
 };
 
 enum { MODE_RAW = 0, MODE_POOL = 1, MODE_NULL = 2 };   // MODE_NULL: drain TMEM only (measurement aid)
@@ -179,40 +184,43 @@ dm_correlation_umma_kernel(const __grid_constant__ CUtensorMap mapA, const __gri
     } else {
         // ------------------------------------------------------------ epilogue
         const int e = warp - 2;
-        const int half = e >> 2;
         const int quarter = warp & 3;                   // TMEM lanes a warp may touch: 32*(warp_id % 4)..+31
-        const int row_local = half * BM + quarter * 32;  // first of this warp's 32 consecutive patches
-        float* stg = smemStg + (size_t)e * (32 * STG_STRIDE);
-        float4* stg_mine = reinterpret_cast<float4*>(stg + lane * STG_STRIDE);
+        const int ch = e >> 2;                          // which half of every map row's columns
+        constexpr int DH = D / 2;                       // columns of a map row handled by this thread
+        constexpr int HWQ = (MODE == MODE_POOL) ? D / 4 : 1;    // pooled outputs per map row per thread
+        float* stgA = smemStg + (size_t)e * (2 * 32 * STG_STRIDE);
+        float* stgB = stgA + 32 * STG_STRIDE;
+        float4* stgA_mine = reinterpret_cast<float4*>(stgA + lane * STG_STRIDE);
+        float4* stgB_mine = reinterpret_cast<float4*>(stgB + lane * STG_STRIDE);
         int acc = 0; uint32_t accph = 0; int cst = 0; uint32_t cph = 0;
         for (int item = blockIdx.x; item < prm.n_items; item += gridDim.x) {
             const int tile = item / prm.items_per_tile;
-            const size_t wrow = (size_t)tile * P + (size_t)(item - tile * prm.items_per_tile) * (HALVES * BM) + row_local;
-            const size_t prow = wrow + lane;
-            const dm_stat s1 = prm.stat1[prow];
-            const bool flat1 = (s1.y == 0.0f);
-            const float ns1 = -s1.x;
-            // MODE_POOL state: st[] = horizontally pooled previous row (odd rows) / running
-            // vertical max (even rows); rmin = running row minimum of the raw values
-            constexpr int HW = (MODE == MODE_POOL) ? D / 2 : 1;
-            float st[HW];
-            float rmin = CUDART_INF_F, rmax = -CUDART_INF_F;
+            const size_t wrow = (size_t)tile * P + (size_t)(item - tile * prm.items_per_tile) * (HALVES * BM) + quarter * 32;
+            const size_t prowA = wrow + lane, prowB = prowA + BM;
+            const dm_stat s1A = prm.stat1[prowA], s1B = prm.stat1[prowB];
+            const bool flatA = (s1A.y == 0.0f), flatB = (s1B.y == 0.0f);
+            const float ns1A = -s1A.x, ns1B = -s1B.x;
+            // MODE_POOL state per row: st[] = horizontally pooled previous map row (odd rows) /
+            // running vertical max (even rows); rmin = running minimum of the raw values
+            float stA[HWQ], stB[HWQ];
+            float rminA = CUDART_INF_F, rmaxA = -CUDART_INF_F, rminB = CUDART_INF_F, rmaxB = -CUDART_INF_F;
             if (MODE == MODE_POOL) {
 #pragma unroll
-                for (int i = 0; i < HW; ++i) st[i] = -CUDART_INF_F;
+                for (int i = 0; i < HWQ; ++i) { stA[i] = -CUDART_INF_F; stB[i] = -CUDART_INF_F; }
             }
-            // output rows of this warp are `ostride` floats apart
+            // output rows of this warp are `ostride` floats apart; half B is 128 rows below half A
             const size_t ostride = (MODE == MODE_RAW) ? (size_t)P : (size_t)(P / 4);
-            float* wout = ((MODE == MODE_RAW) ? prm.raw : prm.pooled) + wrow * ostride;
-            // 16 floats per lane are staged in shared memory, then the warp writes 8 rows x 64 B
-            // per store instruction
-            auto flush16 = [&](size_t col) {
+            float* woutA = ((MODE == MODE_RAW) ? prm.raw : prm.pooled) + wrow * ostride;
+            float* woutB = woutA + (size_t)BM * ostride;
+            // 16 staged floats per lane -> the warp writes 8 rows x 64 B per store instruction.
+            // The 16 floats are SEGS contiguous segments, `segstride` floats apart in the output.
+            auto flush16 = [&](const float* stg, float* wout, size_t col, int seg, size_t segstride) {
                 __syncwarp();
 #pragma unroll
                 for (int it = 0; it < 4; ++it) {
-                    const int r = it * 8 + (lane >> 2), ch = lane & 3;
-                    const float4 v = *reinterpret_cast<const float4*>(stg + r * STG_STRIDE + ch * 4);
-                    *reinterpret_cast<float4*>(wout + (size_t)r * ostride + col + ch * 4) = v;
+                    const int r = it * 8 + (lane >> 2), f4 = (lane & 3) * 4;
+                    const float4 v = *reinterpret_cast<const float4*>(stg + r * STG_STRIDE + f4);
+                    *reinterpret_cast<float4*>(wout + (size_t)r * ostride + col + (size_t)(f4 / seg) * segstride + (f4 % seg)) = v;
                 }
                 __syncwarp();
             };
@@ -220,107 +228,140 @@ dm_correlation_umma_kernel(const __grid_constant__ CUtensorMap mapA, const __gri
                 umma::mbar_wait(c_full + cst, cph);
                 umma::mbar_wait(t_full + acc, accph);
                 umma::tc_fence_after();
-                const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)((half * 2 + acc) * BN);
+                const uint32_t tA = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)((0 * 2 + acc) * BN);
+                const uint32_t tB = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)((1 * 2 + acc) * BN);
                 const uint32_t csm = umma::smem_u32(smemCs + (size_t)cst * CS_BYTES);
-                float zprev = -CUDART_INF_F;            // last raw value of the previous step
-                float v0[STEP], v1[STEP];
-                float4 c0[STEP / 2], c1[STEP / 2];
-                float4 ob;                              // 4 outputs being assembled
-                umma::tmem_ld_32x16_issue(taddr, v0);
+                // column of step s inside the N-tile: map row r = (8 s) / DH, then this thread's half
+                auto step_col = [&](int s) -> int { return ((s * SW) / DH) * D + ch * DH + (s * SW) % DH; };
+                float vA0[SW], vA1[SW], vB0[SW], vB1[SW];
+                float4 c0[SW / 2], c1[SW / 2];
+                float hA = 0.f, hB = 0.f;               // halo column (ch == 1): raw accumulators left of the split
+                float4 hc = make_float4(0.f, 0.f, 0.f, 0.f);
+                float zprevA = -CUDART_INF_F, zprevB = -CUDART_INF_F;
+                float4 obA, obB;
+                {
+                    const int n0 = step_col(0);
+                    umma::tmem_ld_32x8_issue(tA + (uint32_t)n0, vA0);
+                    umma::tmem_ld_32x8_issue(tB + (uint32_t)n0, vB0);
 #pragma unroll
-#ifdef DM_EXP_NOCS
-                for (int i = 0; i < STEP / 2; ++i) c0[i] = make_float4(0.5f, 0.25f, 1.0f, 1.0f);
-#else
-                for (int i = 0; i < STEP / 2; ++i) c0[i] = umma::lds128(csm + 16 * i);
-#endif
+                    for (int i = 0; i < SW / 2; ++i) c0[i] = umma::lds128(csm + 16 * (n0 / 2 + i));
+                    if (MODE == MODE_POOL && ch) {
+                        umma::tmem_ld_32x1_issue(tA + (uint32_t)(n0 - 1), hA);
+                        umma::tmem_ld_32x1_issue(tB + (uint32_t)(n0 - 1), hB);
+                        hc = umma::lds128(csm + 16 * (n0 / 2 - 1));
+                    }
+                }
 #pragma unroll
                 for (int s = 0; s < NSTEP; ++s) {
-                    float (&v)[STEP] = (s & 1) ? v1 : v0;
-                    float (&vn)[STEP] = (s & 1) ? v0 : v1;
-                    float4 (&cc)[STEP / 2] = (s & 1) ? c1 : c0;
-                    float4 (&cn)[STEP / 2] = (s & 1) ? c0 : c1;
-                    umma::tmem_wait_ld();               // step s is in registers
-                    if (s + 1 < NSTEP) {                // step s+1 in flight during the math below
-                        umma::tmem_ld_32x16_issue(taddr + (uint32_t)((s + 1) * STEP), vn);
-#pragma unroll
-#ifdef DM_EXP_NOCS
-                        for (int i = 0; i < STEP / 2; ++i) cn[i] = make_float4(0.5f, 0.25f, 1.0f, 1.0f);
-#else
-                        for (int i = 0; i < STEP / 2; ++i) cn[i] = umma::lds128(csm + 16 * ((s + 1) * (STEP / 2) + i));
-#endif
+                    float (&vA)[SW] = (s & 1) ? vA1 : vA0;
+                    float (&vB)[SW] = (s & 1) ? vB1 : vB0;
+                    float (&vAn)[SW] = (s & 1) ? vA0 : vA1;
+                    float (&vBn)[SW] = (s & 1) ? vB0 : vB1;
+                    float4 (&cc)[SW / 2] = (s & 1) ? c1 : c0;
+                    float4 (&cn)[SW / 2] = (s & 1) ? c0 : c1;
+                    constexpr int dummy = 0; (void)dummy;
+                    const int xo = (s * SW) % DH;           // first column of the step inside this thread's row half
+                    const int r = (s * SW) / DH;            // map row inside the N-tile
+                    umma::tmem_wait_ld();                   // step s (and its halo) is in registers
+                    // halo of THIS step must be consumed before the next step's halo load overwrites it
+                    float zhA = -CUDART_INF_F, zhB = -CUDART_INF_F;
+                    if (MODE == MODE_POOL && xo == 0 && ch) {
+                        zhA = dm_zncc_partial(hA, s1A.x, hc.y, NORMED ? hc.w : 1.0f);
+                        zhB = dm_zncc_partial(hB, s1B.x, hc.y, NORMED ? hc.w : 1.0f);
                     }
-                    if (MODE == MODE_NULL) {            // measurement aid: TMEM drain + barriers only
-                        rmax = fmaxf(rmax, v[0]);
-                        if (s + 1 == NSTEP) {
-                            umma::tc_fence_before();
-                            __syncwarp();
-                            if (lane == 0) { umma::mbar_arrive(t_empty + acc); umma::mbar_arrive(c_empty + cst); }
+                    if (s + 1 < NSTEP) {                    // step s+1 in flight during the math below
+                        const int n1 = step_col(s + 1);
+                        umma::tmem_ld_32x8_issue(tA + (uint32_t)n1, vAn);
+                        umma::tmem_ld_32x8_issue(tB + (uint32_t)n1, vBn);
+#pragma unroll
+                        for (int i = 0; i < SW / 2; ++i) cn[i] = umma::lds128(csm + 16 * (n1 / 2 + i));
+                        if (MODE == MODE_POOL && ((s + 1) * SW) % DH == 0 && ch) {
+                            umma::tmem_ld_32x1_issue(tA + (uint32_t)(n1 - 1), hA);
+                            umma::tmem_ld_32x1_issue(tB + (uint32_t)(n1 - 1), hB);
+                            hc = umma::lds128(csm + 16 * (n1 / 2 - 1));
                         }
-                        continue;
                     }
 #pragma unroll
-                    for (int i = 0; i < STEP; i += 2) {
+                    for (int i = 0; i < SW; i += 2) {
                         const float4 cp = cc[i >> 1];       // {s2k0, s2k1, inv0, inv1} of two columns
-                        if (NORMED) umma::zncc_partial2(v[i], v[i + 1], ns1, cp.x, cp.y, cp.z, cp.w);
-                        else umma::zncc_partial2(v[i], v[i + 1], ns1, cp.x, cp.y, 1.0f, 1.0f);
+                        umma::zncc_partial2(vA[i], vA[i + 1], ns1A, cp.x, cp.y, NORMED ? cp.z : 1.0f, NORMED ? cp.w : 1.0f);
+                        umma::zncc_partial2(vB[i], vB[i + 1], ns1B, cp.x, cp.y, NORMED ? cp.z : 1.0f, NORMED ? cp.w : 1.0f);
                     }
-                    if (s + 1 == NSTEP) {               // accumulator stage and column table consumed
+                    if (s + 1 == NSTEP) {                   // accumulator stage and column table consumed
                         umma::tc_fence_before();
                         __syncwarp();
                         if (lane == 0) { umma::mbar_arrive(t_empty + acc); umma::mbar_arrive(c_empty + cst); }
                     }
+                    if (MODE == MODE_NULL) { rmaxA = fmaxf(rmaxA, vA[0] + vB[0]); continue; }
                     if (MODE == MODE_RAW) {
+                        // D is fixed to 64 here: steps (2k, 2k+1) are 16 consecutive columns
 #pragma unroll
-                        for (int i = 0; i < STEP; i += 4) {
-                            ob.x = dm_zncc_finish(v[i], s1.y, flat1, NORMED);
-                            ob.y = dm_zncc_finish(v[i + 1], s1.y, flat1, NORMED);
-                            ob.z = dm_zncc_finish(v[i + 2], s1.y, flat1, NORMED);
-                            ob.w = dm_zncc_finish(v[i + 3], s1.y, flat1, NORMED);
-                            stg_mine[i >> 2] = ob;
+                        for (int i = 0; i < SW; i += 4) {
+                            obA.x = dm_zncc_finish(vA[i], s1A.y, flatA, NORMED); obA.y = dm_zncc_finish(vA[i + 1], s1A.y, flatA, NORMED);
+                            obA.z = dm_zncc_finish(vA[i + 2], s1A.y, flatA, NORMED); obA.w = dm_zncc_finish(vA[i + 3], s1A.y, flatA, NORMED);
+                            obB.x = dm_zncc_finish(vB[i], s1B.y, flatB, NORMED); obB.y = dm_zncc_finish(vB[i + 1], s1B.y, flatB, NORMED);
+                            obB.z = dm_zncc_finish(vB[i + 2], s1B.y, flatB, NORMED); obB.w = dm_zncc_finish(vB[i + 3], s1B.y, flatB, NORMED);
+                            stgA_mine[(s & 1) * 2 + (i >> 2)] = obA;
+                            stgB_mine[(s & 1) * 2 + (i >> 2)] = obB;
                         }
-                        flush16((size_t)j * BN + s * STEP);
+                        if (s & 1) {
+                            const size_t col = (size_t)j * BN + step_col(s - 1);
+                            flush16(stgA, woutA, col, 16, 0);
+                            flush16(stgB, woutB, col, 16, 0);
+                        }
                     } else {
-                        // map rows per N-tile: BN / D (even) for D <= 64; for D == 128 one N-tile is one
-                        // map row and the row parity alternates with j (warp-uniform runtime branch)
-                        const bool odd_tile = (D == 128) && (j & 1);
+                        // map-row parity: compile time for D <= 64 (an N-tile holds BN / D rows, even);
+                        // for D == 128 an N-tile is one map row and the parity alternates with j
+                        const bool odd_row = (D == 128) ? ((j & 1) != 0) : ((r & 1) != 0);
 #pragma unroll
-                        for (int i = 0; i < STEP; i += 2) {
-                            const int n = s * STEP + i;         // column inside the N-tile
-                            const int x = n % D, r = n / D;     // position inside the map row / row inside the N-tile
-                            const int xh = x >> 1;
-                            const float left = (x == 0) ? -CUDART_INF_F : (i == 0 ? zprev : v[i - 1]);
-                            const float h = umma::max3(left, v[i], v[i + 1]);
-                            rmin = umma::min3(rmin, v[i], v[i + 1]);
-                            if (D == 128 ? !odd_tile : ((r & 1) == 0)) {
-                                st[xh] = fmaxf(st[xh], h);      // rows 2y-1 (carried) and 2y
+                        for (int i = 0; i < SW; i += 2) {
+                            const int xh = (xo + i) >> 1;   // pooled column inside this thread's half
+                            const float leftA = (xo + i == 0) ? zhA : (i == 0 ? zprevA : vA[i - 1]);
+                            const float leftB = (xo + i == 0) ? zhB : (i == 0 ? zprevB : vB[i - 1]);
+                            const float gA = umma::max3(leftA, vA[i], vA[i + 1]);
+                            const float gB = umma::max3(leftB, vB[i], vB[i + 1]);
+                            rminA = umma::min3(rminA, vA[i], vA[i + 1]);
+                            rminB = umma::min3(rminB, vB[i], vB[i + 1]);
+                            if (!odd_row) {
+                                stA[xh] = fmaxf(stA[xh], gA);   // rows 2y-1 (carried) and 2y
+                                stB[xh] = fmaxf(stB[xh], gB);
                             } else {
                                 // pooled output: row factor and upper clamp only.  A flat patch has
-                                // inv1 = 0 -> the whole row is 0 -> min == max -> NaN downstream, exactly
-                                // like OpenCV's all-ones map; a pooled maximum below -1 cannot occur.
-                                float o = fmaxf(st[xh], h);
-                                if (NORMED) o = fminf(__fmul_rn(o, s1.y), 1.0f);
-                                st[xh] = h;                     // becomes row 2(y+1)-1 of the next pooled row
-                                rmax = fmaxf(rmax, o);
-                                // output index inside the pooled rows this N-tile completes
-                                const int oi = (D == 128) ? xh : (r >> 1) * (D / 2) + xh;
-                                if ((oi & 3) == 0) ob.x = o; else if ((oi & 3) == 1) ob.y = o; else if ((oi & 3) == 2) ob.z = o; else ob.w = o;
-                                if ((oi & 3) == 3) stg_mine[(oi & 15) >> 2] = ob;
-                                if ((oi & 15) == 15)
-                                    flush16((D == 128) ? (size_t)(j >> 1) * (D / 2) + (oi - 15) : (size_t)j * (BN / 4) + (oi - 15));
+                                // inv1 = 0 -> the whole row is 0; its min / max are forced to 1 below, so
+                                // the slice turns NaN downstream exactly like OpenCV's all-ones map.
+                                float oA = fmaxf(stA[xh], gA), oB = fmaxf(stB[xh], gB);
+                                if (NORMED) { oA = fminf(__fmul_rn(oA, s1A.y), 1.0f); oB = fminf(__fmul_rn(oB, s1B.y), 1.0f); }
+                                stA[xh] = gA; stB[xh] = gB;     // become row 2(y+1)-1 of the next pooled row
+                                rmaxA = fmaxf(rmaxA, oA); rmaxB = fmaxf(rmaxB, oB);
+                                // output index inside the group of 16 this thread completes
+                                const int ol = (D == 128) ? xh : (r >> 1) * HWQ + xh;
+                                if ((ol & 3) == 0) { obA.x = oA; obB.x = oB; } else if ((ol & 3) == 1) { obA.y = oA; obB.y = oB; }
+                                else if ((ol & 3) == 2) { obA.z = oA; obB.z = oB; } else { obA.w = oA; obB.w = oB; }
+                                if ((ol & 3) == 3) { stgA_mine[(ol & 15) >> 2] = obA; stgB_mine[(ol & 15) >> 2] = obB; }
+                                if ((ol & 15) == 15) {
+                                    // first pooled row / column of the group; segments of min(16, D/4) floats, one per pooled row
+                                    constexpr int SEG = HWQ < 16 ? HWQ : 16;
+                                    const size_t col = (D == 128) ? (size_t)(j >> 1) * DH + (size_t)ch * HWQ + (ol - 15)
+                                                                  : (size_t)j * (BN / 4) + (size_t)ch * HWQ;
+                                    flush16(stgA, woutA, col, SEG, DH);
+                                    flush16(stgB, woutB, col, SEG, DH);
+                                }
                             }
                         }
-                        zprev = v[STEP - 1];
+                        zprevA = vA[SW - 1]; zprevB = vB[SW - 1];
                     }
                 }
                 if (++acc == 2) { acc = 0; accph ^= 1; }
                 if (++cst == CS_STAGES) { cst = 0; cph ^= 1; }
             }
             if (MODE == MODE_POOL) {
-                // flat patch: OpenCV's map is all ones -> min == max == 1 -> NaN slice downstream
-                prm.rowmin[prow] = NORMED ? (flat1 ? 1.0f : fminf(fmaxf(__fmul_rn(rmin, s1.y), -1.0f), 1.0f)) : rmin;
-                prm.rowmax[prow] = (NORMED && flat1) ? 1.0f : rmax;
+                // partial min / max of this column half; flat patch: OpenCV's map is all ones
+                prm.rowmin[2 * prowA + ch] = NORMED ? (flatA ? 1.0f : fminf(fmaxf(__fmul_rn(rminA, s1A.y), -1.0f), 1.0f)) : rminA;
+                prm.rowmax[2 * prowA + ch] = (NORMED && flatA) ? 1.0f : rmaxA;
+                prm.rowmin[2 * prowB + ch] = NORMED ? (flatB ? 1.0f : fminf(fmaxf(__fmul_rn(rminB, s1B.y), -1.0f), 1.0f)) : rminB;
+                prm.rowmax[2 * prowB + ch] = (NORMED && flatB) ? 1.0f : rmaxB;
             }
-            if (MODE == MODE_NULL && rmax == 12345.678f) prm.raw[prow] = rmax;     // keep the loads alive
+            if (MODE == MODE_NULL && rmaxA == 12345.678f) prm.raw[prowA] = rmaxA;     // keep the loads alive
         }
     }
 

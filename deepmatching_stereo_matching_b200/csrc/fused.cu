@@ -45,8 +45,8 @@ size_t carve(char* base, int nt, int t0, int t1, int kpad, int levels, FusedBuff
     fb.stat1 = c.take<float>((size_t)nt * P * DM_STAT_FLOATS);
     fb.stat2 = c.take<float>((size_t)nt * P * DM_STAT_FLOATS);
     fb.pooled = c.take<float>((size_t)nt * P * (P / 4));
-    fb.rowmin = c.take<float>((size_t)nt * P);
-    fb.rowmax = c.take<float>((size_t)nt * P);
+    fb.rowmin = c.take<float>((size_t)nt * P * 2);      // partial min / max of the two column halves
+    fb.rowmax = c.take<float>((size_t)nt * P * 2);
     size_t a = t0 >> 1, b = t1 >> 1;
     fb.level[0] = nullptr;
     for (int k = 1; k < levels; ++k) {
@@ -92,7 +92,9 @@ dm_aggregate_first_kernel(const float* __restrict__ pooled, const float* __restr
 #pragma unroll
     for (int ch = 0; ch < 4; ++ch) {
         const size_t p = n * P + (size_t)(2 * I + (ch >> 1)) * t1 + (2 * J + (ch & 1));
-        mn[ch] = __ldg(rowmin + p); mx[ch] = __ldg(rowmax + p); rinv[ch] = dm_range_inv(mn[ch], mx[ch]);
+        mn[ch] = dm_min_nan(__ldg(rowmin + 2 * p), __ldg(rowmin + 2 * p + 1));
+        mx[ch] = dm_max_nan(__ldg(rowmax + 2 * p), __ldg(rowmax + 2 * p + 1));
+        rinv[ch] = dm_range_inv(mn[ch], mx[ch]);
         src[ch] = reinterpret_cast<const float4*>(pooled + p * (size_t)(P / 4));
     }
     float4* dst = reinterpret_cast<float4*>(out) + (size_t)par * Q4;
@@ -172,7 +174,8 @@ dm_final_quad_kernel(const FinalArgs a, long long n_quads) {
 
     const dm_stat s1 = a.stat1[(size_t)n * P + p];
     const bool flat1 = (s1.y == 0.0f);
-    const float mn = a.rowmin[(size_t)n * P + p], mx = a.rowmax[(size_t)n * P + p], rinv = dm_range_inv(mn, mx);
+    const size_t rp = 2 * ((size_t)n * P + p);
+    const float mn = dm_min_nan(a.rowmin[rp], a.rowmin[rp + 1]), mx = dm_max_nan(a.rowmax[rp], a.rowmax[rp + 1]), rinv = dm_range_inv(mn, mx);
     const dm_stat* st2 = a.stat2 + (size_t)n * P;
     const int m1 = (int)s1.w, S1 = (int)s1.x;
 

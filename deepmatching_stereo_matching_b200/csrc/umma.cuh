@@ -107,6 +107,16 @@ __device__ __forceinline__ void tmem_ld_32x16_issue(uint32_t taddr, float (&v)[1
         : "r"(taddr) : "memory");
 }
 
+__device__ __forceinline__ void tmem_ld_32x8_issue(uint32_t taddr, float (&v)[8]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+        : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7])
+        : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_32x1_issue(uint32_t taddr, float& v) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=f"(v) : "r"(taddr) : "memory");
+}
+
 // 16-byte shared load pinned in program order (volatile): keeps the software pipeline's
 // prefetches where they were written instead of letting the scheduler sink them to the use
 __device__ __forceinline__ float4 lds128(uint32_t saddr) {
