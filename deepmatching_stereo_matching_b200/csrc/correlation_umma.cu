@@ -216,12 +216,14 @@ dm_correlation_umma_kernel(const __grid_constant__ CUtensorMap mapA, const __gri
             // The 16 floats are SEGS contiguous segments, `segstride` floats apart in the output.
             auto flush16 = [&](const float* stg, float* wout, size_t col, int seg, size_t segstride) {
                 __syncwarp();
+                const int f4 = (lane & 3) * 4;
+                const uint32_t sa = umma::smem_u32(stg + (lane >> 2) * STG_STRIDE + f4);
+                float4 v[4];
 #pragma unroll
-                for (int it = 0; it < 4; ++it) {
-                    const int r = it * 8 + (lane >> 2), f4 = (lane & 3) * 4;
-                    const float4 v = *reinterpret_cast<const float4*>(stg + r * STG_STRIDE + f4);
-                    *reinterpret_cast<float4*>(wout + (size_t)r * ostride + col + (size_t)(f4 / seg) * segstride + (f4 % seg)) = v;
-                }
+                for (int it = 0; it < 4; ++it) v[it] = umma::lds128(sa + (uint32_t)(it * 8 * STG_STRIDE * 4));   // all four loads in flight
+                float* dst = wout + (size_t)(lane >> 2) * ostride + col + (size_t)(f4 / seg) * segstride + (f4 % seg);
+#pragma unroll
+                for (int it = 0; it < 4; ++it) *reinterpret_cast<float4*>(dst + (size_t)(it * 8) * ostride) = v[it];
                 __syncwarp();
             };
             for (int j = 0; j < NT; ++j) {
@@ -287,11 +289,6 @@ dm_correlation_umma_kernel(const __grid_constant__ CUtensorMap mapA, const __gri
                         umma::zncc_partial2(vA[i], vA[i + 1], ns1A, cp.x, cp.y, NORMED ? cp.z : 1.0f, NORMED ? cp.w : 1.0f);
                         umma::zncc_partial2(vB[i], vB[i + 1], ns1B, cp.x, cp.y, NORMED ? cp.z : 1.0f, NORMED ? cp.w : 1.0f);
                     }
-                    if (s + 1 == NSTEP) {                   // accumulator stage and column table consumed
-                        umma::tc_fence_before();
-                        __syncwarp();
-                        if (lane == 0) { umma::mbar_arrive(t_empty + acc); umma::mbar_arrive(c_empty + cst); }
-                    }
                     if (MODE == MODE_NULL) { rmaxA = fmaxf(rmaxA, vA[0] + vB[0]); continue; }
                     if (MODE == MODE_RAW) {
                         // D is fixed to 64 here: steps (2k, 2k+1) are 16 consecutive columns
@@ -351,6 +348,9 @@ dm_correlation_umma_kernel(const __grid_constant__ CUtensorMap mapA, const __gri
                         zprevA = vA[SW - 1]; zprevB = vB[SW - 1];
                     }
                 }
+                umma::tc_fence_before();
+                __syncwarp();
+                if (lane == 0) { umma::mbar_arrive(t_empty + acc); umma::mbar_arrive(c_empty + cst); }
                 if (++acc == 2) { acc = 0; accph ^= 1; }
                 if (++cst == CS_STAGES) { cst = 0; cph ^= 1; }
             }

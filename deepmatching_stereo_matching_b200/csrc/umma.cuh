@@ -121,7 +121,7 @@ __device__ __forceinline__ void tmem_ld_32x1_issue(uint32_t taddr, float& v) {
 // prefetches where they were written instead of letting the scheduler sink them to the use
 __device__ __forceinline__ float4 lds128(uint32_t saddr) {
     float4 v;
-    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(saddr));
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(saddr) : "memory");
     return v;
 }
 

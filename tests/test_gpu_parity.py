@@ -102,6 +102,45 @@ def test_tcgen05_correlation_bit_identical_to_simt(dm, t0, t1, ws, n):
     assert np.abs(raw[0].cpu().numpy() - ref).max() <= 1e-6
 
 
+@pytest.mark.parametrize('T,ws,n', [(32, 7, 6), (64, 5, 7), (32, 5, 20), (64, 15, 3)])
+def test_correlation_engines_are_repeatable(dm, T, ws, n):
+    """Race detector for the warp-specialised tcgen05 kernel: the same launch repeated 25 times
+    must produce identical bits (few work items per SM and a short K make the MMA, TMA and
+    epilogue pipelines run at very different speeds -- this caught an early TMEM-stage release)."""
+    import torch
+    from deepmatching_stereo_matching_b200 import _native
+    from deepmatching_stereo_matching_b200.synth import texture
+    lib = _native.lib()
+    e2 = ws - 1
+    H, W = T + e2 + 9, (T + e2) + 11 * (n - 1)
+    s1 = torch.from_numpy(texture((H, W), seed=31)).cuda()
+    s2 = torch.from_numpy(texture((H, W), seed=32, plain_noise=True)).cuda()
+    origin = torch.tensor([[k % 9, 11 * k] for k in range(n)], dtype=torch.int32, device='cuda')
+    P, kpad = T * T, lib.dm_kpad(ws)
+    bufs = []
+    for sc in (s1, s2):
+        desc = torch.empty((n * P, kpad), dtype=torch.bfloat16, device='cuda')
+        stat = torch.empty((n * P * 6,), dtype=torch.float32, device='cuda')
+        _native.check(lib.dm_descriptors(_native.ptr(sc), H, W, W, _native.ptr(origin), n, T, T, ws, _native.ptr(desc), _native.ptr(stat), _native.stream_ptr()))
+        bufs += [desc, stat]
+    ref = torch.empty((n * P * P,), dtype=torch.float32, device='cuda')
+    _native.check(lib.dm_correlation(*[_native.ptr(b) for b in bufs], n, P, kpad, ws, 5, _native.CORR_SIMT, _native.ptr(ref), _native.stream_ptr()))
+    for engine, size in ((_native.CORR_UMMA, n * P * P), (4, n * P * (P // 4) + 4 * n * P)):     # 4 = pooled epilogue (test aid)
+        first = None
+        for _ in range(25):
+            out = torch.full((size,), float('nan'), dtype=torch.float32, device='cuda')
+            _native.check(lib.dm_correlation(*[_native.ptr(b) for b in bufs], n, P, kpad, ws, 5, engine, _native.ptr(out), _native.stream_ptr()))
+            torch.cuda.synchronize()
+            cur = out.view(torch.int32)
+            if first is None:
+                first = cur.clone()
+                assert not torch.isnan(out).any()
+                if engine == _native.CORR_UMMA:
+                    assert torch.equal(cur, ref.view(torch.int32))
+            else:
+                assert torch.equal(cur, first)
+
+
 @pytest.mark.parametrize('name', TILE_CASES)
 def test_aggregate_kernel_given_reference_level(dm, name):
     import torch

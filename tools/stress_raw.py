@@ -1,0 +1,37 @@
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch
+from deepmatching_stereo_matching_b200 import _native
+from deepmatching_stereo_matching_b200.synth import texture
+lib = _native.lib()
+T, ws, n = 64, 5, 7
+e2 = ws - 1
+H, W = T + e2 + 9, (T + e2) + 11 * (n - 1)
+s1 = torch.from_numpy(texture((H, W), seed=31)).cuda(); s2 = torch.from_numpy(texture((H, W), seed=32, plain_noise=True)).cuda()
+origin = torch.tensor([[k % 9, 11 * k] for k in range(n)], dtype=torch.int32, device='cuda')
+P, kpad = T * T, lib.dm_kpad(ws)
+b = []
+for sc in (s1, s2):
+    desc = torch.zeros((n * P, kpad), dtype=torch.bfloat16, device='cuda'); stat = torch.zeros((n * P * 6,), dtype=torch.float32, device='cuda')
+    _native.check(lib.dm_descriptors(_native.ptr(sc), H, W, W, _native.ptr(origin), n, T, T, ws, _native.ptr(desc), _native.ptr(stat), _native.stream_ptr()))
+    b += [desc, stat]
+ref = torch.empty((n, P, P), dtype=torch.float32, device='cuda')
+_native.check(lib.dm_correlation(*[_native.ptr(x) for x in b], n, P, kpad, ws, 5, 1, _native.ptr(ref), _native.stream_ptr()))
+found = 0
+for r in range(200):
+    raw = torch.full((n, P, P), float('nan'), dtype=torch.float32, device='cuda')
+    _native.check(lib.dm_correlation(*[_native.ptr(x) for x in b], n, P, kpad, ws, 5, 2, _native.ptr(raw), _native.stream_ptr()))
+    torch.cuda.synchronize()
+    neq = (raw.view(torch.int32) != ref.view(torch.int32))
+    if neq.any():
+        idx = neq.nonzero()
+        print('run', r, 'bad elems', idx.shape[0], 'tiles', idx[:, 0].unique().tolist(), 'rows', idx[:, 1].min().item(), '..', idx[:, 1].max().item(),
+              'nrows', idx[:, 1].unique().numel(), 'cols', idx[:, 2].min().item(), '..', idx[:, 2].max().item(), 'ncols', idx[:, 2].unique().numel())
+        t, p, q = idx[0].tolist()
+        print('   sample', (t, p, q), 'got', raw[t, p, q].item(), 'ref', ref[t, p, q].item(), ' nan count', int(torch.isnan(raw).sum()))
+        # is the wrong value the right value of another column?
+        row_ref = ref[t, p]
+        print('   got value found in ref row at cols', (row_ref == raw[t, p, q]).nonzero().flatten().tolist()[:8])
+        found += 1
+        if found >= 5: break
+print('done', found)
