@@ -15,9 +15,9 @@
 //
 // Work item = 256 patches of one tile (two M=128 accumulator halves) x all P positions,
 // swept in N-tiles of 128 positions.  Persistent grid, one CTA per SM, 10 warps:
-//   warp 0      TMA producer   A (2 halves x KB boxes, once per item), B ring of STAGES,
+//   warp 0      TMA producer   A (2 halves x KB boxes, once per item), B ring of 3 stages,
 //                              and the N-tile's 1 KiB column table (bulk copy) into a
-//                              2-deep shared-memory ring
+//                              4-deep shared-memory ring
 //   warp 1      MMA issuer     tcgen05.mma cta_group::1 kind::f16, M=128 N=128 K=16;
 //                              TMEM: 2 halves x 2 accumulator stages x 128 columns = 512
 //   warps 2..9  epilogue       tcgen05.ld 32x32b.  A thread owns TWO patch rows -- TMEM lane l

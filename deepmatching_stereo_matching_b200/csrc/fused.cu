@@ -151,6 +151,7 @@ dm_final_quad_kernel(const FinalArgs a, long long n_quads) {
     constexpr int K = WS * WS;
     constexpr int RWQ = WS + 5;
     __shared__ __align__(16) uint8_t region_all[8][2][QROWS * QRS];
+    __shared__ __align__(16) uint8_t patch_all[8][2][16 * QRS];      // the quad's (ws+1)^2 block of image 1, two byte alignments
     const int lane = threadIdx.x & 31;
     uint8_t* reg0 = region_all[threadIdx.x >> 5][0];
     uint8_t* reg1 = region_all[threadIdx.x >> 5][1];
@@ -207,21 +208,39 @@ dm_final_quad_kernel(const FinalArgs a, long long n_quads) {
             for (int ry = 0; ry < RWQ; ++ry) reg1[ry * QRS + 31] = 0;
         }
     }
+    // ---- the four patches of the quad overlap in a (ws+1)^2 block of image 1: stage it with
+    // row-coalesced loads (copy 0: column x at byte x, copy 1: at byte x-1 for cj = 1)
+    {
+        uint8_t* pat0 = patch_all[threadIdx.x >> 5][0];
+        uint8_t* pat1 = patch_all[threadIdx.x >> 5][1];
+        const uint8_t* src = a.img1 + (size_t)(oy + 2 * I) * a.pitch + ox + 2 * J + (lane <= WS ? lane : 0);
+        uint8_t pv[WS + 1];
+#pragma unroll
+        for (int ry = 0; ry <= WS; ++ry) { pv[ry] = __ldg(src); src += a.pitch; }
+#pragma unroll
+        for (int ry = 0; ry <= WS; ++ry) {
+            const uint8_t v = (lane <= WS) ? pv[ry] : (uint8_t)0;
+            pat0[ry * QRS + lane] = v;
+            if (lane >= 1) pat1[ry * QRS + lane - 1] = v;
+        }
+    }
+    __syncwarp();
     // ---- this lane's patch rows ky = l and l + 8, 16 bytes each (zero beyond the window)
     uint32_t aw[2][4];
+    {
+        const uint8_t* patc = patch_all[threadIdx.x >> 5][cj];
+        // bytes >= WS of a row belong to the neighbouring child: masked out
+        constexpr uint32_t M0 = WS >= 4 ? 0xffffffffu : ((1u << (8 * WS)) - 1u);
+        constexpr uint32_t M1 = WS >= 8 ? 0xffffffffu : (WS <= 4 ? 0u : ((1u << (8 * (WS - 4))) - 1u));
+        constexpr uint32_t M2 = WS >= 12 ? 0xffffffffu : (WS <= 8 ? 0u : ((1u << (8 * (WS - 8))) - 1u));
+        constexpr uint32_t M3 = WS >= 16 ? 0xffffffffu : (WS <= 12 ? 0u : ((1u << (8 * (WS - 12))) - 1u));
 #pragma unroll
-    for (int r = 0; r < 2; ++r) {
-        const int ky = l + 8 * r;
-        const bool live = ky < WS;
-        const uint8_t* a_row = a.img1 + (size_t)(oy + i + (live ? ky : 0)) * a.pitch + ox + j;
-#pragma unroll
-        for (int q = 0; q < 4; ++q) aw[r][q] = 0;
-#pragma unroll
-        for (int u = 0; u < 16; ++u) {
-            if (u < WS) {
-                const uint32_t v = live ? (uint32_t)__ldg(a_row + u) : 0u;
-                aw[r][u >> 2] |= v << (8 * (u & 3));
-            }
+        for (int r = 0; r < 2; ++r) {
+            const int ky = l + 8 * r;
+            const bool live = ky < WS;
+            const uint4 w = *reinterpret_cast<const uint4*>(patc + (ci + (live ? ky : 0)) * QRS);
+            aw[r][0] = live ? (w.x & M0) : 0u; aw[r][1] = live ? (w.y & M1) : 0u;
+            aw[r][2] = live ? (w.z & M2) : 0u; aw[r][3] = live ? (w.w & M3) : 0u;
         }
     }
     __syncwarp();

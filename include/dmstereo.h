@@ -48,6 +48,11 @@ extern "C" {
 #define DM_CORR_AUTO          0   /* tcgen05 when the shape allows it, else SIMT   */
 #define DM_CORR_SIMT          1   /* CUDA-core exact reference kernel              */
 #define DM_CORR_UMMA          2   /* tcgen05.mma + TMEM + TMA (errors if unsupported) */
+/* test / measurement aids, not part of the drop-in surface:
+ *   3  tcgen05 MMAs + TMEM drain only (no epilogue math, nothing written): the MMA/TMA floor
+ *   4  tcgen05 with the pooled epilogue of the fused solver; raw_dev then receives
+ *      [n][P][P/4] pooled raw ZNCC, followed by [n][P][2] partial row minima and
+ *      [n][P][2] partial row maxima (square grids only)                                  */
 
 int         dm_version(void);
 const char* dm_last_error(void);
