@@ -295,6 +295,31 @@ def test_fused_path_equals_materialising_path(dm, shape, size, stride, ws, sub):
     assert np.mean(np.abs(s0 - s1) > 1e-5) <= 2e-4
 
 
+@pytest.mark.parametrize('size,stride,ws', [((32, 64), (30, 60), 5), ((64, 32), (64, 32), 7), ((16, 64), (12, 50), 3), ((8, 32), (8, 32), 5)])
+def test_fused_path_non_square_tiles(dm, size, stride, ws):
+    """Non-square patch grids (short side a power of two dividing the long side) on the fused
+    path vs the materialising path, and vs the oracle on one tile."""
+    from deepmatching_stereo_matching_b200.synth import stereo_pair
+    shape = (size[0] * 2 + stride[0] + ws + 9, size[1] * 2 + stride[1] + ws + 5)
+    i1, i2 = stereo_pair(shape, seed=17, mode='sine', amp=3)
+    res = []
+    for fused in (0, 1):
+        s = dm.ImageCutSolver(i1, i2, image_size=list(size), stride=list(stride), window_size=ws,
+                              degree_map_mode=['elevation', 'elevation2'], sub_pix=True)
+        s.log_flg = False
+        s.fused = fused
+        d, sc = s()
+        assert s.info.used_fused == fused
+        res.append((d, sc))
+    assert np.mean(np.abs(res[0][0] - res[1][0]) > 1e-4) <= 5e-4
+    assert np.mean(np.abs(res[0][1] - res[1][1]) > 1e-5) <= 5e-4
+    e2 = ws - 1
+    rd, rs = O.solve_tile(i1[:size[0] + e2, :size[1] + e2], i2[:size[0] + e2, :size[1] + e2], ws, ('elevation', 'elevation2'), True)
+    own0 = min(size[0], stride[0]); own1 = min(size[1], stride[1])      # pixels of tile (0,0) no later tile overwrites
+    got = res[1][0][:, :own0, :own1]
+    assert np.mean(np.abs(got - rd[:, :own0, :own1]) > 0.5) <= 2e-3
+
+
 def test_fused_path_flat_patch_nan(dm):
     """A flat patch poisons its ancestors with NaN in the reference; both GPU paths must
     put the NaNs in the same pixels."""
