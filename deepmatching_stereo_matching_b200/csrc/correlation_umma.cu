@@ -14,13 +14,14 @@
 //               reaches HBM.
 //
 // Work item = 256 patches of one tile (two M=128 accumulator halves) x all P positions,
-// swept in N-tiles of 128 positions.  Persistent grid, one CTA per SM, 10 warps:
+// swept in N-tiles of 128 positions.  Persistent grid, one CTA per SM, 12 warps in three
+// warpgroups (setmaxnreg gives the producer/MMA group 40 registers and the epilogue 232):
 //   warp 0      TMA producer   A (2 halves x KB boxes, once per item), B ring of 3 stages,
 //                              and the N-tile's 1 KiB column table (bulk copy) into a
 //                              4-deep shared-memory ring
 //   warp 1      MMA issuer     tcgen05.mma cta_group::1 kind::f16, M=128 N=128 K=16;
 //                              TMEM: 2 halves x 2 accumulator stages x 128 columns = 512
-//   warps 2..9  epilogue       tcgen05.ld 32x32b.  A thread owns TWO patch rows -- TMEM lane l
+//   warps 4..11 epilogue       tcgen05.ld 32x32b.  A thread owns TWO patch rows -- TMEM lane l
 //                              of both accumulator halves -- and one half of the columns
 //                              of every map row, so the 3x3 pooling, the running row
 //                              minimum and the halo row carried between N-tiles are
@@ -50,11 +51,12 @@ constexpr int STAGES = 3;
 constexpr int MAX_KB = 4;               // kpad <= 256
 constexpr int BOX_BYTES = BM * BK * 2;  // 16 KiB: one [128 rows x 64] bf16 box
 constexpr int EPI_WARPS = 8;
-constexpr int THREADS = 32 * (2 + EPI_WARPS);
+constexpr int FIRST_EPI_WARP = 4;        // warps 0..3 = warpgroup 0: TMA producer, MMA issuer, 2 idle
+constexpr int THREADS = 32 * (FIRST_EPI_WARP + EPI_WARPS);   // 3 warpgroups
 constexpr int TMEM_COLS = 512;
 constexpr int SW = 8;                   // columns per epilogue pipeline step (per accumulator half)
 constexpr int NSTEP = (BN / 2) / SW;    // a thread covers half of the N-tile's columns
-constexpr int STG_STRIDE = 20;          // floats per staged row (16 + 4 pad: conflict-free float4 rows)
+constexpr int STG_STRIDE = 16;          // floats per staged row; float4 slots XOR-swizzled by (row >> 1) & 3: conflict-free both ways
 constexpr int STG_BYTES = 2 * 32 * STG_STRIDE * 4;  // per epilogue warp: one region per accumulator half
 constexpr int CS_BYTES = (BN / 2) * 16; // column table of one N-tile: 64 x {sk0, sk1, inv0, inv1}
 constexpr int CS_STAGES = 4;
@@ -70,10 +72,10 @@ constexpr size_t SMEM_BYTES = 1024 /*align slack*/ + OFF_BAR + 256;
 struct Params {
     const dm_stat* stat1;       // [n*P] float4 {S', inv, S'/K, mean}
     const float4* cstat2;       // [n*P/2] {S'/K even, S'/K odd, inv even, inv odd} of image 2
-    int n_items, P, KB, items_per_tile;
+    int n_items, P, KB, ksteps, items_per_tile;
     float* raw;                 // MODE_RAW : [n][P][P]
     float* pooled;              // MODE_POOL: [n][P][P/4]
-    float* rowmin; float* rowmax;   // MODE_POOL: [n][P][2] partial min / max of the two column halves
+    float* rowmin; float* rowmax;   // MODE_POOL: [n][P][4] partial min / max: each column half writes its value twice (16-warp kernel: quarters)
 };
 
 enum { MODE_RAW = 0, MODE_POOL = 1, MODE_NULL = 2 };   // MODE_NULL: drain TMEM only (measurement aid)
@@ -99,7 +101,7 @@ dm_correlation_umma_kernel(const __grid_constant__ CUtensorMap mapA, const __gri
     uint64_t* c_empty = bars + 6 + 2 * STAGES + CS_STAGES;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 6 + 2 * STAGES + 2 * CS_STAGES);
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;   // provably warp-uniform
     const int P = prm.P, KB = prm.KB, NT = P / BN;
 
     if (threadIdx.x == 0) {
@@ -119,77 +121,95 @@ dm_correlation_umma_kernel(const __grid_constant__ CUtensorMap mapA, const __gri
     umma::tc_fence_before();
     __syncthreads();
     umma::tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
 
+    // register re-partitioning between the warpgroups (setmaxnreg): the producer / MMA
+    // warpgroup keeps 40 registers per thread, the two epilogue warpgroups get 232
+    if (warp < FIRST_EPI_WARP) {
+    umma::reg_dealloc<40>();
     if (warp == 0) {
-        // ------------------------------------------------------------ TMA producer
-        if (lane == 0) {
-            int bs = 0; uint32_t bph = 0, aph = 0; int cst = 0; uint32_t cph = 0;
-            for (int item = blockIdx.x; item < prm.n_items; item += gridDim.x) {
-                const int tile = item / prm.items_per_tile;
-                const int row0 = tile * P + (item - tile * prm.items_per_tile) * (HALVES * BM);
-                umma::mbar_wait(a_empty, aph ^ 1);
+        // ------------------------------------------------------------ TMA producer (converged warp, elected issue)
+        int bs = 0; uint32_t bph = 0, aph = 0; int cst = 0; uint32_t cph = 0;
+        for (int item = blockIdx.x; item < prm.n_items; item += gridDim.x) {
+            const int tile = item / prm.items_per_tile;
+            const int row0 = tile * P + (item - tile * prm.items_per_tile) * (HALVES * BM);
+            umma::mbar_wait(a_empty, aph ^ 1);
+            if (umma::elect_one()) {
                 umma::mbar_expect_tx(a_full, (uint32_t)(HALVES * KB * BOX_BYTES));
                 for (int h = 0; h < HALVES; ++h)
                     for (int kb = 0; kb < KB; ++kb)
                         umma::tma_load_2d(smemA + (size_t)(h * MAX_KB + kb) * BOX_BYTES, &mapA, kb * BK, row0 + h * BM, a_full);
-                aph ^= 1;
-                for (int j = 0; j < NT; ++j) {
-                    for (int kb = 0; kb < KB; ++kb) {
-                        umma::mbar_wait(b_empty + bs, bph ^ 1);
+            }
+            __syncwarp();
+            aph ^= 1;
+            for (int j = 0; j < NT; ++j) {
+                for (int kb = 0; kb < KB; ++kb) {
+                    umma::mbar_wait(b_empty + bs, bph ^ 1);
+                    if (umma::elect_one()) {
                         umma::mbar_expect_tx(b_full + bs, (uint32_t)BOX_BYTES);
                         umma::tma_load_2d(smemB + (size_t)bs * BOX_BYTES, &mapB, kb * BK, tile * P + j * BN, b_full + bs);
-                        if (++bs == STAGES) { bs = 0; bph ^= 1; }
                     }
-                    // column table of this N-tile (needed only by the epilogue, after the MMAs)
-                    umma::mbar_wait(c_empty + cst, cph ^ 1);
+                    __syncwarp();
+                    if (++bs == STAGES) { bs = 0; bph ^= 1; }
+                }
+                // column table of this N-tile (needed only by the epilogue, after the MMAs)
+                umma::mbar_wait(c_empty + cst, cph ^ 1);
+                if (umma::elect_one()) {
                     umma::mbar_expect_tx(c_full + cst, (uint32_t)CS_BYTES);
                     umma::bulk_g2s(smemCs + (size_t)cst * CS_BYTES, prm.cstat2 + ((size_t)tile * P + (size_t)j * BN) / 2, CS_BYTES, c_full + cst);
-                    if (++cst == CS_STAGES) { cst = 0; cph ^= 1; }
                 }
+                __syncwarp();
+                if (++cst == CS_STAGES) { cst = 0; cph ^= 1; }
             }
         }
     } else if (warp == 1) {
-        // ------------------------------------------------------------ MMA issuer
-        if (lane == 0) {
-            constexpr uint32_t idesc = umma::instr_desc_bf16(BM, BN);
-            int bs = 0; uint32_t bph = 0, aph = 0; int acc = 0; uint32_t accph = 0;
-            for (int item = blockIdx.x; item < prm.n_items; item += gridDim.x) {
-                umma::mbar_wait(a_full, aph);
-                aph ^= 1;
-                for (int j = 0; j < NT; ++j) {
-                    umma::mbar_wait(t_empty + acc, accph ^ 1);
+        // ------------------------------------------------------------ MMA issuer (converged warp, elected issue)
+        constexpr uint32_t idesc = umma::instr_desc_bf16(BM, BN);
+        constexpr int KPB = BK / UMMA_K;
+        int bs = 0; uint32_t bph = 0, aph = 0; int acc = 0; uint32_t accph = 0;
+        for (int item = blockIdx.x; item < prm.n_items; item += gridDim.x) {
+            umma::mbar_wait(a_full, aph);
+            aph ^= 1;
+            for (int j = 0; j < NT; ++j) {
+                umma::mbar_wait(t_empty + acc, accph ^ 1);
+                umma::tc_fence_after();
+                const uint32_t d0 = tmem_base + (uint32_t)(acc * BN);
+                for (int kb = 0; kb < KB; ++kb) {
+                    umma::mbar_wait(b_full + bs, bph);
                     umma::tc_fence_after();
-                    for (int kb = 0; kb < KB; ++kb) {
-                        umma::mbar_wait(b_full + bs, bph);
-                        umma::tc_fence_after();
-                        const uint64_t bdesc = umma::smem_desc_sw128(smemB + (size_t)bs * BOX_BYTES);
+                    const uint64_t bdesc = umma::smem_desc_sw128(smemB + (size_t)bs * BOX_BYTES);
+                    const uint64_t adesc0 = umma::smem_desc_sw128(smemA + (size_t)kb * BOX_BYTES);
+                    const int nk = prm.ksteps - kb * KPB;       // padding-only K steps are skipped
 #pragma unroll
-                        for (int h = 0; h < HALVES; ++h) {
-                            const uint64_t adesc = umma::smem_desc_sw128(smemA + (size_t)(h * MAX_KB + kb) * BOX_BYTES);
-                            const uint32_t d = tmem_base + (uint32_t)((h * 2 + acc) * BN);
+                    for (int k = 0; k < KPB; ++k) {             // +32 B per K step inside the swizzle atom
+                        if (k < nk) {
 #pragma unroll
-                            for (int k = 0; k < BK / UMMA_K; ++k)      // +32 B per K step inside the swizzle atom
-                                umma::mma_bf16(d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+                            for (int h = 0; h < HALVES; ++h)
+                                if (umma::elect_one())
+                                    umma::mma_bf16(d0 + (uint32_t)(h * 2 * BN), adesc0 + (uint64_t)(h * ((MAX_KB * BOX_BYTES) >> 4)) + 2 * k,
+                                                   bdesc + 2 * k, idesc, (kb | k) != 0);
                         }
-                        umma::mma_commit(b_empty + bs);                // frees the B stage when these MMAs retire
-                        if (++bs == STAGES) { bs = 0; bph ^= 1; }
                     }
-                    umma::mma_commit(t_full + acc);                    // accumulators of this N-tile complete
-                    if (++acc == 2) { acc = 0; accph ^= 1; }
+                    if (umma::elect_one()) umma::mma_commit(b_empty + bs);      // frees the B stage when these MMAs retire
+                    if (++bs == STAGES) { bs = 0; bph ^= 1; }
                 }
-                umma::mma_commit(a_empty);                             // A may be overwritten
+                if (umma::elect_one()) umma::mma_commit(t_full + acc);          // accumulators of this N-tile complete
+                if (++acc == 2) { acc = 0; accph ^= 1; }
             }
+            if (umma::elect_one()) umma::mma_commit(a_empty);                   // A may be overwritten
         }
+    }
     } else {
+        umma::reg_alloc<232>();
         // ------------------------------------------------------------ epilogue
-        const int e = warp - 2;
+        const int e = warp - FIRST_EPI_WARP;
         const int quarter = warp & 3;                   // TMEM lanes a warp may touch: 32*(warp_id % 4)..+31
         const int ch = e >> 2;                          // which half of every map row's columns
         constexpr int DH = D / 2;                       // columns of a map row handled by this thread
         constexpr int HWQ = (MODE == MODE_POOL) ? D / 4 : 1;    // pooled outputs per map row per thread
         float* stgA = smemStg + (size_t)e * (2 * 32 * STG_STRIDE);
         float* stgB = stgA + 32 * STG_STRIDE;
+        const int wsw = (lane >> 1) & 3;                // XOR swizzle of this lane's own staging row
         float4* stgA_mine = reinterpret_cast<float4*>(stgA + lane * STG_STRIDE);
         float4* stgB_mine = reinterpret_cast<float4*>(stgB + lane * STG_STRIDE);
         int acc = 0; uint32_t accph = 0; int cst = 0; uint32_t cph = 0;
@@ -217,7 +237,7 @@ dm_correlation_umma_kernel(const __grid_constant__ CUtensorMap mapA, const __gri
             auto flush16 = [&](const float* stg, float* wout, size_t col, int seg, size_t segstride) {
                 __syncwarp();
                 const int f4 = (lane & 3) * 4;
-                const uint32_t sa = umma::smem_u32(stg + (lane >> 2) * STG_STRIDE + f4);
+                const uint32_t sa = umma::smem_u32(stg + (lane >> 2) * STG_STRIDE + (((lane & 3) ^ ((lane >> 3) & 3)) << 2));
                 float4 v[4];
 #pragma unroll
                 for (int it = 0; it < 4; ++it) v[it] = umma::lds128(sa + (uint32_t)(it * 8 * STG_STRIDE * 4));   // all four loads in flight
@@ -298,8 +318,8 @@ dm_correlation_umma_kernel(const __grid_constant__ CUtensorMap mapA, const __gri
                             obA.z = dm_zncc_finish(vA[i + 2], s1A.y, flatA, NORMED); obA.w = dm_zncc_finish(vA[i + 3], s1A.y, flatA, NORMED);
                             obB.x = dm_zncc_finish(vB[i], s1B.y, flatB, NORMED); obB.y = dm_zncc_finish(vB[i + 1], s1B.y, flatB, NORMED);
                             obB.z = dm_zncc_finish(vB[i + 2], s1B.y, flatB, NORMED); obB.w = dm_zncc_finish(vB[i + 3], s1B.y, flatB, NORMED);
-                            stgA_mine[(s & 1) * 2 + (i >> 2)] = obA;
-                            stgB_mine[(s & 1) * 2 + (i >> 2)] = obB;
+                            stgA_mine[((s & 1) * 2 + (i >> 2)) ^ wsw] = obA;
+                            stgB_mine[((s & 1) * 2 + (i >> 2)) ^ wsw] = obB;
                         }
                         if (s & 1) {
                             const size_t col = (size_t)j * BN + step_col(s - 1);
@@ -334,7 +354,7 @@ dm_correlation_umma_kernel(const __grid_constant__ CUtensorMap mapA, const __gri
                                 const int ol = (D == 128) ? xh : (r >> 1) * HWQ + xh;
                                 if ((ol & 3) == 0) { obA.x = oA; obB.x = oB; } else if ((ol & 3) == 1) { obA.y = oA; obB.y = oB; }
                                 else if ((ol & 3) == 2) { obA.z = oA; obB.z = oB; } else { obA.w = oA; obB.w = oB; }
-                                if ((ol & 3) == 3) { stgA_mine[(ol & 15) >> 2] = obA; stgB_mine[(ol & 15) >> 2] = obB; }
+                                if ((ol & 3) == 3) { stgA_mine[((ol & 15) >> 2) ^ wsw] = obA; stgB_mine[((ol & 15) >> 2) ^ wsw] = obB; }
                                 if ((ol & 15) == 15) {
                                     // first pooled row / column of the group; segments of min(16, D/4) floats, one per pooled row
                                     constexpr int SEG = HWQ < 16 ? HWQ : 16;
@@ -356,13 +376,14 @@ dm_correlation_umma_kernel(const __grid_constant__ CUtensorMap mapA, const __gri
             }
             if (MODE == MODE_POOL) {
                 // partial min / max of this column half; flat patch: OpenCV's map is all ones
-                prm.rowmin[2 * prowA + ch] = NORMED ? (flatA ? 1.0f : fminf(fmaxf(__fmul_rn(rminA, s1A.y), -1.0f), 1.0f)) : rminA;
-                prm.rowmax[2 * prowA + ch] = (NORMED && flatA) ? 1.0f : rmaxA;
-                prm.rowmin[2 * prowB + ch] = NORMED ? (flatB ? 1.0f : fminf(fmaxf(__fmul_rn(rminB, s1B.y), -1.0f), 1.0f)) : rminB;
-                prm.rowmax[2 * prowB + ch] = (NORMED && flatB) ? 1.0f : rmaxB;
+                { const float v = NORMED ? (flatA ? 1.0f : fminf(fmaxf(__fmul_rn(rminA, s1A.y), -1.0f), 1.0f)) : rminA; prm.rowmin[4 * prowA + 2 * ch] = v; prm.rowmin[4 * prowA + 2 * ch + 1] = v; }
+                { const float v = (NORMED && flatA) ? 1.0f : rmaxA; prm.rowmax[4 * prowA + 2 * ch] = v; prm.rowmax[4 * prowA + 2 * ch + 1] = v; }
+                { const float v = NORMED ? (flatB ? 1.0f : fminf(fmaxf(__fmul_rn(rminB, s1B.y), -1.0f), 1.0f)) : rminB; prm.rowmin[4 * prowB + 2 * ch] = v; prm.rowmin[4 * prowB + 2 * ch + 1] = v; }
+                { const float v = (NORMED && flatB) ? 1.0f : rmaxB; prm.rowmax[4 * prowB + 2 * ch] = v; prm.rowmax[4 * prowB + 2 * ch + 1] = v; }
             }
             if (MODE == MODE_NULL && rmaxA == 12345.678f) prm.raw[prowA] = rmaxA;     // keep the loads alive
         }
+
     }
 
     umma::tc_fence_before();
@@ -431,7 +452,7 @@ bool dm_correlation_umma_pool_supported(int t0, int t1, int kpad) {
 }
 
 static int fill_params(Params& prm, CUtensorMap& mapA, CUtensorMap& mapB, const void* desc1, const float* stat1,
-                       const void* desc2, const float* stat2, int n_tiles, int p, int kpad) {
+                       const void* desc2, const float* stat2, int n_tiles, int p, int kpad, int kreal) {
     const uint64_t rows = (uint64_t)n_tiles * p;
     int rc = dm_make_desc_tensor_map(&mapA, desc1, rows, kpad, BM);
     if (rc != DM_OK) return rc;
@@ -440,15 +461,17 @@ static int fill_params(Params& prm, CUtensorMap& mapA, CUtensorMap& mapB, const 
     prm.stat1 = (const dm_stat*)stat1;
     prm.cstat2 = reinterpret_cast<const float4*>((const dm_stat*)stat2 + rows);
     prm.P = p; prm.KB = kpad / BK; prm.items_per_tile = p / (HALVES * BM);
+    prm.ksteps = (kreal + UMMA_K - 1) / UMMA_K;
+    if (prm.ksteps <= 0 || prm.ksteps > kpad / UMMA_K) prm.ksteps = kpad / UMMA_K;
     prm.n_items = n_tiles * prm.items_per_tile;
     prm.raw = prm.pooled = prm.rowmin = prm.rowmax = nullptr;
     return DM_OK;
 }
 
 int dm_correlation_umma(const void* desc1, const float* stat1, const void* desc2, const float* stat2,
-                        int n_tiles, int p, int kpad, int method, float* raw, cudaStream_t stream) {
+                        int n_tiles, int p, int kpad, int kreal, int method, float* raw, cudaStream_t stream) {
     Params prm; CUtensorMap mapA, mapB;
-    int rc = fill_params(prm, mapA, mapB, desc1, stat1, desc2, stat2, n_tiles, p, kpad);
+    int rc = fill_params(prm, mapA, mapB, desc1, stat1, desc2, stat2, n_tiles, p, kpad, kreal);
     if (rc != DM_OK) return rc;
     prm.raw = raw;
     return launch<MODE_RAW, 64>(mapA, mapB, prm, method == DM_TM_CCOEFF_NORMED, stream);
@@ -456,20 +479,31 @@ int dm_correlation_umma(const void* desc1, const float* stat1, const void* desc2
 
 // measurement aid (DM_CORR_UMMA_NULL): MMAs + TMEM drain, no epilogue math, no output
 int dm_correlation_umma_null(const void* desc1, const float* stat1, const void* desc2, const float* stat2,
-                             int n_tiles, int p, int kpad, float* raw, cudaStream_t stream) {
+                             int n_tiles, int p, int kpad, int kreal, float* raw, cudaStream_t stream) {
     Params prm; CUtensorMap mapA, mapB;
-    int rc = fill_params(prm, mapA, mapB, desc1, stat1, desc2, stat2, n_tiles, p, kpad);
+    int rc = fill_params(prm, mapA, mapB, desc1, stat1, desc2, stat2, n_tiles, p, kpad, kreal);
     if (rc != DM_OK) return rc;
     prm.raw = raw;
     return launch<MODE_NULL, 64>(mapA, mapB, prm, true, stream);
 }
 
+// engine: 0 = the 8-warp kernel of this file (fastest measured: 1.70 ms on the 1024^2 scene),
+// 1 = 16 epilogue warps, four-way column split (correlation_umma_p4.cu: 1.85 ms),
+// 2 = 8 warps with the patch block resident in TMEM (correlation_umma_ts.cu: 1.80 ms),
+// 3 = 16-warp kernel with a drain-only epilogue (measurement aid).  1..3 are kept as measured
+// design alternatives and are covered by the same bit-exactness tests.
 int dm_correlation_umma_pool(const void* desc1, const float* stat1, const void* desc2, const float* stat2,
-                             int n_tiles, int t0, int t1, int kpad, int method,
+                             int n_tiles, int t0, int t1, int kpad, int kreal, int method, int engine,
                              float* pooled, float* rowmin, float* rowmax, cudaStream_t stream) {
     DM_REQUIRE(dm_correlation_umma_pool_supported(t0, t1, kpad), DM_ERR_UNSUPPORTED, "pooled tcgen05 correlation: unsupported grid (%d,%d)", t0, t1);
+    if ((engine == 1 || engine == 3) && dm_correlation_p4_pool_supported(t0, t1, kpad))
+        return dm_correlation_p4_pool(desc1, stat1, desc2, stat2, n_tiles, t0, t1, kpad, kreal, method, engine == 3,
+                                      pooled, rowmin, rowmax, stream);
+    if (engine == 2 && dm_correlation_ts_pool_supported(t0, t1, kpad))
+        return dm_correlation_ts_pool(desc1, stat1, desc2, stat2, n_tiles, t0, t1, kpad, kreal, method, 0,
+                                      pooled, rowmin, rowmax, stream);
     Params prm; CUtensorMap mapA, mapB;
-    int rc = fill_params(prm, mapA, mapB, desc1, stat1, desc2, stat2, n_tiles, t0 * t1, kpad);
+    int rc = fill_params(prm, mapA, mapB, desc1, stat1, desc2, stat2, n_tiles, t0 * t1, kpad, kreal);
     if (rc != DM_OK) return rc;
     prm.pooled = pooled; prm.rowmin = rowmin; prm.rowmax = rowmax;
     const bool normed = method == DM_TM_CCOEFF_NORMED;

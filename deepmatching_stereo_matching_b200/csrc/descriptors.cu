@@ -14,6 +14,8 @@
 // images use the same order, the contraction does not care.
 static __host__ __device__ inline int dm_row_stride(int ws) { return ws <= 8 ? 8 : (ws <= 16 ? 16 : 32); }
 
+int dm_desc_kreal(int ws) { return ws * dm_row_stride(ws); }
+
 extern "C" int dm_kpad(int ws) {
     int k = ws * dm_row_stride(ws);
     return ((k + 63) / 64) * 64;       // multiple of 64 bf16 = one 128-byte swizzle row

@@ -13,6 +13,8 @@
 // (misc/Calc_difference.py:25-49) and the paste of misc/image_cut_solver.py:165-175.
 // HBM traffic per tile drops from ~2.1 * 4 P^2 bytes (write raw, read+write level 0, read
 // level 0) to ~0.6 * 4 P^2.
+#include <stdlib.h>
+
 #include "dm_common.cuh"
 #include "dm_internal.h"
 
@@ -45,8 +47,8 @@ size_t carve(char* base, int nt, int t0, int t1, int kpad, int levels, FusedBuff
     fb.stat1 = c.take<float>((size_t)nt * P * DM_STAT_FLOATS);
     fb.stat2 = c.take<float>((size_t)nt * P * DM_STAT_FLOATS);
     fb.pooled = c.take<float>((size_t)nt * P * (P / 4));
-    fb.rowmin = c.take<float>((size_t)nt * P * 2);      // partial min / max of the two column halves
-    fb.rowmax = c.take<float>((size_t)nt * P * 2);
+    fb.rowmin = c.take<float>((size_t)nt * P * 4);      // four partial min / max per patch (column quarters; the 2-way kernels duplicate)
+    fb.rowmax = c.take<float>((size_t)nt * P * 4);
     size_t a = t0 >> 1, b = t1 >> 1;
     fb.level[0] = nullptr;
     for (int k = 1; k < levels; ++k) {
@@ -92,8 +94,9 @@ dm_aggregate_first_kernel(const float* __restrict__ pooled, const float* __restr
 #pragma unroll
     for (int ch = 0; ch < 4; ++ch) {
         const size_t p = n * P + (size_t)(2 * I + (ch >> 1)) * t1 + (2 * J + (ch & 1));
-        mn[ch] = dm_min_nan(__ldg(rowmin + 2 * p), __ldg(rowmin + 2 * p + 1));
-        mx[ch] = dm_max_nan(__ldg(rowmax + 2 * p), __ldg(rowmax + 2 * p + 1));
+        const float4 pmn = __ldg(reinterpret_cast<const float4*>(rowmin) + p), pmx = __ldg(reinterpret_cast<const float4*>(rowmax) + p);
+        mn[ch] = dm_min_nan(dm_min_nan(pmn.x, pmn.y), dm_min_nan(pmn.z, pmn.w));
+        mx[ch] = dm_max_nan(dm_max_nan(pmx.x, pmx.y), dm_max_nan(pmx.z, pmx.w));
         rinv[ch] = dm_range_inv(mn[ch], mx[ch]);
         src[ch] = reinterpret_cast<const float4*>(pooled + p * (size_t)(P / 4));
     }
@@ -175,8 +178,9 @@ dm_final_quad_kernel(const FinalArgs a, long long n_quads) {
 
     const dm_stat s1 = a.stat1[(size_t)n * P + p];
     const bool flat1 = (s1.y == 0.0f);
-    const size_t rp = 2 * ((size_t)n * P + p);
-    const float mn = dm_min_nan(a.rowmin[rp], a.rowmin[rp + 1]), mx = dm_max_nan(a.rowmax[rp], a.rowmax[rp + 1]), rinv = dm_range_inv(mn, mx);
+    const float4 pmn = reinterpret_cast<const float4*>(a.rowmin)[(size_t)n * P + p], pmx = reinterpret_cast<const float4*>(a.rowmax)[(size_t)n * P + p];
+    const float mn = dm_min_nan(dm_min_nan(pmn.x, pmn.y), dm_min_nan(pmn.z, pmn.w));
+    const float mx = dm_max_nan(dm_max_nan(pmx.x, pmx.y), dm_max_nan(pmx.z, pmx.w)), rinv = dm_range_inv(mn, mx);
     const dm_stat* st2 = a.stat2 + (size_t)n * P;
     const int m1 = (int)s1.w, S1 = (int)s1.x;
 
@@ -432,8 +436,9 @@ int dm_fused_solve_chunk(dm_ctx* ctx, const dm_fused_args* a, int ck) {
     {
         StageTimer tm(ctx, DM_STAGE_CORRELATION);
         if ((rc = tm.begin(ck)) != DM_OK) return rc;
-        if ((rc = dm_correlation_umma_pool(fb.desc1, fb.stat1, fb.desc2, fb.stat2, nt, t0, t1, a->kpad, a->method,
-                                           fb.pooled, fb.rowmin, fb.rowmax, st)) != DM_OK) return rc;
+        static const int pool_engine = getenv("DM_POOL_ENGINE") ? atoi(getenv("DM_POOL_ENGINE")) : 0;   // measurement aid
+        if ((rc = dm_correlation_umma_pool(fb.desc1, fb.stat1, fb.desc2, fb.stat2, nt, t0, t1, a->kpad, dm_desc_kreal(a->ws), a->method,
+                                           pool_engine, fb.pooled, fb.rowmin, fb.rowmax, st)) != DM_OK) return rc;
         ctx->launches[DM_STAGE_CORRELATION] += 1;
         if ((rc = tm.end()) != DM_OK) return rc;
     }

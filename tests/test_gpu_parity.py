@@ -125,7 +125,9 @@ def test_correlation_engines_are_repeatable(dm, T, ws, n):
         bufs += [desc, stat]
     ref = torch.empty((n * P * P,), dtype=torch.float32, device='cuda')
     _native.check(lib.dm_correlation(*[_native.ptr(b) for b in bufs], n, P, kpad, ws, 5, _native.CORR_SIMT, _native.ptr(ref), _native.stream_ptr()))
-    for engine, size in ((_native.CORR_UMMA, n * P * P), (4, n * P * (P // 4) + 4 * n * P)):     # 4 = pooled epilogue (test aid)
+    # 4 / 5 / 6 = pooled epilogue (test aids): shipped 8-warp kernel / 16 epilogue warps / patch block in TMEM
+    psize = n * P * (P // 4) + 8 * n * P
+    for engine, size in ((_native.CORR_UMMA, n * P * P), (4, psize), (5, psize), (6, psize)):
         first = None
         for _ in range(25):
             out = torch.full((size,), float('nan'), dtype=torch.float32, device='cuda')
@@ -139,6 +141,48 @@ def test_correlation_engines_are_repeatable(dm, T, ws, n):
                     assert torch.equal(cur, ref.view(torch.int32))
             else:
                 assert torch.equal(cur, first)
+
+
+@pytest.mark.parametrize('T,ws,n', [(16, 5, 3), (32, 5, 5), (32, 15, 2), (64, 15, 3), (64, 3, 2), (128, 5, 1)])
+def test_pooled_epilogue_equals_maxpool_of_raw_zncc(dm, T, ws, n):
+    """The pooled tcgen05 epilogues (both kernels) against torch's max_pool2d(3, 2, 1) of the
+    SIMT engine's raw ZNCC: min-max, clamp and the row factor are monotone, so the pooled map,
+    the per-patch minimum and the per-patch maximum of the pooled map must agree bit for bit."""
+    import torch
+    from deepmatching_stereo_matching_b200 import _native
+    from deepmatching_stereo_matching_b200.synth import texture
+    lib = _native.lib()
+    e2 = ws - 1
+    H, W = T + e2 + 9, (T + e2) + 11 * (n - 1)
+    s1 = torch.from_numpy(texture((H, W), seed=41)).cuda()
+    s2 = torch.from_numpy(texture((H, W), seed=42, plain_noise=True)).cuda()
+    origin = torch.tensor([[k % 9, 11 * k] for k in range(n)], dtype=torch.int32, device='cuda')
+    P, kpad = T * T, lib.dm_kpad(ws)
+    bufs = []
+    for sc in (s1, s2):
+        desc = torch.empty((n * P, kpad), dtype=torch.bfloat16, device='cuda')
+        stat = torch.empty((n * P * 6,), dtype=torch.float32, device='cuda')
+        _native.check(lib.dm_descriptors(_native.ptr(sc), H, W, W, _native.ptr(origin), n, T, T, ws, _native.ptr(desc), _native.ptr(stat), _native.stream_ptr()))
+        bufs += [desc, stat]
+    for method in (_native.TM_CCOEFF_NORMED, _native.TM_CCOEFF):
+        raw = torch.empty((n * P, 1, T, T), dtype=torch.float32, device='cuda')
+        _native.check(lib.dm_correlation(*[_native.ptr(b) for b in bufs], n, P, kpad, ws, method, _native.CORR_SIMT, _native.ptr(raw), _native.stream_ptr()))
+        want = torch.nn.functional.max_pool2d(raw, 3, 2, 1).reshape(n * P, P // 4)
+        want_min = raw.reshape(n * P, P).min(dim=1).values
+        want_max = want.max(dim=1).values
+        for engine in (4, 5, 6):
+            if (engine == 6 and T > 64) or (engine == 5 and T < 32):
+                continue                    # the alternatives cover map rows of <= 64 / >= 32 positions
+            out = torch.full((n * P * (P // 4) + 8 * n * P,), float('nan'), dtype=torch.float32, device='cuda')
+            _native.check(lib.dm_correlation(*[_native.ptr(b) for b in bufs], n, P, kpad, ws, method, engine, _native.ptr(out), _native.stream_ptr()))
+            torch.cuda.synchronize()
+            pooled = out[:n * P * (P // 4)].reshape(n * P, P // 4)
+            rmin = out[n * P * (P // 4):n * P * (P // 4) + 4 * n * P].reshape(n * P, 4).min(dim=1).values
+            rmax = out[n * P * (P // 4) + 4 * n * P:].reshape(n * P, 4).max(dim=1).values
+            assert not torch.isnan(out).any()
+            assert torch.equal(pooled, want), 'engine %d method %d: %d of %d pooled values differ' % (engine, method, int((pooled != want).sum()), pooled.numel())
+            assert torch.equal(rmin, want_min)
+            assert torch.equal(rmax, want_max)
 
 
 @pytest.mark.parametrize('name', TILE_CASES)
