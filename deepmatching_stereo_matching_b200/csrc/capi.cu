@@ -44,14 +44,11 @@ extern "C" int dm_correlation(const void* desc1_dev, const float* stat1_dev,
         DM_REQUIRE(umma_ok, DM_ERR_UNSUPPORTED, "dm_correlation: unsupported shape");
         return dm_correlation_umma_null(desc1_dev, stat1_dev, desc2_dev, stat2_dev, n_tiles, p, kpad, kreal, raw_dev, st);
     }
-    if (engine >= 4 && engine <= 7) {
-        // undocumented test aids: pooled epilogue; raw_dev = [pooled n*P*P/4][rowmin n*P*4][rowmax n*P*4], square grid.
-        // 4 = the shipped 8-warp kernel, 5 = 16 epilogue warps, 6 = patch block resident in TMEM,
-        // 7 = 16-warp kernel with a drain-only epilogue
+    if (engine == 4) {      // undocumented test aid: pooled epilogue; raw_dev = [pooled n*P*P/4][rowmin n*P*4][rowmax n*P*4], square grid
         int t = 1; while (t * t < p) ++t;
         DM_REQUIRE(t * t == p && dm_correlation_umma_pool_supported(t, t, kpad), DM_ERR_UNSUPPORTED, "dm_correlation: unsupported shape for the pooled test engine");
         float* rmin = raw_dev + (size_t)n_tiles * p * (p / 4);
-        return dm_correlation_umma_pool(desc1_dev, stat1_dev, desc2_dev, stat2_dev, n_tiles, t, t, kpad, kreal, method, engine - 4, raw_dev, rmin, rmin + (size_t)n_tiles * p * 4, st);
+        return dm_correlation_umma_pool(desc1_dev, stat1_dev, desc2_dev, stat2_dev, n_tiles, t, t, kpad, kreal, method, 0, raw_dev, rmin, rmin + (size_t)n_tiles * p * 4, st);
     }
     if (engine == DM_CORR_UMMA) {
         DM_REQUIRE(umma_ok, DM_ERR_UNSUPPORTED, "dm_correlation: tcgen05 engine needs P %% 128 == 0 and kpad <= 256 (P=%d kpad=%d)", p, kpad);

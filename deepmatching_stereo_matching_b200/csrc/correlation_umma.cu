@@ -75,7 +75,7 @@ struct Params {
     int n_items, P, KB, ksteps, items_per_tile;
     float* raw;                 // MODE_RAW : [n][P][P]
     float* pooled;              // MODE_POOL: [n][P][P/4]
-    float* rowmin; float* rowmax;   // MODE_POOL: [n][P][4] partial min / max: each column half writes its value twice (16-warp kernel: quarters)
+    float* rowmin; float* rowmax;   // MODE_POOL: [n][P][4] partial min / max: each column half writes its value twice
 };
 
 enum { MODE_RAW = 0, MODE_POOL = 1, MODE_NULL = 2 };   // MODE_NULL: drain TMEM only (measurement aid)
@@ -487,21 +487,11 @@ int dm_correlation_umma_null(const void* desc1, const float* stat1, const void* 
     return launch<MODE_NULL, 64>(mapA, mapB, prm, true, stream);
 }
 
-// engine: 0 = the 8-warp kernel of this file (fastest measured: 1.70 ms on the 1024^2 scene),
-// 1 = 16 epilogue warps, four-way column split (correlation_umma_p4.cu: 1.85 ms),
-// 2 = 8 warps with the patch block resident in TMEM (correlation_umma_ts.cu: 1.80 ms),
-// 3 = 16-warp kernel with a drain-only epilogue (measurement aid).  1..3 are kept as measured
-// design alternatives and are covered by the same bit-exactness tests.
 int dm_correlation_umma_pool(const void* desc1, const float* stat1, const void* desc2, const float* stat2,
                              int n_tiles, int t0, int t1, int kpad, int kreal, int method, int engine,
                              float* pooled, float* rowmin, float* rowmax, cudaStream_t stream) {
     DM_REQUIRE(dm_correlation_umma_pool_supported(t0, t1, kpad), DM_ERR_UNSUPPORTED, "pooled tcgen05 correlation: unsupported grid (%d,%d)", t0, t1);
-    if ((engine == 1 || engine == 3) && dm_correlation_p4_pool_supported(t0, t1, kpad))
-        return dm_correlation_p4_pool(desc1, stat1, desc2, stat2, n_tiles, t0, t1, kpad, kreal, method, engine == 3,
-                                      pooled, rowmin, rowmax, stream);
-    if (engine == 2 && dm_correlation_ts_pool_supported(t0, t1, kpad))
-        return dm_correlation_ts_pool(desc1, stat1, desc2, stat2, n_tiles, t0, t1, kpad, kreal, method, 0,
-                                      pooled, rowmin, rowmax, stream);
+    (void)engine;
     Params prm; CUtensorMap mapA, mapB;
     int rc = fill_params(prm, mapA, mapB, desc1, stat1, desc2, stat2, n_tiles, t0 * t1, kpad, kreal);
     if (rc != DM_OK) return rc;

@@ -24,17 +24,6 @@ int dm_correlation_umma_pool(const void* desc1, const float* stat1, const void* 
                              int n_tiles, int t0, int t1, int kpad, int kreal, int method, int engine,
                              float* pooled, float* rowmin, float* rowmax, cudaStream_t stream);
 
-// same epilogue with the patch block resident in TMEM (correlation_umma_ts.cu); t1 in {16, 32, 64}.
-// kreal = used entries of a descriptor row (K steps that are pure padding are skipped)
-bool dm_correlation_ts_pool_supported(int t0, int t1, int kpad);
-int dm_correlation_ts_pool(const void* desc1, const float* stat1, const void* desc2, const float* stat2,
-                           int n_tiles, int t0, int t1, int kpad, int kreal, int method, int null_epilogue,
-                           float* pooled, float* rowmin, float* rowmax, cudaStream_t stream);
-// 16 epilogue warps, four-way column split (correlation_umma_p4.cu); t1 in {32, 64, 128}
-bool dm_correlation_p4_pool_supported(int t0, int t1, int kpad);
-int dm_correlation_p4_pool(const void* desc1, const float* stat1, const void* desc2, const float* stat2,
-                           int n_tiles, int t0, int t1, int kpad, int kreal, int method, int null_epilogue,
-                           float* pooled, float* rowmin, float* rowmax, cudaStream_t stream);
 int dm_desc_kreal(int ws);      // ws * row stride of the descriptor K layout (descriptors.cu)
 
 struct dm_ctx {

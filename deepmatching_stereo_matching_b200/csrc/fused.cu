@@ -436,9 +436,8 @@ int dm_fused_solve_chunk(dm_ctx* ctx, const dm_fused_args* a, int ck) {
     {
         StageTimer tm(ctx, DM_STAGE_CORRELATION);
         if ((rc = tm.begin(ck)) != DM_OK) return rc;
-        static const int pool_engine = getenv("DM_POOL_ENGINE") ? atoi(getenv("DM_POOL_ENGINE")) : 0;   // measurement aid
         if ((rc = dm_correlation_umma_pool(fb.desc1, fb.stat1, fb.desc2, fb.stat2, nt, t0, t1, a->kpad, dm_desc_kreal(a->ws), a->method,
-                                           pool_engine, fb.pooled, fb.rowmin, fb.rowmax, st)) != DM_OK) return rc;
+                                           0, fb.pooled, fb.rowmin, fb.rowmax, st)) != DM_OK) return rc;
         ctx->launches[DM_STAGE_CORRELATION] += 1;
         if ((rc = tm.end()) != DM_OK) return rc;
     }

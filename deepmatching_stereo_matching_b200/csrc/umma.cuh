@@ -100,22 +100,6 @@ __device__ __forceinline__ void tmem_ld_32x1_issue(uint32_t taddr, float& v) {
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=f"(v) : "r"(taddr) : "memory");
 }
 
-// tcgen05.st 32x32b: thread i of the warp writes 16 consecutive 32-bit columns of TMEM lane
-// (lane_base + i); complete after tmem_wait_st().
-__device__ __forceinline__ void tmem_st_32x16(uint32_t taddr, const uint32_t (&v)[16]) {
-    asm volatile(
-        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
-        ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]),
-          "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]) : "memory");
-}
-__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
-
-__device__ __forceinline__ uint4 lds128u(uint32_t saddr) {
-    uint4 v;
-    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(saddr) : "memory");
-    return v;
-}
-
 // 16-byte shared load pinned in program order (volatile): keeps the software pipeline's
 // prefetches where they were written instead of letting the scheduler sink them to the use
 __device__ __forceinline__ float4 lds128(uint32_t saddr) {
@@ -172,15 +156,6 @@ __device__ __forceinline__ void mma_bf16(uint32_t d_tmem, uint64_t a_desc, uint6
         "setp.ne.b32 p, %4, 0;\n\t"
         "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
         ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"((uint32_t)accumulate) : "memory");
-}
-// Same with the A operand resident in tensor memory: lane = row, 32-bit column c holds the
-// K entries 2c (low half) and 2c+1; one K = 16 step reads 8 columns.
-__device__ __forceinline__ void mma_bf16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, bool accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
-        ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"((uint32_t)accumulate) : "memory");
 }
 // mbarrier arrive once all MMAs issued so far by this thread have completed
 // (implies tcgen05.fence::before_thread_sync)

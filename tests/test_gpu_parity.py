@@ -125,9 +125,9 @@ def test_correlation_engines_are_repeatable(dm, T, ws, n):
         bufs += [desc, stat]
     ref = torch.empty((n * P * P,), dtype=torch.float32, device='cuda')
     _native.check(lib.dm_correlation(*[_native.ptr(b) for b in bufs], n, P, kpad, ws, 5, _native.CORR_SIMT, _native.ptr(ref), _native.stream_ptr()))
-    # 4 / 5 / 6 = pooled epilogue (test aids): shipped 8-warp kernel / 16 epilogue warps / patch block in TMEM
+    # 4 = pooled epilogue (test aid)
     psize = n * P * (P // 4) + 8 * n * P
-    for engine, size in ((_native.CORR_UMMA, n * P * P), (4, psize), (5, psize), (6, psize)):
+    for engine, size in ((_native.CORR_UMMA, n * P * P), (4, psize)):
         first = None
         for _ in range(25):
             out = torch.full((size,), float('nan'), dtype=torch.float32, device='cuda')
@@ -145,7 +145,7 @@ def test_correlation_engines_are_repeatable(dm, T, ws, n):
 
 @pytest.mark.parametrize('T,ws,n', [(16, 5, 3), (32, 5, 5), (32, 15, 2), (64, 15, 3), (64, 3, 2), (128, 5, 1)])
 def test_pooled_epilogue_equals_maxpool_of_raw_zncc(dm, T, ws, n):
-    """The pooled tcgen05 epilogues (both kernels) against torch's max_pool2d(3, 2, 1) of the
+    """The pooled tcgen05 epilogue against torch's max_pool2d(3, 2, 1) of the
     SIMT engine's raw ZNCC: min-max, clamp and the row factor are monotone, so the pooled map,
     the per-patch minimum and the per-patch maximum of the pooled map must agree bit for bit."""
     import torch
@@ -170,9 +170,7 @@ def test_pooled_epilogue_equals_maxpool_of_raw_zncc(dm, T, ws, n):
         want = torch.nn.functional.max_pool2d(raw, 3, 2, 1).reshape(n * P, P // 4)
         want_min = raw.reshape(n * P, P).min(dim=1).values
         want_max = want.max(dim=1).values
-        for engine in (4, 5, 6):
-            if (engine == 6 and T > 64) or (engine == 5 and T < 32):
-                continue                    # the alternatives cover map rows of <= 64 / >= 32 positions
+        for engine in (4,):
             out = torch.full((n * P * (P // 4) + 8 * n * P,), float('nan'), dtype=torch.float32, device='cuda')
             _native.check(lib.dm_correlation(*[_native.ptr(b) for b in bufs], n, P, kpad, ws, method, engine, _native.ptr(out), _native.stream_ptr()))
             torch.cuda.synchronize()

@@ -7,7 +7,7 @@ from deepmatching_stereo_matching_b200.synth import texture
 
 lib = _native.lib()
 t0 = t1 = 64; ws = 15; n = int(sys.argv[1]) if len(sys.argv) > 1 else 225
-engines = [int(x) for x in sys.argv[2].split(',')] if len(sys.argv) > 2 else [4, 5]
+engines = [int(x) for x in sys.argv[2].split(',')] if len(sys.argv) > 2 else [4]
 P, kpad = t0 * t1, lib.dm_kpad(ws)
 H = W = 1024
 s1 = torch.from_numpy(texture((H, W), seed=1)).cuda(); s2 = torch.from_numpy(texture((H, W), seed=2)).cuda()

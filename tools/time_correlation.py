@@ -19,7 +19,7 @@ for sc in (s1, s2):
     bufs += [desc, stat]
 raw = torch.empty((n, P, P), dtype=torch.float32, device='cuda')
 flops = 2.0 * ws * ws * P * P * n
-for name, engine in (('umma_raw', 2), ('umma_null', 3), ('pool_ss8', 4), ('pool_p4', 5), ('pool_ts8', 6), ('p4_null', 7)):
+for name, engine in (('umma_raw', 2), ('umma_null', 3), ('pool', 4)):
     if os.environ.get('DM_ONLY_POOL'): break
     for _ in range(3):
         _native.check(lib.dm_correlation(*[_native.ptr(b) for b in bufs], n, P, kpad, ws, 5, engine, _native.ptr(raw), _native.stream_ptr()))
