@@ -93,9 +93,20 @@ class Matching():
         return map_here
 
     def _filter_device(self, match, score, torch):
+        """One application of Matching._filter (misc/Matching.py:91-93,136-138): dm_match_filter
+        on square maps (where the reference's filter is defined); the literal host restatement
+        otherwise, with the reference's own behaviour there."""
+        self.filtering_num -= 1
+        _, h, w = match.shape
+        if not (h >= self.filter_window_size and w >= self.filter_window_size):
+            return match
+        if h == w and 0 <= (self.filter_window_size - 1) // 2 <= 4:
+            out = torch.empty_like(match)
+            _native.check(_native.lib().dm_match_filter(_native.ptr(match), 1, h, w, int(self.filter_window_size),
+                                                        _native.FILTER_IDS[self.filtering_mode], _native.ptr(out), _native.stream_ptr()))
+            return out
         mp = np.concatenate([match.cpu().numpy().astype(np.float64), score.cpu().numpy().astype(np.float64)[None]], 0)
         mp = self._filter(mp)
-        self.filtering_num -= 1
         return torch.from_numpy(np.ascontiguousarray(mp[:2]).astype(np.int32)).cuda()
 
     # ------------------------------------------------------------------ reference API

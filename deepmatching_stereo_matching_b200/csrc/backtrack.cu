@@ -1,7 +1,8 @@
 // Top-down backtracking and the level-0 parabola refinement.
 // Replaces Matching._calc_near_match (misc/Matching.py:58-78), _initial_move_map
-// (:80-96), _B (:98-139, filtering off), _sub_pix_compute/_sub_pix_cal (:165-209) and the
-// assembly of the (3,T0,T1) float64 result (:211-222).
+// (:80-96), _B (:98-139), the displacement filter _filter (:224-255),
+// _sub_pix_compute/_sub_pix_cal (:165-209) and the assembly of the (3,T0,T1) float64 result
+// (:211-222).
 //
 // Index results are bit-exact with the reference given the same level data: only
 // comparisons and one addition are involved, and the kernels are instantiated for both
@@ -89,17 +90,22 @@ dm_match_map_kernel(const T* __restrict__ l0, long long total, int T0, int T1,
     const int c0 = match[(size_t)n * 2 * P + p];
     const int c1 = match[(size_t)n * 2 * P + P + p];
     double m0 = (double)c0, m1 = (double)c1;
-    if (sub_pix) {
+    // numpy index rules (misc/Matching.py:186-208): -size <= index < size is accepted and a
+    // negative one wraps; anything else raises IndexError, which the reference swallows ->
+    // that axis stays unrefined.  Matches only leave the map when the displacement filter
+    // ran on level 0.
+    if (sub_pix && dm_np_index_ok(c0, T0) && dm_np_index_ok(c1, T1)) {
         const T* map = l0 + ((size_t)n * P + p) * (size_t)P;    // (C,D) = (T0,T1)
-        const T r0 = map[(size_t)c0 * T1 + c1];
-        if (c0 + 1 < T0) {                                      // else IndexError swallowed (:196)
-            const T r1 = map[(size_t)(c0 + 1) * T1 + c1];
-            const T rm = map[(size_t)(c0 == 0 ? T0 - 1 : c0 - 1) * T1 + c1];   // index -1 wraps
+        const int w0 = dm_np_wrap(c0, T0), w1 = dm_np_wrap(c1, T1);
+        const T r0 = map[(size_t)w0 * T1 + w1];
+        if (dm_np_index_ok(c0 + 1, T0) && dm_np_index_ok(c0 - 1, T0)) {
+            const T r1 = map[(size_t)dm_np_wrap(c0 + 1, T0) * T1 + w1];
+            const T rm = map[(size_t)dm_np_wrap(c0 - 1, T0) * T1 + w1];
             m0 += (double)sub_pix_fit<T>(r0, r1, rm);
         }
-        if (c1 + 1 < T1) {
-            const T r1 = map[(size_t)c0 * T1 + c1 + 1];
-            const T rm = map[(size_t)c0 * T1 + (c1 == 0 ? T1 - 1 : c1 - 1)];
+        if (dm_np_index_ok(c1 + 1, T1) && dm_np_index_ok(c1 - 1, T1)) {
+            const T r1 = map[(size_t)w0 * T1 + dm_np_wrap(c1 + 1, T1)];
+            const T rm = map[(size_t)w0 * T1 + dm_np_wrap(c1 - 1, T1)];
             m1 += (double)sub_pix_fit<T>(r0, r1, rm);
         }
     }
@@ -107,6 +113,56 @@ dm_match_map_kernel(const T* __restrict__ l0, long long total, int T0, int T1,
     o[p] = m0;
     o[P + p] = m1;
     o[2 * P + p] = (double)score[(size_t)n * P + p];
+}
+
+// misc/Matching.py:224-255 (_filter): every interior cell of the (h,w) displacement field is
+// replaced by round(mean | median of its (2e+1)^2 neighbourhood) + its own coordinate.  The
+// neighbourhood is read from the unfiltered field (the reference snapshots it in d_map),
+// Python's round() is half-to-even (rint), the median of an odd count is its middle element.
+// Border cells are copied.  in / out: int32 [n][2][H][W].
+constexpr int DM_FILTER_MAX_E = 4;      // windows up to 9 x 9
+__global__ void __launch_bounds__(256)
+dm_match_filter_kernel(const int32_t* __restrict__ in, long long total, int H, int W, int e, int mode, int32_t* __restrict__ out) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const int j = (int)(idx % W);
+    const long long t = idx / W;
+    const int i = (int)(t % H);
+    const long long n = t / H;
+    const size_t HW = (size_t)H * W, base = (size_t)n * 2 * HW, cell = (size_t)i * W + j;
+    const int32_t* rowp = in + base;        // matched row of every cell
+    const int32_t* colp = in + base + HW;   // matched column
+    int o0 = rowp[cell], o1 = colp[cell];
+    if (i >= e && i < H - e && j >= e && j < W - e) {
+        const int k = 2 * e + 1, cnt = k * k;
+        if (mode == DM_FILTER_AVERAGE) {
+            long long s0 = 0, s1 = 0;
+            for (int y = i - e; y <= i + e; ++y)
+                for (int x = j - e; x <= j + e; ++x) { s0 += rowp[(size_t)y * W + x] - y; s1 += colp[(size_t)y * W + x] - x; }
+            o0 = (int)rint(__ddiv_rn((double)s0, (double)cnt)) + i;     // np.mean = sum / count in float64, then round()
+            o1 = (int)rint(__ddiv_rn((double)s1, (double)cnt)) + j;
+        } else {
+            int v0[(2 * DM_FILTER_MAX_E + 1) * (2 * DM_FILTER_MAX_E + 1)], v1[(2 * DM_FILTER_MAX_E + 1) * (2 * DM_FILTER_MAX_E + 1)];
+            int m = 0;
+            for (int y = i - e; y <= i + e; ++y)
+                for (int x = j - e; x <= j + e; ++x) { v0[m] = rowp[(size_t)y * W + x] - y; v1[m] = colp[(size_t)y * W + x] - x; ++m; }
+            // middle element by rank counting (cnt is odd): the value with <= cnt/2 smaller and > cnt/2 smaller-or-equal
+            const int half = cnt / 2;
+            int med0 = v0[0], med1 = v1[0];
+            for (int a = 0; a < cnt; ++a) {
+                int lt0 = 0, le0 = 0, lt1 = 0, le1 = 0;
+                for (int b = 0; b < cnt; ++b) {
+                    lt0 += v0[b] < v0[a]; le0 += v0[b] <= v0[a];
+                    lt1 += v1[b] < v1[a]; le1 += v1[b] <= v1[a];
+                }
+                if (lt0 <= half && le0 > half) med0 = v0[a];
+                if (lt1 <= half && le1 > half) med1 = v1[a];
+            }
+            o0 = med0 + i; o1 = med1 + j;
+        }
+    }
+    out[base + cell] = o0;
+    out[base + HW + cell] = o1;
 }
 
 // misc/Calc_difference.py:25-49
@@ -174,6 +230,25 @@ extern "C" int dm_backtrack_level(const void* level_dev, int is_f64, int n, int 
     DM_REQUIRE(parent_match_dev != nullptr, DM_ERR_INVALID, "dm_backtrack_level: parent matches missing");
     return is_f64 ? backtrack_launch<double>(level_dev, n, a, b, c, d, parent_match_dev, match_dev, score_dev, (cudaStream_t)stream)
                   : backtrack_launch<float>(level_dev, n, a, b, c, d, parent_match_dev, match_dev, score_dev, (cudaStream_t)stream);
+}
+
+extern "C" int dm_match_filter(const int32_t* match_in_dev, int n, int h, int w, int window, int mode,
+                               int32_t* match_out_dev, void* stream) {
+    DM_REQUIRE(n > 0 && h > 0 && w > 0 && window >= 1, DM_ERR_INVALID, "dm_match_filter: bad shape");
+    DM_REQUIRE(mode == DM_FILTER_MEDIAN || mode == DM_FILTER_AVERAGE, DM_ERR_INVALID, "dm_match_filter: invalid mode %d", mode);
+    DM_REQUIRE(match_in_dev != match_out_dev, DM_ERR_INVALID, "dm_match_filter: in-place filtering is not possible");
+    cudaStream_t st = (cudaStream_t)stream;
+    const long long total = (long long)n * h * w;
+    if (!(h >= window && w >= window)) {        // misc/Matching.py:230: smaller maps pass through
+        DM_CUDA_CHECK(cudaMemcpyAsync(match_out_dev, match_in_dev, (size_t)total * 2 * sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
+        return DM_OK;
+    }
+    DM_REQUIRE(h == w, DM_ERR_UNSUPPORTED, "dm_match_filter: Matching._filter sizes its snapshot (shape[1], shape[1]) and is undefined on non-square maps (%d x %d)", h, w);
+    const int e = (window - 1) / 2;
+    DM_REQUIRE(e <= DM_FILTER_MAX_E, DM_ERR_UNSUPPORTED, "dm_match_filter: filter windows up to %d are supported (got %d)", 2 * DM_FILTER_MAX_E + 1, window);
+    dm_match_filter_kernel<<<dm_div_up(total, 256), 256, 0, st>>>(match_in_dev, total, h, w, e, mode, match_out_dev);
+    DM_LAUNCH_CHECK();
+    return DM_OK;
 }
 
 extern "C" int dm_match_map(const void* level0_dev, int is_f64, int n, int t0, int t1,

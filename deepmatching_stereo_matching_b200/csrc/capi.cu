@@ -203,17 +203,20 @@ dm_planes_kernel(const float* __restrict__ l0, long long total, PlaneArgs a,
     const int c0 = match[(size_t)n * 2 * P + p];
     const int c1 = match[(size_t)n * 2 * P + P + p];
     double m0 = (double)c0, m1 = (double)c1;
-    if (a.sub_pix) {
+    // numpy index rules as in dm_match_map_kernel (backtrack.cu): negative indices wrap, an
+    // index >= size is the reference's swallowed IndexError (only reachable after a level-0 filter)
+    if (a.sub_pix && dm_np_index_ok(c0, a.T0) && dm_np_index_ok(c1, a.T1)) {
         const float* map = l0 + ((size_t)n * P + p) * (size_t)P;
-        const float r0 = map[(size_t)c0 * a.T1 + c1];
-        if (c0 + 1 < a.T0) {
-            const float r1 = map[(size_t)(c0 + 1) * a.T1 + c1];
-            const float rm = map[(size_t)(c0 == 0 ? a.T0 - 1 : c0 - 1) * a.T1 + c1];
+        const int w0 = dm_np_wrap(c0, a.T0), w1 = dm_np_wrap(c1, a.T1);
+        const float r0 = map[(size_t)w0 * a.T1 + w1];
+        if (dm_np_index_ok(c0 + 1, a.T0) && dm_np_index_ok(c0 - 1, a.T0)) {
+            const float r1 = map[(size_t)dm_np_wrap(c0 + 1, a.T0) * a.T1 + w1];
+            const float rm = map[(size_t)dm_np_wrap(c0 - 1, a.T0) * a.T1 + w1];
             if (r0 > r1 && r0 > rm) m0 += (double)(-(r1 - rm) / (2.0f * (r1 + rm - 2.0f * r0)));
         }
-        if (c1 + 1 < a.T1) {
-            const float r1 = map[(size_t)c0 * a.T1 + c1 + 1];
-            const float rm = map[(size_t)c0 * a.T1 + (c1 == 0 ? a.T1 - 1 : c1 - 1)];
+        if (dm_np_index_ok(c1 + 1, a.T1) && dm_np_index_ok(c1 - 1, a.T1)) {
+            const float r1 = map[(size_t)w0 * a.T1 + dm_np_wrap(c1 + 1, a.T1)];
+            const float rm = map[(size_t)w0 * a.T1 + dm_np_wrap(c1 - 1, a.T1)];
             if (r0 > r1 && r0 > rm) m1 += (double)(-(r1 - rm) / (2.0f * (r1 + rm - 2.0f * r0)));
         }
     }
@@ -283,7 +286,16 @@ extern "C" int dm_solve_scene(dm_ctx* ctx, const dm_scene_params* prm,
 
     const int ns = prm->n_scenes > 1 ? prm->n_scenes : 1;
     const bool want_fused = prm->fused != 0;
-    const bool fused = want_fused && dm_fused_supported(t0, t1, kpad) && dm_fused_supported_ws(prm->ws);
+    // displacement filter (misc/Matching.py:224-255): the first filter_num maps of the top-down
+    // pass; when it reaches level 0 (filter_num >= levels) the materialising path runs, because
+    // the fused final kernel produces the planes straight from the level-1 matches
+    const int filter_num = prm->filter_num > 0 ? prm->filter_num : 0;
+    const int filter_win = prm->filter_cfg & 0xff, filter_mode = (prm->filter_cfg >> 8) & 0xff;
+    DM_REQUIRE(filter_num == 0 || (filter_win >= 1 && (filter_mode == DM_FILTER_MEDIAN || filter_mode == DM_FILTER_AVERAGE)),
+               DM_ERR_INVALID, "dm_solve_scene: bad filter configuration 0x%x", prm->filter_cfg);
+    DM_REQUIRE(filter_num == 0 || t0 == t1 || (t0 < filter_win || t1 < filter_win), DM_ERR_UNSUPPORTED,
+               "Matching._filter is undefined on non-square patch grids (%d x %d)", t0, t1);
+    const bool fused = want_fused && dm_fused_supported(t0, t1, kpad) && dm_fused_supported_ws(prm->ws) && filter_num < L;
     DM_REQUIRE(!(prm->fused == 1 && !fused), DM_ERR_UNSUPPORTED, "fused path does not support image_size (%d,%d) with window %d", t0, t1, prm->ws);
 
     // tiles per chunk from the workspace limit
@@ -321,6 +333,7 @@ extern "C" int dm_solve_scene(dm_ctx* ctx, const dm_scene_params* prm,
             fa.s0 = prm->s0; fa.s1 = prm->s1; fa.out_h = info.out_h; fa.out_w = info.out_w;
             fa.n_modes = prm->n_modes; for (int m = 0; m < 4; ++m) fa.modes[m] = prm->modes[m];
             fa.sub_pix = prm->sub_pix; fa.d_map = d_map_dev; fa.out_map = out_map_dev;
+            fa.filter_num = filter_num; fa.filter_win = filter_win; fa.filter_mode = filter_mode;
             rc = dm_fused_solve_chunk(ctx, &fa, ck);
             if (rc != DM_OK) return rc;
             continue;
@@ -359,16 +372,30 @@ extern "C" int dm_solve_scene(dm_ctx* ctx, const dm_scene_params* prm,
             }
             if ((rc = tm.end()) != DM_OK) return rc;
         }
-        int cur = 0;
+        int cur = 0, scur = 0;          // ping-pong index of the matches / of the scores (the filter moves only the matches)
         {
             StageTimer tm(ctx, DM_STAGE_BACKTRACK);
             if ((rc = tm.begin(ck)) != DM_OK) return rc;
-            if ((rc = dm_backtrack_top(tb.level[L - 1], 0, nt, t0 >> (L - 1), t1 >> (L - 1), tb.match[cur], tb.score[cur], st)) != DM_OK) return rc;
-            ctx->launches[DM_STAGE_BACKTRACK] += 1;
-            for (int k = L - 2; k >= 0; --k) {
-                if ((rc = dm_backtrack_level(tb.level[k], 0, nt, t0 >> k, t1 >> k, t0 >> k, t1 >> k, tb.match[cur], tb.match[cur ^ 1], tb.score[cur ^ 1], st)) != DM_OK) return rc;
+            int filters_left = filter_num;
+            auto maybe_filter = [&](int k) -> int {       // misc/Matching.py:91-93,136-138
+                if (filters_left <= 0) return DM_OK;
+                --filters_left;
+                const int h = t0 >> k, w = t1 >> k;
+                if (!(h >= filter_win && w >= filter_win)) return DM_OK;
+                int r = dm_match_filter(tb.match[cur], nt, h, w, filter_win, filter_mode, tb.match[cur ^ 1], st);
+                if (r != DM_OK) return r;
                 cur ^= 1;
                 ctx->launches[DM_STAGE_BACKTRACK] += 1;
+                return DM_OK;
+            };
+            if ((rc = dm_backtrack_top(tb.level[L - 1], 0, nt, t0 >> (L - 1), t1 >> (L - 1), tb.match[cur], tb.score[scur], st)) != DM_OK) return rc;
+            ctx->launches[DM_STAGE_BACKTRACK] += 1;
+            if ((rc = maybe_filter(L - 1)) != DM_OK) return rc;
+            for (int k = L - 2; k >= 0; --k) {
+                if ((rc = dm_backtrack_level(tb.level[k], 0, nt, t0 >> k, t1 >> k, t0 >> k, t1 >> k, tb.match[cur], tb.match[cur ^ 1], tb.score[scur ^ 1], st)) != DM_OK) return rc;
+                cur ^= 1; scur ^= 1;
+                ctx->launches[DM_STAGE_BACKTRACK] += 1;
+                if ((rc = maybe_filter(k)) != DM_OK) return rc;
             }
             if ((rc = tm.end()) != DM_OK) return rc;
         }
@@ -376,7 +403,7 @@ extern "C" int dm_solve_scene(dm_ctx* ctx, const dm_scene_params* prm,
             StageTimer tm(ctx, DM_STAGE_PLANES);
             if ((rc = tm.begin(ck)) != DM_OK) return rc;
             const long long total = (long long)nt * P;
-            dm_planes_kernel<<<dm_div_up(total, 256), 256, 0, st>>>(tb.level[0], total, pa, tb.match[cur], tb.score[cur], d_map_dev, out_map_dev);
+            dm_planes_kernel<<<dm_div_up(total, 256), 256, 0, st>>>(tb.level[0], total, pa, tb.match[cur], tb.score[scur], d_map_dev, out_map_dev);
             DM_LAUNCH_CHECK();
             ctx->launches[DM_STAGE_PLANES] += 1;
             if ((rc = tm.end()) != DM_OK) return rc;

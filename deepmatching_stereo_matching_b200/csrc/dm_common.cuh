@@ -89,6 +89,10 @@ __device__ __forceinline__ float dm_rectify(float x) {
     return r;
 }
 
+// numpy indexing of an axis of length n: -n <= v < n is accepted, negative values wrap
+__device__ __forceinline__ bool dm_np_index_ok(int v, int n) { return v >= -n && v < n; }
+__device__ __forceinline__ int dm_np_wrap(int v, int n) { return v < 0 ? v + n : v; }
+
 __device__ __forceinline__ int dm_round_mean(int sum, int k) {
     // nearest integer to sum/k for sum >= 0 (pixels are unsigned)
     return (2 * sum + k) / (2 * k);

@@ -55,6 +55,7 @@ struct dm_fused_args {
     int t0, t1, ws, kpad, levels, method;
     int first_tile, n_tiles, len0, len1, s0, s1, out_h, out_w;
     int n_modes, modes[4], sub_pix;
+    int filter_num, filter_win, filter_mode;     // Matching._filter on the first filter_num maps (< levels on this path)
     double* d_map; double* out_map;
 };
 bool dm_fused_supported(int t0, int t1, int kpad);

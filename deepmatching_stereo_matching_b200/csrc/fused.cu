@@ -465,12 +465,28 @@ int dm_fused_solve_chunk(dm_ctx* ctx, const dm_fused_args* a, int ck) {
     {
         StageTimer tm(ctx, DM_STAGE_BACKTRACK);
         if ((rc = tm.begin(ck)) != DM_OK) return rc;
+        int filters_left = a->filter_num;
+        auto maybe_filter = [&](int k) -> int {       // misc/Matching.py:91-93,136-138
+            if (filters_left <= 0) return DM_OK;
+            --filters_left;
+            const int h = t0 >> k, w = t1 >> k;
+            if (!(h >= a->filter_win && w >= a->filter_win)) return DM_OK;
+            int r = dm_match_filter(fb.match[cur], nt, h, w, a->filter_win, a->filter_mode, fb.match[cur ^ 1], st);
+            if (r != DM_OK) return r;
+            cur ^= 1;
+            ctx->launches[DM_STAGE_BACKTRACK] += 1;
+            return DM_OK;
+        };
+        // the scores of the levels above 0 are never read on this path (the final kernel
+        // recomputes the level-0 score), so the score buffers simply follow the match index
         if ((rc = dm_backtrack_top(fb.level[L - 1], 0, nt, t0 >> (L - 1), t1 >> (L - 1), fb.match[cur], fb.score[cur], st)) != DM_OK) return rc;
         ctx->launches[DM_STAGE_BACKTRACK] += 1;
+        if ((rc = maybe_filter(L - 1)) != DM_OK) return rc;
         for (int k = L - 2; k >= 1; --k) {
             if ((rc = dm_backtrack_level(fb.level[k], 0, nt, t0 >> k, t1 >> k, t0 >> k, t1 >> k, fb.match[cur], fb.match[cur ^ 1], fb.score[cur ^ 1], st)) != DM_OK) return rc;
             cur ^= 1;
             ctx->launches[DM_STAGE_BACKTRACK] += 1;
+            if ((rc = maybe_filter(k)) != DM_OK) return rc;
         }
         if ((rc = tm.end()) != DM_OK) return rc;
     }

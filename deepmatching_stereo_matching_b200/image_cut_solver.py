@@ -137,8 +137,9 @@ class ImageCutSolver():
         return np.array([Calc_difference.cal_map(out, mode=m) for m in self.degree_map_mode]), out[2, :, :]
 
     def _params(self):
+        filt = (self.filtering_num, self.filtering_window_size, self.filtering_mode) if self.filtering else None
         return _native.scene_params(self.img_shape, self.image_size, self.stride, self.window_size, self.feature_name,
-                                    list(self.degree_map_mode), self.sub_pix, self.tile_rows, self.fused)
+                                    list(self.degree_map_mode), self.sub_pix, self.tile_rows, self.fused, filtering=filt)
 
     def _execute_matching(self):
         """misc/image_cut_solver.py:144-179 -- all tiles batched on the GPU."""
@@ -149,7 +150,7 @@ class ImageCutSolver():
                 print('please input valid mode! {} are ok. yours is \'{}\''.format(MODES, m))
                 import sys
                 sys.exit()
-        if self.filtering:
+        if self.filtering and not self._filter_on_device():
             return self._execute_matching_per_tile(size_list)
         img1 = np.ascontiguousarray(self.img1, dtype=np.uint8)
         img2 = np.ascontiguousarray(self.img2, dtype=np.uint8)
@@ -162,9 +163,17 @@ class ImageCutSolver():
             print('pyramid level: {}, N={}'.format(self.info.levels, self.info.n_map))
             self.log_flg = False
 
+    def _filter_on_device(self):
+        """The batched solver runs Matching._filter (misc/Matching.py:224-255) as a kernel between
+        the levels; the reference's filter is only defined on square patch grids and the kernel
+        covers windows up to 9 x 9 -- everything else goes tile by tile through Matching."""
+        small = self.image_size[0] < self.filtering_window_size or self.image_size[1] < self.filtering_window_size
+        return self.filtering_num <= 0 or small or (self.image_size[0] == self.image_size[1] and (self.filtering_window_size - 1) // 2 <= 4
+                                                     and self.filtering_window_size >= 1)
+
     def _execute_matching_per_tile(self, size_list):
-        """Tile-by-tile variant used when the displacement filter is on (Matching._filter,
-        misc/Matching.py:224-255, runs between the levels on the host)."""
+        """Tile-by-tile variant through the class API (the same kernels, one tile at a time); used
+        for displacement-filter settings the batched solver does not take and by the tests."""
         self.d_map = np.empty([len(self.degree_map_mode)] + size_list, dtype=float)
         self.out_map = np.empty(size_list, dtype=float)
         for idx in range(len(self.img_index)):

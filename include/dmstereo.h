@@ -123,6 +123,16 @@ int dm_backtrack_level(const void* level_dev, int is_f64, int n, int a, int b, i
                        const int32_t* parent_match_dev,
                        int32_t* match_dev, void* score_dev, void* stream);
 
+/* Matching._filter (misc/Matching.py:224-255): outlier filter on the displacement field of a
+ * batch of match maps, int32 [n][2][h][w] -> [n][2][h][w] (out must not alias in).  Interior
+ * cells become round(mean | median of the (2e+1)^2 neighbourhood of displacements) + their
+ * own coordinate, e = (window-1)/2; maps smaller than the window are copied.  The reference
+ * is only defined on square maps: h != w returns DM_ERR_UNSUPPORTED. */
+#define DM_FILTER_MEDIAN   0
+#define DM_FILTER_AVERAGE  1
+int dm_match_filter(const int32_t* match_in_dev, int n, int h, int w, int window, int mode,
+                    int32_t* match_out_dev, void* stream);
+
 /* Matching._sub_pix_cal (misc/Matching.py:165-209) + assembly of Matching.__call__'s
  * return value (misc/Matching.py:211-222): map_dev = double [n][3][T0][T1] =
  * (row (+diff), col (+diff), score).  sub_pix = 0 skips the parabola fit. */
@@ -158,7 +168,10 @@ typedef struct dm_scene_params {
                                        ([n_scenes][S0][S1] inputs, [n_scenes][n_modes][S0'][S1']
                                        and [n_scenes][S0'][S1'] outputs); 0 or 1 = single pair.
                                        Not combinable with a tile-row strip.                */
-    int32_t reserved[2];
+    int32_t filter_num;             /* Matching(filtering=True, filtering_num=...): number of maps of
+                                       the top-down pass that go through Matching._filter
+                                       (misc/Matching.py:91-93,136-138); 0 = filtering off    */
+    int32_t filter_cfg;             /* filter_window_size | (DM_FILTER_* << 8)               */
 } dm_scene_params;
 
 typedef struct dm_scene_info {

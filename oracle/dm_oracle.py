@@ -269,8 +269,12 @@ def backtrack_level(level, parent_map):
 
 
 def sub_pix(l0, mp):
-    """misc/Matching.py:165-209 -- parabola fit on level 0; wraps at index -1, skips at
-    the upper edge (IndexError swallowed); arithmetic in l0.dtype, result float64."""
+    """misc/Matching.py:165-209 -- parabola fit on level 0; arithmetic in l0.dtype, result
+    float64.  numpy index rules decide what happens at the edges: a negative index wraps
+    (match row 0 reads its "-1" neighbour from the last row), an index >= the axis length
+    raises IndexError, which the bare ``except`` swallows -> no refinement along that axis.
+    Matches are inside the map unless the displacement filter ran on level 0, which can move
+    them one step outside (then row/col -1 wraps and row/col == size skips both axes)."""
     t0, t1, c, d = l0.shape
     out = mp.copy()
     ii, jj = np.meshgrid(np.arange(t0), np.arange(t1), indexing='ij')
@@ -284,30 +288,73 @@ def sub_pix(l0, mp):
             diff = -(r1 - r_) / (two * (r1 + r_ - two * r0))
         return np.where(ok, diff, 0).astype(np.float64)
 
-    r0 = l0[ii, jj, c0, c1]
+    def ok_idx(v, n):                                # numpy accepts -n <= v < n
+        return (v >= -n) & (v < n)
+
+    base = ok_idx(c0, c) & ok_idx(c1, d)
+    r0 = l0[ii, jj, c0 % c, c1 % d]
     # rows
-    valid = (c0 + 1) < c
-    r1 = l0[ii, jj, np.minimum(c0 + 1, c - 1), c1]
-    r_ = l0[ii, jj, (c0 - 1) % c, c1]
+    valid = base & ok_idx(c0 + 1, c) & ok_idx(c0 - 1, c)
+    r1 = l0[ii, jj, (c0 + 1) % c, c1 % d]
+    r_ = l0[ii, jj, (c0 - 1) % c, c1 % d]
     d_x = ii - mp[0]
     out[0] = np.where(valid, ii - d_x + fit(r0, r1, r_), ii - d_x)
     # cols
-    valid = (c1 + 1) < d
-    r1 = l0[ii, jj, c0, np.minimum(c1 + 1, d - 1)]
-    r_ = l0[ii, jj, c0, (c1 - 1) % d]
+    valid = base & ok_idx(c1 + 1, d) & ok_idx(c1 - 1, d)
+    r1 = l0[ii, jj, c0 % c, (c1 + 1) % d]
+    r_ = l0[ii, jj, c0 % c, (c1 - 1) % d]
     d_y = jj - mp[1]
     out[1] = np.where(valid, jj - d_y + fit(r0, r1, r_), jj - d_y)
     return out
 
 
-def matching(co_map_list, sub_pix_on=True, return_levels=False):
-    """misc/Matching.py:211-222 with filtering off -> (3,T0,T1) float64."""
-    mp = initial_move_map(co_map_list[-1])
+def match_filter(mp, window=3, mode='median'):
+    """misc/Matching.py:224-255 -- outlier filter on the displacement field of a (3,h,w) map:
+    interior cells get round(mean | median of the (2e+1)^2 neighbourhood of displacements)
+    + their own coordinate (Python round = half to even; the neighbourhood is read from a
+    snapshot, so the update order does not matter); border cells and the score plane are
+    untouched; maps smaller than the window pass through.  The reference sizes its snapshot
+    (shape[1], shape[1]) and is therefore only defined on square maps."""
+    mp = mp.copy()
+    _, h, w = mp.shape
+    if not (h >= window and w >= window):
+        return mp
+    if h != w:
+        raise ValueError('Matching._filter is undefined on non-square maps (%d x %d)' % (h, w))
+    e = int((window - 1) / 2)
+    k = 2 * e + 1
+    d_col = (mp[1] - np.arange(w)[None, :]).astype('int64')
+    d_row = (mp[0] - np.arange(h)[:, None]).astype('int64')
+    red = {'average': np.mean, 'median': np.median}[mode]
+    from numpy.lib.stride_tricks import sliding_window_view
+    if h - 2 * e > 0 and w - 2 * e > 0:
+        ii, jj = np.meshgrid(np.arange(e, h - e), np.arange(e, w - e), indexing='ij')
+        mp[1, e:h - e, e:w - e] = np.rint(red(sliding_window_view(d_col, (k, k)), axis=(-2, -1))) + jj
+        mp[0, e:h - e, e:w - e] = np.rint(red(sliding_window_view(d_row, (k, k)), axis=(-2, -1))) + ii
+    return mp
+
+
+def matching(co_map_list, sub_pix_on=True, return_levels=False, filtering=False, filtering_num=3,
+             filter_window_size=3, filtering_mode='median'):
+    """misc/Matching.py:211-222 -> (3,T0,T1) float64.  With ``filtering`` the first
+    ``filtering_num`` maps of the top-down pass (the top map, then the result of each _B)
+    go through match_filter; the counter runs down even where the map is too small
+    (misc/Matching.py:91-93,136-138)."""
+    left = filtering_num if filtering else 0
+
+    def maybe_filter(m):
+        nonlocal left
+        if left > 0:
+            m = match_filter(m, filter_window_size, filtering_mode)
+            left -= 1
+        return m
+
+    mp = maybe_filter(initial_move_map(co_map_list[-1]))
     levels = [mp]
     idx = len(co_map_list) - 1
     while idx > 0:
         idx -= 1
-        mp = backtrack_level(co_map_list[idx], mp)
+        mp = maybe_filter(backtrack_level(co_map_list[idx], mp))
         levels.append(mp)
     pre = mp
     if sub_pix_on:
@@ -381,10 +428,15 @@ def sub_pix_cal(arr, co_map, direction=0, ratio=100.):
     return image_threshold(arr, threshold=[-3, 3])
 
 
-def solve_tile(img1, img2, ws, modes=('elevation',), sub_pix_on=True, method=TM_CCOEFF_NORMED):
-    """misc/image_cut_solver.py:115-142 -> ((nmodes,T0,T1), (T0,T1))."""
+def solve_tile(img1, img2, ws, modes=('elevation',), sub_pix_on=True, method=TM_CCOEFF_NORMED, filtering=None):
+    """misc/image_cut_solver.py:115-142 -> ((nmodes,T0,T1), (T0,T1)).
+    filtering = None or (filtering_num, filter_window_size, filtering_mode)."""
     cm = correlation_map(img1, img2, ws, method)
-    out = matching(cm['co_map_list'], sub_pix_on)
+    if filtering is None:
+        out = matching(cm['co_map_list'], sub_pix_on)
+    else:
+        out = matching(cm['co_map_list'], sub_pix_on, filtering=True, filtering_num=filtering[0],
+                       filter_window_size=filtering[1], filtering_mode=filtering[2])
     return np.array([cal_map(out, m) for m in modes]), out[2]
 
 
@@ -397,7 +449,7 @@ def tile_grid(img_shape, image_size, stride, ws):
 
 def image_cut_solver(img1, img2, image_size=(32, 32), stride=(32, 32), ws=5,
                      modes=('elevation',), sub_pix_on=True, method=TM_CCOEFF_NORMED,
-                     tile_rows=None):
+                     tile_rows=None, filtering=None):
     """misc/image_cut_solver.py:95-113,144-184 -> (d_map (nmodes,S0',S1'), out_map (S0',S1')).
 
     ``tile_rows=(lo,hi)`` restricts the solve to tile-row indices lo..hi-1 (everything
@@ -414,7 +466,7 @@ def image_cut_solver(img1, img2, image_size=(32, 32), stride=(32, 32), ws=5,
         for i in range(lo, hi):
             y, x = stride[0] * i, stride[1] * j
             d, s = solve_tile(img1[y:y + trimmed[0], x:x + trimmed[1]],
-                              img2[y:y + trimmed[0], x:x + trimmed[1]], ws, modes, sub_pix_on, method)
+                              img2[y:y + trimmed[0], x:x + trimmed[1]], ws, modes, sub_pix_on, method, filtering)
             d_map[:, y:y + image_size[0], x:x + image_size[1]] = d
             out_map[y:y + image_size[0], x:x + image_size[1]] = s
     return d_map, out_map

@@ -235,6 +235,52 @@ def test_backtracking_bit_exact(dm, name):
     assert np.array_equal(dm.Matching(st, sub_pix=True)(), g['map_f32_sub'], equal_nan=True)
 
 
+@pytest.mark.parametrize('name', ['filter_16x16_ws5_sine', 'filter_16x16_ws3_unrelated'])
+def test_displacement_filter_bit_exact(dm, name):
+    """Matching(filtering=True): dm_match_filter between the levels (misc/Matching.py:224-255)
+    against the live reference's maps on the same float32 pyramid -- all 16 settings, with
+    and without the parabola fit (which sees matches one step outside the map after a
+    level-0 filter)."""
+    g = load_golden(name)
+    st = Stub()
+    st.co_map_list = [g['level%d' % k] for k in range(int(g['nlevels']))]
+    st.N_map = st.co_map_list[0].shape[0]
+    for k in [k for k in g if k.startswith('map_')]:
+        _, mode, num, win, sub = k.split('_')
+        got = dm.Matching(st, filter_window_size=int(win[1:]), filtering=True, filtering_num=int(num[1:]),
+                          filtering_mode=mode, sub_pix=(sub == 'sub'))()
+        assert np.array_equal(got, g[k], equal_nan=True), k
+
+
+@pytest.mark.parametrize('mode,num,win,fused_expected', [('median', 3, 3, 1), ('average', 4, 3, 1), ('median', 9, 5, 0), ('average', 2, 9, 1)])
+def test_image_cut_solver_with_displacement_filter(dm, mode, num, win, fused_expected):
+    """ex_deepmatching_rawinput.py:32-35 flags through ImageCutSolver: the batched solver runs the
+    filter kernel between the levels (fused path while the filter stays above level 0, else
+    the materialising path) and must equal the tile-by-tile class path; both against the oracle."""
+    from deepmatching_stereo_matching_b200.synth import texture
+    img1 = texture((120, 120), seed=61)
+    img2 = np.roll(texture((120, 120), seed=61), 2, axis=1)
+    img2[40:80, 30:90] = texture((40, 60), seed=62)          # a block of outliers for the filter to work on
+    kw = dict(image_size=[16, 16], stride=[14, 14], window_size=5, degree_map_mode=['elevation', 'elevation2'], sub_pix=True,
+              filtering=True, filtering_window_size=win, filtering_num=num, filtering_mode=mode)
+    s = dm.ImageCutSolver(img1, img2, **kw)
+    s.log_flg = False
+    d, sc = s()
+    assert s.info.used_fused == fused_expected
+    s2 = dm.ImageCutSolver(img1, img2, **kw)
+    s2.log_flg = False
+    s2._cut_and_pool()
+    s2._execute_matching_per_tile(list(d.shape[1:]))
+    assert np.array_equal(s2.d_map, d, equal_nan=True) and np.array_equal(s2.out_map, sc, equal_nan=True)
+    rd, rs = O.image_cut_solver(img1, img2, (16, 16), (14, 14), 5, ('elevation', 'elevation2'), True, filtering=(num, win, mode))
+    assert np.mean(np.abs(d - rd) > 0.5) <= 5e-3             # outlier blocks: near-ties flip a few more integer matches
+    plain, _ = dm.ImageCutSolver(img1, img2, **dict(kw, filtering=False))()
+    if win <= 16 >> (5 - num if num < 5 else 0):             # some filtered map is at least as large as the window
+        assert np.mean(np.abs(plain - d) > 0.5) > 0          # ... and the filter did change the field
+    else:
+        assert np.array_equal(plain, d, equal_nan=True)
+
+
 @pytest.mark.parametrize('name', TILE_CASES)
 def test_cal_map_bit_exact(dm, name):
     g = load_golden(name)

@@ -131,3 +131,34 @@ def test_raw_read(tmp_path):
     a.tofile(p)
     assert np.array_equal(O.raw_read(str(p), size=(12, 10)), a)
     assert np.array_equal(O.raw_read(str(p), size=(12, 10), rate=2), (a.astype(np.int8) * 2).astype(np.uint8))
+
+
+FILTER_CASES = ['filter_16x16_ws5_sine', 'filter_16x16_ws3_unrelated']
+
+
+@pytest.mark.parametrize('name', FILTER_CASES)
+def test_oracle_displacement_filter_vs_reference(name):
+    """Matching(filtering=True) of the live reference (misc/Matching.py:224-255) on a float32
+    pyramid, 16 settings x sub_pix on/off: the oracle must reproduce every map bit for bit,
+    including the numpy index rules of the parabola fit after a filter on level 0."""
+    g = load_golden(name)
+    lv = [g['level%d' % k] for k in range(int(g['nlevels']))]
+    keys = [k for k in g if k.startswith('map_')]
+    assert len(keys) == 32 and len(g['crashed']) == 0
+    changed = 0
+    plain = O.matching(lv, False)
+    for k in keys:
+        _, mode, num, win, sub = k.split('_')
+        got = O.matching(lv, sub == 'sub', filtering=True, filtering_num=int(num[1:]), filter_window_size=int(win[1:]),
+                         filtering_mode=mode)
+        assert np.array_equal(got, g[k], equal_nan=True), k
+        changed += int((g[k][:2].astype(np.int64) != plain[:2].astype(np.int64)).any())
+    assert changed > 0          # the fixtures do exercise the filter
+
+
+def test_oracle_filter_rejects_non_square_maps():
+    mp = np.zeros((3, 4, 8))
+    with pytest.raises(ValueError):
+        O.match_filter(mp, 3, 'median')
+    small = np.zeros((3, 2, 8))
+    assert np.array_equal(O.match_filter(small, 3, 'median'), small)     # smaller than the window: untouched
