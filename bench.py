@@ -62,7 +62,8 @@ def load_peaks():
 
 
 class ClockSampler(object):
-    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    """nvidia-smi clocks / throttle reasons sampled every 50 ms from the last warm-up steps to the
+    end of the end-to-end loop (the timed region of a default run is a few tens of ms)."""
     Q = ('clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
          'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
 
@@ -71,7 +72,7 @@ class ClockSampler(object):
         self.proc = None
         try:
             self.proc = subprocess.Popen(['nvidia-smi', '-i', str(index), '--query-gpu=' + self.Q, '--format=csv,noheader,nounits',
-                                          '-lms', '200'], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                          '-lms', '50'], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.th = threading.Thread(target=self._read, daemon=True)
             self.th.start()
         except Exception:
@@ -166,7 +167,7 @@ def run_ours(args):
     import torch
     import torch.distributed as dist
     from deepmatching_stereo_matching_b200 import _native
-    from deepmatching_stereo_matching_b200.strips import StripSolver, input_rows
+    from deepmatching_stereo_matching_b200.strips import StripSolver, SharedHostMosaic, input_rows
     from deepmatching_stereo_matching_b200.image_cut_solver import ImageCutSolver, pinned_empty
 
     world = int(os.environ.get('WORLD_SIZE', '1'))
@@ -197,10 +198,10 @@ def run_ours(args):
         solver.solve_local(d1, d2, planes)
         return solver.gather(planes)
 
+    clocks = ClockSampler(local_rank) if rank == 0 else None
     for _ in range(args.warmup):
         step()
     barrier()
-    clocks = ClockSampler(local_rank) if rank == 0 else None
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(args.steps):
@@ -212,14 +213,16 @@ def run_ours(args):
         t = torch.tensor([ms], device='cuda', dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
-    clk = clocks.stop() if clocks else None
     info = solver.info
     launches_per_step = (info.kernel_launches if info is not None else 0)
 
     # ---- end to end through the public API: pinned host scenes -> host float64 planes
     lo, hi = solver.tile_rows
     a, b = input_rows(lo, hi, STRIDE, T, WS)
-    out_host = pinned_empty((solver.n_planes, solver.out_h, solver.out_w), np.float64) if rank == 0 else None
+    # N > 1: the mosaic is assembled on the HOST -- one page-locked buffer shared by the ranks,
+    # every rank reads its own strip back over its own PCIe link (no GPU-side gather, no 8 strips
+    # through rank 0's link)
+    mosaic = SharedHostMosaic((solver.n_planes, solver.out_h, solver.out_w), np.float64) if world > 1 else None
 
     def e2e_step():
         if world == 1:
@@ -230,11 +233,11 @@ def run_ours(args):
             return s()
         d1[a:b].copy_(torch.from_numpy(h1[a:b]), non_blocking=True)
         d2[a:b].copy_(torch.from_numpy(h2[a:b]), non_blocking=True)
-        full_ = step()
-        if rank == 0:
-            torch.from_numpy(out_host).copy_(full_, non_blocking=True)
+        solver.solve_local(d1, d2, planes)
+        mosaic.copy_strip(planes, solver.row_ranges[rank])
         torch.cuda.synchronize()
-        return out_host
+        dist.barrier()                      # every strip has landed: the mosaic is complete for all ranks
+        return mosaic.array
 
     for _ in range(max(1, args.warmup // 2)):
         e2e_step()
@@ -248,8 +251,12 @@ def run_ours(args):
         t = torch.tensor([e2e_s], device='cuda', dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s = float(t.item())
+    clk = clocks.stop() if clocks else None
     h2d = 2 * (b - a) * img1.shape[1] * world if world > 1 else 2 * img1.size
     d2h = solver.n_planes * out_px * 8
+    if mosaic is not None:
+        barrier()
+        mosaic.close()
 
     # ---- per-stage device time (CUDA events on the launching stream) for the roofline
     roofline = None
@@ -286,7 +293,7 @@ def run_ours(args):
             'normalize': ('hbm', (4.0 * (lvl(0) / 4 + lvl(1)) if fused else 8.0 * lvl(0)) * tiles),
             'aggregate': ('hbm', agg_bytes),
         }
-        kern_name = {'descriptors': 'dm_descriptor_fast_kernel', 'correlation': 'dm_correlation_umma_kernel',
+        kern_name = {'descriptors': 'dm_descriptor_row_kernel', 'correlation': 'dm_correlation_umma_kernel',
                      'normalize': 'dm_aggregate_first_kernel' if fused else 'dm_minmax_rectify_kernel',
                      'aggregate': 'dm_aggregate_kernel', 'backtrack': 'dm_backtrack_kernel',
                      'planes': 'dm_final_quad_kernel' if fused else 'dm_planes_kernel'}
@@ -357,7 +364,7 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=10)
+    ap.add_argument('--steps', type=int, default=50)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--fused', type=int, default=-1, help='-1 auto, 0 materialising path, 1 fused tcgen05 path')

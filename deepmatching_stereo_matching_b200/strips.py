@@ -66,6 +66,61 @@ def gather_strips(local, row_ranges, group=None, dst=0):
     return full
 
 
+class SharedHostMosaic(object):
+    """The whole (planes, out_h, out_w) mosaic in ONE host buffer shared by the ranks of a node
+    (POSIX shared memory, page-locked in every process that has a CUDA device).  Every rank
+    copies its own strip device -> host over its own PCIe link with ``copy_strip``; after a
+    barrier the assembled mosaic is visible to all ranks as ``.array`` -- the host-side
+    alternative to gathering the strips on one GPU and reading 8 strips through one link."""
+
+    def __init__(self, shape, dtype=np.float64, group=None):
+        from multiprocessing import shared_memory, resource_tracker
+        import torch.distributed as dist
+        self.group = group
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        nbytes = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        name = [None]
+        if self.rank == 0:
+            self._shm = shared_memory.SharedMemory(create=True, size=nbytes)
+            name = [self._shm.name]
+        if dist.is_initialized():
+            dist.broadcast_object_list(name, src=0, group=group)
+        if self.rank != 0:
+            self._shm = shared_memory.SharedMemory(name=name[0])
+            try:        # the creator unlinks; keep the tracker of this process out of it (Python < 3.13)
+                resource_tracker.unregister(self._shm._name, 'shared_memory')
+            except Exception:
+                pass
+        self.array = np.ndarray(shape, dtype=dtype, buffer=self._shm.buf)
+        self._registered = False
+        try:
+            import torch
+            if torch.cuda.is_available():
+                rc = torch.cuda.cudart().cudaHostRegister(self.array.ctypes.data, nbytes, 0)
+                self._registered = (int(rc) == 0)
+        except Exception:
+            self._registered = False
+
+    def copy_strip(self, planes, row_range):
+        """Asynchronous (when the buffer is page-locked) copy of rows [lo,hi) of every plane."""
+        import torch
+        lo, hi = row_range
+        if hi > lo:
+            dst = torch.from_numpy(self.array)
+            for p in range(dst.shape[0]):           # rows [lo,hi) of one plane are contiguous: one DMA each
+                dst[p, lo:hi].copy_(planes[p, lo:hi], non_blocking=True)
+
+    def close(self):
+        import torch
+        if self._registered:
+            torch.cuda.cudart().cudaHostUnregister(self.array.ctypes.data)
+            self._registered = False
+        self.array = None
+        self._shm.close()
+        if self.rank == 0:
+            self._shm.unlink()
+
+
 class StripSolver(object):
     """Device-resident solve of this rank's strip + gather.  ``solve()`` returns the
     (n_modes+1, out_h, out_w) float64 mosaic (disparity planes, then the score plane) on

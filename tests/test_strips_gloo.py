@@ -41,8 +41,16 @@ def _worker(rank, world, port, q):
         local[:, :a] = float('nan')          # rows this rank does not own must not matter
         local[:, b:] = float('nan')
         full = gather_strips(local, ranges)
+        # host-side assembly: every rank writes its strip into one shared host buffer
+        from deepmatching_stereo_matching_b200.strips import SharedHostMosaic
+        mosaic = SharedHostMosaic(tuple(local.shape), np.float64)
+        mosaic.copy_strip(local, ranges[rank])
+        dist.barrier()
+        shared = mosaic.array.copy()
+        dist.barrier()
+        mosaic.close()
         if rank == 0:
-            q.put(full.numpy())
+            q.put((full.numpy(), shared))
         else:
             assert full is None
     finally:
@@ -58,7 +66,7 @@ def test_two_rank_strip_gather_equals_whole_scene():
     procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
     for p in procs:
         p.start()
-    full = q.get(timeout=240)
+    full, shared = q.get(timeout=240)
     for p in procs:
         p.join(60)
         assert p.exitcode == 0
@@ -67,3 +75,5 @@ def test_two_rank_strip_gather_equals_whole_scene():
                               tuple(str(m) for m in g['modes']), bool(g['sub_pix']))
     assert np.array_equal(full[:-1], d, equal_nan=True)
     assert np.array_equal(full[-1], s, equal_nan=True)
+    # the mosaic assembled in shared host memory (every rank writes its own strip) is the same
+    assert np.array_equal(shared, full, equal_nan=True)
