@@ -103,11 +103,23 @@ dm_descriptor_row_kernel(const uint8_t* __restrict__ scene, int pitch,
     // bytes of scene row (i + ky) this lane needs: columns j0 + 8*hf + [0, nb)
     const int nb = !rowlive ? 0 : (hf == 0 ? (7 + WS < 15 ? 7 + WS : 15) : WS - 8 + 7);
     const uint8_t* src = scene + (size_t)(origin_yx[2 * tile] + i + (rowlive ? ky : 0)) * pitch + origin_yx[2 * tile + 1] + j0 + hf * 8;
-    uint32_t w[4] = {0u, 0u, 0u, 0u};
+    // the (up to 15) bytes as aligned 32-bit loads + funnel shifts: 5 requests instead of 15 (the
+    // kernel was L1/TEX-bound on the byte loads).  Only words that hold a needed byte are read,
+    // so nothing outside the scene's own 4-byte-aligned words is touched.
+    uint32_t w[4];
+    {
+        const uintptr_t addr = reinterpret_cast<uintptr_t>(src);
+        const uint32_t* ap = reinterpret_cast<const uint32_t*>(addr & ~(uintptr_t)3);
+        const int off = (int)(addr & 3);
+        uint32_t a[5];
 #pragma unroll
-    for (int c = 0; c < 15; ++c) {
-        const uint32_t v = (c < nb) ? (uint32_t)__ldg(src + c) : 0u;
-        w[c >> 2] |= v << (8 * (c & 3));
+        for (int k = 0; k < 5; ++k) a[k] = (4 * k < off + nb) ? __ldg(ap + k) : 0u;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int nvk = nb - 4 * k;                 // valid bytes of word k
+            const uint32_t m = nvk >= 4 ? 0xffffffffu : (nvk <= 0 ? 0u : ((1u << (8 * nvk)) - 1u));
+            w[k] = __funnelshift_r(a[k], a[k + 1], 8 * off) & m;
+        }
     }
     // valid bytes of an 8-byte window slice: window columns 8*hf + u < WS
     const int nv = !rowlive ? 0 : (WS - hf * 8 > 8 ? 8 : WS - hf * 8);
