@@ -72,6 +72,8 @@ extern "C" void dm_ctx_destroy(dm_ctx* ctx) {
     if (!ctx) return;
     cudaFree(ctx->ws); cudaFree(ctx->scene1); cudaFree(ctx->scene2); cudaFree(ctx->planes);
     for (auto& v : ctx->ev) for (auto e : v) cudaEventDestroy(e);
+    for (auto e : ctx->band_ev) cudaEventDestroy(e);
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     delete ctx;
 }
 
@@ -88,6 +90,33 @@ static int ctx_reserve(dm_ctx* ctx, size_t bytes) {
     ctx->ws = nullptr; ctx->ws_bytes = 0;
     DM_CUDA_CHECK(cudaMalloc(&ctx->ws, bytes));
     ctx->ws_bytes = bytes;
+    return DM_OK;
+}
+
+// Output rows are final once every tile row above them is done: rows [0, s0 * full_tile_rows), or
+// the whole mosaic after the last tile.  Copies what is new on the copy stream, behind an event.
+int dm_readback_rows(dm_ctx* ctx, long long tiles_done) {
+    dm_ctx::Readback& rb = ctx->rb;
+    if (!rb.active) return DM_OK;
+    const long long full_rows = tiles_done / rb.len1;
+    int upto = full_rows >= rb.len0 ? rb.out_h : (int)(full_rows * rb.s0);
+    if (upto > rb.row_hi) upto = rb.row_hi;
+    if (upto <= rb.rows_done) return DM_OK;
+    if (!ctx->copy_stream) DM_CUDA_CHECK(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+    if (ctx->band_used >= ctx->band_ev.size()) {
+        cudaEvent_t e;
+        DM_CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        ctx->band_ev.push_back(e);
+    }
+    cudaEvent_t ev = ctx->band_ev[ctx->band_used++];
+    DM_CUDA_CHECK(cudaEventRecord(ev, ctx->stream));
+    DM_CUDA_CHECK(cudaStreamWaitEvent(ctx->copy_stream, ev, 0));
+    const size_t plane = (size_t)rb.out_h * rb.out_w;
+    const size_t off = (size_t)rb.rows_done * rb.out_w, bytes = (size_t)(upto - rb.rows_done) * rb.out_w * sizeof(double);
+    for (int m = 0; m < rb.n_modes; ++m)
+        DM_CUDA_CHECK(cudaMemcpyAsync(rb.h_d_map + m * plane + off, rb.d_d_map + m * plane + off, bytes, cudaMemcpyDeviceToHost, ctx->copy_stream));
+    DM_CUDA_CHECK(cudaMemcpyAsync(rb.h_out_map + off, rb.d_out_map + off, bytes, cudaMemcpyDeviceToHost, ctx->copy_stream));
+    rb.rows_done = upto;
     return DM_OK;
 }
 
@@ -453,17 +482,32 @@ extern "C" int dm_solve_scene_host(dm_ctx* ctx, const dm_scene_params* prm,
     double* out_map = ctx->planes + plane * prm->n_modes * ns;
     if (prm->s0 > prm->t0 || prm->s1 > prm->t1)      // gaps between tiles: np.empty in the reference, zeros here
         DM_CUDA_CHECK(cudaMemsetAsync(ctx->planes, 0, pb, st));
+    // single scene: finished row bands stream back to the host behind the final stage
+    dm_ctx::Readback& rb = ctx->rb;
+    rb = dm_ctx::Readback();
+    if (ns == 1) {
+        rb.active = true;
+        rb.h_d_map = d_map_host; rb.h_out_map = out_map_host; rb.d_d_map = d_map; rb.d_out_map = out_map;
+        rb.n_modes = prm->n_modes; rb.out_h = info.out_h; rb.out_w = info.out_w; rb.len0 = info.len0; rb.len1 = info.len1; rb.s0 = prm->s0;
+        rb.rows_done = info.row_lo; rb.row_hi = info.row_hi;
+        ctx->band_used = 0;
+    }
     rc = dm_solve_scene(ctx, prm, ctx->scene1, ctx->scene2, d_map, out_map, &info);
+    rb.active = false;
     if (rc != DM_OK) return rc;
     if (ns > 1) {       // whole batch: both result arrays are contiguous
         DM_CUDA_CHECK(cudaMemcpyAsync(d_map_host, d_map, plane * prm->n_modes * ns * sizeof(double), cudaMemcpyDeviceToHost, st));
         DM_CUDA_CHECK(cudaMemcpyAsync(out_map_host, out_map, plane * ns * sizeof(double), cudaMemcpyDeviceToHost, st));
     } else {
-        const size_t row_off = (size_t)info.row_lo * info.out_w;
-        const size_t row_bytes = (size_t)(info.row_hi - info.row_lo) * info.out_w * sizeof(double);
-        for (int m = 0; m < prm->n_modes; ++m)
-            DM_CUDA_CHECK(cudaMemcpyAsync(d_map_host + m * plane + row_off, d_map + m * plane + row_off, row_bytes, cudaMemcpyDeviceToHost, st));
-        DM_CUDA_CHECK(cudaMemcpyAsync(out_map_host + row_off, out_map + row_off, row_bytes, cudaMemcpyDeviceToHost, st));
+        // whatever the bands have not taken yet (everything on the materialising path)
+        if (rb.rows_done < info.row_hi) {
+            const size_t row_off = (size_t)rb.rows_done * info.out_w;
+            const size_t row_bytes = (size_t)(info.row_hi - rb.rows_done) * info.out_w * sizeof(double);
+            for (int m = 0; m < prm->n_modes; ++m)
+                DM_CUDA_CHECK(cudaMemcpyAsync(d_map_host + m * plane + row_off, d_map + m * plane + row_off, row_bytes, cudaMemcpyDeviceToHost, st));
+            DM_CUDA_CHECK(cudaMemcpyAsync(out_map_host + row_off, out_map + row_off, row_bytes, cudaMemcpyDeviceToHost, st));
+        }
+        if (ctx->copy_stream && ctx->band_used > 0) DM_CUDA_CHECK(cudaStreamSynchronize(ctx->copy_stream));
     }
     DM_CUDA_CHECK(cudaStreamSynchronize(st));
     if (info_out) *info_out = info;

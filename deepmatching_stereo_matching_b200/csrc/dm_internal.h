@@ -34,6 +34,19 @@ struct dm_ctx {
     // host-API staging
     uint8_t* scene1 = nullptr; uint8_t* scene2 = nullptr; size_t scene_bytes = 0;
     double* planes = nullptr; size_t planes_bytes = 0;
+    // host readback streamed behind the final stage (dm_solve_scene_host, single scene, fused path):
+    // finished output rows are copied device -> host on a second stream while the last tiles
+    // are still being solved
+    cudaStream_t copy_stream = nullptr;
+    std::vector<cudaEvent_t> band_ev;
+    size_t band_used = 0;
+    struct Readback {
+        bool active = false;
+        double* h_d_map = nullptr; double* h_out_map = nullptr;
+        const double* d_d_map = nullptr; const double* d_out_map = nullptr;
+        int n_modes = 0, out_h = 0, out_w = 0, len0 = 0, len1 = 0, s0 = 0;
+        int rows_done = 0, row_hi = 0;              // output rows [.., rows_done) are already on their way
+    } rb;
     // timing
     bool timing = false;
     std::vector<cudaEvent_t> ev[DM_STAGE_COUNT];   // pairs (start, stop) per chunk
@@ -62,3 +75,5 @@ bool dm_fused_supported(int t0, int t1, int kpad);
 bool dm_fused_supported_ws(int ws);
 size_t dm_fused_workspace(char* base, int n_tiles, int t0, int t1, int kpad, int levels, void* buffers_out);
 int dm_fused_solve_chunk(dm_ctx* ctx, const dm_fused_args* a, int chunk_index);
+// schedules the device -> host copy of the output rows completed by tiles [0, tiles_done) (global tile index)
+int dm_readback_rows(dm_ctx* ctx, long long tiles_done);

@@ -134,6 +134,7 @@ struct FinalArgs {
     int t0, t1, ws, normed, sub_pix, scene_h;
     int n_modes, modes[4];
     int s0, s1, len0, len1, out_h, out_w, first_tile;
+    long long quad0;            // first quad of this launch (the final stage may run in bands)
     double* d_map; double* out_map;
 };
 
@@ -158,8 +159,8 @@ dm_final_quad_kernel(const FinalArgs a, long long n_quads) {
     const int lane = threadIdx.x & 31;
     uint8_t* reg0 = region_all[threadIdx.x >> 5][0];
     uint8_t* reg1 = region_all[threadIdx.x >> 5][1];
-    const long long w = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (w >= n_quads) return;
+    const long long w = a.quad0 + (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (w >= a.quad0 + n_quads) return;
     const int T0 = a.t0, T1 = a.t1, P = T0 * T1;
     const int hA = T0 >> 1, hB = T1 >> 1, PQ = hA * hB;
     const int n = (int)(w / PQ);                         // tile inside the chunk
@@ -504,18 +505,34 @@ int dm_fused_solve_chunk(dm_ctx* ctx, const dm_fused_args* a, int ck) {
         const long long n_patches = (long long)nt * P;
         fa.scene_h = a->scene_h * a->n_scenes;       // bound of the stacked image
         const long long n_quads = n_patches / 4;
-        switch (a->ws) {
-            case 3: launch_final_quad<3>(fa, n_quads, st); break;
-            case 5: launch_final_quad<5>(fa, n_quads, st); break;
-            case 7: launch_final_quad<7>(fa, n_quads, st); break;
-            case 9: launch_final_quad<9>(fa, n_quads, st); break;
-            case 11: launch_final_quad<11>(fa, n_quads, st); break;
-            case 13: launch_final_quad<13>(fa, n_quads, st); break;
-            case 15: launch_final_quad<15>(fa, n_quads, st); break;
-            default: DM_REQUIRE(false, DM_ERR_UNSUPPORTED, "fused path supports odd window sizes 3..15 (got %d)", a->ws);
+        // host readback active: the stage runs in (up to) three bands of whole tile rows, and the
+        // output rows each band completes start their device -> host copy while the next band runs
+        int bands = 1;
+        if (ctx->rb.active && nt >= 3 * a->len1) bands = 3;
+        const int rows_in_chunk = nt / a->len1;
+        int t_begin = 0;
+        for (int b = 0; b < bands; ++b) {
+            int t_end = (b == bands - 1) ? nt : ((rows_in_chunk * (b + 1)) / bands) * a->len1 + ((a->len1 - a->first_tile % a->len1) % a->len1);
+            if (t_end > nt) t_end = nt;
+            if (t_end <= t_begin) continue;
+            fa.quad0 = (long long)t_begin * (P / 4);
+            const long long nq = (long long)(t_end - t_begin) * (P / 4);
+            switch (a->ws) {
+                case 3: launch_final_quad<3>(fa, nq, st); break;
+                case 5: launch_final_quad<5>(fa, nq, st); break;
+                case 7: launch_final_quad<7>(fa, nq, st); break;
+                case 9: launch_final_quad<9>(fa, nq, st); break;
+                case 11: launch_final_quad<11>(fa, nq, st); break;
+                case 13: launch_final_quad<13>(fa, nq, st); break;
+                case 15: launch_final_quad<15>(fa, nq, st); break;
+                default: DM_REQUIRE(false, DM_ERR_UNSUPPORTED, "fused path supports odd window sizes 3..15 (got %d)", a->ws);
+            }
+            DM_LAUNCH_CHECK();
+            ctx->launches[DM_STAGE_PLANES] += 1;
+            if (ctx->rb.active && (rc = dm_readback_rows(ctx, (long long)a->first_tile + t_end)) != DM_OK) return rc;
+            t_begin = t_end;
         }
-        DM_LAUNCH_CHECK();
-        ctx->launches[DM_STAGE_PLANES] += 1;
+        (void)n_quads;
         if ((rc = tm.end()) != DM_OK) return rc;
     }
     return DM_OK;
