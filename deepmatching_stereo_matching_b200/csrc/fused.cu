@@ -166,6 +166,15 @@ dm_final_quad_kernel(const FinalArgs a, long long n_quads) {
     const int n = (int)(w / PQ);                         // tile inside the chunk
     const int pq = (int)(w - (long long)n * PQ);
     const int I = pq / hB, J = pq - I * hB;
+    {
+        // misc/image_cut_solver.py:165-175: a pixel belongs to the covering tile with the largest
+        // index.  A quad whose two patch rows (or columns) lie at or beyond the stride is pasted
+        // over by the next tile: nothing of it survives, so the warp stops here (12 % of the
+        // quads at image_size 64 / stride 60).
+        const int g = a.first_tile + n, tps = a.len0 * a.len1;
+        const int gr = g % tps, gi = gr / a.len1, gj = gr - gi * a.len1;
+        if ((gi < a.len0 - 1 && 2 * I >= a.s0) || (gj < a.len1 - 1 && 2 * J >= a.s1)) return;
+    }
     const int oy = a.origin[2 * n], ox = a.origin[2 * n + 1];
     const bool normed = a.normed != 0;
     const int c = lane >> 3, l = lane & 7, ci = c >> 1, cj = c & 1;
