@@ -15,5 +15,6 @@ from .sub_pix_cal import sub_pix_cal                # noqa: F401
 from .optimize_loop import image_threshold          # noqa: F401
 from .image_cut_solver import ImageCutSolver        # noqa: F401
 from .raw_read import RawRead                       # noqa: F401
+from .bilateral import bilateral_filter             # noqa: F401
 
 __version__ = '0.1.0'

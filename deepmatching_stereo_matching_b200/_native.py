@@ -54,6 +54,7 @@ SIGNATURES = {
     'dm_match_map': (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
     'dm_cal_map': (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
     'dm_sub_pix_cal': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_double, c_void_p, c_void_p]),
+    'dm_bilateral_u8': (c_int, [c_void_p, c_int, c_int, c_int, c_double, c_double, c_void_p, c_void_p]),
     'dm_ctx_create': (c_int, [POINTER(c_void_p)]),
     'dm_ctx_destroy': (None, [c_void_p]),
     'dm_ctx_set_stream': (c_int, [c_void_p, c_void_p]),

@@ -148,6 +148,13 @@ int dm_cal_map(const double* map_dev, int t0, int t1, int mode, double* out_dev,
 int dm_sub_pix_cal(const double* arr_dev, const double* co_map_dev, int s0, int s1,
                    int direction, double ratio, double* out_dev, void* stream);
 
+/* cv2.bilateralFilter(plane.astype('uint8'), d, sigma_color, sigma_space) -- the live branch of the
+ * reference's post-process (optimize_looper.py:76-77, d = 2*exclusion+1).  uint8 (h,w) planes;
+ * OpenCV's own 8-bit algorithm (BORDER_REFLECT_101, float32 weights, cvRound), bit-identical
+ * to cv2 with IPP off.  dst must not alias src. */
+int dm_bilateral_u8(const uint8_t* src_dev, int h, int w, int d, double sigma_color, double sigma_space,
+                    uint8_t* dst_dev, void* stream);
+
 /* ---------------------------------------------------------------- scene solver -----
  * Replaces ImageCutSolver._cut_and_pool/_solver/_execute_matching
  * (misc/image_cut_solver.py:95-184) for a whole scene or for a strip of tile rows.

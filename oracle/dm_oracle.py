@@ -472,6 +472,39 @@ def image_cut_solver(img1, img2, image_size=(32, 32), stride=(32, 32), ws=5,
     return d_map, out_map
 
 
+def bilateral_filter_u8(src, d, sigma_color, sigma_space):
+    """cv2.bilateralFilter on a uint8 plane (optimize_looper.py:76-77), restating OpenCV's own
+    8-bit algorithm (bilateral_filter.dispatch.cpp / .simd.hpp, non-IPP path): float32 colour
+    and space weights, BORDER_REFLECT_101, neighbours accumulated row by row, cvRound."""
+    import math
+    src = np.ascontiguousarray(src, dtype=np.uint8)
+    if sigma_color <= 0:
+        sigma_color = 1
+    if sigma_space <= 0:
+        sigma_space = 1
+    radius = int(np.rint(sigma_space * 1.5)) if d <= 0 else d // 2
+    radius = max(radius, 1)
+    gc = np.float32(-0.5 / (sigma_color * sigma_color))
+    gs = np.float32(-0.5 / (sigma_space * sigma_space))
+    cw = np.array([np.float32(math.exp(float(np.float32(i * i) * gc))) for i in range(256)], dtype=np.float32)
+    h, w = src.shape
+    t = np.pad(src, radius, mode='reflect').astype(np.int64)
+    c = t[radius:radius + h, radius:radius + w]
+    s = np.zeros((h, w), np.float32)
+    ws = np.zeros((h, w), np.float32)
+    for i in range(-radius, radius + 1):
+        for j in range(-radius, radius + 1):
+            r = math.sqrt(float(i * i + j * j))
+            if r > radius:
+                continue
+            w0 = np.float32(math.exp(r * r * float(gs)))
+            v = t[radius + i:radius + i + h, radius + j:radius + j + w]
+            wk = (w0 * cw[np.abs(v - c)]).astype(np.float32)
+            s = (s + (v.astype(np.float32) * wk).astype(np.float32)).astype(np.float32)
+            ws = (ws + wk).astype(np.float32)
+    return np.rint(s / ws).astype(np.uint8)
+
+
 def raw_read(path, size=(6000, 6000), rate=1):
     """misc/raw_read.py:36-45 -- int8 read, * rate, cast to uint8 (wraps)."""
     c = np.fromfile(path, dtype=np.int8, count=size[0] * size[1]).reshape(1, size[1], size[0])

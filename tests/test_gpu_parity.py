@@ -571,3 +571,22 @@ def test_scene_c2_properties(dm):
         dp, _ = p()
         merged[:, p.info.row_lo:p.info.row_hi] = dp[:, p.info.row_lo:p.info.row_hi]
     assert np.array_equal(merged, d)
+
+
+def test_bilateral_filter_bit_exact(dm):
+    """dm_bilateral_u8 against cv2.bilateralFilter (IPP off) on the golden plane -- the live branch of
+    optimize_looper.py:76-77 -- and against the oracle on a larger random plane."""
+    g = load_golden('bilateral')
+    for k in g:
+        if not k.startswith('out_plain_'):
+            continue
+        _, _, d, sc, ss = k.split('_')
+        got = dm.bilateral_filter(g['img'], int(d[1:]), float(sc), float(ss))
+        assert got.dtype == np.uint8 and np.array_equal(got, g[k]), k
+    rng = np.random.default_rng(9)
+    big = rng.integers(0, 256, size=(301, 517), dtype=np.uint8)
+    big[100:200, 100:300] = 128
+    for d, sc, ss in ((7, 5, 5), (5, 30.0, 2.0), (15, 80.0, 6.0)):
+        assert np.array_equal(dm.bilateral_filter(big, d, sc, ss), O.bilateral_filter_u8(big, d, sc, ss))
+    with pytest.raises(ValueError):
+        dm.bilateral_filter(big.astype(np.float64), 7, 5, 5)

@@ -162,3 +162,23 @@ def test_oracle_filter_rejects_non_square_maps():
         O.match_filter(mp, 3, 'median')
     small = np.zeros((3, 2, 8))
     assert np.array_equal(O.match_filter(small, 3, 'median'), small)     # smaller than the window: untouched
+
+
+def test_oracle_bilateral_filter_vs_cv2():
+    """optimize_looper.py:76-77: cv2.bilateralFilter on the uint8 cast of a disparity plane.  The
+    oracle restates OpenCV's own algorithm: bit exact against cv2 with IPP off; the IPP build's
+    output may differ from that by one grey level (OpenCV against itself)."""
+    g = load_golden('bilateral')
+    assert np.array_equal(g['plane'].astype('uint8'), g['img'])
+    n = 0
+    for k in g:
+        if not k.startswith('out_'):
+            continue
+        _, kind, d, sc, ss = k.split('_')
+        got = O.bilateral_filter_u8(g['img'], int(d[1:]), float(sc), float(ss))
+        if kind == 'plain':
+            assert np.array_equal(got, g[k]), k
+        else:
+            assert np.abs(got.astype(int) - g[k].astype(int)).max() <= 1, k
+        n += 1
+    assert n == 8
