@@ -514,10 +514,10 @@ int dm_fused_solve_chunk(dm_ctx* ctx, const dm_fused_args* a, int ck) {
         const long long n_patches = (long long)nt * P;
         fa.scene_h = a->scene_h * a->n_scenes;       // bound of the stacked image
         const long long n_quads = n_patches / 4;
-        // host readback active: the stage runs in (up to) three bands of whole tile rows, and the
+        // host readback active: the stage runs in (up to) five bands of whole tile rows, and the
         // output rows each band completes start their device -> host copy while the next band runs
         int bands = 1;
-        if (ctx->rb.active && nt >= 3 * a->len1) bands = 3;
+        if (ctx->rb.active) { bands = nt / (2 * a->len1); if (bands > 5) bands = 5; if (bands < 1) bands = 1; }   // only the last band's copy is exposed
         const int rows_in_chunk = nt / a->len1;
         int t_begin = 0;
         for (int b = 0; b < bands; ++b) {

@@ -28,6 +28,49 @@ def _context():
     return _CTX[dev]
 
 
+class _TileIndex(object):
+    """[[i, j], ...] in the reference's order (j outer, i inner), computed on access."""
+
+    def __init__(self, ln):
+        self.len0, self.len1 = max(int(ln[0]), 0), max(int(ln[1]), 0)
+
+    def __len__(self):
+        return self.len0 * self.len1
+
+    def __getitem__(self, k):
+        n = len(self)
+        if isinstance(k, slice):
+            return [self[i] for i in range(*k.indices(n))]
+        if k < 0:
+            k += n
+        if not 0 <= k < n:
+            raise IndexError('list index out of range')
+        return [k % self.len0, k // self.len0]
+
+    def __iter__(self):
+        return (self[k] for k in range(len(self)))
+
+
+class _TileViews(object):
+    """img[s0*i : s0*i + t0, s1*j : s1*j + t1] for every tile of a _TileIndex, computed on access."""
+
+    def __init__(self, img, index, stride, trimmed):
+        self.img, self.index, self.stride, self.trimmed = img, index, stride, trimmed
+
+    def __len__(self):
+        return len(self.index)
+
+    def __getitem__(self, k):
+        if isinstance(k, slice):
+            return [self[i] for i in range(*k.indices(len(self)))]
+        i, j = self.index[k]
+        ys, xs = self.stride[0] * i, self.stride[1] * j
+        return self.img[ys:ys + self.trimmed[0], xs:xs + self.trimmed[1]]
+
+    def __iter__(self):
+        return (self[k] for k in range(len(self)))
+
+
 def set_workspace_limit(nbytes):
     """Caps the device workspace of this process's solver context; scenes whose tiles do not
     fit are processed in equal chunks of tiles (default limit: 48 GB)."""
@@ -110,16 +153,12 @@ class ImageCutSolver():
         raise NotImplementedError('padding=True is broken in the reference (image_cut_solver.py:85-93) and not supported')
 
     def _cut_and_pool(self):
-        """misc/image_cut_solver.py:95-113 -- tile views, j outer / i inner."""
-        self.img1_sub = []
-        self.img2_sub = []
-        self.img_index = []
-        for j in range(self.len[1]):
-            for i in range(self.len[0]):
-                ys, xs = self.stride[0] * i, self.stride[1] * j
-                self.img1_sub.append(self.img1[ys:ys + self.trimed_size[0], xs:xs + self.trimed_size[1]])
-                self.img2_sub.append(self.img2[ys:ys + self.trimed_size[0], xs:xs + self.trimed_size[1]])
-                self.img_index.append([i, j])
+        """misc/image_cut_solver.py:95-113 -- tile views, j outer / i inner.  The three lists are
+        sequences that build their elements when asked: the batched solver never looks at the
+        tiles themselves, and 2 x 225 numpy views cost more host time than its launches."""
+        self.img_index = _TileIndex(self.len)
+        self.img1_sub = _TileViews(self.img1, self.img_index, self.stride, self.trimed_size)
+        self.img2_sub = _TileViews(self.img2, self.img_index, self.stride, self.trimed_size)
 
     def _solver(self, solve_image, solve_template):
         """misc/image_cut_solver.py:115-142 -- one tile through the class API (device kernels)."""
