@@ -74,6 +74,8 @@ extern "C" void dm_ctx_destroy(dm_ctx* ctx) {
     for (auto& v : ctx->ev) for (auto e : v) cudaEventDestroy(e);
     for (auto e : ctx->band_ev) cudaEventDestroy(e);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+    for (auto& g : ctx->upper_graphs) cudaGraphExecDestroy(g.exec);
+    if (ctx->capture_stream) cudaStreamDestroy(ctx->capture_stream);
     delete ctx;
 }
 

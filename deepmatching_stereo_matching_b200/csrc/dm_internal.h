@@ -47,6 +47,14 @@ struct dm_ctx {
         int n_modes = 0, out_h = 0, out_w = 0, len0 = 0, len1 = 0, s0 = 0;
         int rows_done = 0, row_hi = 0;              // output rows [.., rows_done) are already on their way
     } rb;
+    // CUDA graphs of the upper-pyramid + top-down launch sequence (fused.cu), keyed by what they depend on
+    struct UpperGraph {
+        const void* ws; int nt, t0, t1, levels, filter_num, filter_win, filter_mode;
+        int n_agg, n_bt, final_cur;
+        cudaGraphExec_t exec;
+    };
+    std::vector<UpperGraph> upper_graphs;
+    cudaStream_t capture_stream = nullptr;
     // timing
     bool timing = false;
     std::vector<cudaEvent_t> ev[DM_STAGE_COUNT];   // pairs (start, stop) per chunk

@@ -462,43 +462,96 @@ int dm_fused_solve_chunk(dm_ctx* ctx, const dm_fused_args* a, int ck) {
         ctx->launches[DM_STAGE_NORMALIZE] += 1;
         if ((rc = tm.end()) != DM_OK) return rc;
     }
-    {
-        StageTimer tm(ctx, DM_STAGE_AGGREGATE);
-        if ((rc = tm.begin(ck)) != DM_OK) return rc;
-        for (int k = 1; k + 1 < L; ++k) {
-            if ((rc = dm_aggregate(fb.level[k], nt, t0 >> k, t1 >> k, t0 >> k, t1 >> k, 1, fb.level[k + 1], st)) != DM_OK) return rc;
-            ctx->launches[DM_STAGE_AGGREGATE] += 1;
-        }
-        if ((rc = tm.end()) != DM_OK) return rc;
-    }
+    // ---- upper pyramid + top-down pass: up to 2 (levels - 1) small dependent launches that touch
+    // nothing but the workspace.  They are captured once per (workspace, shape, filter) into a CUDA
+    // graph (on a private stream: the caller's may be the legacy default stream, which cannot
+    // capture) and replayed with one launch; with stage timing on they are launched one by one.
     int cur = 0;
-    {
-        StageTimer tm(ctx, DM_STAGE_BACKTRACK);
-        if ((rc = tm.begin(ck)) != DM_OK) return rc;
+    auto run_agg = [&](cudaStream_t s, int* n_agg) -> int {
+        *n_agg = 0;
+        for (int k = 1; k + 1 < L; ++k) {
+            int r = dm_aggregate(fb.level[k], nt, t0 >> k, t1 >> k, t0 >> k, t1 >> k, 1, fb.level[k + 1], s);
+            if (r != DM_OK) return r;
+            ++*n_agg;
+        }
+        return DM_OK;
+    };
+    auto run_bt = [&](cudaStream_t s, int* n_bt) -> int {
+        int r;
+        cur = 0; *n_bt = 0;
         int filters_left = a->filter_num;
         auto maybe_filter = [&](int k) -> int {       // misc/Matching.py:91-93,136-138
             if (filters_left <= 0) return DM_OK;
             --filters_left;
             const int h = t0 >> k, w = t1 >> k;
             if (!(h >= a->filter_win && w >= a->filter_win)) return DM_OK;
-            int r = dm_match_filter(fb.match[cur], nt, h, w, a->filter_win, a->filter_mode, fb.match[cur ^ 1], st);
-            if (r != DM_OK) return r;
+            int rr = dm_match_filter(fb.match[cur], nt, h, w, a->filter_win, a->filter_mode, fb.match[cur ^ 1], s);
+            if (rr != DM_OK) return rr;
             cur ^= 1;
-            ctx->launches[DM_STAGE_BACKTRACK] += 1;
+            ++*n_bt;
             return DM_OK;
         };
         // the scores of the levels above 0 are never read on this path (the final kernel
         // recomputes the level-0 score), so the score buffers simply follow the match index
-        if ((rc = dm_backtrack_top(fb.level[L - 1], 0, nt, t0 >> (L - 1), t1 >> (L - 1), fb.match[cur], fb.score[cur], st)) != DM_OK) return rc;
-        ctx->launches[DM_STAGE_BACKTRACK] += 1;
-        if ((rc = maybe_filter(L - 1)) != DM_OK) return rc;
+        if ((r = dm_backtrack_top(fb.level[L - 1], 0, nt, t0 >> (L - 1), t1 >> (L - 1), fb.match[cur], fb.score[cur], s)) != DM_OK) return r;
+        ++*n_bt;
+        if ((r = maybe_filter(L - 1)) != DM_OK) return r;
         for (int k = L - 2; k >= 1; --k) {
-            if ((rc = dm_backtrack_level(fb.level[k], 0, nt, t0 >> k, t1 >> k, t0 >> k, t1 >> k, fb.match[cur], fb.match[cur ^ 1], fb.score[cur ^ 1], st)) != DM_OK) return rc;
+            if ((r = dm_backtrack_level(fb.level[k], 0, nt, t0 >> k, t1 >> k, t0 >> k, t1 >> k, fb.match[cur], fb.match[cur ^ 1], fb.score[cur ^ 1], s)) != DM_OK) return r;
             cur ^= 1;
-            ctx->launches[DM_STAGE_BACKTRACK] += 1;
-            if ((rc = maybe_filter(k)) != DM_OK) return rc;
+            ++*n_bt;
+            if ((r = maybe_filter(k)) != DM_OK) return r;
         }
-        if ((rc = tm.end()) != DM_OK) return rc;
+        return DM_OK;
+    };
+    if (ctx->timing) {
+        int n = 0;
+        {
+            StageTimer tm(ctx, DM_STAGE_AGGREGATE);
+            if ((rc = tm.begin(ck)) != DM_OK) return rc;
+            if ((rc = run_agg(st, &n)) != DM_OK) return rc;
+            ctx->launches[DM_STAGE_AGGREGATE] += n;
+            if ((rc = tm.end()) != DM_OK) return rc;
+        }
+        {
+            StageTimer tm(ctx, DM_STAGE_BACKTRACK);
+            if ((rc = tm.begin(ck)) != DM_OK) return rc;
+            if ((rc = run_bt(st, &n)) != DM_OK) return rc;
+            ctx->launches[DM_STAGE_BACKTRACK] += n;
+            if ((rc = tm.end()) != DM_OK) return rc;
+        }
+    } else {
+        dm_ctx::UpperGraph* ug = nullptr;
+        for (auto& g : ctx->upper_graphs)
+            if (g.ws == (const void*)ctx->ws && g.nt == nt && g.t0 == t0 && g.t1 == t1 && g.levels == L &&
+                g.filter_num == a->filter_num && g.filter_win == a->filter_win && g.filter_mode == a->filter_mode) { ug = &g; break; }
+        if (!ug) {
+            if (ctx->upper_graphs.size() >= 4) {          // scenes alternate between at most two chunk sizes
+                for (auto& g : ctx->upper_graphs) cudaGraphExecDestroy(g.exec);
+                ctx->upper_graphs.clear();
+            }
+            if (!ctx->capture_stream) DM_CUDA_CHECK(cudaStreamCreateWithFlags(&ctx->capture_stream, cudaStreamNonBlocking));
+            dm_ctx::UpperGraph g;
+            g.ws = ctx->ws; g.nt = nt; g.t0 = t0; g.t1 = t1; g.levels = L;
+            g.filter_num = a->filter_num; g.filter_win = a->filter_win; g.filter_mode = a->filter_mode;
+            DM_CUDA_CHECK(cudaStreamBeginCapture(ctx->capture_stream, cudaStreamCaptureModeThreadLocal));
+            rc = run_agg(ctx->capture_stream, &g.n_agg);
+            if (rc == DM_OK) rc = run_bt(ctx->capture_stream, &g.n_bt);
+            cudaGraph_t graph = nullptr;
+            cudaError_t ce = cudaStreamEndCapture(ctx->capture_stream, &graph);
+            if (rc != DM_OK) { if (graph) cudaGraphDestroy(graph); return rc; }
+            DM_CUDA_CHECK(ce);
+            g.final_cur = cur;
+            ce = cudaGraphInstantiate(&g.exec, graph, 0);
+            cudaGraphDestroy(graph);
+            DM_CUDA_CHECK(ce);
+            ctx->upper_graphs.push_back(g);
+            ug = &ctx->upper_graphs.back();
+        }
+        DM_CUDA_CHECK(cudaGraphLaunch(ug->exec, st));
+        cur = ug->final_cur;
+        ctx->launches[DM_STAGE_AGGREGATE] += ug->n_agg;
+        ctx->launches[DM_STAGE_BACKTRACK] += ug->n_bt;
     }
     {
         StageTimer tm(ctx, DM_STAGE_PLANES);           // level-0 backtracking + sub-pixel + planes
