@@ -58,6 +58,7 @@ SIGNATURES = {
     'dm_ctx_create': (c_int, [POINTER(c_void_p)]),
     'dm_ctx_destroy': (None, [c_void_p]),
     'dm_ctx_set_stream': (c_int, [c_void_p, c_void_p]),
+    'dm_correlation_set_pair_mode': (c_int, [c_int]),
     'dm_ctx_set_workspace_limit': (c_int, [c_void_p, c_size_t]),
     'dm_ctx_workspace_bytes': (c_size_t, [c_void_p]),
     'dm_scene_geometry': (c_int, [POINTER(SceneParams), POINTER(SceneInfo)]),
@@ -90,6 +91,8 @@ def lib():
         fn.restype = res
         fn.argtypes = args
     _lib = handle
+    if os.environ.get('DM_CORR_PAIR') is not None:                 # tuning knob: 0 = no CTA pairs in the tcgen05 correlation
+        handle.dm_correlation_set_pair_mode(int(os.environ['DM_CORR_PAIR']))
     return _lib
 
 

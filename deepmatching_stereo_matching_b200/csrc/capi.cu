@@ -30,6 +30,12 @@ extern "C" int dm_device_cc(void) {
     return major * 10 + minor;
 }
 
+extern "C" int dm_correlation_set_pair_mode(int mode) {
+    DM_REQUIRE(mode >= -1 && mode <= 1, DM_ERR_INVALID, "dm_correlation_set_pair_mode: mode %d", mode);
+    dm_correlation_umma_set_pair_mode(mode);
+    return DM_OK;
+}
+
 // ------------------------------------------------------------------ correlation dispatch
 extern "C" int dm_correlation(const void* desc1_dev, const float* stat1_dev,
                               const void* desc2_dev, const float* stat2_dev,

@@ -36,6 +36,8 @@
 //                              every store instruction writes 8 rows x 64 B.
 // B traffic: every CTA streams the tile's whole position matrix once per item; with
 // M = 256 rows per item that is 32 B/clk/SM from L2 at the MMA's full rate.
+#include <cstdio>
+#include <cstdlib>
 #include "dm_common.cuh"
 #include "dm_internal.h"
 #include "umma.cuh"
@@ -48,6 +50,7 @@ constexpr int BN = 128;                 // positions per N-tile
 constexpr int BK = 64;                  // bf16 per 128-byte swizzle row
 constexpr int UMMA_K = 16;
 constexpr int STAGES = 3;
+constexpr int STAGES_PAIR = 6;          // CTA-pair kernel: a B stage holds 64 of the N-tile's 128 rows (8 KiB)
 constexpr int MAX_KB = 4;               // kpad <= 256
 constexpr int BOX_BYTES = BM * BK * 2;  // 16 KiB: one [128 rows x 64] bf16 box
 constexpr int EPI_WARPS = 8;
@@ -80,7 +83,10 @@ struct Params {
 
 enum { MODE_RAW = 0, MODE_POOL = 1, MODE_NULL = 2 };   // MODE_NULL: drain TMEM only (measurement aid)
 
-template <int MODE, int D, bool NORMED>      // D = positions per map row (T1); only used by MODE_POOL
+// PAIR: the CTA pair of a 2-CTA cluster works on 512 patches of one tile (256 per CTA, epilogue
+// unchanged) with tcgen05.mma.cta_group::2 (M = 256 across the pair, N = 128): each CTA fetches
+// only HALF of every B tile from its own shared memory and streams only half of B from L2.
+template <int MODE, int D, bool NORMED, bool PAIR>      // D = positions per map row (T1); only used by MODE_POOL
 __global__ void __launch_bounds__(THREADS, 1)
 dm_correlation_umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const Params prm) {
     extern __shared__ uint8_t smem_raw[];
@@ -93,33 +99,45 @@ dm_correlation_umma_kernel(const __grid_constant__ CUtensorMap mapA, const __gri
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
     uint64_t* a_full = bars;
     uint64_t* a_empty = bars + 1;
+    constexpr int NSTG = PAIR ? STAGES_PAIR : STAGES;
+    constexpr int ISSUERS = 1;              // 2: warps 1 and 2 of the leader each issue the MMAs of one accumulator half
+    constexpr int B_STAGE_BYTES = PAIR ? BOX_BYTES / 2 : BOX_BYTES;
     uint64_t* b_full = bars + 2;
-    uint64_t* b_empty = bars + 2 + STAGES;
-    uint64_t* t_full = bars + 2 + 2 * STAGES;
-    uint64_t* t_empty = bars + 4 + 2 * STAGES;
-    uint64_t* c_full = bars + 6 + 2 * STAGES;
-    uint64_t* c_empty = bars + 6 + 2 * STAGES + CS_STAGES;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 6 + 2 * STAGES + 2 * CS_STAGES);
+    uint64_t* b_empty = bars + 2 + NSTG;
+    uint64_t* t_full = bars + 2 + 2 * NSTG;
+    uint64_t* t_empty = bars + 4 + 2 * NSTG;
+    uint64_t* c_full = bars + 6 + 2 * NSTG;
+    uint64_t* c_empty = bars + 6 + 2 * NSTG + CS_STAGES;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 6 + 2 * NSTG + 2 * CS_STAGES);
 
     const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;   // provably warp-uniform
     const int P = prm.P, KB = prm.KB, NT = P / BN;
+    // work slots: a slot is a CTA (or a CTA pair); the pair's work unit is two consecutive items of one tile
+    // (shuffled so that ptxas can prove the value warp-uniform: otherwise every MMA / TMA issue behind
+    //  `rank == 0` is wrapped in an ELECT / BRA.U.ANY loop, ~150 cycles per MMA)
+    //  the cluster is (2,1,1) on a 1-D grid, so %cluster_ctarank == blockIdx.x & 1
+    const int rank = PAIR ? (int)(blockIdx.x & 1u) : 0;
+    const int slot = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+    const int n_slots = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+    const int n_units = PAIR ? prm.n_items >> 1 : prm.n_items;
 
     if (threadIdx.x == 0) {
         umma::mbar_init(a_full, 1);
-        umma::mbar_init(a_empty, 1);
-        for (int s = 0; s < STAGES; ++s) { umma::mbar_init(b_full + s, 1); umma::mbar_init(b_empty + s, 1); }
-        for (int s = 0; s < 2; ++s) { umma::mbar_init(t_full + s, 1); umma::mbar_init(t_empty + s, EPI_WARPS); }
+        umma::mbar_init(a_empty, ISSUERS);
+        for (int s = 0; s < NSTG; ++s) { umma::mbar_init(b_full + s, 1); umma::mbar_init(b_empty + s, ISSUERS); }
+        for (int s = 0; s < 2; ++s) { umma::mbar_init(t_full + s, ISSUERS); umma::mbar_init(t_empty + s, (PAIR ? 2 : 1) * EPI_WARPS); }
         for (int s = 0; s < CS_STAGES; ++s) { umma::mbar_init(c_full + s, 1); umma::mbar_init(c_empty + s, EPI_WARPS); }
         umma::fence_barrier_init();
         umma::tma_prefetch_desc(&mapA);
         umma::tma_prefetch_desc(&mapB);
     }
     if (warp == 1) {
-        umma::tmem_alloc(tmem_slot, TMEM_COLS);
-        umma::tmem_relinquish();
+        if (PAIR) { umma::tmem_alloc_pair(tmem_slot, TMEM_COLS); umma::tmem_relinquish_pair(); }
+        else { umma::tmem_alloc(tmem_slot, TMEM_COLS); umma::tmem_relinquish(); }
     }
     umma::tc_fence_before();
     __syncthreads();
+    if (PAIR) umma::cluster_sync_all();     // the peer's barriers are initialised before anything signals them
     umma::tc_fence_after();
     const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
 
@@ -129,16 +147,24 @@ dm_correlation_umma_kernel(const __grid_constant__ CUtensorMap mapA, const __gri
     umma::reg_dealloc<40>();
     if (warp == 0) {
         // ------------------------------------------------------------ TMA producer (converged warp, elected issue)
+        // PAIR: both CTAs load into their own shared memory; the bytes of both are counted by the
+        // LEADER's full barriers (the MMA issuer waits there), the empty barriers are local
+        // (the leader's commits are multicast to both CTAs)
         int bs = 0; uint32_t bph = 0, aph = 0; int cst = 0; uint32_t cph = 0;
-        for (int item = blockIdx.x; item < prm.n_items; item += gridDim.x) {
+        const uint32_t a_full_lead = PAIR ? umma::mapa_u32(a_full, 0) : 0;
+        const uint32_t b_full_lead = PAIR ? umma::mapa_u32(b_full, 0) : 0;
+        for (int unit = slot; unit < n_units; unit += n_slots) {
+            const int item = PAIR ? unit * 2 + rank : unit;
             const int tile = item / prm.items_per_tile;
             const int row0 = tile * P + (item - tile * prm.items_per_tile) * (HALVES * BM);
             umma::mbar_wait(a_empty, aph ^ 1);
             if (umma::elect_one()) {
-                umma::mbar_expect_tx(a_full, (uint32_t)(HALVES * KB * BOX_BYTES));
+                if (!PAIR || rank == 0) umma::mbar_expect_tx(a_full, (uint32_t)((PAIR ? 2 : 1) * HALVES * KB * BOX_BYTES));
                 for (int h = 0; h < HALVES; ++h)
-                    for (int kb = 0; kb < KB; ++kb)
-                        umma::tma_load_2d(smemA + (size_t)(h * MAX_KB + kb) * BOX_BYTES, &mapA, kb * BK, row0 + h * BM, a_full);
+                    for (int kb = 0; kb < KB; ++kb) {
+                        if (PAIR) umma::tma_load_2d_pair(smemA + (size_t)(h * MAX_KB + kb) * BOX_BYTES, &mapA, kb * BK, row0 + h * BM, a_full_lead);
+                        else umma::tma_load_2d(smemA + (size_t)(h * MAX_KB + kb) * BOX_BYTES, &mapA, kb * BK, row0 + h * BM, a_full);
+                    }
             }
             __syncwarp();
             aph ^= 1;
@@ -146,11 +172,17 @@ dm_correlation_umma_kernel(const __grid_constant__ CUtensorMap mapA, const __gri
                 for (int kb = 0; kb < KB; ++kb) {
                     umma::mbar_wait(b_empty + bs, bph ^ 1);
                     if (umma::elect_one()) {
-                        umma::mbar_expect_tx(b_full + bs, (uint32_t)BOX_BYTES);
-                        umma::tma_load_2d(smemB + (size_t)bs * BOX_BYTES, &mapB, kb * BK, tile * P + j * BN, b_full + bs);
+                        if (PAIR) {     // this CTA's half of the N-tile's rows: rank 0 supplies columns 0..63 of the MMA, rank 1 columns 64..127
+                            if (rank == 0) umma::mbar_expect_tx(b_full + bs, (uint32_t)(2 * B_STAGE_BYTES));
+                            umma::tma_load_2d_pair(smemB + (size_t)bs * B_STAGE_BYTES, &mapB, kb * BK, tile * P + j * BN + rank * (BN / 2),
+                                                   b_full_lead + (uint32_t)(bs * 8));
+                        } else {
+                            umma::mbar_expect_tx(b_full + bs, (uint32_t)BOX_BYTES);
+                            umma::tma_load_2d(smemB + (size_t)bs * BOX_BYTES, &mapB, kb * BK, tile * P + j * BN, b_full + bs);
+                        }
                     }
                     __syncwarp();
-                    if (++bs == STAGES) { bs = 0; bph ^= 1; }
+                    if (++bs == NSTG) { bs = 0; bph ^= 1; }
                 }
                 // column table of this N-tile (needed only by the epilogue, after the MMAs)
                 umma::mbar_wait(c_empty + cst, cph ^ 1);
@@ -162,12 +194,13 @@ dm_correlation_umma_kernel(const __grid_constant__ CUtensorMap mapA, const __gri
                 if (++cst == CS_STAGES) { cst = 0; cph ^= 1; }
             }
         }
-    } else if (warp == 1) {
-        // ------------------------------------------------------------ MMA issuer (converged warp, elected issue)
-        constexpr uint32_t idesc = umma::instr_desc_bf16(BM, BN);
+    } else if ((warp == 1 || (ISSUERS == 2 && warp == 2)) && rank == 0) {
+        const int hsel = warp - 1;
+        // ------------------------------------------------------------ MMA issuer (converged warp, elected issue; PAIR: leader CTA only)
+        constexpr uint32_t idesc = umma::instr_desc_bf16(PAIR ? 2 * BM : BM, BN);
         constexpr int KPB = BK / UMMA_K;
         int bs = 0; uint32_t bph = 0, aph = 0; int acc = 0; uint32_t accph = 0;
-        for (int item = blockIdx.x; item < prm.n_items; item += gridDim.x) {
+        for (int unit = slot; unit < n_units; unit += n_slots) {
             umma::mbar_wait(a_full, aph);
             aph ^= 1;
             for (int j = 0; j < NT; ++j) {
@@ -177,7 +210,7 @@ dm_correlation_umma_kernel(const __grid_constant__ CUtensorMap mapA, const __gri
                 for (int kb = 0; kb < KB; ++kb) {
                     umma::mbar_wait(b_full + bs, bph);
                     umma::tc_fence_after();
-                    const uint64_t bdesc = umma::smem_desc_sw128(smemB + (size_t)bs * BOX_BYTES);
+                    const uint64_t bdesc = umma::smem_desc_sw128(smemB + (size_t)bs * B_STAGE_BYTES);
                     const uint64_t adesc0 = umma::smem_desc_sw128(smemA + (size_t)kb * BOX_BYTES);
                     const int nk = prm.ksteps - kb * KPB;       // padding-only K steps are skipped
 #pragma unroll
@@ -185,18 +218,21 @@ dm_correlation_umma_kernel(const __grid_constant__ CUtensorMap mapA, const __gri
                         if (k < nk) {
 #pragma unroll
                             for (int h = 0; h < HALVES; ++h)
-                                if (umma::elect_one())
-                                    umma::mma_bf16(d0 + (uint32_t)(h * 2 * BN), adesc0 + (uint64_t)(h * ((MAX_KB * BOX_BYTES) >> 4)) + 2 * k,
-                                                   bdesc + 2 * k, idesc, (kb | k) != 0);
+                                if ((ISSUERS == 1 || h == hsel) && umma::elect_one()) {
+                                    if (PAIR) umma::mma_bf16_pair(d0 + (uint32_t)(h * 2 * BN), adesc0 + (uint64_t)(h * ((MAX_KB * BOX_BYTES) >> 4)) + 2 * k,
+                                                                  bdesc + 2 * k, idesc, (kb | k) != 0);
+                                    else umma::mma_bf16(d0 + (uint32_t)(h * 2 * BN), adesc0 + (uint64_t)(h * ((MAX_KB * BOX_BYTES) >> 4)) + 2 * k,
+                                                        bdesc + 2 * k, idesc, (kb | k) != 0);
+                                }
                         }
                     }
-                    if (umma::elect_one()) umma::mma_commit(b_empty + bs);      // frees the B stage when these MMAs retire
-                    if (++bs == STAGES) { bs = 0; bph ^= 1; }
+                    if (umma::elect_one()) { if (PAIR) umma::mma_commit_pair(b_empty + bs); else umma::mma_commit(b_empty + bs); }   // frees the B stage when these MMAs retire
+                    if (++bs == NSTG) { bs = 0; bph ^= 1; }
                 }
-                if (umma::elect_one()) umma::mma_commit(t_full + acc);          // accumulators of this N-tile complete
+                if (umma::elect_one()) { if (PAIR) umma::mma_commit_pair(t_full + acc); else umma::mma_commit(t_full + acc); }       // accumulators of this N-tile complete
                 if (++acc == 2) { acc = 0; accph ^= 1; }
             }
-            if (umma::elect_one()) umma::mma_commit(a_empty);                   // A may be overwritten
+            if (umma::elect_one()) { if (PAIR) umma::mma_commit_pair(a_empty); else umma::mma_commit(a_empty); }                     // A may be overwritten
         }
     }
     } else {
@@ -213,7 +249,9 @@ dm_correlation_umma_kernel(const __grid_constant__ CUtensorMap mapA, const __gri
         float4* stgA_mine = reinterpret_cast<float4*>(stgA + lane * STG_STRIDE);
         float4* stgB_mine = reinterpret_cast<float4*>(stgB + lane * STG_STRIDE);
         int acc = 0; uint32_t accph = 0; int cst = 0; uint32_t cph = 0;
-        for (int item = blockIdx.x; item < prm.n_items; item += gridDim.x) {
+        const uint32_t t_empty_lead = PAIR ? umma::mapa_u32(t_empty, 0) : 0;     // the leader's MMA warp waits for both CTAs' epilogues
+        for (int unit = slot; unit < n_units; unit += n_slots) {
+            const int item = PAIR ? unit * 2 + rank : unit;
             const int tile = item / prm.items_per_tile;
             const size_t wrow = (size_t)tile * P + (size_t)(item - tile * prm.items_per_tile) * (HALVES * BM) + quarter * 32;
             const size_t prowA = wrow + lane, prowB = prowA + BM;
@@ -370,7 +408,10 @@ dm_correlation_umma_kernel(const __grid_constant__ CUtensorMap mapA, const __gri
                 }
                 umma::tc_fence_before();
                 __syncwarp();
-                if (lane == 0) { umma::mbar_arrive(t_empty + acc); umma::mbar_arrive(c_empty + cst); }
+                if (lane == 0) {
+                    if (PAIR) umma::mbar_arrive_cluster(t_empty_lead + (uint32_t)(acc * 8)); else umma::mbar_arrive(t_empty + acc);
+                    umma::mbar_arrive(c_empty + cst);
+                }
                 if (++acc == 2) { acc = 0; accph ^= 1; }
                 if (++cst == CS_STAGES) { cst = 0; cph ^= 1; }
             }
@@ -388,9 +429,10 @@ dm_correlation_umma_kernel(const __grid_constant__ CUtensorMap mapA, const __gri
 
     umma::tc_fence_before();
     __syncthreads();
+    if (PAIR) umma::cluster_sync_all();     // the leader's MMAs read the peer's shared memory and signal its barriers until here
     if (warp == 1) {
         umma::tc_fence_after();
-        umma::tmem_dealloc(tmem_base, TMEM_COLS);
+        if (PAIR) umma::tmem_dealloc_pair(tmem_base, TMEM_COLS); else umma::tmem_dealloc(tmem_base, TMEM_COLS);
     }
 }
 
@@ -405,26 +447,60 @@ dm_encode_tiled_fn get_encode_fn() {
     return fn;
 }
 
-template <int MODE, int D, bool NORMED>
-int launch2(const CUtensorMap& mapA, const CUtensorMap& mapB, const Params& prm, cudaStream_t stream) {
+int g_pair_mode = -1;       // -1: CTA pairs whenever the shape allows, 0: never, 1: same as -1 (dm_correlation_set_pair_mode)
+
+template <int MODE, int D, bool NORMED, bool PAIR>
+int launch3(const CUtensorMap& mapA, const CUtensorMap& mapB, const Params& prm, cudaStream_t stream) {
     static bool configured = false;
-    auto kern = dm_correlation_umma_kernel<MODE, D, NORMED>;
-    if (!configured) {
-        DM_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
-        configured = true;
-    }
+    static int max_pairs = 0;
+    auto kern = dm_correlation_umma_kernel<MODE, D, NORMED, PAIR>;
     int dev = 0, sms = 0;
     DM_CUDA_CHECK(cudaGetDevice(&dev));
     DM_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    const int grid = prm.n_items < sms ? prm.n_items : sms;
-    kern<<<grid, THREADS, SMEM_BYTES, stream>>>(mapA, mapB, prm);
+    if (!configured) {
+        DM_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+        if (PAIR) {
+            cudaLaunchConfig_t q = {};
+            cudaLaunchAttribute qa[1];
+            qa[0].id = cudaLaunchAttributeClusterDimension;
+            qa[0].val.clusterDim.x = 2; qa[0].val.clusterDim.y = 1; qa[0].val.clusterDim.z = 1;
+            q.gridDim = dim3(sms & ~1); q.blockDim = dim3(THREADS); q.dynamicSmemBytes = SMEM_BYTES; q.attrs = qa; q.numAttrs = 1;
+            DM_CUDA_CHECK(cudaOccupancyMaxActiveClusters(&max_pairs, kern, &q));
+            DM_REQUIRE(max_pairs > 0, DM_ERR_CUDA, "tcgen05 correlation: no 2-CTA cluster fits on this device");
+            if (getenv("DM_DEBUG")) fprintf(stderr, "[dm] correlation CTA pairs: %d co-resident 2-CTA clusters on %d SMs\n", max_pairs, sms);
+        }
+        configured = true;
+    }
+    if (!PAIR) {
+        const int grid = prm.n_items < sms ? prm.n_items : sms;
+        kern<<<grid, THREADS, SMEM_BYTES, stream>>>(mapA, mapB, prm);
+        DM_LAUNCH_CHECK();
+        return DM_OK;
+    }
+    // persistent grid of CTA pairs: one 2-CTA cluster per TPC
+    const int units = prm.n_items / 2;
+    const int pairs = units < max_pairs ? units : max_pairs;
+    cudaLaunchConfig_t cfg = {};
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.gridDim = dim3(2 * pairs); cfg.blockDim = dim3(THREADS); cfg.dynamicSmemBytes = SMEM_BYTES; cfg.stream = stream;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    DM_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, mapA, mapB, prm));
     DM_LAUNCH_CHECK();
     return DM_OK;
 }
 
+template <int MODE, int D, bool NORMED>
+int launch2(const CUtensorMap& mapA, const CUtensorMap& mapB, const CUtensorMap& mapB_pair, const Params& prm, cudaStream_t stream) {
+    // a pair's work unit is two consecutive items of the same tile
+    if (g_pair_mode != 0 && prm.items_per_tile % 2 == 0) return launch3<MODE, D, NORMED, true>(mapA, mapB_pair, prm, stream);
+    return launch3<MODE, D, NORMED, false>(mapA, mapB, prm, stream);
+}
+
 template <int MODE, int D>
-int launch(const CUtensorMap& mapA, const CUtensorMap& mapB, const Params& prm, bool normed, cudaStream_t stream) {
-    return normed ? launch2<MODE, D, true>(mapA, mapB, prm, stream) : launch2<MODE, D, false>(mapA, mapB, prm, stream);
+int launch(const CUtensorMap& mapA, const CUtensorMap& mapB, const CUtensorMap& mapB_pair, const Params& prm, bool normed, cudaStream_t stream) {
+    return normed ? launch2<MODE, D, true>(mapA, mapB, mapB_pair, prm, stream) : launch2<MODE, D, false>(mapA, mapB, mapB_pair, prm, stream);
 }
 
 }  // namespace
@@ -451,12 +527,14 @@ bool dm_correlation_umma_pool_supported(int t0, int t1, int kpad) {
     return dm_correlation_umma_supported(t0 * t1, kpad) && (t1 == 16 || t1 == 32 || t1 == 64 || t1 == 128) && t0 % 2 == 0;
 }
 
-static int fill_params(Params& prm, CUtensorMap& mapA, CUtensorMap& mapB, const void* desc1, const float* stat1,
+static int fill_params(Params& prm, CUtensorMap& mapA, CUtensorMap& mapB, CUtensorMap& mapB_pair, const void* desc1, const float* stat1,
                        const void* desc2, const float* stat2, int n_tiles, int p, int kpad, int kreal) {
     const uint64_t rows = (uint64_t)n_tiles * p;
     int rc = dm_make_desc_tensor_map(&mapA, desc1, rows, kpad, BM);
     if (rc != DM_OK) return rc;
     rc = dm_make_desc_tensor_map(&mapB, desc2, rows, kpad, BN);
+    if (rc != DM_OK) return rc;
+    rc = dm_make_desc_tensor_map(&mapB_pair, desc2, rows, kpad, BN / 2);     // each CTA of a pair loads half of the N-tile
     if (rc != DM_OK) return rc;
     prm.stat1 = (const dm_stat*)stat1;
     prm.cstat2 = reinterpret_cast<const float4*>((const dm_stat*)stat2 + rows);
@@ -470,21 +548,21 @@ static int fill_params(Params& prm, CUtensorMap& mapA, CUtensorMap& mapB, const 
 
 int dm_correlation_umma(const void* desc1, const float* stat1, const void* desc2, const float* stat2,
                         int n_tiles, int p, int kpad, int kreal, int method, float* raw, cudaStream_t stream) {
-    Params prm; CUtensorMap mapA, mapB;
-    int rc = fill_params(prm, mapA, mapB, desc1, stat1, desc2, stat2, n_tiles, p, kpad, kreal);
+    Params prm; CUtensorMap mapA, mapB, mapBp;
+    int rc = fill_params(prm, mapA, mapB, mapBp, desc1, stat1, desc2, stat2, n_tiles, p, kpad, kreal);
     if (rc != DM_OK) return rc;
     prm.raw = raw;
-    return launch<MODE_RAW, 64>(mapA, mapB, prm, method == DM_TM_CCOEFF_NORMED, stream);
+    return launch<MODE_RAW, 64>(mapA, mapB, mapBp, prm, method == DM_TM_CCOEFF_NORMED, stream);
 }
 
 // measurement aid (DM_CORR_UMMA_NULL): MMAs + TMEM drain, no epilogue math, no output
 int dm_correlation_umma_null(const void* desc1, const float* stat1, const void* desc2, const float* stat2,
                              int n_tiles, int p, int kpad, int kreal, float* raw, cudaStream_t stream) {
-    Params prm; CUtensorMap mapA, mapB;
-    int rc = fill_params(prm, mapA, mapB, desc1, stat1, desc2, stat2, n_tiles, p, kpad, kreal);
+    Params prm; CUtensorMap mapA, mapB, mapBp;
+    int rc = fill_params(prm, mapA, mapB, mapBp, desc1, stat1, desc2, stat2, n_tiles, p, kpad, kreal);
     if (rc != DM_OK) return rc;
     prm.raw = raw;
-    return launch<MODE_NULL, 64>(mapA, mapB, prm, true, stream);
+    return launch<MODE_NULL, 64>(mapA, mapB, mapBp, prm, true, stream);
 }
 
 int dm_correlation_umma_pool(const void* desc1, const float* stat1, const void* desc2, const float* stat2,
@@ -492,13 +570,15 @@ int dm_correlation_umma_pool(const void* desc1, const float* stat1, const void* 
                              float* pooled, float* rowmin, float* rowmax, cudaStream_t stream) {
     DM_REQUIRE(dm_correlation_umma_pool_supported(t0, t1, kpad), DM_ERR_UNSUPPORTED, "pooled tcgen05 correlation: unsupported grid (%d,%d)", t0, t1);
     (void)engine;
-    Params prm; CUtensorMap mapA, mapB;
-    int rc = fill_params(prm, mapA, mapB, desc1, stat1, desc2, stat2, n_tiles, t0 * t1, kpad, kreal);
+    Params prm; CUtensorMap mapA, mapB, mapBp;
+    int rc = fill_params(prm, mapA, mapB, mapBp, desc1, stat1, desc2, stat2, n_tiles, t0 * t1, kpad, kreal);
     if (rc != DM_OK) return rc;
     prm.pooled = pooled; prm.rowmin = rowmin; prm.rowmax = rowmax;
     const bool normed = method == DM_TM_CCOEFF_NORMED;
-    if (t1 == 128) return launch<MODE_POOL, 128>(mapA, mapB, prm, normed, stream);
-    if (t1 == 64) return launch<MODE_POOL, 64>(mapA, mapB, prm, normed, stream);
-    if (t1 == 32) return launch<MODE_POOL, 32>(mapA, mapB, prm, normed, stream);
-    return launch<MODE_POOL, 16>(mapA, mapB, prm, normed, stream);
+    if (t1 == 128) return launch<MODE_POOL, 128>(mapA, mapB, mapBp, prm, normed, stream);
+    if (t1 == 64) return launch<MODE_POOL, 64>(mapA, mapB, mapBp, prm, normed, stream);
+    if (t1 == 32) return launch<MODE_POOL, 32>(mapA, mapB, mapBp, prm, normed, stream);
+    return launch<MODE_POOL, 16>(mapA, mapB, mapBp, prm, normed, stream);
 }
+
+void dm_correlation_umma_set_pair_mode(int mode) { g_pair_mode = mode; }

@@ -24,6 +24,8 @@ int dm_correlation_umma_pool(const void* desc1, const float* stat1, const void* 
                              int n_tiles, int t0, int t1, int kpad, int kreal, int method, int engine,
                              float* pooled, float* rowmin, float* rowmax, cudaStream_t stream);
 
+void dm_correlation_umma_set_pair_mode(int mode);     // -1 auto (CTA pairs when possible), 0 single CTA
+
 int dm_desc_kreal(int ws);      // ws * row stride of the descriptor K layout (descriptors.cu)
 
 struct dm_ctx {

@@ -54,6 +54,11 @@ extern "C" {
  *      [n][P][P/4] pooled raw ZNCC, followed by [n][P][2] partial row minima and
  *      [n][P][2] partial row maxima (square grids only)                                  */
 
+/* tcgen05 correlation: -1 (default) = run on CTA pairs (tcgen05.mma.cta_group::2, one 2-CTA
+ * cluster per TPC) whenever a tile holds an even number of 256-patch work items, 0 = always
+ * one CTA per work item.  Both produce bit-identical results; a tuning / test knob. */
+int         dm_correlation_set_pair_mode(int mode);
+
 int         dm_version(void);
 const char* dm_last_error(void);
 /* compute capability of the current device as major*10+minor, or <0 */

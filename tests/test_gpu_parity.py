@@ -32,6 +32,17 @@ class Stub(object):
     pass
 
 
+@pytest.fixture(params=[-1, 0], ids=['cta_pair', 'single_cta'])
+def pair_mode(request, dm):
+    """Runs a test on both builds of the tcgen05 correlation kernel: CTA pairs
+    (tcgen05.mma.cta_group::2, the default where a tile has an even number of work items)
+    and one CTA per work item."""
+    from deepmatching_stereo_matching_b200 import _native
+    _native.check(_native.lib().dm_correlation_set_pair_mode(request.param))
+    yield request.param
+    _native.check(_native.lib().dm_correlation_set_pair_mode(-1))
+
+
 @pytest.mark.parametrize('engine', [1, 0])
 @pytest.mark.parametrize('name', TILE_CASES)
 def test_correlation_and_pyramid_vs_reference(dm, name, engine):
@@ -63,7 +74,7 @@ def test_correlation_and_pyramid_vs_reference(dm, name, engine):
 
 
 @pytest.mark.parametrize('t0,t1,ws,n', [(16, 16, 5, 3), (8, 32, 3, 2), (32, 32, 5, 5), (32, 32, 15, 2), (64, 64, 15, 3), (32, 64, 7, 2)])
-def test_tcgen05_correlation_bit_identical_to_simt(dm, t0, t1, ws, n):
+def test_tcgen05_correlation_bit_identical_to_simt(dm, t0, t1, ws, n, pair_mode):
     """Both engines accumulate exact integers, so raw ZNCC must agree bit for bit."""
     import torch
     from deepmatching_stereo_matching_b200 import _native
@@ -103,7 +114,7 @@ def test_tcgen05_correlation_bit_identical_to_simt(dm, t0, t1, ws, n):
 
 
 @pytest.mark.parametrize('T,ws,n', [(32, 7, 6), (64, 5, 7), (32, 5, 20), (64, 15, 3)])
-def test_correlation_engines_are_repeatable(dm, T, ws, n):
+def test_correlation_engines_are_repeatable(dm, T, ws, n, pair_mode):
     """Race detector for the warp-specialised tcgen05 kernel: the same launch repeated 25 times
     must produce identical bits (few work items per SM and a short K make the MMA, TMA and
     epilogue pipelines run at very different speeds -- this caught an early TMEM-stage release)."""
@@ -144,7 +155,7 @@ def test_correlation_engines_are_repeatable(dm, T, ws, n):
 
 
 @pytest.mark.parametrize('T,ws,n', [(16, 5, 3), (32, 5, 5), (32, 15, 2), (64, 15, 3), (64, 3, 2), (128, 5, 1)])
-def test_pooled_epilogue_equals_maxpool_of_raw_zncc(dm, T, ws, n):
+def test_pooled_epilogue_equals_maxpool_of_raw_zncc(dm, T, ws, n, pair_mode):
     """The pooled tcgen05 epilogue against torch's max_pool2d(3, 2, 1) of the
     SIMT engine's raw ZNCC: min-max, clamp and the row factor are monotone, so the pooled map,
     the per-patch minimum and the per-patch maximum of the pooled map must agree bit for bit."""
