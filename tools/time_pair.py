@@ -6,11 +6,11 @@ from deepmatching_stereo_matching_b200 import _native
 from deepmatching_stereo_matching_b200.synth import texture
 
 lib = _native.lib()
-t0 = t1 = 64; ws = 15; n = int(sys.argv[1]) if len(sys.argv) > 1 else 225
+t0 = t1 = int(os.environ.get('DM_T', 64)); ws = int(os.environ.get('DM_WS', 15)); n = int(sys.argv[1]) if len(sys.argv) > 1 else 225
 P, kpad = t0 * t1, lib.dm_kpad(ws)
-H = W = 1024
+H = W = max(1024, t0 + ws + 60 * 15)
 s1 = torch.from_numpy(texture((H, W), seed=1)).cuda(); s2 = torch.from_numpy(texture((H, W), seed=2)).cuda()
-origin = torch.tensor([[60 * (k // 15), 60 * (k % 15)] for k in range(n)], dtype=torch.int32, device='cuda')
+origin = torch.tensor([[60 * ((k % 225) // 15), 60 * (k % 15)] for k in range(n)], dtype=torch.int32, device='cuda')
 bufs = []
 for sc in (s1, s2):
     desc = torch.empty((n * P, kpad), dtype=torch.bfloat16, device='cuda')
