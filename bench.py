@@ -177,7 +177,8 @@ def run_ours(args):
     torch.cuda.set_device(local_rank)
     if world > 1:
         if not os.environ.get('DM_KEEP_NCCL_DEBUG'):
-            os.environ['NCCL_DEBUG'] = 'WARN'       # keep stdout to the one JSON line (NCCL prints its version there)
+            os.environ['NCCL_DEBUG'] = 'WARN'
+            os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')    # keep stdout to the one JSON line (NCCL prints its version there)
         dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
 
     def barrier():
