@@ -126,6 +126,7 @@ dm_descriptor_row_kernel(const uint8_t* __restrict__ scene, int pitch,
     const uint32_t mlo = nv >= 4 ? 0xffffffffu : ((1u << (8 * nv)) - 1u);
     const uint32_t mhi = nv <= 4 ? 0u : (nv >= 8 ? 0xffffffffu : ((1u << (8 * (nv - 4))) - 1u));
     const long long p0 = ((long long)tile * t0 + i) * t1 + j0;        // first patch of the group
+    int myS = 0, myQ = 0, myMean = 0;                                 // lane gl < 8 keeps the sums of patch gl
 #pragma unroll
     for (int q = 0; q < 8; ++q) {
         const uint32_t lo = __funnelshift_r(w[q >> 2], w[(q >> 2) + 1], 8 * (q & 3)) & mlo;
@@ -156,8 +157,11 @@ dm_descriptor_row_kernel(const uint8_t* __restrict__ scene, int pitch,
             pk.z = *reinterpret_cast<uint32_t*>(&b2); pk.w = *reinterpret_cast<uint32_t*>(&b3);
             *reinterpret_cast<uint4*>(desc + (size_t)(p0 + q) * KPAD + gl * 8) = pk;
         }
-        if (gl == q) dm_write_stats(stat, n_patches, p0 + q, K, S, Q, mean);
+        if (gl == q) { myS = S; myQ = Q; myMean = mean; }
     }
+    // the statistics (a division, a square root and a reciprocal, ~60 instructions) once for the
+    // eight patches in parallel instead of once per patch behind a one-lane branch
+    if (live && gl < 8) dm_write_stats(stat, n_patches, p0 + gl, K, myS, myQ, myMean);
 }
 
 template <int WS>
