@@ -154,11 +154,10 @@ __global__ void __launch_bounds__(256)
 dm_final_quad_kernel(const FinalArgs a, long long n_quads) {
     constexpr int K = WS * WS;
     constexpr int RWQ = WS + 5;
-    __shared__ __align__(16) uint8_t region_all[8][2][QROWS * QRS];
-    __shared__ __align__(16) uint8_t patch_all[8][2][16 * QRS];      // the quad's (ws+1)^2 block of image 1, two byte alignments
+    __shared__ __align__(16) uint8_t region_all[8][QROWS * QRS];
+    __shared__ __align__(16) uint8_t patch_all[8][16 * QRS];         // the quad's (ws+1)^2 block of image 1
     const int lane = threadIdx.x & 31;
-    uint8_t* reg0 = region_all[threadIdx.x >> 5][0];
-    uint8_t* reg1 = region_all[threadIdx.x >> 5][1];
+    uint8_t* reg0 = region_all[threadIdx.x >> 5];
     const long long w = a.quad0 + (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (w >= a.quad0 + n_quads) return;
     const int T0 = a.t0, T1 = a.t1, P = T0 * T1;
@@ -214,19 +213,13 @@ dm_final_quad_kernel(const FinalArgs a, long long n_quads) {
 #pragma unroll
         for (int ry = 0; ry < RWQ; ++ry) {
             const uint8_t v = (lane < RWQ) ? vals[ry] : (uint8_t)0;
-            reg0[ry * QRS + lane] = v;                   // copy 0: column x at byte x
-            if (lane >= 1) reg1[ry * QRS + lane - 1] = v;    // copy 1: column x at byte x - 1
-        }
-        if (lane == 0) {
-#pragma unroll
-            for (int ry = 0; ry < RWQ; ++ry) reg1[ry * QRS + 31] = 0;
+            reg0[ry * QRS + lane] = v;                   // column x at byte x, zero beyond the region
         }
     }
     // ---- the four patches of the quad overlap in a (ws+1)^2 block of image 1: stage it with
-    // row-coalesced loads (copy 0: column x at byte x, copy 1: at byte x-1 for cj = 1)
+    // row-coalesced loads (column x at byte x; the children with cj = 1 shift by one byte when they read)
     {
-        uint8_t* pat0 = patch_all[threadIdx.x >> 5][0];
-        uint8_t* pat1 = patch_all[threadIdx.x >> 5][1];
+        uint8_t* pat0 = patch_all[threadIdx.x >> 5];
         const uint8_t* src = a.img1 + (size_t)(oy + 2 * I) * a.pitch + ox + 2 * J + (lane <= WS ? lane : 0);
         uint8_t pv[WS + 1];
 #pragma unroll
@@ -235,14 +228,14 @@ dm_final_quad_kernel(const FinalArgs a, long long n_quads) {
         for (int ry = 0; ry <= WS; ++ry) {
             const uint8_t v = (lane <= WS) ? pv[ry] : (uint8_t)0;
             pat0[ry * QRS + lane] = v;
-            if (lane >= 1) pat1[ry * QRS + lane - 1] = v;
         }
     }
     __syncwarp();
     // ---- this lane's patch rows ky = l and l + 8, 16 bytes each (zero beyond the window)
+    const int psh = 8 * cj;                              // this child's columns start at byte cj of a staged row
     uint32_t aw[2][4];
     {
-        const uint8_t* patc = patch_all[threadIdx.x >> 5][cj];
+        const uint8_t* patc = patch_all[threadIdx.x >> 5];
         // bytes >= WS of a row belong to the neighbouring child: masked out
         constexpr uint32_t M0 = WS >= 4 ? 0xffffffffu : ((1u << (8 * WS)) - 1u);
         constexpr uint32_t M1 = WS >= 8 ? 0xffffffffu : (WS <= 4 ? 0u : ((1u << (8 * (WS - 4))) - 1u));
@@ -253,12 +246,13 @@ dm_final_quad_kernel(const FinalArgs a, long long n_quads) {
             const int ky = l + 8 * r;
             const bool live = ky < WS;
             const uint4 w = *reinterpret_cast<const uint4*>(patc + (ci + (live ? ky : 0)) * QRS);
-            aw[r][0] = live ? (w.x & M0) : 0u; aw[r][1] = live ? (w.y & M1) : 0u;
-            aw[r][2] = live ? (w.z & M2) : 0u; aw[r][3] = live ? (w.w & M3) : 0u;
+            const uint32_t w4 = *reinterpret_cast<const uint32_t*>(patc + (ci + (live ? ky : 0)) * QRS + 16);
+            aw[r][0] = live ? (__funnelshift_r(w.x, w.y, psh) & M0) : 0u; aw[r][1] = live ? (__funnelshift_r(w.y, w.z, psh) & M1) : 0u;
+            aw[r][2] = live ? (__funnelshift_r(w.z, w.w, psh) & M2) : 0u; aw[r][3] = live ? (__funnelshift_r(w.w, w4, psh) & M3) : 0u;
         }
     }
     __syncwarp();
-    const uint8_t* regc = cj ? reg1 : reg0;              // this child's view: window column x at byte x
+    const uint8_t* regc = reg0;                          // region column x at byte x; this child's windows start cj bytes in
 
     // level-0 value of position (qy,qx) from sum a*b
     auto value_at = [&](int sum_ab, int qy, int qx) -> float {
@@ -270,8 +264,8 @@ dm_final_quad_kernel(const FinalArgs a, long long n_quads) {
     };
     // 16 bytes of a against region row `row`, window starting at byte `bo` (dynamic)
     auto row_dot = [&](const uint32_t (&aq)[4], int row, int bo) -> uint32_t {
-        const uint32_t* rr = reinterpret_cast<const uint32_t*>(regc + row * QRS) + (bo >> 2);
-        const int sh = (bo & 3) * 8;
+        const uint32_t* rr = reinterpret_cast<const uint32_t*>(regc + row * QRS) + ((bo + cj) >> 2);
+        const int sh = ((bo + cj) & 3) * 8;
         const uint32_t w0 = rr[0], w1 = rr[1], w2 = rr[2], w3 = rr[3], w4 = rr[4];
         uint32_t acc = __dp4a(aq[0], __funnelshift_r(w0, w1, sh), 0u);
         acc = __dp4a(aq[1], __funnelshift_r(w1, w2, sh), acc);
@@ -294,11 +288,11 @@ dm_final_quad_kernel(const FinalArgs a, long long n_quads) {
                 const uint32_t w4 = *reinterpret_cast<const uint32_t*>(regc + (ky + ci + dy + 1) * QRS + 16);
 #pragma unroll
                 for (int dx = 0; dx < 3; ++dx) {
-                    const int sh = 8 * (dx + 1);
-                    uint32_t t = __dp4a(aw[r][0], __funnelshift_r(lo.x, lo.y, sh), acc[dy * 3 + dx]);
-                    t = __dp4a(aw[r][1], __funnelshift_r(lo.y, lo.z, sh), t);
-                    t = __dp4a(aw[r][2], __funnelshift_r(lo.z, lo.w, sh), t);
-                    acc[dy * 3 + dx] = __dp4a(aw[r][3], __funnelshift_r(lo.w, w4, sh), t);
+                    const int sh = 8 * (dx + 1) + psh;       // 8 .. 32: the clamping funnel shift returns the high word at 32
+                    uint32_t t = __dp4a(aw[r][0], __funnelshift_rc(lo.x, lo.y, sh), acc[dy * 3 + dx]);
+                    t = __dp4a(aw[r][1], __funnelshift_rc(lo.y, lo.z, sh), t);
+                    t = __dp4a(aw[r][2], __funnelshift_rc(lo.z, lo.w, sh), t);
+                    acc[dy * 3 + dx] = __dp4a(aw[r][3], __funnelshift_rc(lo.w, w4, sh), t);
                 }
             }
         }

@@ -26,6 +26,18 @@ def test_library_exports_every_declared_symbol():
     assert lib.dm_kpad(15) == 256 and lib.dm_kpad(5) == 64 and lib.dm_kpad(3) == 64
 
 
+def test_pair_mode_knob_validates_its_argument():
+    """dm_correlation_set_pair_mode is host-only state: -1 / 1 = CTA pairs when the shape allows,
+    0 = one CTA per work item; anything else is DM_ERR_INVALID with a message."""
+    from deepmatching_stereo_matching_b200 import _native
+    lib = _native.lib()
+    for mode in (0, 1, -1):
+        assert lib.dm_correlation_set_pair_mode(mode) == 0
+    assert lib.dm_correlation_set_pair_mode(7) < 0
+    assert b'pair_mode' in lib.dm_last_error()
+    assert lib.dm_correlation_set_pair_mode(-1) == 0
+
+
 def test_struct_layout_matches_header():
     from deepmatching_stereo_matching_b200 import _native
     assert ctypes.sizeof(_native.SceneParams) == 4 * (9 + 4 + 4 + 3)
