@@ -206,7 +206,140 @@ __global__ void dm_sub_pix_cal_kernel(const double* __restrict__ arr, const doub
     out[idx] = clamp3(dis);
 }
 
+// ---------------------------------------------------------------------------------------
+// Upper pyramid tail + whole top-down pass of ONE tile in one CTA (fused scene solver, no
+// displacement filter).  Level `ks` (at most 16 KiB per tile) has been built by dm_aggregate;
+// the CTA builds the levels above it in shared memory (Correlation_map._aggregation,
+// misc/Correlation_map.py:100-128) and then walks back down to level 1
+// (Matching._initial_move_map / _B, misc/Matching.py:80-139) with the matches of the level above
+// in shared memory.  Same arithmetic and tie-breaks as dm_aggregate_*_kernel and
+// dm_backtrack_kernel; replaces ~9 small dependent launches.  (Building level ks here as well --
+// 4096 outputs of 36 gathered loads each per CTA -- took 0.1 ms and lost to the generic kernel.)
+struct TailArgs {
+    float* level[16];           // global level buffers [n][A][B][C][D] (levels >= ks are also written)
+    int t0, t1, L, ks;
+    int32_t* match1;            // [n][2][t0/2][t1/2]: matches of level 1
+};
+
+__device__ __forceinline__ void tail_aggregate(const float* __restrict__ in, int A, int B, int C, int D,
+                                               float* __restrict__ out_s, float* __restrict__ out_g) {
+    const int hB = B >> 1, oc = C >> 1, od = D >> 1;
+    const int total = (A >> 1) * hB * oc * od;
+    for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
+        const int x = idx % od;
+        int t = idx / od;
+        const int y = t % oc; t /= oc;
+        const int J = t % hB, I = t / hB;
+        float sum = 0.f;
+#pragma unroll
+        for (int ch = 0; ch < 4; ++ch) {
+            const float* src = in + ((size_t)(2 * I + (ch >> 1)) * B + (2 * J + (ch & 1))) * (size_t)(C * D);
+            float m = -CUDART_INF_F;
+#pragma unroll
+            for (int dy = -1; dy <= 1; ++dy) {
+                const int r = 2 * y + dy;                 // r < C always (C even)
+                if (r < 0) continue;
+#pragma unroll
+                for (int dx = -1; dx <= 1; ++dx) {
+                    const int c = 2 * x + dx;
+                    if (c < 0) continue;
+                    m = dm_max_nan(m, src[(size_t)r * D + c]);
+                }
+            }
+            sum = (ch == 0) ? m : __fadd_rn(sum, m);      // ((ul + ur) + ll) + lr
+        }
+        const float o = dm_rectify(__fmul_rn(sum, 0.25f));
+        out_s[idx] = o;
+        out_g[idx] = o;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+dm_upper_tail_kernel(const TailArgs a) {
+    extern __shared__ __align__(16) float tail_smem[];
+    const int n = blockIdx.x, L = a.L, ks = a.ks;
+    // shared levels ks+1 .. L-1, then two match buffers of [2][cells of level 2]
+    float* slevel[16];
+    size_t off = 0;
+    for (int k = ks + 1; k < L; ++k) {
+        slevel[k] = tail_smem + off;
+        const size_t cells = (size_t)(a.t0 >> k) * (a.t1 >> k);
+        off += cells * cells;
+    }
+    const int cells2 = (a.t0 >> 2) * (a.t1 >> 2);
+    int32_t* mprev = reinterpret_cast<int32_t*>(tail_smem + off);
+    int32_t* mcur = mprev + 2 * cells2;
+
+    for (int k = ks; k + 1 < L; ++k) {                    // level k -> k + 1
+        const int A = a.t0 >> k, B = a.t1 >> k;
+        const size_t cells = (size_t)A * B, ncells = (size_t)(A >> 1) * (B >> 1);
+        const float* in = (k > ks) ? slevel[k] : a.level[k] + (size_t)n * cells * cells;
+        tail_aggregate(in, A, B, A, B, slevel[k + 1], a.level[k + 1] + (size_t)n * ncells * ncells);
+        __syncthreads();
+    }
+    for (int k = L - 1; k >= 1; --k) {
+        const int A = a.t0 >> k, B = a.t1 >> k, cells = A * B;
+        const float* lv = (k > ks) ? slevel[k] : a.level[k] + (size_t)n * cells * cells;
+        for (int idx = threadIdx.x; idx < cells; idx += blockDim.x) {
+            const int i = idx / B, j = idx - i * B;
+            int d0 = i, d1 = j;
+            if (k < L - 1) {                              // misc/Matching.py:116-124
+                const int hA = A >> 1, hB = B >> 1, pidx = (i >> 1) * hB + (j >> 1);
+                d0 = 2 * mprev[pidx] + (i & 1);
+                d1 = 2 * mprev[hA * hB + pidx] + (j & 1);
+            }
+            int r0, r1;
+            float sc;
+            near_match<float>(lv + (size_t)idx * cells, A, B, d0, d1, r0, r1, sc);
+            if (k == 1) {
+                a.match1[(size_t)n * 2 * cells + idx] = r0;
+                a.match1[(size_t)n * 2 * cells + cells + idx] = r1;
+            } else {
+                mcur[idx] = r0;
+                mcur[cells + idx] = r1;
+            }
+        }
+        __syncthreads();
+        int32_t* t = mprev; mprev = mcur; mcur = t;
+    }
+}
+
 }  // namespace
+
+// the level dm_upper_tail starts from (the last one dm_aggregate builds): the smallest k >= 2 whose
+// per-tile level is <= 16 KiB
+int dm_upper_tail_first_level(int t0, int t1, int levels) {
+    int ks = 2;
+    while (ks < levels - 1) {
+        const size_t cells = (size_t)(t0 >> ks) * (t1 >> ks);
+        if (cells * cells * sizeof(float) <= 16 * 1024) break;
+        ++ks;
+    }
+    return ks;
+}
+
+bool dm_upper_tail_supported(int t0, int t1, int levels) {
+    if (levels < 3 || levels > 16) return false;
+    const int ks = dm_upper_tail_first_level(t0, t1, levels);
+    size_t floats = 0;
+    for (int k = ks + 1; k < levels; ++k) { const size_t c = (size_t)(t0 >> k) * (t1 >> k); floats += c * c; }
+    const size_t bytes = floats * 4 + (size_t)4 * (t0 >> 2) * (t1 >> 2) * 4;
+    return bytes <= 48 * 1024;
+}
+
+int dm_upper_tail(float* const* levels_dev, int n_tiles, int t0, int t1, int levels, int32_t* match1_dev, cudaStream_t stream) {
+    DM_REQUIRE(dm_upper_tail_supported(t0, t1, levels), DM_ERR_UNSUPPORTED, "dm_upper_tail: unsupported grid (%d,%d), %d levels", t0, t1, levels);
+    TailArgs a;
+    for (int k = 0; k < 16; ++k) a.level[k] = k < levels ? levels_dev[k] : nullptr;
+    a.t0 = t0; a.t1 = t1; a.L = levels; a.ks = dm_upper_tail_first_level(t0, t1, levels);
+    a.match1 = match1_dev;
+    size_t floats = 0;
+    for (int k = a.ks + 1; k < levels; ++k) { const size_t c = (size_t)(t0 >> k) * (t1 >> k); floats += c * c; }
+    const size_t smem = floats * 4 + (size_t)4 * (t0 >> 2) * (t1 >> 2) * 4;
+    dm_upper_tail_kernel<<<n_tiles, 256, smem, stream>>>(a);
+    DM_LAUNCH_CHECK();
+    return DM_OK;
+}
 
 template <typename T>
 static int backtrack_launch(const void* level, long long n, int a, int b, int c, int d,

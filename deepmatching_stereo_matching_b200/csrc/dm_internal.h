@@ -26,6 +26,11 @@ int dm_correlation_umma_pool(const void* desc1, const float* stat1, const void* 
 
 void dm_correlation_umma_set_pair_mode(int mode);     // -1 auto (CTA pairs when possible), 0 single CTA
 
+// upper pyramid tail + top-down pass of one tile per CTA (backtrack.cu); levels_dev[k] = level k of the fused workspace
+bool dm_upper_tail_supported(int t0, int t1, int levels);
+int dm_upper_tail_first_level(int t0, int t1, int levels);
+int dm_upper_tail(float* const* levels_dev, int n_tiles, int t0, int t1, int levels, int32_t* match1_dev, cudaStream_t stream);
+
 int dm_desc_kreal(int ws);      // ws * row stride of the descriptor K layout (descriptors.cu)
 
 struct dm_ctx {

@@ -505,9 +505,14 @@ int dm_fused_solve_chunk(dm_ctx* ctx, const dm_fused_args* a, int ck) {
     // graph (on a private stream: the caller's may be the legacy default stream, which cannot
     // capture) and replayed with one launch; with stage timing on they are launched one by one.
     int cur = 0;
+    // without the displacement filter the levels above ks and the whole top-down pass run as ONE
+    // kernel (one CTA per tile, dm_upper_tail); the generic kernels then only build levels 2 .. ks
+    static const bool no_tail = getenv("DM_NO_TAIL") != nullptr;
+    const bool tail = !no_tail && a->filter_num <= 0 && dm_upper_tail_supported(t0, t1, L);
+    const int agg_end = tail ? dm_upper_tail_first_level(t0, t1, L) : L - 1;          // last level built by dm_aggregate
     auto run_agg = [&](cudaStream_t s, int* n_agg) -> int {
         *n_agg = 0;
-        for (int k = 1; k + 1 < L; ++k) {
+        for (int k = 1; k + 1 <= agg_end; ++k) {
             int r = dm_aggregate(fb.level[k], nt, t0 >> k, t1 >> k, t0 >> k, t1 >> k, 1, fb.level[k + 1], s);
             if (r != DM_OK) return r;
             ++*n_agg;
@@ -517,6 +522,11 @@ int dm_fused_solve_chunk(dm_ctx* ctx, const dm_fused_args* a, int ck) {
     auto run_bt = [&](cudaStream_t s, int* n_bt) -> int {
         int r;
         cur = 0; *n_bt = 0;
+        if (tail) {
+            if ((r = dm_upper_tail(fb.level, nt, t0, t1, L, fb.match[0], s)) != DM_OK) return r;
+            *n_bt = 1;
+            return DM_OK;
+        }
         int filters_left = a->filter_num;
         auto maybe_filter = [&](int k) -> int {       // misc/Matching.py:91-93,136-138
             if (filters_left <= 0) return DM_OK;
