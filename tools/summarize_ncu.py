@@ -50,7 +50,7 @@ def short(name):
     return name.split('(')[0]
 
 
-def launches(tag, path):
+def launches(tag, path, fused_only=True):
     rows = [r for r in csv.reader(open(path, errors='replace')) if r and not r[0].startswith('==')]
     hdr = next(i for i, r in enumerate(rows) if 'Kernel Name' in r)
     h = rows[hdr]
@@ -62,6 +62,11 @@ def launches(tag, path):
         for r in rows[hdr + 1:]:
             if len(r) <= mv:
                 continue
+            # bench.py ends with a pass over the materialising path (for the stand-alone aggregation
+            # kernel); the launch list and the shares are those of the product (fused) path only
+            k0 = short(r[kn])
+            if fused_only and (k0 == 'dm_tile_origin_kernel' or any(t in k0 for t in ('dm_minmax_rectify', 'umma_kernel<0', 'umma_kernel<(int)0', 'dm_planes_kernel'))):
+                break
             ms = to_ms(r[mv], r[mu])
             k = short(r[kn])
             tot.setdefault(k, [0, 0.0])
