@@ -149,13 +149,15 @@ struct FinalArgs {
 constexpr int QRS = 32;                 // region row stride in bytes (16-byte aligned rows)
 constexpr int QROWS = 20;               // ws + 5 <= 20
 
+constexpr int FQ_WARPS = 4;             // quads (warps) per CTA: 0.371 -> 0.359 ms against 8
+
 template <int WS>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(32 * FQ_WARPS)
 dm_final_quad_kernel(const FinalArgs a, long long n_quads) {
     constexpr int K = WS * WS;
     constexpr int RWQ = WS + 5;
-    __shared__ __align__(16) uint8_t region_all[8][QROWS * QRS];
-    __shared__ __align__(16) uint8_t patch_all[8][16 * QRS];         // the quad's (ws+1)^2 block of image 1
+    __shared__ __align__(16) uint8_t region_all[FQ_WARPS][QROWS * QRS];
+    __shared__ __align__(16) uint8_t patch_all[FQ_WARPS][16 * QRS];         // the quad's (ws+1)^2 block of image 1
     const int lane = threadIdx.x & 31;
     uint8_t* reg0 = region_all[threadIdx.x >> 5];
     const long long w = a.quad0 + (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -448,7 +450,7 @@ dm_final_quad_kernel(const FinalArgs a, long long n_quads) {
 
 template <int WS>
 static void launch_final_quad(const FinalArgs& fa, long long n_quads, cudaStream_t st) {
-    dm_final_quad_kernel<WS><<<dm_div_up(n_quads, 8), 256, 0, st>>>(fa, n_quads);
+    dm_final_quad_kernel<WS><<<dm_div_up(n_quads, FQ_WARPS), 32 * FQ_WARPS, 0, st>>>(fa, n_quads);
 }
 
 }  // namespace
