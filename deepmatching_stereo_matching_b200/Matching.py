@@ -75,39 +75,22 @@ class Matching():
             out.append(torch.from_numpy(a).cuda())
         return out, f64
 
-    def _filter(self, map_here):
-        """misc/Matching.py:224-255 on the small (3,h,w) host map (default off; includes the
-        reference's square-grid sizing of d_map)."""
-        map_shape = map_here.shape
-        if map_shape[1] >= self.filter_window_size and map_shape[2] >= self.filter_window_size:
-            e = int((self.filter_window_size - 1) / 2)
-            n = map_shape[1]
-            jj = np.arange(n)
-            d_map = (map_here[1, :n, :n] - jj[None, :]).astype('int64')
-            d_map2 = (map_here[0, :n, :n] - jj[:, None]).astype('int64')
-            red = np.mean if self.filtering_mode == 'average' else np.median
-            for i in range(e, map_shape[1] - e):
-                for j in range(e, map_shape[2] - e):
-                    map_here[1, i, j] = round(red(d_map[i - e:i + e + 1, j - e:j + e + 1])) + j
-                    map_here[0, i, j] = round(red(d_map2[i - e:i + e + 1, j - e:j + e + 1])) + i
-        return map_here
-
     def _filter_device(self, match, score, torch):
-        """One application of Matching._filter (misc/Matching.py:91-93,136-138): dm_match_filter
-        on square maps (where the reference's filter is defined); the literal host restatement
-        otherwise, with the reference's own behaviour there."""
+        """One application of Matching._filter (misc/Matching.py:91-93,136-138) = dm_match_filter.
+        The reference sizes its snapshot (shape[1], shape[1]) (:235-236): on a non-square map it
+        raises ValueError (operands cannot be broadcast, or round() of the NaN mean of an empty
+        window), and so does this class -- there is nothing to accelerate and no host fallback."""
         self.filtering_num -= 1
         _, h, w = match.shape
         if not (h >= self.filter_window_size and w >= self.filter_window_size):
             return match
-        if h == w and 0 <= (self.filter_window_size - 1) // 2 <= 4:
-            out = torch.empty_like(match)
-            _native.check(_native.lib().dm_match_filter(_native.ptr(match), 1, h, w, int(self.filter_window_size),
-                                                        _native.FILTER_IDS[self.filtering_mode], _native.ptr(out), _native.stream_ptr()))
-            return out
-        mp = np.concatenate([match.cpu().numpy().astype(np.float64), score.cpu().numpy().astype(np.float64)[None]], 0)
-        mp = self._filter(mp)
-        return torch.from_numpy(np.ascontiguousarray(mp[:2]).astype(np.int32)).cuda()
+        if h != w:
+            raise ValueError('Matching._filter is undefined on non-square maps (%d x %d): the reference '
+                             'fails in misc/Matching.py:235-248' % (h, w))
+        out = torch.empty_like(match)
+        _native.check(_native.lib().dm_match_filter(_native.ptr(match), 1, h, w, int(self.filter_window_size),
+                                                    _native.FILTER_IDS[self.filtering_mode], _native.ptr(out), _native.stream_ptr()))
+        return out
 
     # ------------------------------------------------------------------ reference API
     def __call__(self):

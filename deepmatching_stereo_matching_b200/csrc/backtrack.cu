@@ -120,7 +120,7 @@ dm_match_map_kernel(const T* __restrict__ l0, long long total, int T0, int T1,
 // neighbourhood is read from the unfiltered field (the reference snapshots it in d_map),
 // Python's round() is half-to-even (rint), the median of an odd count is its middle element.
 // Border cells are copied.  in / out: int32 [n][2][H][W].
-constexpr int DM_FILTER_MAX_E = 4;      // windows up to 9 x 9
+constexpr int DM_FILTER_MAX_E = 4;      // windows up to 9 x 9 are ranked in registers, larger ones by bisection
 __global__ void __launch_bounds__(256)
 dm_match_filter_kernel(const int32_t* __restrict__ in, long long total, int H, int W, int e, int mode, int32_t* __restrict__ out) {
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -141,6 +141,25 @@ dm_match_filter_kernel(const int32_t* __restrict__ in, long long total, int H, i
                 for (int x = j - e; x <= j + e; ++x) { s0 += rowp[(size_t)y * W + x] - y; s1 += colp[(size_t)y * W + x] - x; }
             o0 = (int)rint(__ddiv_rn((double)s0, (double)cnt)) + i;     // np.mean = sum / count in float64, then round()
             o1 = (int)rint(__ddiv_rn((double)s1, (double)cnt)) + j;
+        } else if (e > DM_FILTER_MAX_E) {
+            // large windows: the middle element is the smallest value v with count(x <= v) > cnt / 2;
+            // bisection over the displacement range, the window is re-read from memory each time
+            const int half = cnt / 2;
+            int med[2];
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+                const int32_t* p = c == 0 ? rowp : colp;
+                int lo = -(1 << 20), hi = 1 << 20;
+                while (lo < hi) {
+                    const int mid = lo + ((hi - lo) >> 1);
+                    int le = 0;
+                    for (int y = i - e; y <= i + e; ++y)
+                        for (int x = j - e; x <= j + e; ++x) le += (p[(size_t)y * W + x] - (c == 0 ? y : x)) <= mid;
+                    if (le > half) hi = mid; else lo = mid + 1;
+                }
+                med[c] = lo;
+            }
+            o0 = med[0] + i; o1 = med[1] + j;
         } else {
             int v0[(2 * DM_FILTER_MAX_E + 1) * (2 * DM_FILTER_MAX_E + 1)], v1[(2 * DM_FILTER_MAX_E + 1) * (2 * DM_FILTER_MAX_E + 1)];
             int m = 0;
@@ -378,7 +397,6 @@ extern "C" int dm_match_filter(const int32_t* match_in_dev, int n, int h, int w,
     }
     DM_REQUIRE(h == w, DM_ERR_UNSUPPORTED, "dm_match_filter: Matching._filter sizes its snapshot (shape[1], shape[1]) and is undefined on non-square maps (%d x %d)", h, w);
     const int e = (window - 1) / 2;
-    DM_REQUIRE(e <= DM_FILTER_MAX_E, DM_ERR_UNSUPPORTED, "dm_match_filter: filter windows up to %d are supported (got %d)", 2 * DM_FILTER_MAX_E + 1, window);
     dm_match_filter_kernel<<<dm_div_up(total, 256), 256, 0, st>>>(match_in_dev, total, h, w, e, mode, match_out_dev);
     DM_LAUNCH_CHECK();
     return DM_OK;

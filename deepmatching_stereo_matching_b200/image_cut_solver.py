@@ -204,15 +204,14 @@ class ImageCutSolver():
 
     def _filter_on_device(self):
         """The batched solver runs Matching._filter (misc/Matching.py:224-255) as a kernel between
-        the levels; the reference's filter is only defined on square patch grids and the kernel
-        covers windows up to 9 x 9 -- everything else goes tile by tile through Matching."""
+        the levels.  The reference's filter is only defined on square patch grids: on the others
+        it raises in the first tile, which is what the tile-by-tile path through Matching does."""
         small = self.image_size[0] < self.filtering_window_size or self.image_size[1] < self.filtering_window_size
-        return self.filtering_num <= 0 or small or (self.image_size[0] == self.image_size[1] and (self.filtering_window_size - 1) // 2 <= 4
-                                                     and self.filtering_window_size >= 1)
+        return self.filtering_num <= 0 or small or (self.image_size[0] == self.image_size[1] and 1 <= self.filtering_window_size <= 255)
 
     def _execute_matching_per_tile(self, size_list):
         """Tile-by-tile variant through the class API (the same kernels, one tile at a time); used
-        for displacement-filter settings the batched solver does not take and by the tests."""
+        by the tests and for a displacement filter on non-square grids (raises like the reference)."""
         self.d_map = np.empty([len(self.degree_map_mode)] + size_list, dtype=float)
         self.out_map = np.empty(size_list, dtype=float)
         for idx in range(len(self.img_index)):

@@ -263,6 +263,44 @@ def test_displacement_filter_bit_exact(dm, name):
         assert np.array_equal(got, g[k], equal_nan=True), k
 
 
+@pytest.mark.parametrize('mode', ['median', 'average'])
+@pytest.mark.parametrize('h,win', [(32, 3), (32, 9), (32, 11), (32, 15), (16, 13), (64, 31)])
+def test_match_filter_kernel_any_window(dm, mode, h, win):
+    """dm_match_filter on random displacement fields against the oracle, including the windows
+    above 9 x 9 that the kernel ranks by bisection (no host path for any window size)."""
+    import torch
+    from deepmatching_stereo_matching_b200 import _native
+    rng = np.random.default_rng(7 * h + win)
+    n = 3
+    ii, jj = np.meshgrid(np.arange(h), np.arange(h), indexing='ij')
+    match = np.stack([np.stack([ii + rng.integers(-6, 7, (h, h)), jj + rng.integers(-6, 7, (h, h))]) for _ in range(n)]).astype(np.int32)
+    dev = torch.from_numpy(match).cuda()
+    out = torch.empty_like(dev)
+    _native.check(_native.lib().dm_match_filter(_native.ptr(dev), n, h, h, win, _native.FILTER_IDS[mode], _native.ptr(out), _native.stream_ptr()))
+    got = out.cpu().numpy()
+    for k in range(n):
+        mp = np.concatenate([match[k].astype(np.float64), np.zeros((1, h, h))], 0)
+        want = O.match_filter(mp, win, mode)[:2]
+        assert np.array_equal(got[k], want.astype(np.int32)), (mode, h, win, k)
+
+
+def test_filter_on_non_square_maps_raises_like_the_reference(dm):
+    """misc/Matching.py:235-248 fails on non-square maps (broadcast error or round(NaN)); the
+    class raises ValueError as well instead of falling back to a host computation."""
+    rng = np.random.default_rng(5)
+    st = Stub()
+    st.co_map_list = [rng.random((8 >> k, 32 >> k, 8 >> k, 32 >> k)).astype(np.float32) for k in range(4)]
+    st.N_map = 8
+    with pytest.raises(ValueError):
+        dm.Matching(st, filter_window_size=3, filtering=True, filtering_num=4, filtering_mode='median', sub_pix=False)()
+    img1 = (rng.random((60, 120)) * 255).astype(np.uint8)
+    with pytest.raises(ValueError):
+        s = dm.ImageCutSolver(img1, img1.copy(), image_size=[8, 32], stride=[8, 32], window_size=3, filtering=True,
+                              filtering_window_size=3, filtering_num=4, filtering_mode='median')
+        s.log_flg = False
+        s()
+
+
 @pytest.mark.parametrize('mode,num,win,fused_expected', [('median', 3, 3, 1), ('average', 4, 3, 1), ('median', 9, 5, 0), ('average', 2, 9, 1)])
 def test_image_cut_solver_with_displacement_filter(dm, mode, num, win, fused_expected):
     """ex_deepmatching_rawinput.py:32-35 flags through ImageCutSolver: the batched solver runs the
