@@ -26,6 +26,44 @@ def test_library_exports_every_declared_symbol():
     assert lib.dm_kpad(15) == 256 and lib.dm_kpad(5) == 64 and lib.dm_kpad(3) == 64
 
 
+def test_header_is_plain_c_and_a_c_program_links(tmp_path):
+    """include/dmstereo.h is the drop-in boundary: it must compile as C (not only C++), and a C
+    program that calls only host-side entry points must link against libdmstereo.so and run
+    without a GPU (geometry, kpad, the error path of dm_correlation_set_pair_mode)."""
+    import shutil
+    import subprocess
+    from deepmatching_stereo_matching_b200 import _native
+    _native.lib()
+    gcc = shutil.which('gcc')
+    if gcc is None:
+        pytest.skip('gcc not available')
+    src = tmp_path / 'abi.c'
+    src.write_text(r'''
+#include <stdio.h>
+#include <string.h>
+#include "dmstereo.h"
+int main(void) {
+    dm_scene_params p;
+    dm_scene_info info;
+    memset(&p, 0, sizeof p);
+    p.scene_h = 1024; p.scene_w = 1024; p.t0 = 64; p.t1 = 64; p.s0 = 60; p.s1 = 60; p.ws = 15;
+    p.method = DM_TM_CCOEFF_NORMED; p.n_modes = 1; p.modes[0] = DM_MODE_ELEVATION; p.sub_pix = 1; p.fused = -1;
+    if (dm_scene_geometry(&p, &info) != DM_OK) { printf("geometry failed: %s\n", dm_last_error()); return 1; }
+    if (dm_correlation_set_pair_mode(9) != DM_ERR_INVALID) return 2;
+    if (dm_correlation_set_pair_mode(-1) != DM_OK) return 3;
+    printf("%d %d %d %d %d %d\n", info.len0, info.len1, info.out_h, info.out_w, info.n_tiles, dm_kpad(15));
+    return 0;
+}
+''')
+    exe = tmp_path / 'abi'
+    libdir = os.path.dirname(_native.LIB_PATH)
+    cmd = [gcc, '-std=c99', '-Wall', '-Werror', '-I', os.path.join(REPO, 'include'), str(src), '-o', str(exe),
+           '-L', libdir, '-ldmstereo', '-Wl,-rpath,' + libdir]
+    subprocess.run(cmd, check=True, capture_output=True, text=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split()
+    assert [int(x) for x in out] == [15, 15, 904, 904, 225, 256]
+
+
 def test_pair_mode_knob_validates_its_argument():
     """dm_correlation_set_pair_mode is host-only state: -1 / 1 = CTA pairs when the shape allows,
     0 = one CTA per work item; anything else is DM_ERR_INVALID with a message."""
