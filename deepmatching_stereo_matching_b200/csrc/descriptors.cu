@@ -81,7 +81,8 @@ template <int WS>
 __global__ void __launch_bounds__(256)
 dm_descriptor_row_kernel(const uint8_t* __restrict__ scene, int pitch,
                          const int32_t* __restrict__ origin_yx, long long n_groups, long long n_patches,
-                         int t0, int t1, __nv_bfloat16* __restrict__ desc, dm_stat* __restrict__ stat) {
+                         int t0, int t1, dm_fastdiv fd_jb, dm_fastdiv fd_t0,
+                         __nv_bfloat16* __restrict__ desc, dm_stat* __restrict__ stat) {
     constexpr int K = WS * WS;
     constexpr int RSTR = WS <= 8 ? 8 : 16;
     constexpr int KPAD = ((WS * RSTR + 63) / 64) * 64;
@@ -92,11 +93,15 @@ dm_descriptor_row_kernel(const uint8_t* __restrict__ scene, int pitch,
     long long g = ((long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * GPW + lane / LPG;
     const bool live = g < n_groups;
     if (!live) g = n_groups - 1;                                      // keep the group converged for REDUX
+    // group -> (tile, grid row i, block of 8 columns jb) with exact multiply-shift divisions (the
+    // group count fits 32 bits: the host checks it); three 64-bit `/` and `%` here were a quarter
+    // of the kernel's instructions
     const int jb_n = t1 >> 3;
-    const int jb = (int)(g % jb_n);
-    const long long t = g / jb_n;
-    const int i = (int)(t % t0);
-    const int tile = (int)(t / t0);
+    const uint32_t g32 = (uint32_t)g;
+    const uint32_t t = dm_fd_div(g32, fd_jb);
+    const int jb = (int)(g32 - t * (uint32_t)jb_n);
+    const int tile = (int)dm_fd_div(t, fd_t0);
+    const int i = (int)(t - (uint32_t)tile * (uint32_t)t0);
     const int j0 = jb * 8;
     const int ky = RSTR == 16 ? (gl >> 1) : gl, hf = RSTR == 16 ? (gl & 1) : 0;
     const bool rowlive = ky < WS;
@@ -172,6 +177,7 @@ static void launch_descriptor_row(const uint8_t* scene, int pitch, const int32_t
     const long long n_groups = n_patches / 8;
     const long long warps = (n_groups + GPW - 1) / GPW;
     dm_descriptor_row_kernel<WS><<<dm_div_up(warps, 8), 256, 0, st>>>(scene, pitch, origin, n_groups, n_patches, t0, t1,
+                                                                       dm_make_fastdiv((uint32_t)(t1 >> 3)), dm_make_fastdiv((uint32_t)t0),
                                                                        (__nv_bfloat16*)desc, (dm_stat*)stat);
 }
 
@@ -184,7 +190,7 @@ extern "C" int dm_descriptors(const uint8_t* scene_dev, int scene_h, int scene_w
                "dm_descriptors: scene %dx%d smaller than a tile", scene_h, scene_w);
     const long long n_patches = (long long)n_tiles * t0 * t1;
     cudaStream_t st = (cudaStream_t)stream;
-    const bool rowk = (t1 % 8 == 0);
+    const bool rowk = (t1 % 8 == 0) && n_patches / 8 < (1LL << 32);
     switch (rowk ? ws : 0) {
         case 3:  launch_descriptor_row<3>(scene_dev, pitch, origin_yx_dev, n_patches, t0, t1, desc_bf16_dev, stat_dev, st); break;
         case 5:  launch_descriptor_row<5>(scene_dev, pitch, origin_yx_dev, n_patches, t0, t1, desc_bf16_dev, stat_dev, st); break;

@@ -99,3 +99,22 @@ __device__ __forceinline__ int dm_round_mean(int sum, int k) {
 }
 
 static inline int dm_div_up(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+// Exact unsigned 32-bit division by a runtime constant (Granlund & Montgomery, round-up method):
+// q = (t + ((x - t) >> s1)) >> s2 with t = umulhi(m, x); valid for every 32-bit x.  The constants
+// are made on the host once per launch; a runtime-divisor `/` costs ~20 instructions (32-bit) to
+// ~80 (64-bit), and index arithmetic of that kind was 15-30 % of two kernels' instructions.
+struct dm_fastdiv { uint32_t m, s1, s2; };
+static inline dm_fastdiv dm_make_fastdiv(uint32_t d) {
+    dm_fastdiv f;
+    uint32_t l = 0;
+    while ((1ull << l) < d) ++l;                          // ceil(log2 d)
+    f.m = (uint32_t)(((1ull << 32) * ((1ull << l) - d)) / d + 1);
+    f.s1 = l < 1 ? l : 1;
+    f.s2 = l > 0 ? l - 1 : 0;
+    return f;
+}
+__device__ __forceinline__ uint32_t dm_fd_div(uint32_t x, const dm_fastdiv& f) {
+    const uint32_t t = __umulhi(f.m, x);
+    return (t + ((x - t) >> f.s1)) >> f.s2;
+}

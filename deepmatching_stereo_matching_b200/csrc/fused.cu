@@ -21,7 +21,7 @@
 namespace {
 
 struct FusedBuffers {
-    int32_t* origin; void* desc1; void* desc2; float* stat1; float* stat2;
+    int32_t* origin; int32_t* tinfo; void* desc1; void* desc2; float* stat1; float* stat2;
     float* pooled; float* rowmin; float* rowmax;
     float* level[16];           // level[0] unused
     int32_t* match[2]; float* score[2];
@@ -42,6 +42,7 @@ size_t carve(char* base, int nt, int t0, int t1, int kpad, int levels, FusedBuff
     Carve c(base);
     const size_t P = (size_t)t0 * t1;
     fb.origin = c.take<int32_t>((size_t)nt * 2);
+    fb.tinfo = c.take<int32_t>((size_t)nt * 4);
     fb.desc1 = c.take<__nv_bfloat16>((size_t)nt * P * kpad);
     fb.desc2 = c.take<__nv_bfloat16>((size_t)nt * P * kpad);
     fb.stat1 = c.take<float>((size_t)nt * P * DM_STAT_FLOATS);
@@ -63,13 +64,17 @@ size_t carve(char* base, int nt, int t0, int t1, int kpad, int levels, FusedBuff
 }
 
 // tile g of a (batch of) scene(s) stacked along rows: origin = (scene*S0 + s0*gi, s1*gj)
-__global__ void dm_tile_origin_kernel2(int32_t* origin, int n, int first_tile, int len0, int len1, int s0, int s1, int scene_h) {
+// tinfo = (tile row gi, tile column gj, scene, 0): the final-level kernel needs them per quad and
+// would otherwise redo these divisions in every warp
+__global__ void dm_tile_origin_kernel2(int32_t* origin, int32_t* tinfo, int n, int first_tile, int len0, int len1, int s0, int s1, int scene_h) {
     int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n) return;
     const int g = first_tile + t, tps = len0 * len1;
     const int sc = g / tps, r = g - sc * tps;
-    origin[2 * t] = sc * scene_h + s0 * (r / len1);
-    origin[2 * t + 1] = s1 * (r % len1);
+    const int gi = r / len1, gj = r - gi * len1;
+    origin[2 * t] = sc * scene_h + s0 * gi;
+    origin[2 * t + 1] = s1 * gj;
+    reinterpret_cast<int4*>(tinfo)[t] = make_int4(gi, gj, sc, 0);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -128,13 +133,14 @@ dm_aggregate_first_kernel(const float* __restrict__ pooled, const float* __restr
 // ---------------------------------------------------------------------------------------
 struct FinalArgs {
     const uint8_t* img1; const uint8_t* img2; int pitch;
-    const int32_t* origin; const dm_stat* stat1; const dm_stat* stat2;
+    const int32_t* origin; const int32_t* tinfo; const dm_stat* stat1; const dm_stat* stat2;
+    dm_fastdiv fd_pq, fd_hb, fd_s0, fd_s1;     // divisors PQ = (t0/2)(t1/2), t1/2, s0, s1
     const float* rowmin; const float* rowmax;
     const int32_t* parent;      // level-1 matches [n][2][t0/2][t1/2]
     int t0, t1, ws, normed, sub_pix, scene_h;
     int n_modes, modes[4];
     int s0, s1, len0, len1, out_h, out_w, first_tile;
-    long long quad0;            // first quad of this launch (the final stage may run in bands)
+    int tile0;                  // first tile of this launch (the final stage may run in bands of whole tiles)
     double* d_map; double* out_map;
 };
 
@@ -160,20 +166,23 @@ dm_final_quad_kernel(const FinalArgs a, long long n_quads) {
     __shared__ __align__(16) uint8_t patch_all[FQ_WARPS][16 * QRS];         // the quad's (ws+1)^2 block of image 1
     const int lane = threadIdx.x & 31;
     uint8_t* reg0 = region_all[threadIdx.x >> 5];
-    const long long w = a.quad0 + (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (w >= a.quad0 + n_quads) return;
+    // quad index relative to this launch (a launch starts at a tile boundary and never holds 2^32 quads)
+    const long long wl = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (wl >= n_quads) return;
+    const uint32_t wq = (uint32_t)wl;
     const int T0 = a.t0, T1 = a.t1, P = T0 * T1;
     const int hA = T0 >> 1, hB = T1 >> 1, PQ = hA * hB;
-    const int n = (int)(w / PQ);                         // tile inside the chunk
-    const int pq = (int)(w - (long long)n * PQ);
-    const int I = pq / hB, J = pq - I * hB;
+    const uint32_t nrel = dm_fd_div(wq, a.fd_pq);
+    const int n = a.tile0 + (int)nrel;                   // tile inside the chunk
+    const int pq = (int)(wq - nrel * (uint32_t)PQ);
+    const int I = (int)dm_fd_div((uint32_t)pq, a.fd_hb), J = pq - I * hB;
+    const int4 ti = __ldg(reinterpret_cast<const int4*>(a.tinfo) + n);      // (gi, gj, scene, -)
     {
         // misc/image_cut_solver.py:165-175: a pixel belongs to the covering tile with the largest
         // index.  A quad whose two patch rows (or columns) lie at or beyond the stride is pasted
         // over by the next tile: nothing of it survives, so the warp stops here (12 % of the
         // quads at image_size 64 / stride 60).
-        const int g = a.first_tile + n, tps = a.len0 * a.len1;
-        const int gr = g % tps, gi = gr / a.len1, gj = gr - gi * a.len1;
+        const int gi = ti.x, gj = ti.y;
         if ((gi < a.len0 - 1 && 2 * I >= a.s0) || (gj < a.len1 - 1 && 2 * J >= a.s1)) return;
     }
     const int oy = a.origin[2 * n], ox = a.origin[2 * n + 1];
@@ -432,11 +441,10 @@ dm_final_quad_kernel(const FinalArgs a, long long n_quads) {
     if (l != 0) return;
 
     // ---- planes + paste (misc/Calc_difference.py:36-48, misc/image_cut_solver.py:165-175)
-    const int g = a.first_tile + n, tps = a.len0 * a.len1;
-    const int sc = g / tps, gr = g - sc * tps;
-    const int gi = gr / a.len1, gj = gr - gi * a.len1;
+    const int gi = ti.x, gj = ti.y, sc = ti.z;
     const int Y = a.s0 * gi + i, X = a.s1 * gj + j;
-    if (min(Y / a.s0, a.len0 - 1) != gi || min(X / a.s1, a.len1 - 1) != gj) return;   // a later tile owns this pixel
+    // owner = min(Y / s0, len0 - 1) with Y / s0 = gi + i / s0 (same for the columns)
+    if (min(gi + (int)dm_fd_div((uint32_t)i, a.fd_s0), a.len0 - 1) != gi || min(gj + (int)dm_fd_div((uint32_t)j, a.fd_s1), a.len1 - 1) != gj) return;   // a later tile owns this pixel
     const double e0 = __dsub_rn((double)i, mrow), e1 = __dsub_rn((double)j, mcol);
     const size_t plane = (size_t)a.out_h * a.out_w, pix = (size_t)Y * a.out_w + X;
     for (int m = 0; m < a.n_modes; ++m) {
@@ -476,7 +484,7 @@ int dm_fused_solve_chunk(dm_ctx* ctx, const dm_fused_args* a, int ck) {
     {
         StageTimer tm(ctx, DM_STAGE_DESCRIPTORS);
         if ((rc = tm.begin(ck)) != DM_OK) return rc;
-        dm_tile_origin_kernel2<<<dm_div_up(nt, 128), 128, 0, st>>>(fb.origin, nt, a->first_tile, a->len0, a->len1, a->s0, a->s1, a->scene_h);
+        dm_tile_origin_kernel2<<<dm_div_up(nt, 128), 128, 0, st>>>(fb.origin, fb.tinfo, nt, a->first_tile, a->len0, a->len1, a->s0, a->s1, a->scene_h);
         DM_LAUNCH_CHECK();
         if ((rc = dm_descriptors(a->img1, a->scene_h * a->n_scenes, a->scene_w, a->scene_w, fb.origin, nt, t0, t1, a->ws, fb.desc1, fb.stat1, st)) != DM_OK) return rc;
         if ((rc = dm_descriptors(a->img2, a->scene_h * a->n_scenes, a->scene_w, a->scene_w, fb.origin, nt, t0, t1, a->ws, fb.desc2, fb.stat2, st)) != DM_OK) return rc;
@@ -611,7 +619,10 @@ int dm_fused_solve_chunk(dm_ctx* ctx, const dm_fused_args* a, int ck) {
         if ((rc = tm.begin(ck)) != DM_OK) return rc;
         FinalArgs fa;
         fa.img1 = a->img1; fa.img2 = a->img2; fa.pitch = a->scene_w;
-        fa.origin = fb.origin; fa.stat1 = (const dm_stat*)fb.stat1; fa.stat2 = (const dm_stat*)fb.stat2;
+        fa.origin = fb.origin; fa.tinfo = fb.tinfo;
+        fa.fd_pq = dm_make_fastdiv((uint32_t)(P / 4)); fa.fd_hb = dm_make_fastdiv((uint32_t)(t1 >> 1));
+        fa.fd_s0 = dm_make_fastdiv((uint32_t)a->s0); fa.fd_s1 = dm_make_fastdiv((uint32_t)a->s1);
+        fa.stat1 = (const dm_stat*)fb.stat1; fa.stat2 = (const dm_stat*)fb.stat2;
         fa.rowmin = fb.rowmin; fa.rowmax = fb.rowmax; fa.parent = fb.match[cur];
         fa.t0 = t0; fa.t1 = t1; fa.ws = a->ws; fa.normed = a->method == DM_TM_CCOEFF_NORMED; fa.sub_pix = a->sub_pix;
         fa.n_modes = a->n_modes; for (int m = 0; m < 4; ++m) fa.modes[m] = a->modes[m];
@@ -630,7 +641,7 @@ int dm_fused_solve_chunk(dm_ctx* ctx, const dm_fused_args* a, int ck) {
             int t_end = (b == bands - 1) ? nt : ((rows_in_chunk * (b + 1)) / bands) * a->len1 + ((a->len1 - a->first_tile % a->len1) % a->len1);
             if (t_end > nt) t_end = nt;
             if (t_end <= t_begin) continue;
-            fa.quad0 = (long long)t_begin * (P / 4);
+            fa.tile0 = t_begin;
             const long long nq = (long long)(t_end - t_begin) * (P / 4);
             switch (a->ws) {
                 case 3: launch_final_quad<3>(fa, nq, st); break;
