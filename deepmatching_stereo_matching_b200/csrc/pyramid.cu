@@ -112,7 +112,7 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
 // Requirements of this kernel: D % 4 == 0 (16-byte rows), C even.
 __global__ void __launch_bounds__(256)
 dm_aggregate_kernel(const float* __restrict__ in, long long n_parents, int A, int B, int C, int D,
-                    int pp, int rb, int rect, float* __restrict__ out) {
+                    int pp, int rb, int rect, dm_fastdiv fd_xp, dm_fastdiv fd_oc, float* __restrict__ out) {
     extern __shared__ __align__(16) float smem[];
     __shared__ __align__(8) uint64_t bar;
     const int hA = A >> 1, hB = B >> 1, oc = C >> 1, od = D >> 1;
@@ -157,7 +157,15 @@ dm_aggregate_kernel(const float* __restrict__ in, long long n_parents, int A, in
         const int it = it0 + threadIdx.x;
         const bool active = it < items;
         int xp = 0, y = 0, k = 0;
-        if (active) { xp = it % xpairs; int t = it / xpairs; y = t % rows; k = t / rows; }
+        if (active) {
+            // item -> (parent k, row y, pair of columns xp) by exact multiply-shift divisions (four
+            // runtime-divisor / and % per item were 40 % of the kernel's instructions).  Several
+            // parents per CTA only occur with one band, i.e. rows == C / 2.
+            const uint32_t t = dm_fd_div((uint32_t)it, fd_xp);
+            xp = it - (int)t * xpairs;
+            k = pp > 1 ? (int)dm_fd_div(t, fd_oc) : 0;
+            y = (int)t - k * rows;
+        }
         const int yy = y0 + y;                            // output row
         float sum0 = 0.f, sum1 = 0.f;
 #pragma unroll
@@ -287,7 +295,7 @@ extern "C" int dm_aggregate(const float* in_dev, int n, int a, int b, int c, int
         attr_set = true;
     }
     dim3 grid((unsigned)dm_div_up(n_parents, pp), bands);
-    dm_aggregate_kernel<<<grid, 256, smem, st>>>(in_dev, n_parents, a, b, c, d, pp, rb, rectify, out_dev);
+    dm_aggregate_kernel<<<grid, 256, smem, st>>>(in_dev, n_parents, a, b, c, d, pp, rb, rectify, dm_make_fastdiv((uint32_t)(d >> 2)), dm_make_fastdiv((uint32_t)oc), out_dev);
     DM_LAUNCH_CHECK();
     return DM_OK;
 }
