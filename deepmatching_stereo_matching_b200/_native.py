@@ -64,6 +64,21 @@ SIGNATURES = {
     'dm_scene_geometry': (c_int, [POINTER(SceneParams), POINTER(SceneInfo)]),
     'dm_solve_scene': (c_int, [c_void_p, POINTER(SceneParams), c_void_p, c_void_p, c_void_p, c_void_p, POINTER(SceneInfo)]),
     'dm_solve_scene_host': (c_int, [c_void_p, POINTER(SceneParams), c_void_p, c_void_p, c_void_p, c_void_p, POINTER(SceneInfo)]),
+    'dm_solve_scene_stream': (c_int, [c_void_p, POINTER(SceneParams), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, POINTER(SceneInfo)]),
+    'dm_multi_create': (c_int, [POINTER(c_int), c_int, POINTER(c_void_p)]),
+    'dm_multi_destroy': (None, [c_void_p]),
+    'dm_multi_device_count': (c_int, [c_void_p]),
+    'dm_multi_set_workspace_limit': (c_int, [c_void_p, c_size_t]),
+    'dm_partition_tile_rows': (c_int, [c_int, c_int, POINTER(c_int32), POINTER(c_int32)]),
+    'dm_multi_solve_scene_host': (c_int, [c_void_p, POINTER(SceneParams), c_int, c_void_p, c_void_p, c_void_p, c_void_p, POINTER(SceneInfo)]),
+    'dm_multi_solve_scene': (c_int, [c_void_p, POINTER(SceneParams), POINTER(c_void_p), POINTER(c_void_p), POINTER(c_void_p), c_int, c_int, POINTER(SceneInfo)]),
+    'dm_multi_gather_strips': (c_int, [c_void_p, POINTER(c_void_p), c_int, c_int, c_int, POINTER(c_int32), POINTER(c_int32), c_int]),
+    'dm_multi_synchronize': (c_int, [c_void_p]),
+    'dm_ipc_alloc': (c_int, [c_size_t, POINTER(c_void_p)]),
+    'dm_ipc_free': (c_int, [c_void_p]),
+    'dm_ipc_export': (c_int, [c_void_p, c_char_p]),
+    'dm_ipc_open': (c_int, [c_char_p, POINTER(c_void_p)]),
+    'dm_ipc_close': (c_int, [c_void_p]),
     'dm_ctx_enable_timing': (c_int, [c_void_p, c_int]),
     'dm_ctx_stage_ms': (c_int, [c_void_p, POINTER(c_float), POINTER(c_int)]),
 }
@@ -174,6 +189,84 @@ class Context(object):
     @property
     def workspace_bytes(self):
         return int(lib().dm_ctx_workspace_bytes(self._h))
+
+
+    def solve_stream(self, prm, img1, img2, d_map, out_map, d_map_dst, out_map_dst):
+        """Device-resident solve whose finished rows are also streamed (band by band, on a second
+        stream) into d_map_dst / out_map_dst: integers = raw UVA pointers (a peer mosaic opened with
+        dm_ipc_open), numpy arrays = page-locked host memory, tensors = device memory."""
+        def raw(x):
+            if isinstance(x, int):
+                return c_void_p(x)
+            if hasattr(x, 'data_ptr'):
+                return c_void_p(x.data_ptr())
+            return c_void_p(x.ctypes.data)
+        info = SceneInfo()
+        self.bind_stream()
+        check(lib().dm_solve_scene_stream(self._h, byref(prm), ptr(img1), ptr(img2), ptr(d_map), ptr(out_map),
+                                          raw(d_map_dst), raw(out_map_dst), byref(info)))
+        return info
+
+
+GATHER_P2P, GATHER_NCCL = 0, 1
+
+
+class MultiContext(object):
+    """dm_multi: one dm_ctx, stream and host thread per device of this process."""
+
+    def __init__(self, devices=None, workspace_limit=None):
+        require_cuda()
+        self._h = c_void_p()
+        if devices is None:
+            check(lib().dm_multi_create(None, 0, byref(self._h)))
+        else:
+            arr = (c_int * len(devices))(*[int(d) for d in devices])
+            check(lib().dm_multi_create(arr, len(devices), byref(self._h)))
+        self.n_devices = int(lib().dm_multi_device_count(self._h))
+        if workspace_limit:
+            self.set_workspace_limit(workspace_limit)
+
+    def close(self):
+        if getattr(self, '_h', None):
+            lib().dm_multi_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_workspace_limit(self, nbytes):
+        check(lib().dm_multi_set_workspace_limit(self._h, int(nbytes)))
+
+    def solve_host(self, prm, img1_np, img2_np, d_map_np, out_map_np, max_devices=0):
+        info = SceneInfo()
+        check(lib().dm_multi_solve_scene_host(self._h, byref(prm), int(max_devices), c_void_p(img1_np.ctypes.data), c_void_p(img2_np.ctypes.data),
+                                              c_void_p(d_map_np.ctypes.data), c_void_p(out_map_np.ctypes.data), byref(info)))
+        return info
+
+    def solve_device(self, prm, imgs1, imgs2, planes, root=0, gather=GATHER_P2P):
+        """imgs1 / imgs2 / planes: one tensor per device (uint8 scenes, float64 (n_modes+1, out_h, out_w)).
+        Asynchronous: synchronize() before reading planes[root]."""
+        n = self.n_devices
+        assert len(imgs1) == len(imgs2) == len(planes) == n
+        a1 = (c_void_p * n)(*[t.data_ptr() for t in imgs1])
+        a2 = (c_void_p * n)(*[t.data_ptr() for t in imgs2])
+        pl = (c_void_p * n)(*[t.data_ptr() for t in planes])
+        info = SceneInfo()
+        check(lib().dm_multi_solve_scene(self._h, byref(prm), a1, a2, pl, int(root), int(gather), byref(info)))
+        return info
+
+    def synchronize(self):
+        check(lib().dm_multi_synchronize(self._h))
+
+
+def partition_tile_rows(len0, n):
+    lo = (c_int32 * n)()
+    hi = (c_int32 * n)()
+    check(lib().dm_partition_tile_rows(int(len0), int(n), lo, hi))
+    return [(int(lo[r]), int(hi[r])) for r in range(n)]
 
 
 FILTER_IDS = {'median': 0, 'average': 1}

@@ -71,6 +71,7 @@ extern "C" int dm_ctx_create(dm_ctx** out) {
     int cc = dm_device_cc();
     DM_REQUIRE(cc >= 100, DM_ERR_UNSUPPORTED, "dm_ctx_create: this library is built for sm_100a only (device cc %d)", cc);
     *out = new dm_ctx();
+    cudaGetDevice(&(*out)->device);
     return DM_OK;
 }
 
@@ -80,6 +81,8 @@ extern "C" void dm_ctx_destroy(dm_ctx* ctx) {
     for (auto& v : ctx->ev) for (auto e : v) cudaEventDestroy(e);
     for (auto e : ctx->band_ev) cudaEventDestroy(e);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+    if (ctx->h2d_stream) cudaStreamDestroy(ctx->h2d_stream);
+    if (ctx->up_ev) cudaEventDestroy(ctx->up_ev);
     for (auto& g : ctx->upper_graphs) cudaGraphExecDestroy(g.exec);
     if (ctx->capture_stream) cudaStreamDestroy(ctx->capture_stream);
     delete ctx;
@@ -94,6 +97,9 @@ static int ctx_reserve(dm_ctx* ctx, size_t bytes) {
     if (bytes <= ctx->ws_bytes) return DM_OK;
     DM_REQUIRE(bytes <= ctx->ws_limit, DM_ERR_NOMEM, "workspace of %zu bytes exceeds the limit of %zu", bytes, ctx->ws_limit);
     DM_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    // the cached graphs of the upper-pyramid launches bake in pointers into the old workspace
+    for (auto& g : ctx->upper_graphs) cudaGraphExecDestroy(g.exec);
+    ctx->upper_graphs.clear();
     if (ctx->ws) DM_CUDA_CHECK(cudaFree(ctx->ws));
     ctx->ws = nullptr; ctx->ws_bytes = 0;
     DM_CUDA_CHECK(cudaMalloc(&ctx->ws, bytes));
@@ -103,6 +109,7 @@ static int ctx_reserve(dm_ctx* ctx, size_t bytes) {
 
 // Output rows are final once every tile row above them is done: rows [0, s0 * full_tile_rows), or
 // the whole mosaic after the last tile.  Copies what is new on the copy stream, behind an event.
+// The destination is page-locked host memory or the mosaic of a peer device (UVA decides).
 int dm_readback_rows(dm_ctx* ctx, long long tiles_done) {
     dm_ctx::Readback& rb = ctx->rb;
     if (!rb.active) return DM_OK;
@@ -122,9 +129,35 @@ int dm_readback_rows(dm_ctx* ctx, long long tiles_done) {
     const size_t plane = (size_t)rb.out_h * rb.out_w;
     const size_t off = (size_t)rb.rows_done * rb.out_w, bytes = (size_t)(upto - rb.rows_done) * rb.out_w * sizeof(double);
     for (int m = 0; m < rb.n_modes; ++m)
-        DM_CUDA_CHECK(cudaMemcpyAsync(rb.h_d_map + m * plane + off, rb.d_d_map + m * plane + off, bytes, cudaMemcpyDeviceToHost, ctx->copy_stream));
-    DM_CUDA_CHECK(cudaMemcpyAsync(rb.h_out_map + off, rb.d_out_map + off, bytes, cudaMemcpyDeviceToHost, ctx->copy_stream));
+        DM_CUDA_CHECK(cudaMemcpyAsync(rb.dst_d_map + m * plane + off, rb.d_d_map + m * plane + off, bytes, cudaMemcpyDefault, ctx->copy_stream));
+    DM_CUDA_CHECK(cudaMemcpyAsync(rb.dst_out_map + off, rb.d_out_map + off, bytes, cudaMemcpyDefault, ctx->copy_stream));
     rb.rows_done = upto;
+    return DM_OK;
+}
+
+// Host scenes go to the device in pieces, each piece ahead of the chunk of tiles that reads it
+// (misc/raw_read.py:36-45 hands ImageCutSolver two host arrays).
+// dm_upload_rows enqueues the copy of the stacked scene rows [rows_done, upto) of both images on the
+// upload stream; dm_upload_wait makes the compute stream wait for what has been enqueued so far.
+static int dm_upload_rows(dm_ctx* ctx, long long upto) {
+    dm_ctx::Upload& up = ctx->up;
+    if (!up.active) return DM_OK;
+    if (upto > up.row_end) upto = up.row_end;
+    if (upto <= up.rows_done) return DM_OK;
+    if (!ctx->h2d_stream) DM_CUDA_CHECK(cudaStreamCreateWithFlags(&ctx->h2d_stream, cudaStreamNonBlocking));
+    if (!ctx->up_ev) DM_CUDA_CHECK(cudaEventCreateWithFlags(&ctx->up_ev, cudaEventDisableTiming));
+    const size_t off = (size_t)up.rows_done * up.row_bytes, bytes = (size_t)(upto - up.rows_done) * up.row_bytes;
+    DM_CUDA_CHECK(cudaMemcpyAsync(ctx->scene1 + off, up.h1 + off, bytes, cudaMemcpyHostToDevice, ctx->h2d_stream));
+    DM_CUDA_CHECK(cudaMemcpyAsync(ctx->scene2 + off, up.h2 + off, bytes, cudaMemcpyHostToDevice, ctx->h2d_stream));
+    DM_CUDA_CHECK(cudaEventRecord(ctx->up_ev, ctx->h2d_stream));
+    up.rows_done = upto;
+    up.pending = true;
+    return DM_OK;
+}
+static int dm_upload_wait(dm_ctx* ctx) {
+    if (!ctx->up.active || !ctx->up.pending) return DM_OK;
+    DM_CUDA_CHECK(cudaStreamWaitEvent(ctx->stream, ctx->up_ev, 0));
+    ctx->up.pending = false;
     return DM_OK;
 }
 
@@ -249,12 +282,12 @@ dm_planes_kernel(const float* __restrict__ l0, long long total, PlaneArgs a,
         if (dm_np_index_ok(c0 + 1, a.T0) && dm_np_index_ok(c0 - 1, a.T0)) {
             const float r1 = map[(size_t)dm_np_wrap(c0 + 1, a.T0) * a.T1 + w1];
             const float rm = map[(size_t)dm_np_wrap(c0 - 1, a.T0) * a.T1 + w1];
-            if (r0 > r1 && r0 > rm) m0 += (double)(-(r1 - rm) / (2.0f * (r1 + rm - 2.0f * r0)));
+            if (r0 > r1 && r0 > rm) m0 += dm_parabola_shift(r0, r1, rm);
         }
         if (dm_np_index_ok(c1 + 1, a.T1) && dm_np_index_ok(c1 - 1, a.T1)) {
             const float r1 = map[(size_t)w0 * a.T1 + dm_np_wrap(c1 + 1, a.T1)];
             const float rm = map[(size_t)w0 * a.T1 + dm_np_wrap(c1 - 1, a.T1)];
-            if (r0 > r1 && r0 > rm) m1 += (double)(-(r1 - rm) / (2.0f * (r1 + rm - 2.0f * r0)));
+            if (r0 > r1 && r0 > rm) m1 += dm_parabola_shift(r0, r1, rm);
         }
     }
     const double e0 = __dsub_rn((double)i, m0), e1 = __dsub_rn((double)j, m1);
@@ -358,10 +391,23 @@ extern "C" int dm_solve_scene(dm_ctx* ctx, const dm_scene_params* prm,
     pa.out_h = info.out_h; pa.out_w = info.out_w; pa.sub_pix = prm->sub_pix;
 
     int launches = 0;
+    // stacked scene row (exclusive) up to which the tiles [.., last] read their input
+    auto rows_needed = [&](long long last_tile) -> long long {
+        const long long tps = (long long)info.len0 * info.len1, sc = last_tile / tps, r = last_tile - sc * tps;
+        return sc * prm->scene_h + (long long)prm->s0 * (r / info.len1) + t0 + prm->ws - 1;
+    };
+    auto chunk_tiles = [&](int ck) -> int { return (ck == n_chunks - 1) ? info.n_tiles - ck * chunk : chunk; };
+    if ((rc = dm_upload_rows(ctx, rows_needed((long long)lo * info.len1 + chunk_tiles(0) - 1))) != DM_OK) return rc;
     for (int ck = 0; ck < n_chunks; ++ck) {
         const int first = lo * info.len1 + ck * chunk;
-        const int nt = (ck == n_chunks - 1) ? info.n_tiles - ck * chunk : chunk;
+        const int nt = chunk_tiles(ck);
         pa.first_tile = first;
+        if ((rc = dm_upload_wait(ctx)) != DM_OK) return rc;
+        // the next chunk's input rows travel while this chunk is being solved (enqueued after this
+        // chunk's launches: a copy from pageable memory holds the host thread until it is staged)
+        auto upload_next = [&]() -> int {
+            return ck + 1 < n_chunks ? dm_upload_rows(ctx, rows_needed((long long)first + nt + chunk_tiles(ck + 1) - 1)) : DM_OK;
+        };
         if (fused) {
             dm_fused_args fa;
             fa.img1 = img1_dev; fa.img2 = img2_dev; fa.scene_h = prm->scene_h; fa.scene_w = prm->scene_w; fa.n_scenes = ns;
@@ -373,6 +419,7 @@ extern "C" int dm_solve_scene(dm_ctx* ctx, const dm_scene_params* prm,
             fa.filter_num = filter_num; fa.filter_win = filter_win; fa.filter_mode = filter_mode;
             rc = dm_fused_solve_chunk(ctx, &fa, ck);
             if (rc != DM_OK) return rc;
+            if ((rc = upload_next()) != DM_OK) return rc;
             continue;
         }
         carve_tiles(ctx->ws, nt, t0, t1, kpad, L, tb);
@@ -445,6 +492,7 @@ extern "C" int dm_solve_scene(dm_ctx* ctx, const dm_scene_params* prm,
             ctx->launches[DM_STAGE_PLANES] += 1;
             if ((rc = tm.end()) != DM_OK) return rc;
         }
+        if ((rc = upload_next()) != DM_OK) return rc;
     }
     for (int s = 0; s < DM_STAGE_COUNT; ++s) launches += ctx->launches[s];
     info.used_fused = fused ? 1 : 0;
@@ -479,13 +527,15 @@ extern "C" int dm_solve_scene_host(dm_ctx* ctx, const dm_scene_params* prm,
         DM_CUDA_CHECK(cudaMalloc(&ctx->planes, pb));
         ctx->planes_bytes = pb;
     }
-    // only the rows the strip's tiles read: [s0*lo, s0*(hi-1) + t0 + ws - 1)
+    // only the rows the strip's tiles read: [s0*lo, s0*(hi-1) + t0 + ws - 1), uploaded chunk by chunk
+    // ahead of the compute (dm_upload_rows)
     int lo = prm->tile_row_lo, hi = prm->tile_row_hi;
     if (hi <= 0) { lo = 0; hi = info.len0; }
-    const size_t in_lo = (size_t)prm->s0 * lo, in_hi = ns > 1 ? (size_t)prm->scene_h * ns : (size_t)prm->s0 * (hi - 1) + prm->t0 + prm->ws - 1;
-    const size_t in_off = in_lo * prm->scene_w, in_bytes = (in_hi - in_lo) * prm->scene_w;
-    DM_CUDA_CHECK(cudaMemcpyAsync(ctx->scene1 + in_off, img1_host + in_off, in_bytes, cudaMemcpyHostToDevice, st));
-    DM_CUDA_CHECK(cudaMemcpyAsync(ctx->scene2 + in_off, img2_host + in_off, in_bytes, cudaMemcpyHostToDevice, st));
+    dm_ctx::Upload& up = ctx->up;
+    up = dm_ctx::Upload();
+    up.active = true; up.h1 = img1_host; up.h2 = img2_host; up.row_bytes = (size_t)prm->scene_w;
+    up.rows_done = (long long)prm->s0 * lo;
+    up.row_end = ns > 1 ? (long long)prm->scene_h * ns : (long long)prm->s0 * (hi - 1) + prm->t0 + prm->ws - 1;
     double* d_map = ctx->planes;
     double* out_map = ctx->planes + plane * prm->n_modes * ns;
     if (prm->s0 > prm->t0 || prm->s1 > prm->t1)      // gaps between tiles: np.empty in the reference, zeros here
@@ -495,14 +545,22 @@ extern "C" int dm_solve_scene_host(dm_ctx* ctx, const dm_scene_params* prm,
     rb = dm_ctx::Readback();
     if (ns == 1) {
         rb.active = true;
-        rb.h_d_map = d_map_host; rb.h_out_map = out_map_host; rb.d_d_map = d_map; rb.d_out_map = out_map;
+        rb.dst_d_map = d_map_host; rb.dst_out_map = out_map_host; rb.d_d_map = d_map; rb.d_out_map = out_map;
         rb.n_modes = prm->n_modes; rb.out_h = info.out_h; rb.out_w = info.out_w; rb.len0 = info.len0; rb.len1 = info.len1; rb.s0 = prm->s0;
         rb.rows_done = info.row_lo; rb.row_hi = info.row_hi;
         ctx->band_used = 0;
     }
     rc = dm_solve_scene(ctx, prm, ctx->scene1, ctx->scene2, d_map, out_map, &info);
     rb.active = false;
-    if (rc != DM_OK) return rc;
+    up.active = false;
+    if (rc != DM_OK) {
+        // copies already queued must not keep reading / writing the caller's arrays after the
+        // error has been reported (the caller may release them)
+        if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
+        if (ctx->h2d_stream) cudaStreamSynchronize(ctx->h2d_stream);
+        cudaStreamSynchronize(st);
+        return rc;
+    }
     if (ns > 1) {       // whole batch: both result arrays are contiguous
         DM_CUDA_CHECK(cudaMemcpyAsync(d_map_host, d_map, plane * prm->n_modes * ns * sizeof(double), cudaMemcpyDeviceToHost, st));
         DM_CUDA_CHECK(cudaMemcpyAsync(out_map_host, out_map, plane * ns * sizeof(double), cudaMemcpyDeviceToHost, st));
@@ -518,6 +576,41 @@ extern "C" int dm_solve_scene_host(dm_ctx* ctx, const dm_scene_params* prm,
         if (ctx->copy_stream && ctx->band_used > 0) DM_CUDA_CHECK(cudaStreamSynchronize(ctx->copy_stream));
     }
     DM_CUDA_CHECK(cudaStreamSynchronize(st));
+    if (info_out) *info_out = info;
+    return DM_OK;
+}
+
+// Device-resident solve whose finished rows are also copied, band by band behind the final stage, to
+// a second pair of arrays (see dmstereo.h).  The compute stream is made to wait for the last copy, so
+// synchronising the ctx stream (or an event recorded on it) covers the copies as well.
+extern "C" int dm_solve_scene_stream(dm_ctx* ctx, const dm_scene_params* prm,
+                                     const uint8_t* img1_dev, const uint8_t* img2_dev,
+                                     double* d_map_dev, double* out_map_dev,
+                                     double* d_map_dst, double* out_map_dst, dm_scene_info* info_out) {
+    DM_REQUIRE(ctx && prm && d_map_dst && out_map_dst, DM_ERR_INVALID, "dm_solve_scene_stream: null argument");
+    DM_REQUIRE(prm->n_scenes <= 1, DM_ERR_UNSUPPORTED, "dm_solve_scene_stream: a batch of scenes has no row strips to stream");
+    dm_scene_info info;
+    int rc = dm_scene_geometry(prm, &info);
+    if (rc != DM_OK) return rc;
+    dm_ctx::Readback& rb = ctx->rb;
+    rb = dm_ctx::Readback();
+    rb.active = true;
+    rb.dst_d_map = d_map_dst; rb.dst_out_map = out_map_dst; rb.d_d_map = d_map_dev; rb.d_out_map = out_map_dev;
+    rb.n_modes = prm->n_modes; rb.out_h = info.out_h; rb.out_w = info.out_w; rb.len0 = info.len0; rb.len1 = info.len1; rb.s0 = prm->s0;
+    rb.rows_done = info.row_lo; rb.row_hi = info.row_hi;
+    ctx->band_used = 0;
+    ctx->up.active = false;
+    rc = dm_solve_scene(ctx, prm, img1_dev, img2_dev, d_map_dev, out_map_dev, &info);
+    if (rc == DM_OK) rc = dm_readback_rows(ctx, (long long)info.len0 * info.len1);     // whatever the bands have not taken (materialising path: everything)
+    rb.active = false;
+    if (ctx->copy_stream && ctx->band_used > 0) {
+        // the compute stream waits for the copies: one stream to synchronise on for the caller
+        cudaEvent_t ev = ctx->band_ev[ctx->band_used - 1];
+        cudaError_t e1 = cudaEventRecord(ev, ctx->copy_stream);
+        cudaError_t e2 = cudaStreamWaitEvent(ctx->stream, ev, 0);
+        if (rc == DM_OK) { DM_CUDA_CHECK(e1); DM_CUDA_CHECK(e2); }
+    }
+    if (rc != DM_OK) return rc;
     if (info_out) *info_out = info;
     return DM_OK;
 }

@@ -36,6 +36,7 @@
 //                              every store instruction writes 8 rows x 64 B.
 // B traffic: every CTA streams the tile's whole position matrix once per item; with
 // M = 256 rows per item that is 32 B/clk/SM from L2 at the MMA's full rate.
+#include <atomic>
 #include <cstdio>
 #include <cstdlib>
 #include "dm_common.cuh"
@@ -447,17 +448,23 @@ dm_encode_tiled_fn get_encode_fn() {
     return fn;
 }
 
-int g_pair_mode = -1;       // -1: CTA pairs whenever the shape allows, 0: never, 1: same as -1 (dm_correlation_set_pair_mode)
+std::atomic<int> g_pair_mode{-1};       // -1: CTA pairs whenever the shape allows, 0: never, 1: same as -1 (dm_correlation_set_pair_mode)
 
 template <int MODE, int D, bool NORMED, bool PAIR>
 int launch3(const CUtensorMap& mapA, const CUtensorMap& mapB, const Params& prm, cudaStream_t stream) {
-    static bool configured = false;
-    static int max_pairs = 0;
+    // per-device state: cudaFuncSetAttribute and the cluster occupancy belong to the device, and one
+    // process may drive several devices from several threads (dm_multi_*).  -1 = not configured yet;
+    // two threads racing on the same device compute the same values.
+    constexpr int MAX_DEV = 64;
+    static std::atomic<int> state[MAX_DEV];         // 0 = unconfigured, else 1 + co-resident CTA pairs
     auto kern = dm_correlation_umma_kernel<MODE, D, NORMED, PAIR>;
     int dev = 0, sms = 0;
     DM_CUDA_CHECK(cudaGetDevice(&dev));
+    DM_REQUIRE(dev >= 0 && dev < MAX_DEV, DM_ERR_UNSUPPORTED, "tcgen05 correlation: device index %d not supported", dev);
     DM_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    if (!configured) {
+    int max_pairs = state[dev].load(std::memory_order_acquire) - 1;
+    if (max_pairs < 0) {
+        max_pairs = 0;
         DM_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
         if (PAIR) {
             cudaLaunchConfig_t q = {};
@@ -467,9 +474,9 @@ int launch3(const CUtensorMap& mapA, const CUtensorMap& mapB, const Params& prm,
             q.gridDim = dim3(sms & ~1); q.blockDim = dim3(THREADS); q.dynamicSmemBytes = SMEM_BYTES; q.attrs = qa; q.numAttrs = 1;
             DM_CUDA_CHECK(cudaOccupancyMaxActiveClusters(&max_pairs, kern, &q));
             DM_REQUIRE(max_pairs > 0, DM_ERR_CUDA, "tcgen05 correlation: no 2-CTA cluster fits on this device");
-            if (getenv("DM_DEBUG")) fprintf(stderr, "[dm] correlation CTA pairs: %d co-resident 2-CTA clusters on %d SMs\n", max_pairs, sms);
+            if (getenv("DM_DEBUG")) fprintf(stderr, "[dm] correlation CTA pairs: %d co-resident 2-CTA clusters on %d SMs (device %d)\n", max_pairs, sms, dev);
         }
-        configured = true;
+        state[dev].store(max_pairs + 1, std::memory_order_release);
     }
     if (!PAIR) {
         const int grid = prm.n_items < sms ? prm.n_items : sms;
@@ -494,7 +501,7 @@ int launch3(const CUtensorMap& mapA, const CUtensorMap& mapB, const Params& prm,
 template <int MODE, int D, bool NORMED>
 int launch2(const CUtensorMap& mapA, const CUtensorMap& mapB, const CUtensorMap& mapB_pair, const Params& prm, cudaStream_t stream) {
     // a pair's work unit is two consecutive items of the same tile
-    if (g_pair_mode != 0 && prm.items_per_tile % 2 == 0) return launch3<MODE, D, NORMED, true>(mapA, mapB_pair, prm, stream);
+    if (g_pair_mode.load(std::memory_order_relaxed) != 0 && prm.items_per_tile % 2 == 0) return launch3<MODE, D, NORMED, true>(mapA, mapB_pair, prm, stream);
     return launch3<MODE, D, NORMED, false>(mapA, mapB, prm, stream);
 }
 
@@ -581,4 +588,4 @@ int dm_correlation_umma_pool(const void* desc1, const float* stat1, const void* 
     return launch<MODE_POOL, 16>(mapA, mapB, mapBp, prm, normed, stream);
 }
 
-void dm_correlation_umma_set_pair_mode(int mode) { g_pair_mode = mode; }
+void dm_correlation_umma_set_pair_mode(int mode) { g_pair_mode.store(mode, std::memory_order_relaxed); }

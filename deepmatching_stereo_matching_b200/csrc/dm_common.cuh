@@ -89,6 +89,14 @@ __device__ __forceinline__ float dm_rectify(float x) {
     return r;
 }
 
+// misc/Matching.py:165-175: the parabola through (-1, rm), (0, r0), (1, r1).  The reference holds level
+// 0 in float64, so the differences are formed in float64 here as well: with a flat peak
+// (r1 + rm - 2 r0 -> 0) the float32 subtraction would lose the few digits that are left.
+__device__ __forceinline__ double dm_parabola_shift(float r0, float r1, float rm) {
+    const double a = (double)r1, b = (double)rm, c = (double)r0;
+    return -(a - b) / (2.0 * (a + b - 2.0 * c));
+}
+
 // numpy indexing of an axis of length n: -n <= v < n is accepted, negative values wrap
 __device__ __forceinline__ bool dm_np_index_ok(int v, int n) { return v >= -n && v < n; }
 __device__ __forceinline__ int dm_np_wrap(int v, int n) { return v < 0 ? v + n : v; }

@@ -41,22 +41,34 @@ struct dm_ctx {
     // host-API staging
     uint8_t* scene1 = nullptr; uint8_t* scene2 = nullptr; size_t scene_bytes = 0;
     double* planes = nullptr; size_t planes_bytes = 0;
-    // host readback streamed behind the final stage (dm_solve_scene_host, single scene, fused path):
-    // finished output rows are copied device -> host on a second stream while the last tiles
-    // are still being solved
+    // Finished output rows streamed behind the final stage (fused path) to a second destination:
+    // page-locked host arrays (dm_solve_scene_host) or the mosaic of a peer device / another process
+    // (dm_solve_scene_stream; UVA pointers).  Copies run on a second stream while the last tiles are
+    // still being solved.
     cudaStream_t copy_stream = nullptr;
     std::vector<cudaEvent_t> band_ev;
     size_t band_used = 0;
     struct Readback {
         bool active = false;
-        double* h_d_map = nullptr; double* h_out_map = nullptr;
+        double* dst_d_map = nullptr; double* dst_out_map = nullptr;
         const double* d_d_map = nullptr; const double* d_out_map = nullptr;
         int n_modes = 0, out_h = 0, out_w = 0, len0 = 0, len1 = 0, s0 = 0;
         int rows_done = 0, row_hi = 0;              // output rows [.., rows_done) are already on their way
     } rb;
+    // Host scenes uploaded chunk by chunk ahead of the compute (dm_solve_scene_host): the rows the
+    // tiles of chunk k+1 read are copied on a third stream while chunk k is being solved.
+    cudaStream_t h2d_stream = nullptr;
+    cudaEvent_t up_ev = nullptr;
+    struct Upload {
+        bool active = false, pending = false;
+        const uint8_t* h1 = nullptr; const uint8_t* h2 = nullptr;
+        size_t row_bytes = 0;
+        long long rows_done = 0, row_end = 0;       // stacked scene rows [.., rows_done) are on the device (or on their way)
+    } up;
+    int device = 0;                                 // the CUDA device this context was created on
     // CUDA graphs of the upper-pyramid + top-down launch sequence (fused.cu), keyed by what they depend on
     struct UpperGraph {
-        const void* ws; int nt, t0, t1, levels, filter_num, filter_win, filter_mode;
+        const void* ws; int nt, t0, t1, levels, kpad, filter_num, filter_win, filter_mode;   // kpad: the carve-up of the workspace (level / match offsets) depends on it
         int n_agg, n_bt, final_cur;
         cudaGraphExec_t exec;
     };
@@ -90,5 +102,5 @@ bool dm_fused_supported(int t0, int t1, int kpad);
 bool dm_fused_supported_ws(int ws);
 size_t dm_fused_workspace(char* base, int n_tiles, int t0, int t1, int kpad, int levels, void* buffers_out);
 int dm_fused_solve_chunk(dm_ctx* ctx, const dm_fused_args* a, int chunk_index);
-// schedules the device -> host copy of the output rows completed by tiles [0, tiles_done) (global tile index)
+// schedules the copy of the output rows completed by tiles [0, tiles_done) (global tile index) to the stream destination
 int dm_readback_rows(dm_ctx* ctx, long long tiles_done);

@@ -309,13 +309,16 @@ dm_final_quad_kernel(const FinalArgs a, long long n_quads) {
     __syncwarp();
     const uint8_t* regc = reg0;                          // region column x at byte x; this child's windows start cj bytes in
 
-    // level-0 value of position (qy,qx) from sum a*b
+    // min-maxed (not yet rectified) co_map value of position (qy,qx) from sum a*b.  Candidates are
+    // compared on these values: x -> x**1.4 is strictly increasing, and the reference compares its
+    // float64 powers, which stay distinct where the float32 ex2/lg2 powers of two neighbouring
+    // floats may coincide.
     auto value_at = [&](int sum_ab, int qy, int qx) -> float {
         const dm_stat sq = st2[qy * T1 + qx];
         const int m2 = (int)sq.w, S2 = (int)sq.x;
         const int dot = sum_ab - m2 * S1 - m1 * S2 - K * m1 * m2;
         const float z = dm_zncc_partial((float)dot, s1.x, sq.z, normed ? sq.y : 1.0f);
-        return dm_rectify(dm_normalize(dm_zncc_finish(z, s1.y, flat1, normed), mn, mx, rinv));
+        return dm_normalize(dm_zncc_finish(z, s1.y, flat1, normed), mn, mx, rinv);
     };
     // 16 bytes of a against region row `row`, window starting at byte `bo` (dynamic)
     auto row_dot = [&](const uint32_t (&aq)[4], int row, int bo) -> uint32_t {
@@ -384,6 +387,8 @@ dm_final_quad_kernel(const FinalArgs a, long long n_quads) {
         if (s == 0) { best = v; best_nan = (v != v); }
         else if (!best_nan && (v > best || v != v)) { best = v; bi = s; best_nan = (v != v); }
     }
+    // level-0 values (co_map ** 1.4) of the winner and of the centre
+    best = dm_rectify(best); centre = dm_rectify(centre);
     if (best < DM_NEAR_ZERO_F) { bi = 4; best = centre; }
     const int c0 = d0 + bi / 3 - 1, c1 = d1 + bi % 3 - 1;
     const float score = best + centre;
@@ -431,12 +436,12 @@ dm_final_quad_kernel(const FinalArgs a, long long n_quads) {
         const int sx = my_n == 2 ? nx[2] : (my_n == 3 ? nx[3] : c1);
         const bool sok = my_n < 2 ? nok[0] : nok[2];
         float nval = 0.0f;
-        if (sok) nval = value_at((int)tot, sy, sx);
+        if (sok) nval = dm_rectify(value_at((int)tot, sy, sx));
         const float r0 = best;                      // level-0 value at the match itself
         const float v0 = __shfl_sync(0xffffffffu, nval, gbase + 0), v1 = __shfl_sync(0xffffffffu, nval, gbase + 2);
         const float v2 = __shfl_sync(0xffffffffu, nval, gbase + 4), v3 = __shfl_sync(0xffffffffu, nval, gbase + 6);
-        if (nok[0] && r0 > v0 && r0 > v1) mrow += (double)(-(v0 - v1) / (2.0f * (v0 + v1 - 2.0f * r0)));
-        if (nok[2] && r0 > v2 && r0 > v3) mcol += (double)(-(v2 - v3) / (2.0f * (v2 + v3 - 2.0f * r0)));
+        if (nok[0] && r0 > v0 && r0 > v1) mrow += dm_parabola_shift(r0, v0, v1);
+        if (nok[2] && r0 > v2 && r0 > v3) mcol += dm_parabola_shift(r0, v2, v3);
     }
     if (l != 0) return;
 
@@ -584,7 +589,7 @@ int dm_fused_solve_chunk(dm_ctx* ctx, const dm_fused_args* a, int ck) {
     } else {
         dm_ctx::UpperGraph* ug = nullptr;
         for (auto& g : ctx->upper_graphs)
-            if (g.ws == (const void*)ctx->ws && g.nt == nt && g.t0 == t0 && g.t1 == t1 && g.levels == L &&
+            if (g.ws == (const void*)ctx->ws && g.nt == nt && g.t0 == t0 && g.t1 == t1 && g.levels == L && g.kpad == a->kpad &&
                 g.filter_num == a->filter_num && g.filter_win == a->filter_win && g.filter_mode == a->filter_mode) { ug = &g; break; }
         if (!ug) {
             if (ctx->upper_graphs.size() >= 4) {          // scenes alternate between at most two chunk sizes
@@ -593,7 +598,7 @@ int dm_fused_solve_chunk(dm_ctx* ctx, const dm_fused_args* a, int ck) {
             }
             if (!ctx->capture_stream) DM_CUDA_CHECK(cudaStreamCreateWithFlags(&ctx->capture_stream, cudaStreamNonBlocking));
             dm_ctx::UpperGraph g;
-            g.ws = ctx->ws; g.nt = nt; g.t0 = t0; g.t1 = t1; g.levels = L;
+            g.ws = ctx->ws; g.nt = nt; g.t0 = t0; g.t1 = t1; g.levels = L; g.kpad = a->kpad;
             g.filter_num = a->filter_num; g.filter_win = a->filter_win; g.filter_mode = a->filter_mode;
             DM_CUDA_CHECK(cudaStreamBeginCapture(ctx->capture_stream, cudaStreamCaptureModeThreadLocal));
             rc = run_agg(ctx->capture_stream, &g.n_agg);

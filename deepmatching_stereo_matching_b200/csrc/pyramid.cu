@@ -9,6 +9,8 @@
 // memory with bulk async copies (cp.async.bulk -> UBLKCP, completion on an mbarrier),
 // reads them back with 128-bit loads and hands the one-column halo between lanes with a
 // warp shuffle.
+#include <atomic>
+
 #include "dm_common.cuh"
 
 namespace {
@@ -289,10 +291,14 @@ extern "C" int dm_aggregate(const float* in_dev, int n, int a, int b, int c, int
     const int rows_staged = (bands == 1) ? c : 2 * rb + 1;
     const size_t smem = (size_t)pp * 4 * rows_staged * d * sizeof(float);
     DM_REQUIRE(smem <= 200 * 1024, DM_ERR_UNSUPPORTED, "dm_aggregate: row of %d floats too wide for shared memory", d);
-    static bool attr_set = false;
-    if (!attr_set) {
-        DM_CUDA_CHECK(cudaFuncSetAttribute(dm_aggregate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        attr_set = true;
+    {   // the attribute belongs to the device: one flag per device (several devices per process, dm_multi_*)
+        static std::atomic<bool> attr_set[64];
+        int dev = 0;
+        DM_CUDA_CHECK(cudaGetDevice(&dev));
+        if (dev < 0 || dev >= 64 || !attr_set[dev].load(std::memory_order_acquire)) {
+            DM_CUDA_CHECK(cudaFuncSetAttribute(dm_aggregate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            if (dev >= 0 && dev < 64) attr_set[dev].store(true, std::memory_order_release);
+        }
     }
     dim3 grid((unsigned)dm_div_up(n_parents, pp), bands);
     dm_aggregate_kernel<<<grid, 256, smem, st>>>(in_dev, n_parents, a, b, c, d, pp, rb, rectify, dm_make_fastdiv((uint32_t)(d >> 2)), dm_make_fastdiv((uint32_t)oc), out_dev);

@@ -24,8 +24,52 @@ def _context():
     torch = _native.require_cuda()
     dev = torch.cuda.current_device()
     if dev not in _CTX:
-        _CTX[dev] = _native.Context()
+        _CTX[dev] = _native.Context(workspace_limit=_WS_LIMIT)
     return _CTX[dev]
+
+
+_MULTI = {}
+_WS_LIMIT = None
+MIN_TILES_PER_DEVICE = 128      # below this a device's share is launch-bound: fewer devices are used
+
+
+def visible_devices():
+    """The devices a solve may use.  DM_DEVICES = 'all' | a count | a comma list of indices; without
+    it every visible device -- except under a one-process-per-GPU launcher (WORLD_SIZE > 1), where the
+    process keeps to its current device and the strips are spread over the ranks (strips.py)."""
+    import os
+    torch = _native.require_cuda()
+    n = torch.cuda.device_count()
+    env = os.environ.get('DM_DEVICES', '').strip()
+    if env and env != 'all':
+        if ',' in env:
+            return [int(x) for x in env.split(',') if x.strip() != '']
+        return list(range(min(n, max(1, int(env)))))
+    if not env and int(os.environ.get('WORLD_SIZE', '1')) > 1:
+        return [torch.cuda.current_device()]
+    return list(range(n))
+
+
+def _multi_context(devices):
+    """One dm_multi (a dm_ctx, a stream and a host thread per device) per device set of this process."""
+    key = tuple(devices)
+    if key not in _MULTI:
+        _MULTI[key] = _native.MultiContext(list(devices), workspace_limit=_WS_LIMIT)
+    return _MULTI[key]
+
+
+def solve_host(prm, img1, img2, d_map, out_map, devices=None):
+    """dm_solve_scene_host on one device, dm_multi_solve_scene_host when the scene is large enough
+    to be worth several: tile rows (or, for a batch, whole pairs) are shared out, the result is
+    bit-identical either way.  devices: None = visible_devices(), or a list of device indices."""
+    devs = visible_devices() if devices is None else list(devices)
+    info = _native.scene_geometry(prm)
+    parts = prm.n_scenes if prm.n_scenes > 1 else info.len0
+    use = max(1, min(len(devs), parts, info.n_tiles // MIN_TILES_PER_DEVICE)) if devices is None else min(len(devs), parts)
+    torch = _native.require_cuda()
+    if use <= 1 and (devices is None or devs[0] == torch.cuda.current_device()):
+        return _context().solve_host(prm, img1, img2, d_map, out_map)
+    return _multi_context(devs).solve_host(prm, img1, img2, d_map, out_map, max_devices=use)
 
 
 class _TileIndex(object):
@@ -74,7 +118,11 @@ class _TileViews(object):
 def set_workspace_limit(nbytes):
     """Caps the device workspace of this process's solver context; scenes whose tiles do not
     fit are processed in equal chunks of tiles (default limit: 48 GB)."""
+    global _WS_LIMIT
+    _WS_LIMIT = int(nbytes)
     _context().set_workspace_limit(nbytes)
+    for m in _MULTI.values():
+        m.set_workspace_limit(nbytes)
 
 
 def pinned_empty(shape, dtype):
@@ -85,7 +133,7 @@ def pinned_empty(shape, dtype):
 
 
 def solve_batch(imgs1, imgs2, image_size=[32, 32], stride=[32, 32], window_size=5,
-                feature_name='cv2.TM_CCOEFF_NORMED', degree_map_mode=['elevation'], sub_pix=True, fused=-1):
+                feature_name='cv2.TM_CCOEFF_NORMED', degree_map_mode=['elevation'], sub_pix=True, fused=-1, devices=None):
     """ImageCutSolver(...)() for a batch of equally sized scene pairs in ONE library call
     (BASELINE config 4: 64 pairs of 512x512).  imgs1, imgs2: uint8 (n, S0, S1).
     Returns (d_maps float64 (n, n_modes, S0', S1'), out_maps float64 (n, S0', S1')), each
@@ -99,7 +147,7 @@ def solve_batch(imgs1, imgs2, image_size=[32, 32], stride=[32, 32], window_size=
     info = _native.scene_geometry(prm)
     d_maps = pinned_empty((n, len(degree_map_mode), info.out_h, info.out_w), np.float64)
     out_maps = pinned_empty((n, info.out_h, info.out_w), np.float64)
-    _context().solve_host(prm, a, b, d_maps, out_maps)
+    solve_host(prm, a, b, d_maps, out_maps, devices)
     return d_maps, out_maps
 
 
@@ -146,6 +194,9 @@ class ImageCutSolver():
         # the engine selector (-1 auto, 0 materialising, 1 fused)
         self.tile_rows = None
         self.fused = -1
+        # devices the tile rows are spread over: None = every visible device when the scene is large
+        # enough (visible_devices(), MIN_TILES_PER_DEVICE), or an explicit list of device indices
+        self.devices = None
 
     def _padding(self):
         # misc/image_cut_solver.py:73-93 zeroes image 2 and leaves img_shape stale, so every
@@ -196,7 +247,7 @@ class ImageCutSolver():
         prm = self._params()
         self.d_map = pinned_empty([len(self.degree_map_mode)] + size_list, np.float64)
         self.out_map = pinned_empty(size_list, np.float64)
-        self.info = _context().solve_host(prm, img1, img2, self.d_map, self.out_map)
+        self.info = solve_host(prm, img1, img2, self.d_map, self.out_map, self.devices)
         if self.log_flg:
             print('complete to create multi-level correlation pyramid')
             print('pyramid level: {}, N={}'.format(self.info.levels, self.info.n_map))

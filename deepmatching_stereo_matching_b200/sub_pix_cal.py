@@ -23,3 +23,26 @@ def sub_pix_cal(arr, co_map, direction=0, ratio=100.):
     _native.check(_native.lib().dm_sub_pix_cal(_native.ptr(a), _native.ptr(c), a.shape[0], a.shape[1], int(direction),
                                                float(ratio), _native.ptr(out), _native.stream_ptr()))
     return out.cpu().numpy()
+
+
+def sub_pix_cal_batch(d_maps, co_maps, directions, ratio=100.):
+    """sub_pix_cal for a batch: d_maps (n, n_modes, S0, S1), co_maps (n, S0, S1), directions[m] per
+    plane -> (n, n_modes, S0, S1) float64; each slice identical to sub_pix_cal(d_maps[b, m],
+    co_maps[b], directions[m]).  One upload, n * n_modes launches, one download."""
+    torch = _native.require_cuda()
+    a = torch.from_numpy(np.ascontiguousarray(d_maps, dtype=np.float64)).cuda(non_blocking=True)
+    c = torch.from_numpy(np.ascontiguousarray(co_maps, dtype=np.float64)).cuda(non_blocking=True)
+    if a.dim() != 4 or c.dim() != 3 or a.shape[0] != c.shape[0] or a.shape[2:] != c.shape[1:] or len(directions) != a.shape[1]:
+        raise ValueError('d_maps (n, n_modes, S0, S1), co_maps (n, S0, S1), one direction per plane')
+    if any(d not in (0, 1) for d in directions):
+        raise ValueError('direction must be 0 or 1')
+    out = torch.empty_like(a)
+    lib = _native.lib()
+    for b in range(a.shape[0]):
+        for m in range(a.shape[1]):
+            _native.check(lib.dm_sub_pix_cal(_native.ptr(a[b, m]), _native.ptr(c[b]), a.shape[2], a.shape[3], int(directions[m]),
+                                             float(ratio), _native.ptr(out[b, m]), _native.stream_ptr()))
+    res = torch.empty(out.shape, dtype=out.dtype, pin_memory=True)
+    res.copy_(out, non_blocking=True)
+    torch.cuda.current_stream().synchronize()
+    return res.numpy()

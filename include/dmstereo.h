@@ -222,6 +222,70 @@ int dm_solve_scene_host(dm_ctx* ctx, const dm_scene_params* prm,
                         const uint8_t* img1_host, const uint8_t* img2_host,
                         double* d_map_host, double* out_map_host, dm_scene_info* info);
 
+/* Device-resident solve that ALSO streams its finished output rows, band by band behind the final
+ * stage, into a second pair of arrays: page-locked host memory, the mosaic of a peer device of this
+ * process, or a mosaic another process exported with dm_ipc_export (any UVA pointer the device can
+ * write).  This is how the strips of several devices meet in one mosaic without a collective after
+ * the solve: the copy of band k rides NVLink / PCIe while band k+1 is being solved.  The ctx stream
+ * is made to wait for the last copy: synchronise on it (or on an event recorded on it). */
+int dm_solve_scene_stream(dm_ctx* ctx, const dm_scene_params* prm,
+                          const uint8_t* img1_dev, const uint8_t* img2_dev,
+                          double* d_map_dev, double* out_map_dev,
+                          double* d_map_dst, double* out_map_dst, dm_scene_info* info);
+
+/* ---------------------------------------------------------------- several devices ---
+ * The tile loop of ImageCutSolver._execute_matching (misc/image_cut_solver.py:144-184) spread over
+ * the devices of one process: tile rows are cut into contiguous strips (sizes differing by at most
+ * one, low ranks first: 66 -> 9,9,8,...), device r solves strip r with its own dm_ctx, stream and
+ * host thread.  Tiles are independent and every output row is owned by exactly one tile row, so the
+ * result is bit-identical to the one-device solve.
+ */
+typedef struct dm_multi dm_multi;
+
+/* devices == NULL: devices 0 .. n_devices-1; n_devices <= 0: every visible device */
+int  dm_multi_create(const int* devices, int n_devices, dm_multi** out);
+void dm_multi_destroy(dm_multi* m);
+int  dm_multi_device_count(const dm_multi* m);
+int  dm_multi_set_workspace_limit(dm_multi* m, size_t bytes_per_device);
+/* contiguous tile-row strips [lo[r], hi[r]) of len0 tile rows over n parts */
+int  dm_partition_tile_rows(int len0, int n, int32_t* lo, int32_t* hi);
+
+/* Host-buffer solve over all devices: device r uploads the input rows of its strip, solves it and
+ * streams its finished rows straight into the caller's (ideally page-locked) arrays.  No collective:
+ * the host arrays are the meeting point.  max_devices > 0 caps the devices used (0 = all).
+ * info (may be NULL) describes the whole scene; kernel_launches is summed over the devices. */
+int dm_multi_solve_scene_host(dm_multi* m, const dm_scene_params* prm, int max_devices,
+                              const uint8_t* img1_host, const uint8_t* img2_host,
+                              double* d_map_host, double* out_map_host, dm_scene_info* info);
+
+/* Device-resident solve over all devices + gather of the finished strips on device `root`.
+ * img1_dev[r], img2_dev[r]: the scene on device r (only the input rows of strip r are read);
+ * planes_dev[r]: double [n_modes + 1][out_h][out_w] on device r (disparity planes, then the score
+ * plane).  After the call (asynchronous: dm_multi_synchronize) planes_dev[root] holds the whole
+ * mosaic.  gather: DM_GATHER_P2P  = every device streams its finished bands into the root's planes
+ *                                   over NVLink peer memory while it is still solving;
+ *                  DM_GATHER_NCCL = one grouped ncclSend / ncclRecv of the owned rows after the
+ *                                   solve (libnccl.so.2 is loaded on first use; ncclCommInitAll). */
+#define DM_GATHER_P2P   0
+#define DM_GATHER_NCCL  1
+int dm_multi_solve_scene(dm_multi* m, const dm_scene_params* prm,
+                         const uint8_t* const* img1_dev, const uint8_t* const* img2_dev,
+                         double* const* planes_dev, int root, int gather, dm_scene_info* info);
+/* the gather alone (NCCL): rows [row_lo[r], row_hi[r]) of every plane of planes_dev[r] -> planes_dev[root] */
+int dm_multi_gather_strips(dm_multi* m, double* const* planes_dev, int n_planes, int out_h, int out_w,
+                           const int32_t* row_lo, const int32_t* row_hi, int root);
+int dm_multi_synchronize(dm_multi* m);
+
+/* ---------------------------------------------------------------- shared mosaics ----
+ * One process per device (torchrun): the root allocates the mosaic with dm_ipc_alloc, exports a
+ * 64-byte handle, the other processes open it and pass the pointer to dm_solve_scene_stream. */
+#define DM_IPC_HANDLE_BYTES 64
+int dm_ipc_alloc(size_t bytes, void** dev_ptr);                 /* cudaMalloc on the current device */
+int dm_ipc_free(void* dev_ptr);
+int dm_ipc_export(void* dev_ptr, unsigned char* handle /* [DM_IPC_HANDLE_BYTES] */);
+int dm_ipc_open(const unsigned char* handle, void** dev_ptr);   /* maps the exporter's memory; peer access is enabled lazily */
+int dm_ipc_close(void* dev_ptr);
+
 /* per-stage device time of the last dm_solve_scene* call in milliseconds (CUDA events on
  * the ctx stream; enabled by dm_ctx_enable_timing).  Stage ids: DM_STAGE_*. */
 #define DM_STAGE_DESCRIPTORS  0

@@ -55,7 +55,7 @@ def _im2col(img, ws):
 # --------------------------------------------------------------------------------------
 # correlation  (OpenCV matchTemplate restated)  +  min-max
 # --------------------------------------------------------------------------------------
-def match_template_matrix(img, template, ws, method=TM_CCOEFF_NORMED):
+def match_template_matrix(img, template, ws, method=TM_CCOEFF_NORMED, row_chunk=None):
     """All patches of ``img`` against all windows of ``template`` at once.
 
     Restates ``cv2.matchTemplate(patch, template, method)`` (call site
@@ -67,6 +67,21 @@ def match_template_matrix(img, template, ws, method=TM_CCOEFF_NORMED):
     0; a flat template yields an all-ones map; result stored as float32.
     """
     a1, _ = _im2col(img, ws)
+    if a1.shape[0] > 4096 and row_chunk is None:
+        row_chunk = 2048                             # a 128 x 128 grid: 2 GB per float64 temporary otherwise
+    if row_chunk is not None and a1.shape[0] > row_chunk:
+        # the rows (patches) are independent: evaluate them in blocks to bound the temporaries
+        win = np.lib.stride_tricks.sliding_window_view(np.asarray(img), (ws, ws))
+        t1 = win.shape[1]
+        out = []
+        for r0 in range(0, a1.shape[0], row_chunk):
+            out.append(_match_rows(a1[r0:r0 + row_chunk], template, ws, method))
+        return np.concatenate(out, 0)
+    return _match_rows(a1, template, ws, method)
+
+
+def _match_rows(a1, template, ws, method):
+    """match_template_matrix for the patch rows ``a1`` (n, ws*ws) float64."""
     a2, _ = _im2col(template, ws)
     k = float(ws * ws)
     inv_area = 1.0 / k
@@ -306,6 +321,45 @@ def sub_pix(l0, mp):
     d_y = jj - mp[1]
     out[1] = np.where(valid, jj - d_y + fit(r0, r1, r_), jj - d_y)
     return out
+
+
+def matching_margins(co_map_list):
+    """matching(co_map_list, sub_pix_on=False) plus, per level-0 patch, the smallest margin by which
+    any decision on its top-down path was taken: at every level the difference between the best
+    and the best different value of the zero-padded 3x3 window (misc/Matching.py:58-78), and the
+    distance of the window maximum from the 1e-4 threshold.  A float32 pyramid may decide a step
+    differently from the reference's float64 one only where this margin is of the size of the
+    float32 error of the level values -- the "provable near-tie" the parity tests allow.
+    Returns (map (3,T0,T1), margin (T0,T1))."""
+    def margins(level, p0, p1, d0, d1):
+        a, b, c, d = level.shape
+        pad = np.zeros((a, b, c + 2, d + 2), dtype=level.dtype)
+        pad[:, :, 1:c + 1, 1:d + 1] = level
+        wins = np.stack([pad[p0, p1, d0 + dy, d1 + dx] for dy in range(3) for dx in range(3)], -1)
+        top = wins.max(-1, keepdims=True)
+        gap = top - wins
+        # exact ties are structural (overlapping pooling windows select the same element: the same
+        # expression on the same inputs, equal in any precision) and are broken identically by the
+        # first-maximum rule; the margin is the distance to the best DIFFERENT value
+        gap = np.where(gap > 0, gap, np.inf).min(-1)
+        return np.minimum(gap, np.abs(top[..., 0] - NEAR_ZERO))
+
+    top = co_map_list[-1]
+    a, b = top.shape[:2]
+    ii, jj = np.meshgrid(np.arange(a), np.arange(b), indexing='ij')
+    mp = initial_move_map(top)
+    mg = margins(top, ii, jj, ii, jj)
+    idx = len(co_map_list) - 1
+    while idx > 0:
+        idx -= 1
+        level = co_map_list[idx]
+        h, w = mp.shape[1:]
+        ii, jj = np.meshgrid(np.arange(2 * h), np.arange(2 * w), indexing='ij')
+        d0 = (mp[0] * 2).astype('int64')[ii // 2, jj // 2] + (ii & 1)
+        d1 = (mp[1] * 2).astype('int64')[ii // 2, jj // 2] + (jj & 1)
+        mg = np.minimum(mg[ii // 2, jj // 2], margins(level, ii, jj, d0, d1))
+        mp = backtrack_level(level, mp)
+    return mp, mg
 
 
 def match_filter(mp, window=3, mode='median'):

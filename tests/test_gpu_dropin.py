@@ -4,6 +4,7 @@ import numpy as np
 import pytest
 
 from oracle import dm_oracle as O
+from parity_util import NEAR_TIE
 
 pytestmark = pytest.mark.gpu
 
@@ -29,7 +30,11 @@ def test_deep_dem_mathing_sequence(tmp_path):
     ref = O.correlation_map(img1, img2, 5)
     ro = O.matching(ref['co_map_list'], True)
     assert co_cls.N_map == ref['N_map'] == 32 and co_cls.iteration == ref['iteration'] == 6
-    assert np.mean(np.abs(O.cal_map(ro, 'elevation') - d_map) > 0.5) <= 2e-3
+    # <= 0.1 % integer disagreement (2 of 2048 pixels), each one a near-tie of the oracle's own decision
+    _, margin = O.matching_margins(ref['co_map_list'])
+    bad = np.abs(O.cal_map(ro, 'elevation') - d_map) > 0.5
+    print('deep_dem_mathing sequence: %d of %d pixels differ, worst margin %.2e' % (bad.sum(), bad.size, margin[bad].max() if bad.any() else 0))
+    assert bad.mean() <= 1e-3 and not (bad & ~(margin < NEAR_TIE)).any()
     assert np.allclose(np.load(tmp_path / 'response.npy'), out)
     # co_map_list behaves like the reference's list of float64 arrays
     lst = co_cls.co_map_list
@@ -50,7 +55,13 @@ def test_bad_matching_sequence():
             dis[i, j] = j - np.argmax(co_cls.co_map[i, j, i, :])
     ref = O.initial_co_map(img1, img2, 5)
     rd = np.array([[j - np.argmax(ref[i, j, i, :]) for j in range(ref.shape[1])] for i in range(ref.shape[0])])
-    assert np.mean(dis != rd) <= 0.01
+    # the row argmax may only differ where the oracle's two best values of that row are closer than the
+    # float32 error of co_map (2e-6 against the exact value, twice)
+    rows = np.stack([[ref[i, j, i, :] for j in range(ref.shape[1])] for i in range(ref.shape[0])])
+    top2 = np.sort(rows, axis=-1)[..., -2:]
+    near = (top2[..., 1] - top2[..., 0]) < 1e-5
+    print('bad_matching sequence: %d of %d row maxima differ' % ((dis != rd).sum(), dis.size))
+    assert not ((dis != rd) & ~near).any() and np.mean(dis != rd) <= 1e-3
     assert co_cls.atomic_patch.shape == (16, 32, 5, 5) and co_cls.atomic_patch.dtype == np.uint8
 
 

@@ -5,6 +5,7 @@ import pytest
 
 from conftest import load_golden, TILE_CASES, SOLVER_CASES, co_map_atol
 from oracle import dm_oracle as O
+from parity_util import scene_report, assert_parity, NEAR_TIE
 
 pytestmark = pytest.mark.gpu
 
@@ -321,8 +322,23 @@ def test_image_cut_solver_with_displacement_filter(dm, mode, num, win, fused_exp
     s2._cut_and_pool()
     s2._execute_matching_per_tile(list(d.shape[1:]))
     assert np.array_equal(s2.d_map, d, equal_nan=True) and np.array_equal(s2.out_map, sc, equal_nan=True)
+    # "bit-exact given identical correlation inputs": the oracle's top-down pass + filter on the GPU's own
+    # (float32) pyramid of a tile must reproduce the GPU's matches exactly -- whatever differs from the
+    # float64 oracle below comes from the float32 level values alone
+    for (ty, tx) in ((0, 0), (42, 28), (56, 84)):           # the last two lie in / at the outlier block
+        co = dm.Correlation_map(img1[ty:ty + 20, tx:tx + 20], img2[ty:ty + 20, tx:tx + 20], window_size=5)
+        lv32 = [np.asarray(x, dtype=np.float32) for x in co()]
+        got = dm.Matching(co, sub_pix=False, filtering=True, filter_window_size=win, filtering_num=num, filtering_mode=mode)()
+        want = O.matching(lv32, False, filtering=True, filtering_num=num, filter_window_size=win, filtering_mode=mode)
+        assert np.array_equal(got, want, equal_nan=True)
     rd, rs = O.image_cut_solver(img1, img2, (16, 16), (14, 14), 5, ('elevation', 'elevation2'), True, filtering=(num, win, mode))
-    assert np.mean(np.abs(d - rd) > 0.5) <= 5e-3             # outlier blocks: near-ties flip a few more integer matches
+    bad = np.abs(d - rd) > 0.5
+    inside = np.zeros(d.shape[1:], bool)
+    inside[40 - 16:80 + 4, 30 - 16:90 + 4] = True           # pixels whose tile or filter window can see the uncorrelated block
+    print('filter %s num %d win %d: disagreement %.5f outside the outlier block, %.5f in its neighbourhood' % (
+        mode, num, win, bad[:, ~inside].mean(), bad[:, inside].mean()))
+    assert bad[:, ~inside].mean() <= MAX_INDEX_DISAGREEMENT
+    assert bad.mean() <= 5e-3                               # uncorrelated texture: the matches are near-ties by construction
     plain, _ = dm.ImageCutSolver(img1, img2, **dict(kw, filtering=False))()
     if win <= 16 >> (5 - num if num < 5 else 0):             # some filtered map is at least as large as the window
         assert np.mean(np.abs(plain - d) > 0.5) > 0          # ... and the filter did change the field
@@ -450,11 +466,8 @@ def test_fused_path_non_square_tiles(dm, size, stride, ws):
         res.append((d, sc))
     assert np.mean(np.abs(res[0][0] - res[1][0]) > 1e-4) <= 5e-4
     assert np.mean(np.abs(res[0][1] - res[1][1]) > 1e-5) <= 5e-4
-    e2 = ws - 1
-    rd, rs = O.solve_tile(i1[:size[0] + e2, :size[1] + e2], i2[:size[0] + e2, :size[1] + e2], ws, ('elevation', 'elevation2'), True)
-    own0 = min(size[0], stride[0]); own1 = min(size[1], stride[1])      # pixels of tile (0,0) no later tile overwrites
-    got = res[1][0][:, :own0, :own1]
-    assert np.mean(np.abs(got - rd[:, :own0, :own1]) > 0.5) <= 2e-3
+    # every tile against the oracle: <= 0.1 % integer disagreement, each one a near-tie of the oracle's own decision
+    assert_parity(scene_report(i1, i2, size, stride, ws, ['elevation', 'elevation2'], res[1][0], res[1][1], True))
 
 
 def test_fused_path_flat_patch_nan(dm):
@@ -549,8 +562,23 @@ def test_batch_of_pairs_equals_one_by_one(dm):
     rd, rs = O.image_cut_solver(pairs[0][0], pairs[0][1], (32, 32), (32, 32), 5, ('elevation', 'elevation2'), True)
     got = dm.sub_pix_cal(d[0, 0], sc[0], direction=1)
     ref = O.sub_pix_cal(rd[0], rs, direction=1)
-    ok = ~(np.isnan(got) | np.isnan(ref))
-    assert np.mean(np.abs(got[ok] - ref[ok]) > 1e-2) <= 5e-3
+    # sub_pix_cal has no peak guard (misc/sub_pix_cal.py:39-44): dis = d - (r1 - r_) / (2 (r1 + r_ - 2 r0)) amplifies
+    # a score difference eps by ~eps / curvature^2, and |shift| > 1 is thrown away.  Where the
+    # curvature of the oracle's own score mosaic is not degenerate the result must agree to 1e-3;
+    # the rest is counted.
+    r0, r1, rm = rs[1:-1, 1:-1], rs[1:-1, 2:], rs[1:-1, :-2]
+    curv = np.abs(r1 + rm - 2 * r0)
+    same_int = np.abs(d[0, 0] - rd[0])[1:-1, 1:-1] < 1e-3
+    well = (curv > 3e-3) & same_int & (np.abs(sc[0] - rs)[1:-1, 1:-1] < 1e-5)
+    diff = np.abs(got - ref)[1:-1, 1:-1]
+    ok = ~(np.isnan(diff))
+    print('sub_pix_cal: %.4f of the pixels well conditioned, worst error there %.2e; overall fraction above 1e-2: %.5f' % (
+        well.mean(), diff[well & ok].max(), np.mean(diff[ok] > 1e-2)))
+    assert well.mean() > 0.5
+    assert np.mean(diff[well & ok] > 1e-3) <= 1e-3
+    assert np.mean(diff[ok] > 1e-2) <= 5e-3
+    # and the bit-exact statement: the same float64 arithmetic on the GPU's own planes
+    assert np.array_equal(got, O.sub_pix_cal(d[0, 0], sc[0], direction=1), equal_nan=True)
 
 
 def test_chunked_scene_equals_single_chunk(dm):
@@ -639,3 +667,104 @@ def test_bilateral_filter_bit_exact(dm):
         assert np.array_equal(dm.bilateral_filter(big, d, sc, ss), O.bilateral_filter_u8(big, d, sc, ss))
     with pytest.raises(ValueError):
         dm.bilateral_filter(big.astype(np.float64), 7, 5, 5)
+
+
+def test_window_size_sweep_on_one_context(dm):
+    """Solves with different window sizes on ONE context: the cached CUDA graph of the upper-pyramid
+    launches bakes in workspace offsets that depend on kpad (64 for ws 3-7, 192 / 256 above); same scene
+    and tile geometry with another window must not replay it.  Each result equals a fresh context's."""
+    from deepmatching_stereo_matching_b200 import image_cut_solver as ics
+    from deepmatching_stereo_matching_b200.synth import stereo_pair
+    i1, i2 = stereo_pair((300, 300), seed=23, mode='sine', amp=5)
+
+    def solve(ws):
+        s = dm.ImageCutSolver(i1, i2, image_size=[32, 32], stride=[30, 30], window_size=ws, degree_map_mode=['elevation', 'elevation2'], sub_pix=True)
+        s.log_flg = False
+        s.fused = 1
+        s.devices = [0]
+        d, sc = s()
+        return d.copy(), sc.copy()
+
+    fresh = {}
+    for ws in (15, 9, 5):
+        ics._CTX.clear()
+        fresh[ws] = solve(ws)
+    ics._CTX.clear()
+    for ws in (15, 5, 9, 15, 5):            # one context: large workspace first, then smaller needs inside it
+        d, sc = solve(ws)
+        assert np.array_equal(d, fresh[ws][0], equal_nan=True) and np.array_equal(sc, fresh[ws][1], equal_nan=True), ws
+
+
+def test_c2_bench_workload_vs_oracle(dm):
+    """The benchmarked workload itself (bench.py config c2: 1024^2 sine warp, ws 15, image_size 64,
+    stride 60, sub_pix, fused path): 16 evenly spaced tiles of the mosaic against the oracle with
+    bench.py's own parity block, and four of them with the near-tie classification."""
+    import bench
+    i1, i2 = bench.make_scene('c2')
+    c = bench.CONFIGS['c2']
+    s = dm.ImageCutSolver(i1, i2, image_size=[c['T']] * 2, stride=[c['stride']] * 2, window_size=c['ws'], degree_map_mode=bench.MODES, sub_pix=True)
+    s.log_flg = False
+    s.devices = [0]
+    d, sc = s()
+    assert s.info.used_fused == 1 and d.shape == (2, 904, 904)
+    planes = np.concatenate([d, sc[None]], 0)[None]
+    par = bench.parity_block('c2', i1, i2, planes, 16)
+    print('c2 parity block: %s' % par)
+    assert par['ok'], par
+    assert par['int_disagreement'] <= MAX_INDEX_DISAGREEMENT and par['score_max_abs'] <= 1e-3
+    assert_parity(scene_report(i1, i2, (64, 64), (60, 60), 15, bench.MODES, d, sc, True, tiles=[0, 37, 112, 224]))
+
+
+@pytest.mark.timeout(1500)
+def test_full_t128_tile_vs_oracle(dm):
+    """One FULL tile at the C5 geometry (image_size 128, ws 15): both GPU paths against the oracle
+    (float64 pyramid of 16384 x 16384 entries; the oracle evaluates its correlation in row blocks)."""
+    from deepmatching_stereo_matching_b200.synth import stereo_pair
+    i1, i2 = stereo_pair((266, 266), seed=33, mode='sine', amp=32)      # one 128 x 128 tile (len = floor((266 - 142) / 124) = 1)
+    res = []
+    for fused in (1, 0):
+        s = dm.ImageCutSolver(i1, i2, image_size=[128, 128], stride=[124, 124], window_size=15, degree_map_mode=['elevation', 'elevation2'], sub_pix=True)
+        s.log_flg = False
+        s.fused = fused
+        s.devices = [0]
+        d, sc = s()
+        assert list(s.len) == [1, 1] and d.shape == (2, 128, 128) and s.info.used_fused == fused and s.info.levels == 8
+        res.append((d.copy(), sc.copy()))
+    (len0, len1), trimmed = O.tile_grid(i1.shape, (128, 128), (124, 124), 15)
+    a, b = i1[:trimmed[0], :trimmed[1]], i2[:trimmed[0], :trimmed[1]]
+    cm = O.correlation_map(a, b, 15)
+    pre, margin = O.matching_margins(cm['co_map_list'])
+    out = O.sub_pix(cm['co_map_list'][0], pre)
+    del cm
+    for (d, sc), label in zip(res, ('fused', 'materialising')):
+        n_bad = 0
+        bad_any = np.zeros((128, 128), bool)
+        for m, mode in enumerate(('elevation', 'elevation2')):
+            ref = O.cal_map(out, mode)
+            bad = np.abs(d[m] - ref) > 0.5
+            bad_any |= bad
+            n_bad += int(bad.sum())
+            rel = np.abs(d[m] - ref) / np.maximum(1.0, np.abs(ref))
+            assert np.mean(rel[~bad] > 1e-3) <= 1e-3, label
+        print('T=128 %s: %d of %d integer disparities differ, worst margin %.2e; score max abs %.2e' % (
+            label, n_bad, 2 * 128 * 128, margin[bad_any].max() if bad_any.any() else 0.0, np.abs(sc - out[2])[~bad_any].max()))
+        assert n_bad <= MAX_INDEX_DISAGREEMENT * 2 * 128 * 128, label
+        assert not (bad_any & ~(margin < NEAR_TIE)).any(), label
+        assert np.mean(np.abs(sc - out[2])[~bad_any] > 1e-3) <= 1e-3, label
+
+
+def test_c4_pair_vs_oracle(dm):
+    """One pair of the C4 workload (512^2, image_size 32, ws 5, stride 32, sub_pix, then sub_pix_cal on
+    both planes with the direction rule of image_cut_solver.py:137): all 196 tiles against the oracle."""
+    import bench
+    from deepmatching_stereo_matching_b200.synth import stereo_pair
+    i1, i2 = stereo_pair((512, 512), seed=100, mode='sine', amp=8)
+    s = dm.ImageCutSolver(i1, i2, image_size=[32, 32], stride=[32, 32], window_size=5, degree_map_mode=bench.MODES, sub_pix=True)
+    s.log_flg = False
+    s.devices = [0]
+    d, sc = s()
+    assert s.info.used_fused == 1 and d.shape == (2, 448, 448) and s.info.n_tiles == 196
+    assert_parity(scene_report(i1, i2, (32, 32), (32, 32), 5, bench.MODES, d, sc, True))
+    for m, direction in ((0, 1), (1, 0)):
+        got = dm.sub_pix_cal(d[m], sc, direction=direction)
+        assert np.array_equal(got, O.sub_pix_cal(d[m], sc, direction=direction), equal_nan=True)
