@@ -403,6 +403,7 @@ def run_ours(args):
     lib = _native.lib()
     clocks = ClockSampler(local_rank) if rank == 0 else None
     peer = None
+    checks = {}
 
     if B == 1:
         # ---------------------------------------------------------------- one scene: strips of tile rows
@@ -515,6 +516,7 @@ def run_ours(args):
         g1.record()
         barrier()
         gms = max_over_ranks(g0.elapsed_time(g1))
+        checks['nccl_gather_equals_streamed_mosaic'] = bool(torch.equal(planes, peer.tensor)) if rank == 0 else None
         gather_nccl = {'value': out_px * args.steps / 1e6 / (gms * 1e-3), 'unit': 'MP/s', 'ms_per_step': gms / args.steps,
                        'how': 'solve the strip, then point-to-point NCCL transfers of the owned rows (float64) to rank 0'}
 
@@ -536,6 +538,7 @@ def run_ours(args):
             q1.record()
             torch.cuda.synchronize()
             qms = q0.elapsed_time(q1) / reps
+            checks['strips_equal_single_gpu_solve'] = bool(torch.equal(planes, peer.tensor))      # bit for bit
             single = {'value': out_px / 1e6 / (qms * 1e-3), 'unit': 'MP/s', 'ms_per_step': qms, 'n_gpus': 1,
                       'how': 'the same workload solved by rank 0 alone (device-resident), for the strong-scaling ratio'}
             sctx.close()
@@ -602,6 +605,8 @@ def run_ours(args):
     clk = clocks.stop() if clocks else None
     if mosaic is not None:
         barrier()
+        if rank == 0:
+            checks['host_mosaic_equals_streamed_mosaic'] = bool(np.array_equal(mosaic.array, peer.tensor.cpu().numpy(), equal_nan=True))
         mosaic.close()
     if raw_paths is not None:
         for p_ in raw_paths:
@@ -733,7 +738,7 @@ def run_ours(args):
             'config': config_dict(name, world), 'gather': gather_name,
             'e2e': e2e, 'gpu_launches': int(launches_per_step * args.steps),
             'clocks': clk, 'roofline': roofline, 'cpu_baseline': cpu, 'parity': parity,
-            'sustained': sustained, 'gather_nccl': gather_nccl, 'single_gpu_same_workload': single,
+            'sustained': sustained, 'gather_nccl': gather_nccl, 'single_gpu_same_workload': single, 'checks': checks,
         }
         sys.stdout.flush()
         print(json.dumps(line))
@@ -741,6 +746,9 @@ def run_ours(args):
         if parity is not None and not parity['ok']:
             sys.stderr.write('PARITY FAILED: %s\n' % json.dumps(parity))
             rc = 3
+        if any(v is False for v in checks.values()):
+            sys.stderr.write('MULTI-GPU CHECK FAILED: %s\n' % json.dumps(checks))
+            rc = 4
     return rc
 
 

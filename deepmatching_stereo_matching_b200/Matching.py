@@ -67,7 +67,7 @@ class Matching():
         torch = _native.require_cuda()
         lst = self.obj.co_map_list
         if isinstance(lst, DeviceLevels):
-            return lst.device, False
+            return lst.device, False      # float32 on the device; __call__ asks for the float64 parabola (is_f64 = 2)
         out = []
         f64 = any(np.asarray(x).dtype != np.float32 for x in lst)
         for x in lst:
@@ -118,7 +118,8 @@ class Matching():
                 match = self._filter_device(match, score, torch)
         t0, t1 = levels[0].shape[:2]
         out = torch.empty((3, t0, t1), dtype=torch.float64, device='cuda')
-        _native.check(lib.dm_match_map(_native.ptr(levels[0]), int(f64), 1, t0, t1, _native.ptr(match), _native.ptr(score),
+        own = isinstance(self.obj.co_map_list, DeviceLevels)      # the library's own pyramid: the reference sees float64 values
+        _native.check(lib.dm_match_map(_native.ptr(levels[0]), 2 if own else int(f64), 1, t0, t1, _native.ptr(match), _native.ptr(score),
                                        1 if self.sub_pix else 0, _native.ptr(out), st()))
         self.map = out.cpu().numpy()
         return self.map

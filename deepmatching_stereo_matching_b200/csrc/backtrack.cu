@@ -77,7 +77,10 @@ __device__ __forceinline__ T sub_pix_fit(T r0, T r1, T rm) {
     return T(0);
 }
 
-template <typename T>
+// WIDE: float32 storage of the library's own pyramid, differences formed in float64 -- the
+// reference holds those values in float64 arrays (dm_parabola_shift); otherwise the arithmetic is
+// the storage type's, as numpy does for a float32 / float64 co_map_list handed in by the caller.
+template <typename T, bool WIDE>
 __global__ void __launch_bounds__(256)
 dm_match_map_kernel(const T* __restrict__ l0, long long total, int T0, int T1,
                     const int32_t* __restrict__ match, const T* __restrict__ score, int sub_pix,
@@ -101,12 +104,12 @@ dm_match_map_kernel(const T* __restrict__ l0, long long total, int T0, int T1,
         if (dm_np_index_ok(c0 + 1, T0) && dm_np_index_ok(c0 - 1, T0)) {
             const T r1 = map[(size_t)dm_np_wrap(c0 + 1, T0) * T1 + w1];
             const T rm = map[(size_t)dm_np_wrap(c0 - 1, T0) * T1 + w1];
-            m0 += (double)sub_pix_fit<T>(r0, r1, rm);
+            m0 += WIDE ? ((r0 > r1 && r0 > rm) ? dm_parabola_shift((float)r0, (float)r1, (float)rm) : 0.0) : (double)sub_pix_fit<T>(r0, r1, rm);
         }
         if (dm_np_index_ok(c1 + 1, T1) && dm_np_index_ok(c1 - 1, T1)) {
             const T r1 = map[(size_t)w0 * T1 + dm_np_wrap(c1 + 1, T1)];
             const T rm = map[(size_t)w0 * T1 + dm_np_wrap(c1 - 1, T1)];
-            m1 += (double)sub_pix_fit<T>(r0, r1, rm);
+            m1 += WIDE ? ((r0 > r1 && r0 > rm) ? dm_parabola_shift((float)r0, (float)r1, (float)rm) : 0.0) : (double)sub_pix_fit<T>(r0, r1, rm);
         }
     }
     double* o = out + (size_t)n * 3 * P;
@@ -408,10 +411,13 @@ extern "C" int dm_match_map(const void* level0_dev, int is_f64, int n, int t0, i
     DM_REQUIRE(n > 0 && t0 > 0 && t1 > 0, DM_ERR_INVALID, "dm_match_map: bad shape");
     const long long total = (long long)n * t0 * t1;
     cudaStream_t st = (cudaStream_t)stream;
-    if (is_f64)
-        dm_match_map_kernel<double><<<dm_div_up(total, 256), 256, 0, st>>>((const double*)level0_dev, total, t0, t1, match_dev, (const double*)score_dev, sub_pix, map_dev);
+    DM_REQUIRE(is_f64 >= 0 && is_f64 <= 2, DM_ERR_INVALID, "dm_match_map: is_f64 %d", is_f64);
+    if (is_f64 == 1)
+        dm_match_map_kernel<double, false><<<dm_div_up(total, 256), 256, 0, st>>>((const double*)level0_dev, total, t0, t1, match_dev, (const double*)score_dev, sub_pix, map_dev);
+    else if (is_f64 == 2)
+        dm_match_map_kernel<float, true><<<dm_div_up(total, 256), 256, 0, st>>>((const float*)level0_dev, total, t0, t1, match_dev, (const float*)score_dev, sub_pix, map_dev);
     else
-        dm_match_map_kernel<float><<<dm_div_up(total, 256), 256, 0, st>>>((const float*)level0_dev, total, t0, t1, match_dev, (const float*)score_dev, sub_pix, map_dev);
+        dm_match_map_kernel<float, false><<<dm_div_up(total, 256), 256, 0, st>>>((const float*)level0_dev, total, t0, t1, match_dev, (const float*)score_dev, sub_pix, map_dev);
     DM_LAUNCH_CHECK();
     return DM_OK;
 }

@@ -140,7 +140,10 @@ int dm_match_filter(const int32_t* match_in_dev, int n, int h, int w, int window
 
 /* Matching._sub_pix_cal (misc/Matching.py:165-209) + assembly of Matching.__call__'s
  * return value (misc/Matching.py:211-222): map_dev = double [n][3][T0][T1] =
- * (row (+diff), col (+diff), score).  sub_pix = 0 skips the parabola fit. */
+ * (row (+diff), col (+diff), score).  sub_pix = 0 skips the parabola fit.
+ * is_f64: 0 = float32 level, float32 arithmetic (what numpy does with a float32 co_map_list),
+ *         1 = float64 level, 2 = float32 level of the library's own pyramid with the parabola
+ *         evaluated in float64 (the reference holds these values in float64 arrays). */
 int dm_match_map(const void* level0_dev, int is_f64, int n, int t0, int t1,
                  const int32_t* match_dev, const void* score_dev, int sub_pix,
                  double* map_dev, void* stream);

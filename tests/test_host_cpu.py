@@ -199,3 +199,33 @@ def test_raw_read(tmp_path):
     a.tofile(p)
     assert np.array_equal(dm.RawRead.read(str(p), size=(12, 10)), O.raw_read(str(p), size=(12, 10)))
     assert np.array_equal(dm.RawRead.read(str(p), size=(12, 10), rate=2), O.raw_read(str(p), size=(12, 10), rate=2))
+
+
+def test_partition_rule_is_the_same_in_c_and_python():
+    from deepmatching_stereo_matching_b200 import _native
+    from deepmatching_stereo_matching_b200.strips import partition_tile_rows
+    for len0, n in [(66, 8), (64, 8), (15, 4), (3, 8), (1, 1), (33, 2)]:
+        assert _native.partition_tile_rows(len0, n) == partition_tile_rows(len0, n)
+    assert _native.partition_tile_rows(66, 8)[:3] == [(0, 9), (9, 18), (18, 26)]
+
+
+def test_bench_arms_print_the_same_config():
+    import bench
+    for name in bench.CONFIGS:
+        for n in (1, 8):
+            a, b = bench.config_dict(name, n), bench.config_dict(name, n)
+            assert a == b and a['name'] == name and a['workload'] == bench.workload_name(name)
+    assert bench.config_dict('c3', 8)['tiles'] == 4356 and bench.config_dict('c5', 8)['output'] == [1, 7940, 7940]
+    assert bench.config_dict('c4', 2)['tiles'] == 12544
+
+
+def test_oracle_margins_follow_the_matching():
+    """matching_margins walks the same path as matching() and its margins are positive distances."""
+    from deepmatching_stereo_matching_b200.synth import stereo_pair
+    i1, i2 = stereo_pair((24, 40), seed=5, mode='sine', amp=2)
+    cm = O.correlation_map(i1, i2, 5)
+    mp, mg = O.matching_margins(cm['co_map_list'])
+    assert np.array_equal(mp, O.matching(cm['co_map_list'], False), equal_nan=True)
+    assert mg.shape == mp.shape[1:] and (mg > 0).all()
+    r = O.match_template_matrix(i1, i2, 5)
+    assert np.array_equal(r, O.match_template_matrix(i1, i2, 5, row_chunk=37))

@@ -45,7 +45,8 @@ def _worker(rank, world, port, q):
         from deepmatching_stereo_matching_b200.strips import SharedHostMosaic
         mosaic = SharedHostMosaic(tuple(local.shape), np.float64)
         mosaic.copy_strip(local, ranges[rank])
-        dist.barrier()
+        mosaic.publish(1)                    # a flag per rank in the shared segment instead of a collective
+        mosaic.wait(1)
         shared = mosaic.array.copy()
         dist.barrier()
         mosaic.close()
