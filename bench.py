@@ -727,7 +727,21 @@ def run_ours(args):
         barrier()
         peer.close()
     if world > 1:
+        # the JSON line must be the LAST line on stdout: with NCCL_DEBUG=INFO every rank still prints while
+        # it tears its communicator down, so rank 0 prints only after the other ranks have left
+        done_dir = [tempfile.mkdtemp(prefix='dm_done_') if rank == 0 else None]
+        dist.broadcast_object_list(done_dir, src=0)
         dist.destroy_process_group()
+        sys.stdout.flush(); sys.stderr.flush()
+        if rank != 0:
+            open(os.path.join(done_dir[0], 'rank%d' % rank), 'w').close()
+            os._exit(0)                     # no library destructors: nothing more is printed by this rank
+        t_wait = time.perf_counter()
+        while len(os.listdir(done_dir[0])) < world - 1 and time.perf_counter() - t_wait < 20:
+            time.sleep(0.05)
+        time.sleep(0.3)
+        import shutil
+        shutil.rmtree(done_dir[0], ignore_errors=True)
     rc = 0
     if rank == 0:
         value = out_px * args.steps / 1e6 / (ms * 1e-3)
@@ -749,6 +763,9 @@ def run_ours(args):
         if any(v is False for v in checks.values()):
             sys.stderr.write('MULTI-GPU CHECK FAILED: %s\n' % json.dumps(checks))
             rc = 4
+        if world > 1:
+            sys.stdout.flush(); sys.stderr.flush()
+            os._exit(rc)
     return rc
 
 
