@@ -12,7 +12,7 @@ sub-pixel -> planes / mosaic) over one synthetic workload of BASELINE.json (SURV
   c2 (default at N = 1)  1024x1024 pair, ws 15, image_size 64 (+/-64 px), stride 60
                          (ex_deepmatching_rawinput.py:28-30) -> 225 tiles, 904x904 output
   c3 (default at N > 1)  4096x4096 scene, same tiling -> 66x66 tiles, 3964x3964 output; STRONG
-                         scaling: the 66 tile rows are cut into N strips, one per rank
+                         scaling: the 4356 tiles (row-major) are cut into N contiguous ranges, one per rank
   c4                     64 pairs of 512x512, ws 5, image_size 32, stride 32, sub_pix=True, then
                          sub_pix_cal(elevation, score, 1) and (elevation2, score, 0); whole pairs per rank
   c5                     8192x8192 scene written as a headerless .raw file and read back with
@@ -89,7 +89,7 @@ def config_dict(name, n_gpus):
     if c['batch'] > 1:
         par = 'whole pairs per GPU (%d pairs over %d)' % (c['batch'], n_gpus)
     else:
-        par = '%d tile rows cut into %d contiguous strips, one per GPU' % (len0, n_gpus)
+        par = '%d x %d tiles in row-major order cut into %d contiguous ranges, one per GPU' % (len0, len1, n_gpus)
     return {'workload': workload_name(name), 'name': name, 'tiles': int(len0 * len1 * c['batch']), 'output': [int(c['batch']), int(out[0]), int(out[1])],
             'l2': 'no flush: a step streams GBs of pyramid levels through the 126 MB L2 (working set >> L2)',
             'parallelism': par}
@@ -408,8 +408,7 @@ def run_ours(args):
     if B == 1:
         # ---------------------------------------------------------------- one scene: strips of tile rows
         solver = StripSolver(c['shape'], [T, T], [STRIDE, STRIDE], WS, FEATURE, MODES, SUB_PIX, fused=args.fused)
-        lo, hi = solver.tile_rows
-        a, b = input_rows(lo, hi, STRIDE, T, WS)
+        a, b = solver.input_rows
         d1 = torch.zeros(c['shape'], dtype=torch.uint8, device='cuda')
         d2 = torch.zeros(c['shape'], dtype=torch.uint8, device='cuda')
         d1[a:b].copy_(torch.from_numpy(h1[a:b])); d2[a:b].copy_(torch.from_numpy(h2[a:b]))      # a rank holds only the rows its strip reads
@@ -582,7 +581,7 @@ def run_ours(args):
     e2e_s = max_over_ranks(time.perf_counter() - t0)
     e2e = {'value': out_px * e2e_steps / 1e6 / e2e_s, 'unit': 'MP/s', 'steps': e2e_steps, 'ms_per_step': 1e3 * e2e_s / e2e_steps}
     if B == 1:
-        rows_in = [input_rows(l, h, STRIDE, T, WS) for (l, h) in solver.parts if h > l]
+        rows_in = [input_rows(l // len1, (h - 1) // len1 + 1, STRIDE, T, WS) for (l, h) in solver.tile_parts if h > l]
         e2e['h2d_bytes_per_step'] = int(sum(2 * (bb - aa) * c['shape'][1] for aa, bb in rows_in))
         e2e['d2h_bytes_per_step'] = int((nm + 1) * out_px * 8)
     else:

@@ -27,7 +27,8 @@ class SceneParams(Structure):
                 ('s0', c_int32), ('s1', c_int32), ('ws', c_int32), ('method', c_int32),
                 ('n_modes', c_int32), ('modes', c_int32 * 4), ('sub_pix', c_int32),
                 ('tile_row_lo', c_int32), ('tile_row_hi', c_int32), ('fused', c_int32),
-                ('n_scenes', c_int32), ('filter_num', c_int32), ('filter_cfg', c_int32)]
+                ('n_scenes', c_int32), ('filter_num', c_int32), ('filter_cfg', c_int32),
+                ('tile_lo', c_int32), ('tile_hi', c_int32)]
 
 
 class SceneInfo(Structure):
@@ -273,8 +274,9 @@ FILTER_IDS = {'median': 0, 'average': 1}
 
 
 def scene_params(shape, image_size, stride, window_size, feature_name, modes, sub_pix, tile_rows=None, fused=-1, n_scenes=1,
-                 filtering=None):
-    """filtering = None or (filtering_num, filter_window_size, filtering_mode) of Matching(filtering=True)."""
+                 filtering=None, tiles=None):
+    """filtering = None or (filtering_num, filter_window_size, filtering_mode) of Matching(filtering=True);
+    tile_rows = (lo, hi) strip of tile rows, or tiles = (lo, hi) range of tiles in row-major order."""
     prm = SceneParams()
     prm.scene_h, prm.scene_w = int(shape[0]), int(shape[1])
     prm.t0, prm.t1 = int(image_size[0]), int(image_size[1])
@@ -288,6 +290,8 @@ def scene_params(shape, image_size, stride, window_size, feature_name, modes, su
     prm.tile_row_lo, prm.tile_row_hi = (0, 0) if tile_rows is None else (int(tile_rows[0]), int(tile_rows[1]))
     prm.fused = int(fused)
     prm.n_scenes = int(n_scenes)
+    if tiles is not None:
+        prm.tile_lo, prm.tile_hi = int(tiles[0]), int(tiles[1])
     if filtering is not None and int(filtering[0]) > 0:
         prm.filter_num = int(filtering[0])
         prm.filter_cfg = int(filtering[1]) | (FILTER_IDS[filtering[2]] << 8)

@@ -2,6 +2,7 @@
 // and the batched scene solver that replaces ImageCutSolver._cut_and_pool / _solver /
 // _execute_matching (misc/image_cut_solver.py:95-184).
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <vector>
@@ -107,16 +108,38 @@ static int ctx_reserve(dm_ctx* ctx, size_t bytes) {
     return DM_OK;
 }
 
-// Output rows are final once every tile row above them is done: rows [0, s0 * full_tile_rows), or
-// the whole mosaic after the last tile.  Copies what is new on the copy stream, behind an event.
-// The destination is page-locked host memory or the mosaic of a peer device (UVA decides).
+// The pixels a contiguous range of tiles [a,b) (row-major global index) OWNS -- the reference pastes
+// tiles j-outer / i-inner, so a pixel belongs to the covering tile with the largest index
+// (misc/image_cut_solver.py:165-175): tile row g owns output rows [s0 g, s0 (g+1)) (the last tile row
+// up to out_h), tile column c owns columns [s1 c, s1 (c+1)) (the last one up to out_w).  At most three
+// rectangles: the tail of the first tile row, whole tile rows, the head of the last tile row.
+struct OwnedRect { int r0, r1, c0, c1; };
+static int owned_rects(int len0, int len1, int s0, int s1, int out_h, int out_w, long long a, long long b, OwnedRect out[3]) {
+    if (b <= a) return 0;
+    auto row_lo = [&](long long g) { return (int)(s0 * g); };
+    auto row_hi = [&](long long g) { return g >= len0 - 1 ? out_h : (int)(s0 * (g + 1)); };
+    auto col_lo = [&](long long c) { return (int)(s1 * c); };
+    auto col_hi = [&](long long c) { return c >= len1 - 1 ? out_w : (int)(s1 * (c + 1)); };
+    const long long ga = a / len1, ca = a % len1, gb = (b - 1) / len1, cb = (b - 1) % len1;
+    int n = 0;
+    if (ga == gb) { out[n++] = {row_lo(ga), row_hi(ga), col_lo(ca), col_hi(cb)}; return n; }
+    long long mid_a = ga, mid_b = gb;               // whole tile rows [mid_a, mid_b]
+    if (ca != 0) { out[n++] = {row_lo(ga), row_hi(ga), col_lo(ca), out_w}; mid_a = ga + 1; }
+    const bool tail = cb != len1 - 1;
+    if (tail) mid_b = gb - 1;
+    if (mid_b >= mid_a) out[n++] = {row_lo(mid_a), row_hi(mid_b), 0, out_w};
+    if (tail) out[n++] = {row_lo(gb), row_hi(gb), 0, col_hi(cb)};
+    return n;
+}
+
+// Copies what the tiles [rb.tiles_copied, tiles_done) own to the stream destination, on the copy stream
+// and behind an event: a tile's pixels are written by that tile alone, so they are final as soon as
+// the tile is.  The destination is page-locked host memory or the mosaic of a peer device (UVA decides).
 int dm_readback_rows(dm_ctx* ctx, long long tiles_done) {
     dm_ctx::Readback& rb = ctx->rb;
-    if (!rb.active) return DM_OK;
-    const long long full_rows = tiles_done / rb.len1;
-    int upto = full_rows >= rb.len0 ? rb.out_h : (int)(full_rows * rb.s0);
-    if (upto > rb.row_hi) upto = rb.row_hi;
-    if (upto <= rb.rows_done) return DM_OK;
+    if (!rb.active || tiles_done <= rb.tiles_copied) return DM_OK;
+    OwnedRect rc[3];
+    const int n = owned_rects(rb.len0, rb.len1, rb.s0, rb.s1, rb.out_h, rb.out_w, rb.tiles_copied, tiles_done, rc);
     if (!ctx->copy_stream) DM_CUDA_CHECK(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
     if (ctx->band_used >= ctx->band_ev.size()) {
         cudaEvent_t e;
@@ -126,12 +149,18 @@ int dm_readback_rows(dm_ctx* ctx, long long tiles_done) {
     cudaEvent_t ev = ctx->band_ev[ctx->band_used++];
     DM_CUDA_CHECK(cudaEventRecord(ev, ctx->stream));
     DM_CUDA_CHECK(cudaStreamWaitEvent(ctx->copy_stream, ev, 0));
-    const size_t plane = (size_t)rb.out_h * rb.out_w;
-    const size_t off = (size_t)rb.rows_done * rb.out_w, bytes = (size_t)(upto - rb.rows_done) * rb.out_w * sizeof(double);
-    for (int m = 0; m < rb.n_modes; ++m)
-        DM_CUDA_CHECK(cudaMemcpyAsync(rb.dst_d_map + m * plane + off, rb.d_d_map + m * plane + off, bytes, cudaMemcpyDefault, ctx->copy_stream));
-    DM_CUDA_CHECK(cudaMemcpyAsync(rb.dst_out_map + off, rb.d_out_map + off, bytes, cudaMemcpyDefault, ctx->copy_stream));
-    rb.rows_done = upto;
+    const size_t plane = (size_t)rb.out_h * rb.out_w, pitch = (size_t)rb.out_w * sizeof(double);
+    for (int k = 0; k < n; ++k) {
+        const size_t off = (size_t)rc[k].r0 * rb.out_w + rc[k].c0;
+        const size_t width = (size_t)(rc[k].c1 - rc[k].c0) * sizeof(double), rows = (size_t)(rc[k].r1 - rc[k].r0);
+        for (int m = 0; m <= rb.n_modes; ++m) {
+            double* dst = (m < rb.n_modes ? rb.dst_d_map + m * plane : rb.dst_out_map) + off;
+            const double* src = (m < rb.n_modes ? rb.d_d_map + m * plane : rb.d_out_map) + off;
+            if (width == pitch) DM_CUDA_CHECK(cudaMemcpyAsync(dst, src, rows * pitch, cudaMemcpyDefault, ctx->copy_stream));
+            else DM_CUDA_CHECK(cudaMemcpy2DAsync(dst, pitch, src, pitch, width, rows, cudaMemcpyDefault, ctx->copy_stream));
+        }
+    }
+    rb.tiles_copied = tiles_done;
     return DM_OK;
 }
 
@@ -194,6 +223,23 @@ extern "C" int dm_ctx_stage_ms(dm_ctx* ctx, float* ms_out, int* launches_out) {
 // ------------------------------------------------------------------ geometry
 static int ilog2_exact(int v) { int l = 0; while ((1 << l) < v) ++l; return ((1 << l) == v) ? l : -1; }
 
+// the tiles [a,b) (row-major index of one scene) a solve covers: a tile range, a strip of tile rows, or all
+int dm_tile_range(const dm_scene_params* prm, int len0, int len1, long long* a, long long* b) {
+    const long long all = (long long)len0 * len1;
+    if (prm->tile_hi > 0) {
+        DM_REQUIRE(prm->tile_row_hi <= 0, DM_ERR_INVALID, "tile_lo/tile_hi and tile_row_lo/tile_row_hi exclude each other");
+        DM_REQUIRE(prm->tile_lo >= 0 && prm->tile_lo < prm->tile_hi && prm->tile_hi <= all, DM_ERR_INVALID,
+                   "tile range [%d,%d) outside [0,%lld)", prm->tile_lo, prm->tile_hi, all);
+        *a = prm->tile_lo; *b = prm->tile_hi;
+        return DM_OK;
+    }
+    int lo = prm->tile_row_lo, hi = prm->tile_row_hi;
+    if (hi <= 0) { lo = 0; hi = len0; }
+    DM_REQUIRE(lo >= 0 && lo < hi && hi <= len0, DM_ERR_INVALID, "tile row strip [%d,%d) outside [0,%d)", lo, hi, len0);
+    *a = (long long)lo * len1; *b = (long long)hi * len1;
+    return DM_OK;
+}
+
 extern "C" int dm_scene_geometry(const dm_scene_params* prm, dm_scene_info* info) {
     DM_REQUIRE(prm && info, DM_ERR_INVALID, "dm_scene_geometry: null argument");
     DM_REQUIRE(prm->ws >= 1 && (prm->ws & 1) && prm->ws <= 31, DM_ERR_INVALID, "window_size must be odd and <= 31 (got %d)", prm->ws);
@@ -217,15 +263,16 @@ extern "C" int dm_scene_geometry(const dm_scene_params* prm, dm_scene_info* info
     DM_REQUIRE(info->len0 >= 1 && info->len1 >= 1, DM_ERR_INVALID, "scene %dx%d yields no tiles (len = %d,%d)", prm->scene_h, prm->scene_w, info->len0, info->len1);
     info->out_h = prm->s0 * (info->len0 - 1) + prm->t0;
     info->out_w = prm->s1 * (info->len1 - 1) + prm->t1;
-    int lo = prm->tile_row_lo, hi = prm->tile_row_hi;
-    if (hi <= 0) { lo = 0; hi = info->len0; }
-    DM_REQUIRE(lo >= 0 && lo < hi && hi <= info->len0, DM_ERR_INVALID, "tile row strip [%d,%d) outside [0,%d)", lo, hi, info->len0);
-    info->row_lo = prm->s0 * lo;
-    info->row_hi = (hi == info->len0) ? info->out_h : prm->s0 * hi;
     const int ns = prm->n_scenes > 1 ? prm->n_scenes : 1;
-    DM_REQUIRE(ns == 1 || (lo == 0 && hi == info->len0), DM_ERR_INVALID, "a batch of scenes cannot be combined with a tile-row strip");
     DM_REQUIRE((long long)ns * info->len0 * info->len1 < (1LL << 31), DM_ERR_INVALID, "too many tiles");
-    info->n_tiles = (hi - lo) * info->len1 * ns;
+    long long ta, tb;
+    int rc = dm_tile_range(prm, info->len0, info->len1, &ta, &tb);
+    if (rc != DM_OK) return rc;
+    const int ga = (int)(ta / info->len1), gb = (int)((tb - 1) / info->len1);
+    info->row_lo = prm->s0 * ga;
+    info->row_hi = (gb == info->len0 - 1) ? info->out_h : prm->s0 * (gb + 1);
+    DM_REQUIRE(ns == 1 || (ta == 0 && tb == (long long)info->len0 * info->len1), DM_ERR_INVALID, "a batch of scenes cannot be combined with a strip or a tile range");
+    info->n_tiles = (int)(tb - ta) * ns;
     info->levels = lg + 1;
     info->n_map = mn;
     return DM_OK;
@@ -351,8 +398,6 @@ extern "C" int dm_solve_scene(dm_ctx* ctx, const dm_scene_params* prm,
     if (rc != DM_OK) return rc;
     cudaStream_t st = ctx->stream;
     const int t0 = prm->t0, t1 = prm->t1, P = t0 * t1, kpad = dm_kpad(prm->ws), L = info.levels;
-    int lo = prm->tile_row_lo, hi = prm->tile_row_hi;
-    if (hi <= 0) { lo = 0; hi = info.len0; }
 
     const int ns = prm->n_scenes > 1 ? prm->n_scenes : 1;
     const bool want_fused = prm->fused != 0;
@@ -375,10 +420,30 @@ extern "C" int dm_solve_scene(dm_ctx* ctx, const dm_scene_params* prm,
     long long max_chunk = (long long)(ctx->ws_limit / (per_tile + 4096));
     if (max_chunk > 16384) max_chunk = 16384;
     DM_REQUIRE(max_chunk >= 1, DM_ERR_NOMEM, "one tile needs %zu bytes of workspace, limit is %zu", per_tile, ctx->ws_limit);
-    const int n_chunks = dm_div_up(info.n_tiles, max_chunk);
-    const int chunk = dm_div_up(info.n_tiles, n_chunks);
-    const size_t need = fused ? dm_fused_workspace(nullptr, chunk, t0, t1, kpad, L, nullptr)
-                              : carve_tiles(nullptr, chunk, t0, t1, kpad, L, tb);
+    // Chunks of tiles.  As few as the workspace limit allows -- except when the finished pixels are streamed
+    // somewhere (host arrays, a peer's mosaic): then the strip is cut into a few chunks so that the copy of
+    // chunk k rides behind the compute of chunk k+1 instead of behind the last stage alone.  Chunk boundaries
+    // are multiples of the number of tiles that fill whole rounds of the persistent correlation grid.
+    long long ta, tb_;
+    if ((rc = dm_tile_range(prm, info.len0, info.len1, &ta, &tb_)) != DM_OK) return rc;
+    const int granule = fused ? dm_correlation_round_tiles(P) : 1;
+    int n_chunks = dm_div_up(info.n_tiles, max_chunk);
+    if (ctx->rb.active && fused) {
+        static const int want = getenv("DM_STREAM_CHUNKS") ? atoi(getenv("DM_STREAM_CHUNKS")) : 3;
+        if (want > n_chunks && info.n_tiles / want >= 2 * granule) n_chunks = want;
+    }
+    int chunk = dm_div_up(info.n_tiles, n_chunks);
+    if (chunk >= 2 * granule) {
+        // whole rounds per chunk; the last chunk takes the remainder, if the workspace limit lets it
+        const int whole = chunk / granule * granule;
+        if (info.n_tiles - (long long)(n_chunks - 1) * whole <= max_chunk) chunk = whole;
+    }
+    auto chunk_begin = [&](int ck) -> int { return ck * chunk; };
+    auto chunk_tiles = [&](int ck) -> int { return (ck == n_chunks - 1) ? info.n_tiles - ck * chunk : chunk; };
+    int largest = 0;
+    for (int ck = 0; ck < n_chunks; ++ck) if (chunk_tiles(ck) > largest) largest = chunk_tiles(ck);
+    const size_t need = fused ? dm_fused_workspace(nullptr, largest, t0, t1, kpad, L, nullptr)
+                              : carve_tiles(nullptr, largest, t0, t1, kpad, L, tb);
     rc = ctx_reserve(ctx, need);
     if (rc != DM_OK) return rc;
     for (int s = 0; s < DM_STAGE_COUNT; ++s) ctx->launches[s] = 0;
@@ -396,10 +461,9 @@ extern "C" int dm_solve_scene(dm_ctx* ctx, const dm_scene_params* prm,
         const long long tps = (long long)info.len0 * info.len1, sc = last_tile / tps, r = last_tile - sc * tps;
         return sc * prm->scene_h + (long long)prm->s0 * (r / info.len1) + t0 + prm->ws - 1;
     };
-    auto chunk_tiles = [&](int ck) -> int { return (ck == n_chunks - 1) ? info.n_tiles - ck * chunk : chunk; };
-    if ((rc = dm_upload_rows(ctx, rows_needed((long long)lo * info.len1 + chunk_tiles(0) - 1))) != DM_OK) return rc;
+    if ((rc = dm_upload_rows(ctx, rows_needed(ta + chunk_tiles(0) - 1))) != DM_OK) return rc;
     for (int ck = 0; ck < n_chunks; ++ck) {
-        const int first = lo * info.len1 + ck * chunk;
+        const int first = (int)ta + chunk_begin(ck);
         const int nt = chunk_tiles(ck);
         pa.first_tile = first;
         if ((rc = dm_upload_wait(ctx)) != DM_OK) return rc;
@@ -496,7 +560,7 @@ extern "C" int dm_solve_scene(dm_ctx* ctx, const dm_scene_params* prm,
     }
     for (int s = 0; s < DM_STAGE_COUNT; ++s) launches += ctx->launches[s];
     info.used_fused = fused ? 1 : 0;
-    info.chunk_tiles = chunk;
+    info.chunk_tiles = largest;
     info.kernel_launches = launches;
     if (info_out) *info_out = info;
     return DM_OK;
@@ -527,30 +591,31 @@ extern "C" int dm_solve_scene_host(dm_ctx* ctx, const dm_scene_params* prm,
         DM_CUDA_CHECK(cudaMalloc(&ctx->planes, pb));
         ctx->planes_bytes = pb;
     }
-    // only the rows the strip's tiles read: [s0*lo, s0*(hi-1) + t0 + ws - 1), uploaded chunk by chunk
-    // ahead of the compute (dm_upload_rows)
-    int lo = prm->tile_row_lo, hi = prm->tile_row_hi;
-    if (hi <= 0) { lo = 0; hi = info.len0; }
+    // only the rows the tiles of the range read, uploaded chunk by chunk ahead of the compute (dm_upload_rows)
+    long long ta, tb;
+    if ((rc = dm_tile_range(prm, info.len0, info.len1, &ta, &tb)) != DM_OK) return rc;
     dm_ctx::Upload& up = ctx->up;
     up = dm_ctx::Upload();
     up.active = true; up.h1 = img1_host; up.h2 = img2_host; up.row_bytes = (size_t)prm->scene_w;
-    up.rows_done = (long long)prm->s0 * lo;
-    up.row_end = ns > 1 ? (long long)prm->scene_h * ns : (long long)prm->s0 * (hi - 1) + prm->t0 + prm->ws - 1;
+    up.rows_done = (long long)prm->s0 * (ta / info.len1);
+    up.row_end = ns > 1 ? (long long)prm->scene_h * ns : (long long)prm->s0 * ((tb - 1) / info.len1) + prm->t0 + prm->ws - 1;
     double* d_map = ctx->planes;
     double* out_map = ctx->planes + plane * prm->n_modes * ns;
     if (prm->s0 > prm->t0 || prm->s1 > prm->t1)      // gaps between tiles: np.empty in the reference, zeros here
         DM_CUDA_CHECK(cudaMemsetAsync(ctx->planes, 0, pb, st));
-    // single scene: finished row bands stream back to the host behind the final stage
+    // single scene: what the finished tiles own streams back to the host behind the compute
     dm_ctx::Readback& rb = ctx->rb;
     rb = dm_ctx::Readback();
     if (ns == 1) {
         rb.active = true;
         rb.dst_d_map = d_map_host; rb.dst_out_map = out_map_host; rb.d_d_map = d_map; rb.d_out_map = out_map;
-        rb.n_modes = prm->n_modes; rb.out_h = info.out_h; rb.out_w = info.out_w; rb.len0 = info.len0; rb.len1 = info.len1; rb.s0 = prm->s0;
-        rb.rows_done = info.row_lo; rb.row_hi = info.row_hi;
+        rb.n_modes = prm->n_modes; rb.out_h = info.out_h; rb.out_w = info.out_w; rb.len0 = info.len0; rb.len1 = info.len1;
+        rb.s0 = prm->s0; rb.s1 = prm->s1;
+        rb.tiles_copied = ta;
         ctx->band_used = 0;
     }
     rc = dm_solve_scene(ctx, prm, ctx->scene1, ctx->scene2, d_map, out_map, &info);
+    if (rc == DM_OK && ns == 1) rc = dm_readback_rows(ctx, tb);     // whatever has not left yet (everything on the materialising path)
     rb.active = false;
     up.active = false;
     if (rc != DM_OK) {
@@ -564,16 +629,8 @@ extern "C" int dm_solve_scene_host(dm_ctx* ctx, const dm_scene_params* prm,
     if (ns > 1) {       // whole batch: both result arrays are contiguous
         DM_CUDA_CHECK(cudaMemcpyAsync(d_map_host, d_map, plane * prm->n_modes * ns * sizeof(double), cudaMemcpyDeviceToHost, st));
         DM_CUDA_CHECK(cudaMemcpyAsync(out_map_host, out_map, plane * ns * sizeof(double), cudaMemcpyDeviceToHost, st));
-    } else {
-        // whatever the bands have not taken yet (everything on the materialising path)
-        if (rb.rows_done < info.row_hi) {
-            const size_t row_off = (size_t)rb.rows_done * info.out_w;
-            const size_t row_bytes = (size_t)(info.row_hi - rb.rows_done) * info.out_w * sizeof(double);
-            for (int m = 0; m < prm->n_modes; ++m)
-                DM_CUDA_CHECK(cudaMemcpyAsync(d_map_host + m * plane + row_off, d_map + m * plane + row_off, row_bytes, cudaMemcpyDeviceToHost, st));
-            DM_CUDA_CHECK(cudaMemcpyAsync(out_map_host + row_off, out_map + row_off, row_bytes, cudaMemcpyDeviceToHost, st));
-        }
-        if (ctx->copy_stream && ctx->band_used > 0) DM_CUDA_CHECK(cudaStreamSynchronize(ctx->copy_stream));
+    } else if (ctx->copy_stream && ctx->band_used > 0) {
+        DM_CUDA_CHECK(cudaStreamSynchronize(ctx->copy_stream));
     }
     DM_CUDA_CHECK(cudaStreamSynchronize(st));
     if (info_out) *info_out = info;
@@ -596,12 +653,15 @@ extern "C" int dm_solve_scene_stream(dm_ctx* ctx, const dm_scene_params* prm,
     rb = dm_ctx::Readback();
     rb.active = true;
     rb.dst_d_map = d_map_dst; rb.dst_out_map = out_map_dst; rb.d_d_map = d_map_dev; rb.d_out_map = out_map_dev;
-    rb.n_modes = prm->n_modes; rb.out_h = info.out_h; rb.out_w = info.out_w; rb.len0 = info.len0; rb.len1 = info.len1; rb.s0 = prm->s0;
-    rb.rows_done = info.row_lo; rb.row_hi = info.row_hi;
+    rb.n_modes = prm->n_modes; rb.out_h = info.out_h; rb.out_w = info.out_w; rb.len0 = info.len0; rb.len1 = info.len1;
+    rb.s0 = prm->s0; rb.s1 = prm->s1;
+    long long ta, tb;
+    if ((rc = dm_tile_range(prm, info.len0, info.len1, &ta, &tb)) != DM_OK) return rc;
+    rb.tiles_copied = ta;
     ctx->band_used = 0;
     ctx->up.active = false;
     rc = dm_solve_scene(ctx, prm, img1_dev, img2_dev, d_map_dev, out_map_dev, &info);
-    if (rc == DM_OK) rc = dm_readback_rows(ctx, (long long)info.len0 * info.len1);     // whatever the bands have not taken (materialising path: everything)
+    if (rc == DM_OK) rc = dm_readback_rows(ctx, tb);     // whatever has not left yet (materialising path: everything)
     rb.active = false;
     if (ctx->copy_stream && ctx->band_used > 0) {
         // the compute stream waits for the copies: one stream to synchronise on for the caller

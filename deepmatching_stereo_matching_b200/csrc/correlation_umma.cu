@@ -588,4 +588,16 @@ int dm_correlation_umma_pool(const void* desc1, const float* stat1, const void* 
     return launch<MODE_POOL, 16>(mapA, mapB, mapBp, prm, normed, stream);
 }
 
+int dm_correlation_round_tiles(int p) {
+    int dev = 0, sms = 148;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int items = p / (HALVES * BM);
+    if (items < 1) return 1;
+    const bool pair = g_pair_mode.load(std::memory_order_relaxed) != 0 && items % 2 == 0;
+    const int units = pair ? items / 2 : items, slots = pair ? sms / 2 : sms;
+    int a = slots, b = units;
+    while (b) { const int t = a % b; a = b; b = t; }       // gcd
+    return slots / a;
+}
+
 void dm_correlation_umma_set_pair_mode(int mode) { g_pair_mode.store(mode, std::memory_order_relaxed); }

@@ -25,6 +25,10 @@ int dm_correlation_umma_pool(const void* desc1, const float* stat1, const void* 
                              float* pooled, float* rowmin, float* rowmax, cudaStream_t stream);
 
 void dm_correlation_umma_set_pair_mode(int mode);     // -1 auto (CTA pairs when possible), 0 single CTA
+// number of tiles of P patches whose work units fill whole rounds of the persistent grid of this device
+int dm_correlation_round_tiles(int p);
+// the tiles [a,b) (row-major index of one scene) a solve covers: a tile range, a strip of tile rows, or all (capi.cu)
+int dm_tile_range(const dm_scene_params* prm, int len0, int len1, long long* a, long long* b);
 
 // upper pyramid tail + top-down pass of one tile per CTA (backtrack.cu); levels_dev[k] = level k of the fused workspace
 bool dm_upper_tail_supported(int t0, int t1, int levels);
@@ -52,8 +56,8 @@ struct dm_ctx {
         bool active = false;
         double* dst_d_map = nullptr; double* dst_out_map = nullptr;
         const double* d_d_map = nullptr; const double* d_out_map = nullptr;
-        int n_modes = 0, out_h = 0, out_w = 0, len0 = 0, len1 = 0, s0 = 0;
-        int rows_done = 0, row_hi = 0;              // output rows [.., rows_done) are already on their way
+        int n_modes = 0, out_h = 0, out_w = 0, len0 = 0, len1 = 0, s0 = 0, s1 = 0;
+        long long tiles_copied = 0;                 // the pixels owned by tiles [.., tiles_copied) (global index) are already on their way
     } rb;
     // Host scenes uploaded chunk by chunk ahead of the compute (dm_solve_scene_host): the rows the
     // tiles of chunk k+1 read are copied on a third stream while chunk k is being solved.

@@ -592,7 +592,7 @@ int dm_fused_solve_chunk(dm_ctx* ctx, const dm_fused_args* a, int ck) {
             if (g.ws == (const void*)ctx->ws && g.nt == nt && g.t0 == t0 && g.t1 == t1 && g.levels == L && g.kpad == a->kpad &&
                 g.filter_num == a->filter_num && g.filter_win == a->filter_win && g.filter_mode == a->filter_mode) { ug = &g; break; }
         if (!ug) {
-            if (ctx->upper_graphs.size() >= 4) {          // scenes alternate between at most two chunk sizes
+            if (ctx->upper_graphs.size() >= 8) {          // a scene uses at most two chunk sizes per geometry
                 for (auto& g : ctx->upper_graphs) cudaGraphExecDestroy(g.exec);
                 ctx->upper_graphs.clear();
             }
@@ -636,15 +636,13 @@ int dm_fused_solve_chunk(dm_ctx* ctx, const dm_fused_args* a, int ck) {
         const long long n_patches = (long long)nt * P;
         fa.scene_h = a->scene_h * a->n_scenes;       // bound of the stacked image
         const long long n_quads = n_patches / 4;
-        // host readback active: the stage runs in (up to) five bands of whole tile rows, and the
-        // output rows each band completes start their device -> host copy while the next band runs
+        // streaming active: the stage runs in (up to) four bands of tiles, and what each band's tiles own starts
+        // its copy while the next band runs
         int bands = 1;
-        if (ctx->rb.active) { bands = nt / (2 * a->len1); if (bands > 5) bands = 5; if (bands < 1) bands = 1; }   // only the last band's copy is exposed
-        const int rows_in_chunk = nt / a->len1;
+        if (ctx->rb.active) { bands = nt / (2 * a->len1); if (bands > 4) bands = 4; if (bands < 1) bands = 1; }   // only the last band's copy is exposed
         int t_begin = 0;
         for (int b = 0; b < bands; ++b) {
-            int t_end = (b == bands - 1) ? nt : ((rows_in_chunk * (b + 1)) / bands) * a->len1 + ((a->len1 - a->first_tile % a->len1) % a->len1);
-            if (t_end > nt) t_end = nt;
+            int t_end = (b == bands - 1) ? nt : (int)((long long)nt * (b + 1) / bands);
             if (t_end <= t_begin) continue;
             fa.tile0 = t_begin;
             const long long nq = (long long)(t_end - t_begin) * (P / 4);

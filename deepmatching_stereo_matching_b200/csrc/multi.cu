@@ -237,7 +237,10 @@ extern "C" int dm_multi_synchronize(dm_multi* m) {
 // how a scene (or a batch of scenes) is spread over `n` devices
 struct Share { dm_scene_params prm; size_t img_off, dmap_off, omap_off; bool any; };
 
-static int make_shares(const dm_scene_params* prm, const dm_scene_info& info, int n, std::vector<Share>& sh) {
+// by_rows: whole tile rows per device (what a gather of contiguous row strips needs: DM_GATHER_NCCL);
+// otherwise the tiles themselves are shared out, so the shares differ by at most one tile (66 tile rows
+// over 8 devices are 9,9,8,... rows = 9 % imbalance; 4356 tiles over 8 are 545,545,545,545,544,...).
+static int make_shares(const dm_scene_params* prm, const dm_scene_info& info, int n, bool by_rows, std::vector<Share>& sh) {
     sh.assign(n, Share());
     const int ns = prm->n_scenes > 1 ? prm->n_scenes : 1;
     const size_t plane = (size_t)info.out_h * info.out_w;
@@ -255,15 +258,29 @@ static int make_shares(const dm_scene_params* prm, const dm_scene_info& info, in
         }
         return DM_OK;
     }
-    int tlo = prm->tile_row_lo, thi = prm->tile_row_hi;
-    if (thi <= 0) { tlo = 0; thi = info.len0; }
-    partition(thi - tlo, n, lo.data(), hi.data());
+    long long ta, tb;
+    int rc = dm_tile_range(prm, info.len0, info.len1, &ta, &tb);
+    if (rc != DM_OK) return rc;
+    if (by_rows) {
+        DM_REQUIRE(ta % info.len1 == 0 && tb % info.len1 == 0, DM_ERR_UNSUPPORTED, "a gather of row strips needs whole tile rows");
+        const int tlo = (int)(ta / info.len1), thi = (int)(tb / info.len1);
+        partition(thi - tlo, n, lo.data(), hi.data());
+        for (int r = 0; r < n; ++r) {
+            sh[r].any = hi[r] > lo[r];
+            sh[r].prm = *prm;
+            sh[r].prm.tile_lo = sh[r].prm.tile_hi = 0;
+            sh[r].prm.tile_row_lo = tlo + lo[r];
+            sh[r].prm.tile_row_hi = tlo + hi[r];
+        }
+        return DM_OK;
+    }
+    partition((int)(tb - ta), n, lo.data(), hi.data());
     for (int r = 0; r < n; ++r) {
         sh[r].any = hi[r] > lo[r];
         sh[r].prm = *prm;
-        sh[r].prm.tile_row_lo = tlo + lo[r];
-        sh[r].prm.tile_row_hi = tlo + hi[r];
-        sh[r].img_off = sh[r].dmap_off = sh[r].omap_off = 0;
+        sh[r].prm.tile_row_lo = sh[r].prm.tile_row_hi = 0;
+        sh[r].prm.tile_lo = (int32_t)ta + lo[r];
+        sh[r].prm.tile_hi = (int32_t)ta + hi[r];
     }
     return DM_OK;
 }
@@ -292,7 +309,7 @@ extern "C" int dm_multi_solve_scene_host(dm_multi* m, const dm_scene_params* prm
     int n = (int)m->w.size();
     if (max_devices > 0 && max_devices < n) n = max_devices;
     std::vector<Share> sh;
-    if ((rc = make_shares(prm, info, n, sh)) != DM_OK) return rc;
+    if ((rc = make_shares(prm, info, n, false, sh)) != DM_OK) return rc;
     std::vector<dm_scene_info> infos(n);
     std::vector<std::function<int()>> jobs(n);
     for (int r = 0; r < n; ++r) {
@@ -372,7 +389,7 @@ extern "C" int dm_multi_solve_scene(dm_multi* m, const dm_scene_params* prm,
     const int n = (int)m->w.size();
     DM_REQUIRE(root >= 0 && root < n, DM_ERR_INVALID, "dm_multi_solve_scene: root %d of %d devices", root, n);
     std::vector<Share> sh;
-    if ((rc = make_shares(prm, info, n, sh)) != DM_OK) return rc;
+    if ((rc = make_shares(prm, info, n, gather == DM_GATHER_NCCL, sh)) != DM_OK) return rc;
     const size_t plane = (size_t)info.out_h * info.out_w;
     std::vector<dm_scene_info> infos(n);
     std::vector<std::function<int()>> jobs(n);

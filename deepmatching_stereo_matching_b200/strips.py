@@ -204,9 +204,14 @@ class PeerMosaic(object):
 
 
 class StripSolver(object):
-    """Device-resident solve of this rank's strip + gather.  ``solve()`` returns the
-    (n_modes+1, out_h, out_w) float64 mosaic (disparity planes, then the score plane) on
-    rank 0 and None on the other ranks."""
+    """This rank's share of a scene.  Two partitions of the same scene are kept:
+
+    * ``prm``      -- a contiguous range of TILES (row-major), shares differing by at most one tile; used
+      wherever the finished pixels are streamed to their destination rectangle by rectangle
+      (``solve_into`` a PeerMosaic, ``solve_host_into`` a host mosaic);
+    * ``prm_rows`` -- a strip of whole tile rows (66 rows over 8 ranks = 9,9,8,...), whose output is a
+      contiguous block of rows: what ``solve_local`` + ``gather`` (NCCL) needs.
+    """
 
     def __init__(self, shape, image_size, stride, window_size, feature_name='cv2.TM_CCOEFF_NORMED',
                  degree_map_mode=('elevation',), sub_pix=True, group=None, fused=-1):
@@ -216,15 +221,25 @@ class StripSolver(object):
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
-        full = _native.scene_geometry(_native.scene_params(shape, image_size, stride, window_size, feature_name,
-                                                           list(degree_map_mode), sub_pix))
+        args = (shape, image_size, stride, window_size, feature_name, list(degree_map_mode), sub_pix)
+        full = _native.scene_geometry(_native.scene_params(*args))
         self.len0, self.len1, self.out_h, self.out_w = full.len0, full.len1, full.out_h, full.out_w
         self.parts = partition_tile_rows(full.len0, self.world)
         self.row_ranges = [strip_rows(lo, hi, full.len0, stride[0], image_size[0]) if hi > lo else (0, 0) for lo, hi in self.parts]
         lo, hi = self.parts[self.rank]
         self.tile_rows = (lo, hi)
-        self.prm = _native.scene_params(shape, image_size, stride, window_size, feature_name, list(degree_map_mode),
-                                        sub_pix, (lo, hi), fused) if hi > lo else None
+        self.prm_rows = _native.scene_params(*args, tile_rows=(lo, hi), fused=fused) if hi > lo else None
+        self.tile_parts = partition_tile_rows(full.len0 * full.len1, self.world)
+        ta, tb = self.tile_parts[self.rank]
+        self.tiles = (ta, tb)
+        self.prm = _native.scene_params(*args, fused=fused, tiles=(ta, tb)) if tb > ta else None
+        # scene rows either share reads
+        rows = []
+        if hi > lo:
+            rows.append(input_rows(lo, hi, stride[0], image_size[0], window_size))
+        if tb > ta:
+            rows.append(input_rows(ta // full.len1, (tb - 1) // full.len1 + 1, stride[0], image_size[0], window_size))
+        self.input_rows = (min(r[0] for r in rows), max(r[1] for r in rows)) if rows else (0, 0)
         self.n_planes = len(degree_map_mode) + 1
         self.ctx = _native.Context()
         self.info = None
@@ -234,8 +249,9 @@ class StripSolver(object):
         return torch.zeros((self.n_planes, self.out_h, self.out_w), dtype=torch.float64, device='cuda')
 
     def solve_local(self, img1_dev, img2_dev, planes):
-        if self.prm is not None:
-            self.info = self.ctx.solve_device(self.prm, img1_dev, img2_dev, planes[:-1], planes[-1])
+        """Solves this rank's strip of tile rows into ``planes`` (rows ``row_ranges[rank]``)."""
+        if self.prm_rows is not None:
+            self.info = self.ctx.solve_device(self.prm_rows, img1_dev, img2_dev, planes[:-1], planes[-1])
         return planes
 
     def gather(self, planes):
@@ -244,9 +260,9 @@ class StripSolver(object):
         return gather_strips(planes, self.row_ranges, self.group)
 
     def solve_into(self, img1_dev, img2_dev, planes, mosaic):
-        """Solves this rank's strip and streams its finished row bands into ``mosaic`` (a PeerMosaic)
-        while the rest of the strip is still being solved.  The owner of the mosaic solves in place.
-        Asynchronous on the current stream, which also waits for the copies."""
+        """Solves this rank's tiles and streams what they own into ``mosaic`` (a PeerMosaic) while the
+        rest is still being solved.  The owner of the mosaic solves in place.  Asynchronous on the
+        current stream, which also waits for the copies."""
         if self.prm is None:
             return
         if mosaic.tensor is not None:
@@ -255,9 +271,9 @@ class StripSolver(object):
             self.info = self.ctx.solve_stream(self.prm, img1_dev, img2_dev, planes[:-1], planes[-1], mosaic.ptr, mosaic.score_ptr())
 
     def solve_host_into(self, img1_host, img2_host, host_mosaic):
-        """End to end for this rank's strip: uploads the strip's input rows from the (page-locked)
-        host scenes, solves, and streams the finished rows into ``host_mosaic`` (a SharedHostMosaic
-        or any (n_modes+1, out_h, out_w) float64 array).  Returns when the strip has landed."""
+        """End to end for this rank's tiles: uploads the scene rows they read from the (page-locked)
+        host scenes, solves, and streams the finished pixels into ``host_mosaic`` (a SharedHostMosaic
+        or any (n_modes+1, out_h, out_w) float64 array).  Returns when everything has landed."""
         if self.prm is None:
             return
         arr = host_mosaic.array if hasattr(host_mosaic, 'array') else host_mosaic

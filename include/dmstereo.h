@@ -187,12 +187,17 @@ typedef struct dm_scene_params {
                                        the top-down pass that go through Matching._filter
                                        (misc/Matching.py:91-93,136-138); 0 = filtering off    */
     int32_t filter_cfg;             /* filter_window_size | (DM_FILTER_* << 8)               */
+    int32_t tile_lo, tile_hi;       /* range of tiles [lo,hi) in row-major order (tile = gi * len1 + gj); hi <= 0
+                                       means "not used".  Finer than a strip of tile rows: the shares of several
+                                       devices differ by at most one TILE.  The pixels a range owns are up to three
+                                       rectangles of the mosaic (a partial tile row, whole rows, a partial tile row).
+                                       Not combinable with tile_row_lo/hi or a batch of scenes.                  */
 } dm_scene_params;
 
 typedef struct dm_scene_info {
     int32_t len0, len1;             /* tile grid (misc/image_cut_solver.py:62)            */
     int32_t out_h, out_w;           /* S0', S1' of the full mosaic                        */
-    int32_t row_lo, row_hi;         /* output rows owned by the strip                     */
+    int32_t row_lo, row_hi;         /* output rows owned by the strip (tile range: the rows it touches) */
     int32_t n_tiles;                /* tiles in the strip (all scenes of a batch)         */
     int32_t levels;                 /* pyramid depth ("iteration")                        */
     int32_t n_map;                  /* N_map                                              */

@@ -768,3 +768,43 @@ def test_c4_pair_vs_oracle(dm):
     for m, direction in ((0, 1), (1, 0)):
         got = dm.sub_pix_cal(d[m], sc, direction=direction)
         assert np.array_equal(got, O.sub_pix_cal(d[m], sc, direction=direction), equal_nan=True)
+
+
+@pytest.mark.parametrize('fused', [1, 0])
+def test_tile_ranges_assemble_the_whole_scene(dm, fused):
+    """Ranges of tiles with boundaries in the middle of tile rows (what dm_multi_* and the ranks of
+    bench.py use: shares differ by at most one tile), each solved on its own into the same host
+    arrays / streamed into the same device mosaic: the pieces must assemble the bits of the whole solve."""
+    import torch
+    from deepmatching_stereo_matching_b200 import _native
+    from deepmatching_stereo_matching_b200.image_cut_solver import pinned_empty
+    from deepmatching_stereo_matching_b200.synth import stereo_pair
+    i1, i2 = stereo_pair((420, 520), seed=19, mode='sine', amp=5)
+    args = (i1.shape, [32, 32], [30, 30], 5, 'cv2.TM_CCOEFF_NORMED', ['elevation', 'distance'], True)
+    whole = _native.scene_params(*args, fused=fused)
+    info = _native.scene_geometry(whole)
+    n_tiles = info.len0 * info.len1
+    assert info.len1 > 3 and n_tiles > 40
+    ctx = _native.Context()
+    ref_d = pinned_empty((2, info.out_h, info.out_w), np.float64); ref_s = pinned_empty((info.out_h, info.out_w), np.float64)
+    ctx.solve_host(whole, i1, i2, ref_d, ref_s)
+    cuts = [0, 1, info.len1 + 3, 2 * info.len1, n_tiles // 2 + 1, n_tiles - 2, n_tiles]       # one tile, mid-row cuts, a whole-row cut, a 2-tile tail
+    got_d = pinned_empty(ref_d.shape, np.float64); got_s = pinned_empty(ref_s.shape, np.float64)
+    got_d[...] = np.nan; got_s[...] = np.nan
+    d1, d2 = torch.from_numpy(i1).cuda(), torch.from_numpy(i2).cuda()
+    local = torch.zeros((3, info.out_h, info.out_w), dtype=torch.float64, device='cuda')
+    mosaic = torch.full((3, info.out_h, info.out_w), float('nan'), dtype=torch.float64, device='cuda')
+    tiles = 0
+    for a, b in zip(cuts[:-1], cuts[1:]):
+        prm = _native.scene_params(*args, fused=fused, tiles=(a, b))
+        part = _native.scene_geometry(prm)
+        assert part.n_tiles == b - a and part.row_lo == 30 * (a // info.len1)
+        inf = ctx.solve_host(prm, i1, i2, got_d, got_s)
+        assert inf.used_fused == fused
+        tiles += inf.n_tiles
+        ctx.solve_stream(prm, d1, d2, local[:-1], local[-1], mosaic[:-1], mosaic[-1])
+    torch.cuda.synchronize()
+    assert tiles == n_tiles
+    assert np.array_equal(got_d, ref_d) and np.array_equal(got_s, ref_s)
+    assert np.array_equal(mosaic[:-1].cpu().numpy(), ref_d) and np.array_equal(mosaic[-1].cpu().numpy(), ref_s)
+    ctx.close()

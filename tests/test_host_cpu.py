@@ -78,7 +78,7 @@ def test_pair_mode_knob_validates_its_argument():
 
 def test_struct_layout_matches_header():
     from deepmatching_stereo_matching_b200 import _native
-    assert ctypes.sizeof(_native.SceneParams) == 4 * (9 + 4 + 4 + 3)
+    assert ctypes.sizeof(_native.SceneParams) == 4 * (9 + 4 + 4 + 3 + 2)
     assert ctypes.sizeof(_native.SceneInfo) == 4 * 12
 
 
@@ -229,3 +229,19 @@ def test_oracle_margins_follow_the_matching():
     assert mg.shape == mp.shape[1:] and (mg > 0).all()
     r = O.match_template_matrix(i1, i2, 5)
     assert np.array_equal(r, O.match_template_matrix(i1, i2, 5, row_chunk=37))
+
+
+def test_tile_range_geometry():
+    from deepmatching_stereo_matching_b200 import _native
+    args = ((4096, 4096), (64, 64), (60, 60), 15, 'cv2.TM_CCOEFF_NORMED', ['elevation'], True)
+    parts = _native.partition_tile_rows(66 * 66, 8)
+    assert [b - a for a, b in parts] == [545, 545, 545, 545, 544, 544, 544, 544]
+    for a, b in parts:
+        info = _native.scene_geometry(_native.scene_params(*args, tiles=(a, b)))
+        assert info.n_tiles == b - a and info.row_lo == 60 * (a // 66)
+        assert info.row_hi == (3964 if (b - 1) // 66 == 65 else 60 * ((b - 1) // 66 + 1))
+    for bad in [(5, 5), (-1, 4), (0, 66 * 66 + 1)]:
+        with pytest.raises(_native.DmError):
+            _native.scene_geometry(_native.scene_params(*args, tiles=bad))
+    with pytest.raises(_native.DmError):        # a tile range and a strip of tile rows exclude each other
+        _native.scene_geometry(_native.scene_params(*args, tile_rows=(0, 3), tiles=(0, 10)))
