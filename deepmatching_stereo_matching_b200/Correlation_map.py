@@ -44,6 +44,84 @@ class DeviceLevels(list):
         return (self._get(k) for k in range(len(self)))
 
 
+class DeviceCoMap(np.lib.mixins.NDArrayOperatorsMixin):
+    """``co_map``: the reference's 4-D float64 array (misc/Correlation_map.py:69-87), but the data
+    lives on the GPU (``.device``: float32 tensor (T0,T1,T0,T1)).  It turns into a host float64 array
+    the first time it is used as one (arithmetic, numpy functions, general indexing).  The one access
+    pattern of bad_matching.py:68-70 -- ``co_map[i, j, i, :]``, a patch's own map row -- is served from
+    P rows of T1 values fetched with one dm_row_argmax launch instead of the P x P map; the argmax of
+    every such row is available directly as ``row_argmax()``."""
+
+    def __init__(self, tensor):
+        self.device = tensor
+        self._host_arr = None
+        self._rows = None
+        self._arg = None
+
+    shape = property(lambda self: tuple(self.device.shape))
+    ndim = property(lambda self: self.device.dim())
+    dtype = property(lambda self: np.dtype(np.float64))
+    size = property(lambda self: int(self.device.numel()))
+
+    def __len__(self):
+        return self.device.shape[0]
+
+    def _host(self):
+        if self._host_arr is None:
+            self._host_arr = self.device.cpu().numpy().astype(np.float64)
+        return self._host_arr
+
+    def _own_rows(self):
+        if self._rows is None:
+            torch = _native.require_cuda()
+            t0, t1 = self.device.shape[:2]
+            arg = torch.empty((t0, t1), dtype=torch.int32, device='cuda')
+            rows = torch.empty((t0, t1, t1), dtype=torch.float32, device='cuda')
+            _native.check(_native.lib().dm_row_argmax(_native.ptr(self.device), 1, t0, t1, _native.ptr(arg), _native.ptr(rows),
+                                                      _native.stream_ptr()))
+            self._arg = arg.cpu().numpy().astype(np.int64)
+            self._rows = rows.cpu().numpy().astype(np.float64)
+        return self._rows
+
+    def row_argmax(self):
+        """(T0,T1) int64: np.argmax(co_map[i, j, i, :]) for every patch, computed on the device."""
+        self._own_rows()
+        return self._arg
+
+    def __getitem__(self, idx):
+        if (self._host_arr is None and isinstance(idx, tuple) and len(idx) == 4 and idx[3] == slice(None)
+                and all(isinstance(k, (int, np.integer)) for k in idx[:3])):
+            t0 = self.device.shape[0]
+            i, j, k = int(idx[0]), int(idx[1]), int(idx[2])
+            if i % t0 == k % t0 and -t0 <= i < t0 and -t0 <= k < t0:
+                return self._own_rows()[i, j]
+        return self._host()[idx]
+
+    def __array__(self, dtype=None, copy=None):
+        a = self._host()
+        return a if dtype is None else a.astype(dtype)
+
+    def __array_ufunc__(self, ufunc, method, *inputs, **kwargs):
+        inputs = tuple(x._host() if isinstance(x, DeviceCoMap) else x for x in inputs)
+        if 'out' in kwargs:
+            kwargs['out'] = tuple(x._host() if isinstance(x, DeviceCoMap) else x for x in kwargs['out'])
+        return getattr(ufunc, method)(*inputs, **kwargs)
+
+    def __array_function__(self, func, types, args, kwargs):
+        def conv(x):
+            if isinstance(x, DeviceCoMap):
+                return x._host()
+            if isinstance(x, (list, tuple)):
+                return type(x)(conv(y) for y in x)
+            return x
+        return func(*conv(args), **{k: conv(v) for k, v in kwargs.items()})
+
+    def __getattr__(self, name):            # everything else an ndarray has (astype, reshape, max, ...)
+        if name.startswith('__'):
+            raise AttributeError(name)
+        return getattr(self._host(), name)
+
+
 class Maxpool(object):
     """misc/Correlation_map.py:176-184 -- MaxPool2d(3, 2, padding=1) over the last two axes
     of a numpy / torch array, evaluated by the aggregation kernel's pooling stage."""
@@ -141,7 +219,7 @@ class Correlation_map():
         if 'co_map' not in self.__dict__:
             if 'co_map' not in self._dev:
                 raise AttributeError('co_map')
-            self.__dict__['co_map'] = self._dev['co_map'].cpu().numpy().astype(np.float64)
+            self.__dict__['co_map'] = DeviceCoMap(self._dev['co_map'])
         return self.__dict__['co_map']
 
     @co_map.setter

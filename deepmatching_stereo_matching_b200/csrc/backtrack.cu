@@ -363,6 +363,40 @@ int dm_upper_tail(float* const* levels_dev, int n_tiles, int t0, int t1, int lev
     return DM_OK;
 }
 
+// bad_matching.py:68-70: dis[i,j] = j - np.argmax(co_map[i, j, i, :]) -- the best column of a patch's OWN map row
+// (a one-dimensional, same-row disparity search).  One warp per patch: first maximum, the first NaN wins
+// (np.argmax).  Optionally also copies the row itself out (rows[n][i][j][:]), so that a host caller that
+// indexes co_map[i, j, i, :] gets P rows of T1 values instead of the P x P map.
+__global__ void __launch_bounds__(256)
+dm_row_argmax_kernel(const float* __restrict__ co_map, long long n_patches, int T0, int T1,
+                     int32_t* __restrict__ arg, float* __restrict__ rows) {
+    const int lane = threadIdx.x & 31;
+    const long long w = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (w >= n_patches) return;
+    const int P = T0 * T1;
+    const int p = (int)(w % P), i = p / T1;
+    const float* row = co_map + (size_t)w * P + (size_t)i * T1;
+    float best = 0.f; int bi = 0x7fffffff; bool nan = false;      // bi = INT_MAX: nothing seen yet
+    for (int x = lane; x < T1; x += 32) {
+        const float v = row[x];
+        if (rows) rows[(size_t)w * T1 + x] = v;
+        const bool vn = v != v;
+        if (bi == 0x7fffffff || (!nan && (vn || v > best))) { best = v; bi = x; nan = vn; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        const bool on = __shfl_xor_sync(0xffffffffu, (int)nan, o) != 0;
+        if (oi == 0x7fffffff) continue;
+        // the other lane's candidate wins if it is a NaN at a smaller index (or mine is not a NaN),
+        // or a larger value, or an equal value at a smaller index
+        const bool take = bi == 0x7fffffff || (on && (!nan || oi < bi)) || (!on && !nan && (ob > best || (ob == best && oi < bi)));
+        if (take) { best = ob; bi = oi; nan = on; }
+    }
+    if (lane == 0) arg[w] = bi;
+}
+
 template <typename T>
 static int backtrack_launch(const void* level, long long n, int a, int b, int c, int d,
                             const int32_t* parent, int32_t* match, void* score, cudaStream_t st) {
@@ -433,6 +467,14 @@ extern "C" int dm_sub_pix_cal(const double* arr_dev, const double* co_map_dev, i
                               int direction, double ratio, double* out_dev, void* stream) {
     DM_REQUIRE(s0 > 0 && s1 > 0 && (direction == 0 || direction == 1), DM_ERR_INVALID, "dm_sub_pix_cal: bad arguments");
     dm_sub_pix_cal_kernel<<<dm_div_up((long long)s0 * s1, 256), 256, 0, (cudaStream_t)stream>>>(arr_dev, co_map_dev, s0, s1, direction, ratio, out_dev);
+    DM_LAUNCH_CHECK();
+    return DM_OK;
+}
+
+extern "C" int dm_row_argmax(const float* co_map_dev, int n, int t0, int t1, int32_t* arg_dev, float* rows_dev, void* stream) {
+    DM_REQUIRE(co_map_dev && arg_dev && n > 0 && t0 > 0 && t1 > 0, DM_ERR_INVALID, "dm_row_argmax: bad arguments");
+    const long long n_patches = (long long)n * t0 * t1;
+    dm_row_argmax_kernel<<<dm_div_up(n_patches, 8), 256, 0, (cudaStream_t)stream>>>(co_map_dev, n_patches, t0, t1, arg_dev, rows_dev);
     DM_LAUNCH_CHECK();
     return DM_OK;
 }

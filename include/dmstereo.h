@@ -128,6 +128,12 @@ int dm_backtrack_level(const void* level_dev, int is_f64, int n, int a, int b, i
                        const int32_t* parent_match_dev,
                        int32_t* match_dev, void* score_dev, void* stream);
 
+/* bad_matching.py:68-70 -- np.argmax(co_map[i, j, i, :]) for every patch (i, j): the best column of the
+ * patch's OWN map row (first maximum, the first NaN wins).  co_map = float32 [n][t0][t1][t0][t1] (min-maxed
+ * level 0, Correlation_map.co_map); arg = int32 [n][t0][t1].  rows (may be NULL) = float32 [n][t0][t1][t1]
+ * receives the rows themselves, so that a host loop over co_map[i, j, i, :] needs P x T1 values, not P x P. */
+int dm_row_argmax(const float* co_map_dev, int n, int t0, int t1, int32_t* arg_dev, float* rows_dev, void* stream);
+
 /* Matching._filter (misc/Matching.py:224-255): outlier filter on the displacement field of a
  * batch of match maps, int32 [n][2][h][w] -> [n][2][h][w] (out must not alias in).  Interior
  * cells become round(mean | median of the (2e+1)^2 neighbourhood of displacements) + their

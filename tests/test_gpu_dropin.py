@@ -53,6 +53,9 @@ def test_bad_matching_sequence():
     for i in range(co_cls.co_map.shape[0]):
         for j in range(co_cls.co_map.shape[1]):
             dis[i, j] = j - np.argmax(co_cls.co_map[i, j, i, :])
+    # the loop above was served from P own-row slices (one dm_row_argmax launch): the P x P map never came to the host
+    assert co_cls.co_map._host_arr is None
+    assert np.array_equal(co_cls.co_map.row_argmax(), np.arange(dis.shape[1])[None, :] - dis)
     ref = O.initial_co_map(img1, img2, 5)
     rd = np.array([[j - np.argmax(ref[i, j, i, :]) for j in range(ref.shape[1])] for i in range(ref.shape[0])])
     # the row argmax may only differ where the oracle's two best values of that row are closer than the

@@ -808,3 +808,25 @@ def test_tile_ranges_assemble_the_whole_scene(dm, fused):
     assert np.array_equal(got_d, ref_d) and np.array_equal(got_s, ref_s)
     assert np.array_equal(mosaic[:-1].cpu().numpy(), ref_d) and np.array_equal(mosaic[-1].cpu().numpy(), ref_s)
     ctx.close()
+
+
+def test_row_argmax_kernel(dm):
+    """dm_row_argmax (bad_matching.py:68-70) against np.argmax of every patch's own map row: first
+    maximum on ties, the first NaN wins, rows shorter and longer than a warp."""
+    import torch
+    from deepmatching_stereo_matching_b200 import _native
+    rng = np.random.default_rng(3)
+    for (n, t0, t1) in [(2, 8, 16), (1, 4, 80), (3, 16, 32), (1, 2, 5)]:
+        x = rng.integers(0, 6, size=(n, t0, t1, t0, t1)).astype(np.float32) / 5.0        # many exact ties
+        x[0, 1, 2, 1, 3] = np.nan
+        x[0, 1, 2, 1, 4] = np.nan
+        x[-1, 0, 0, 0, :] = 0.25
+        dev = torch.from_numpy(x).cuda()
+        arg = torch.empty((n, t0, t1), dtype=torch.int32, device='cuda')
+        rows = torch.empty((n, t0, t1, t1), dtype=torch.float32, device='cuda')
+        _native.check(_native.lib().dm_row_argmax(_native.ptr(dev), n, t0, t1, _native.ptr(arg), _native.ptr(rows), _native.stream_ptr()))
+        want_rows = np.stack([[[x[k, i, j, i, :] for j in range(t1)] for i in range(t0)] for k in range(n)])
+        assert np.array_equal(rows.cpu().numpy(), want_rows, equal_nan=True)
+        assert np.array_equal(arg.cpu().numpy(), np.argmax(want_rows, axis=-1))
+        _native.check(_native.lib().dm_row_argmax(_native.ptr(dev), n, t0, t1, _native.ptr(arg), None, _native.stream_ptr()))
+        assert np.array_equal(arg.cpu().numpy(), np.argmax(want_rows, axis=-1))
