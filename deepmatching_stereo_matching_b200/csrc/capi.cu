@@ -138,8 +138,6 @@ static int owned_rects(int len0, int len1, int s0, int s1, int out_h, int out_w,
 int dm_readback_rows(dm_ctx* ctx, long long tiles_done) {
     dm_ctx::Readback& rb = ctx->rb;
     if (!rb.active || tiles_done <= rb.tiles_copied) return DM_OK;
-    OwnedRect rc[3];
-    const int n = owned_rects(rb.len0, rb.len1, rb.s0, rb.s1, rb.out_h, rb.out_w, rb.tiles_copied, tiles_done, rc);
     if (!ctx->copy_stream) DM_CUDA_CHECK(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
     if (ctx->band_used >= ctx->band_ev.size()) {
         cudaEvent_t e;
@@ -150,6 +148,23 @@ int dm_readback_rows(dm_ctx* ctx, long long tiles_done) {
     DM_CUDA_CHECK(cudaEventRecord(ev, ctx->stream));
     DM_CUDA_CHECK(cudaStreamWaitEvent(ctx->copy_stream, ev, 0));
     const size_t plane = (size_t)rb.out_h * rb.out_w, pitch = (size_t)rb.out_w * sizeof(double);
+    if (rb.n_scenes > 1) {
+        // a batch of scenes ([scene][mode][plane] and [scene][plane]) leaves scene by scene: whole
+        // scenes are two contiguous blocks each, no rectangles
+        const long long tps = (long long)rb.len0 * rb.len1;
+        const long long s_a = rb.tiles_copied / tps, s_b = tiles_done / tps;
+        if (s_b > s_a) {
+            const size_t cnt = (size_t)(s_b - s_a);
+            DM_CUDA_CHECK(cudaMemcpyAsync(rb.dst_d_map + (size_t)s_a * rb.n_modes * plane, rb.d_d_map + (size_t)s_a * rb.n_modes * plane,
+                                          cnt * rb.n_modes * plane * sizeof(double), cudaMemcpyDefault, ctx->copy_stream));
+            DM_CUDA_CHECK(cudaMemcpyAsync(rb.dst_out_map + (size_t)s_a * plane, rb.d_out_map + (size_t)s_a * plane,
+                                          cnt * plane * sizeof(double), cudaMemcpyDefault, ctx->copy_stream));
+            rb.tiles_copied = s_b * tps;
+        }
+        return DM_OK;
+    }
+    OwnedRect rc[3];
+    const int n = owned_rects(rb.len0, rb.len1, rb.s0, rb.s1, rb.out_h, rb.out_w, rb.tiles_copied, tiles_done, rc);
     for (int k = 0; k < n; ++k) {
         const size_t off = (size_t)rc[k].r0 * rb.out_w + rc[k].c0;
         const size_t width = (size_t)(rc[k].c1 - rc[k].c0) * sizeof(double), rows = (size_t)(rc[k].r1 - rc[k].r0);
@@ -603,19 +618,19 @@ extern "C" int dm_solve_scene_host(dm_ctx* ctx, const dm_scene_params* prm,
     double* out_map = ctx->planes + plane * prm->n_modes * ns;
     if (prm->s0 > prm->t0 || prm->s1 > prm->t1)      // gaps between tiles: np.empty in the reference, zeros here
         DM_CUDA_CHECK(cudaMemsetAsync(ctx->planes, 0, pb, st));
-    // single scene: what the finished tiles own streams back to the host behind the compute
+    // what the finished tiles own streams back to the host behind the compute (a batch: scene after scene)
     dm_ctx::Readback& rb = ctx->rb;
     rb = dm_ctx::Readback();
-    if (ns == 1) {
+    {
         rb.active = true;
         rb.dst_d_map = d_map_host; rb.dst_out_map = out_map_host; rb.d_d_map = d_map; rb.d_out_map = out_map;
         rb.n_modes = prm->n_modes; rb.out_h = info.out_h; rb.out_w = info.out_w; rb.len0 = info.len0; rb.len1 = info.len1;
-        rb.s0 = prm->s0; rb.s1 = prm->s1;
+        rb.s0 = prm->s0; rb.s1 = prm->s1; rb.n_scenes = ns;
         rb.tiles_copied = ta;
         ctx->band_used = 0;
     }
     rc = dm_solve_scene(ctx, prm, ctx->scene1, ctx->scene2, d_map, out_map, &info);
-    if (rc == DM_OK && ns == 1) rc = dm_readback_rows(ctx, tb);     // whatever has not left yet (everything on the materialising path)
+    if (rc == DM_OK) rc = dm_readback_rows(ctx, tb * ns);     // whatever has not left yet (everything on the materialising path)
     rb.active = false;
     up.active = false;
     if (rc != DM_OK) {
@@ -626,12 +641,7 @@ extern "C" int dm_solve_scene_host(dm_ctx* ctx, const dm_scene_params* prm,
         cudaStreamSynchronize(st);
         return rc;
     }
-    if (ns > 1) {       // whole batch: both result arrays are contiguous
-        DM_CUDA_CHECK(cudaMemcpyAsync(d_map_host, d_map, plane * prm->n_modes * ns * sizeof(double), cudaMemcpyDeviceToHost, st));
-        DM_CUDA_CHECK(cudaMemcpyAsync(out_map_host, out_map, plane * ns * sizeof(double), cudaMemcpyDeviceToHost, st));
-    } else if (ctx->copy_stream && ctx->band_used > 0) {
-        DM_CUDA_CHECK(cudaStreamSynchronize(ctx->copy_stream));
-    }
+    if (ctx->copy_stream && ctx->band_used > 0) DM_CUDA_CHECK(cudaStreamSynchronize(ctx->copy_stream));
     DM_CUDA_CHECK(cudaStreamSynchronize(st));
     if (info_out) *info_out = info;
     return DM_OK;

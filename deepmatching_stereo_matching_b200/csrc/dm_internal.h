@@ -56,7 +56,7 @@ struct dm_ctx {
         bool active = false;
         double* dst_d_map = nullptr; double* dst_out_map = nullptr;
         const double* d_d_map = nullptr; const double* d_out_map = nullptr;
-        int n_modes = 0, out_h = 0, out_w = 0, len0 = 0, len1 = 0, s0 = 0, s1 = 0;
+        int n_modes = 0, out_h = 0, out_w = 0, len0 = 0, len1 = 0, s0 = 0, s1 = 0, n_scenes = 1;
         long long tiles_copied = 0;                 // the pixels owned by tiles [.., tiles_copied) (global index) are already on their way
     } rb;
     // Host scenes uploaded chunk by chunk ahead of the compute (dm_solve_scene_host): the rows the
