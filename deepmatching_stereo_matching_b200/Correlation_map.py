@@ -191,7 +191,7 @@ class Correlation_map():
             desc = torch.empty((P, kpad), dtype=torch.bfloat16, device='cuda')
             stat = torch.empty((P * 6,), dtype=torch.float32, device='cuda')   # DM_STAT_FLOATS
             _native.check(lib.dm_descriptors(_native.ptr(scene), a.shape[0], a.shape[1], a.shape[1], _native.ptr(origin),
-                                             1, t0, t1, ws, _native.ptr(desc), _native.ptr(stat), _native.stream_ptr()))
+                                             1, t0, t1, ws, int(name), _native.ptr(desc), _native.ptr(stat), _native.stream_ptr()))
             d['desc' + name], d['stat' + name] = desc, stat
         d['kpad'] = kpad
         self._dev.update(d)

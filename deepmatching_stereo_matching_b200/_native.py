@@ -44,7 +44,7 @@ SIGNATURES = {
     'dm_last_error': (c_char_p, []),
     'dm_device_cc': (c_int, []),
     'dm_kpad': (c_int, [c_int]),
-    'dm_descriptors': (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    'dm_descriptors': (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     'dm_correlation': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     'dm_feature_value': (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
     'dm_minmax_rectify': (c_int, [c_void_p, c_longlong, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
@@ -133,6 +133,32 @@ def stream_ptr():
 
 def ptr(t):
     return c_void_p(t.data_ptr()) if t is not None else c_void_p(None)
+
+
+_PINNED_POOL = {}
+
+
+def pinned_empty(shape, dtype):
+    """numpy array backed by page-locked host memory, from a small pool of this process: results of
+    the solvers are handed out in such arrays so that the device can write them asynchronously, and
+    page-locking a few hundred MB costs tens of milliseconds every time it is done anew.  A buffer
+    returns to the pool when the array AND every view derived from it have been garbage collected."""
+    import weakref
+    import numpy as np
+    torch = require_cuda()
+    shape = tuple(int(x) for x in shape)
+    dt = np.dtype(dtype)
+    nbytes = max(1, int(np.prod(shape, dtype=np.int64)) * dt.itemsize)
+    key = (nbytes + (1 << 20) - 1) >> 20 << 20                      # pooled by size rounded up to 1 MiB
+    pool = _PINNED_POOL.setdefault(key, [])
+    t = pool.pop() if pool else torch.empty(key, dtype=torch.uint8, pin_memory=True)
+    base = t.numpy()                                                # owns the reference to t; every view keeps it alive
+
+    def give_back(pool=pool, t=t):
+        if len(pool) < 4:
+            pool.append(t)
+    weakref.finalize(base, give_back)
+    return base[:nbytes].view(dt).reshape(shape)
 
 
 def method_id(feature_name):

@@ -63,7 +63,7 @@ extern "C" int dm_correlation(const void* desc1_dev, const float* stat1_dev,
     }
     if (engine == DM_CORR_AUTO && umma_ok)
         return dm_correlation_umma(desc1_dev, stat1_dev, desc2_dev, stat2_dev, n_tiles, p, kpad, kreal, method, raw_dev, st);
-    return dm_correlation_simt(desc1_dev, stat1_dev, desc2_dev, stat2_dev, n_tiles, p, kpad, method, raw_dev, st);
+    return dm_correlation_simt(desc1_dev, stat1_dev, desc2_dev, stat2_dev, n_tiles, p, kpad, ws, method, raw_dev, st);
 }
 
 // ------------------------------------------------------------------ context
@@ -507,8 +507,8 @@ extern "C" int dm_solve_scene(dm_ctx* ctx, const dm_scene_params* prm,
             if ((rc = tm.begin(ck)) != DM_OK) return rc;
             dm_tile_origin_kernel<<<dm_div_up(nt, 128), 128, 0, st>>>(tb.origin, nt, first, info.len0, info.len1, prm->s0, prm->s1, prm->scene_h);
             DM_LAUNCH_CHECK();
-            if ((rc = dm_descriptors(img1_dev, prm->scene_h * ns, prm->scene_w, prm->scene_w, tb.origin, nt, t0, t1, prm->ws, tb.desc1, tb.stat1, st)) != DM_OK) return rc;
-            if ((rc = dm_descriptors(img2_dev, prm->scene_h * ns, prm->scene_w, prm->scene_w, tb.origin, nt, t0, t1, prm->ws, tb.desc2, tb.stat2, st)) != DM_OK) return rc;
+            if ((rc = dm_descriptors(img1_dev, prm->scene_h * ns, prm->scene_w, prm->scene_w, tb.origin, nt, t0, t1, prm->ws, 1, tb.desc1, tb.stat1, st)) != DM_OK) return rc;
+            if ((rc = dm_descriptors(img2_dev, prm->scene_h * ns, prm->scene_w, prm->scene_w, tb.origin, nt, t0, t1, prm->ws, 2, tb.desc2, tb.stat2, st)) != DM_OK) return rc;
             ctx->launches[DM_STAGE_DESCRIPTORS] += 3;
             if ((rc = tm.end()) != DM_OK) return rc;
         }

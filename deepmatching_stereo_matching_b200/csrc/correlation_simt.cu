@@ -4,7 +4,9 @@
 // Correlation_map._create_simple_initial_co_map (misc/Correlation_map.py:69-87).
 //
 // raw[t][p][q] = ZNCC( desc1[t][p][:], desc2[t][q][:] ); bf16 operands hold exact
-// integers, the fp32 accumulation is exact (|sum| <= 225*255^2 < 2^24 for ws <= 15).
+// integers, the fp32 accumulation is exact (|sum| <= 225*255^2 < 2^24 for ws <= 15).  The tensor-core
+// kernel gets the -S1' S2'/K term from three correction entries of the descriptor rows and may
+// differ from this engine by the rounding of their accumulation (a few ulp of the accumulator).
 #include "dm_common.cuh"
 
 namespace {
@@ -14,7 +16,7 @@ constexpr int TM = 64, TN = 64, TK = 32;
 __global__ void __launch_bounds__(256)
 dm_correlation_simt_kernel(const __nv_bfloat16* __restrict__ d1, const dm_stat* __restrict__ st1,
                            const __nv_bfloat16* __restrict__ d2, const dm_stat* __restrict__ st2,
-                           int P, int kpad, int normed, float* __restrict__ raw) {
+                           int P, int kpad, int normed, int slot0, int slot1, int slot2, float* __restrict__ raw) {
     __shared__ float As[TK][TM + 4];
     __shared__ float Bs[TK][TN + 4];
     const int tile = blockIdx.z;
@@ -30,8 +32,12 @@ dm_correlation_simt_kernel(const __nv_bfloat16* __restrict__ d1, const dm_stat* 
             int e = it * 256 + threadIdx.x;
             int r = e >> 5, k = e & 31;
             float va = 0.f, vb = 0.f;
-            if (m0 + r < P) va = __bfloat162float(a[(size_t)(m0 + r) * kpad + k0 + k]);
-            if (n0 + r < P) vb = __bfloat162float(b[(size_t)(n0 + r) * kpad + k0 + k]);
+            // the correction slots (descriptors.cu) are for the tensor-core kernel: this engine keeps the dot
+            // product an exact integer and applies -S1' S2'/K with one FMA in the epilogue
+            const int kk = k0 + k;
+            const bool special = kk == slot0 || kk == slot1 || kk == slot2;
+            if (m0 + r < P && !special) va = __bfloat162float(a[(size_t)(m0 + r) * kpad + kk]);
+            if (n0 + r < P && !special) vb = __bfloat162float(b[(size_t)(n0 + r) * kpad + kk]);
             As[k][r] = va;
             Bs[k][r] = vb;
         }
@@ -68,13 +74,17 @@ dm_correlation_simt_kernel(const __nv_bfloat16* __restrict__ d1, const dm_stat* 
 
 }  // namespace
 
+void dm_desc_special_slots(int ws, int k[3]);
+
 int dm_correlation_simt(const void* desc1, const float* stat1, const void* desc2, const float* stat2,
-                        int n_tiles, int p, int kpad, int method, float* raw, cudaStream_t stream) {
+                        int n_tiles, int p, int kpad, int ws, int method, float* raw, cudaStream_t stream) {
+    int slot[3];
+    dm_desc_special_slots(ws, slot);
     dim3 grid(dm_div_up(p, TN), dm_div_up(p, TM), n_tiles);
     DM_REQUIRE(n_tiles <= 65535, DM_ERR_INVALID, "dm_correlation: more than 65535 tiles per call");
     dm_correlation_simt_kernel<<<grid, 256, 0, stream>>>(
         (const __nv_bfloat16*)desc1, (const dm_stat*)stat1, (const __nv_bfloat16*)desc2, (const dm_stat*)stat2,
-        p, kpad, method == DM_TM_CCOEFF_NORMED, raw);
+        p, kpad, method == DM_TM_CCOEFF_NORMED, slot[0], slot[1], slot[2], raw);
     DM_LAUNCH_CHECK();
     return DM_OK;
 }

@@ -62,7 +62,7 @@ constexpr int SW = 8;                   // columns per epilogue pipeline step (p
 constexpr int NSTEP = (BN / 2) / SW;    // a thread covers half of the N-tile's columns
 constexpr int STG_STRIDE = 16;          // floats per staged row; float4 slots XOR-swizzled by (row >> 1) & 3: conflict-free both ways
 constexpr int STG_BYTES = 2 * 32 * STG_STRIDE * 4;  // per epilogue warp: one region per accumulator half
-constexpr int CS_BYTES = (BN / 2) * 16; // column table of one N-tile: 64 x {sk0, sk1, inv0, inv1}
+constexpr int CS_BYTES = BN * 4;        // column table of one N-tile: inv2 of its 128 positions (the S'/K term rides in the descriptors' correction slots)
 constexpr int CS_STAGES = 4;
 
 // shared memory carve-up (offsets from the 1024-aligned base)
@@ -75,7 +75,7 @@ constexpr size_t SMEM_BYTES = 1024 /*align slack*/ + OFF_BAR + 256;
 
 struct Params {
     const dm_stat* stat1;       // [n*P] float4 {S', inv, S'/K, mean}
-    const float4* cstat2;       // [n*P/2] {S'/K even, S'/K odd, inv even, inv odd} of image 2
+    const float* inv2;          // [n*P] inv of the windows of image 2 (compact table written by dm_descriptors)
     int n_items, P, KB, ksteps, items_per_tile;
     float* raw;                 // MODE_RAW : [n][P][P]
     float* pooled;              // MODE_POOL: [n][P][P/4]
@@ -189,7 +189,7 @@ dm_correlation_umma_kernel(const __grid_constant__ CUtensorMap mapA, const __gri
                 umma::mbar_wait(c_empty + cst, cph ^ 1);
                 if (umma::elect_one()) {
                     umma::mbar_expect_tx(c_full + cst, (uint32_t)CS_BYTES);
-                    umma::bulk_g2s(smemCs + (size_t)cst * CS_BYTES, prm.cstat2 + ((size_t)tile * P + (size_t)j * BN) / 2, CS_BYTES, c_full + cst);
+                    umma::bulk_g2s(smemCs + (size_t)cst * CS_BYTES, prm.inv2 + ((size_t)tile * P + (size_t)j * BN), CS_BYTES, c_full + cst);
                 }
                 __syncwarp();
                 if (++cst == CS_STAGES) { cst = 0; cph ^= 1; }
@@ -258,7 +258,6 @@ dm_correlation_umma_kernel(const __grid_constant__ CUtensorMap mapA, const __gri
             const size_t prowA = wrow + lane, prowB = prowA + BM;
             const dm_stat s1A = prm.stat1[prowA], s1B = prm.stat1[prowB];
             const bool flatA = (s1A.y == 0.0f), flatB = (s1B.y == 0.0f);
-            const float ns1A = -s1A.x, ns1B = -s1B.x;
             // MODE_POOL state per row: st[] = horizontally pooled previous map row (odd rows) /
             // running vertical max (even rows); rmin = running minimum of the raw values
             float stA[HWQ], stB[HWQ];
@@ -295,21 +294,23 @@ dm_correlation_umma_kernel(const __grid_constant__ CUtensorMap mapA, const __gri
                 // column of step s inside the N-tile: map row r = (8 s) / DH, then this thread's half
                 auto step_col = [&](int s) -> int { return ((s * SW) / DH) * D + ch * DH + (s * SW) % DH; };
                 float vA0[SW], vA1[SW], vB0[SW], vB1[SW];
-                float4 c0[SW / 2], c1[SW / 2];
+                float4 c0[SW / 4], c1[SW / 4];          // inv2 of the step's 8 columns
                 float hA = 0.f, hB = 0.f;               // halo column (ch == 1): raw accumulators left of the split
-                float4 hc = make_float4(0.f, 0.f, 0.f, 0.f);
+                float hc = 0.f;                         // its inv2
                 float zprevA = -CUDART_INF_F, zprevB = -CUDART_INF_F;
                 float4 obA, obB;
                 {
                     const int n0 = step_col(0);
                     umma::tmem_ld_32x8_issue(tA + (uint32_t)n0, vA0);
                     umma::tmem_ld_32x8_issue(tB + (uint32_t)n0, vB0);
+                    if (NORMED) {
 #pragma unroll
-                    for (int i = 0; i < SW / 2; ++i) c0[i] = umma::lds128(csm + 16 * (n0 / 2 + i));
+                        for (int i = 0; i < SW / 4; ++i) c0[i] = umma::lds128(csm + 4 * n0 + 16 * i);
+                    }
                     if (MODE == MODE_POOL && ch) {
                         umma::tmem_ld_32x1_issue(tA + (uint32_t)(n0 - 1), hA);
                         umma::tmem_ld_32x1_issue(tB + (uint32_t)(n0 - 1), hB);
-                        hc = umma::lds128(csm + 16 * (n0 / 2 - 1));
+                        if (NORMED) hc = umma::lds32(csm + 4 * (n0 - 1));
                     }
                 }
 #pragma unroll
@@ -318,8 +319,8 @@ dm_correlation_umma_kernel(const __grid_constant__ CUtensorMap mapA, const __gri
                     float (&vB)[SW] = (s & 1) ? vB1 : vB0;
                     float (&vAn)[SW] = (s & 1) ? vA0 : vA1;
                     float (&vBn)[SW] = (s & 1) ? vB0 : vB1;
-                    float4 (&cc)[SW / 2] = (s & 1) ? c1 : c0;
-                    float4 (&cn)[SW / 2] = (s & 1) ? c0 : c1;
+                    float4 (&cc)[SW / 4] = (s & 1) ? c1 : c0;
+                    float4 (&cn)[SW / 4] = (s & 1) ? c0 : c1;
                     constexpr int dummy = 0; (void)dummy;
                     const int xo = (s * SW) % DH;           // first column of the step inside this thread's row half
                     const int r = (s * SW) / DH;            // map row inside the N-tile
@@ -327,26 +328,31 @@ dm_correlation_umma_kernel(const __grid_constant__ CUtensorMap mapA, const __gri
                     // halo of THIS step must be consumed before the next step's halo load overwrites it
                     float zhA = -CUDART_INF_F, zhB = -CUDART_INF_F;
                     if (MODE == MODE_POOL && xo == 0 && ch) {
-                        zhA = dm_zncc_partial(hA, s1A.x, hc.y, NORMED ? hc.w : 1.0f);
-                        zhB = dm_zncc_partial(hB, s1B.x, hc.y, NORMED ? hc.w : 1.0f);
+                        zhA = NORMED ? __fmul_rn(hA, hc) : hA;
+                        zhB = NORMED ? __fmul_rn(hB, hc) : hB;
                     }
                     if (s + 1 < NSTEP) {                    // step s+1 in flight during the math below
                         const int n1 = step_col(s + 1);
                         umma::tmem_ld_32x8_issue(tA + (uint32_t)n1, vAn);
                         umma::tmem_ld_32x8_issue(tB + (uint32_t)n1, vBn);
+                        if (NORMED) {
 #pragma unroll
-                        for (int i = 0; i < SW / 2; ++i) cn[i] = umma::lds128(csm + 16 * (n1 / 2 + i));
+                            for (int i = 0; i < SW / 4; ++i) cn[i] = umma::lds128(csm + 4 * n1 + 16 * i);
+                        }
                         if (MODE == MODE_POOL && ((s + 1) * SW) % DH == 0 && ch) {
                             umma::tmem_ld_32x1_issue(tA + (uint32_t)(n1 - 1), hA);
                             umma::tmem_ld_32x1_issue(tB + (uint32_t)(n1 - 1), hB);
-                            hc = umma::lds128(csm + 16 * (n1 / 2 - 1));
+                            if (NORMED) hc = umma::lds32(csm + 4 * (n1 - 1));
                         }
                     }
+                    // the accumulators already hold dot - S1' S2'/K (correction slots): one factor per column is left
+                    if (NORMED) {
 #pragma unroll
-                    for (int i = 0; i < SW; i += 2) {
-                        const float4 cp = cc[i >> 1];       // {s2k0, s2k1, inv0, inv1} of two columns
-                        umma::zncc_partial2(vA[i], vA[i + 1], ns1A, cp.x, cp.y, NORMED ? cp.z : 1.0f, NORMED ? cp.w : 1.0f);
-                        umma::zncc_partial2(vB[i], vB[i + 1], ns1B, cp.x, cp.y, NORMED ? cp.z : 1.0f, NORMED ? cp.w : 1.0f);
+                        for (int i = 0; i < SW; i += 4) {
+                            const float4 cp = cc[i >> 2];       // inv2 of four columns
+                            umma::mul2(vA[i], vA[i + 1], cp.x, cp.y); umma::mul2(vA[i + 2], vA[i + 3], cp.z, cp.w);
+                            umma::mul2(vB[i], vB[i + 1], cp.x, cp.y); umma::mul2(vB[i + 2], vB[i + 3], cp.z, cp.w);
+                        }
                     }
                     if (MODE == MODE_NULL) { rmaxA = fmaxf(rmaxA, vA[0] + vB[0]); continue; }
                     if (MODE == MODE_RAW) {
@@ -544,7 +550,7 @@ static int fill_params(Params& prm, CUtensorMap& mapA, CUtensorMap& mapB, CUtens
     rc = dm_make_desc_tensor_map(&mapB_pair, desc2, rows, kpad, BN / 2);     // each CTA of a pair loads half of the N-tile
     if (rc != DM_OK) return rc;
     prm.stat1 = (const dm_stat*)stat1;
-    prm.cstat2 = reinterpret_cast<const float4*>((const dm_stat*)stat2 + rows);
+    prm.inv2 = reinterpret_cast<const float*>((const dm_stat*)stat2 + rows);
     prm.P = p; prm.KB = kpad / BK; prm.items_per_tile = p / (HALVES * BM);
     prm.ksteps = (kreal + UMMA_K - 1) / UMMA_K;
     if (prm.ksteps <= 0 || prm.ksteps > kpad / UMMA_K) prm.ksteps = kpad / UMMA_K;

@@ -16,6 +16,41 @@ static __host__ __device__ inline int dm_row_stride(int ws) { return ws <= 8 ? 8
 
 int dm_desc_kreal(int ws) { return ws * dm_row_stride(ws); }
 
+// Correction slots.  ZNCC needs  dot - S1' * S2' / K  (S' = residual sum of a centred window).  A window row
+// occupies ws of its rstride entries, so every descriptor row has unused entries; three of them carry the
+// correction INTO the contraction: the patch side (side 1) stores S1' three times (an integer, |S'| <= K/2,
+// exact in bf16), the search side (side 2) stores the three bf16 parts hi + mid + lo of the float32 value
+// -S2'/K (an exact split: 3 x 8 mantissa bits).  The tensor core then accumulates
+//     sum a1' a2'  +  S1' (hi + mid + lo)  =  dot - S1' * fl(S2'/K)
+// -- every product is exact, only the accumulation of the three fractional terms rounds (<= 1 ulp of the
+// accumulator each) -- and the epilogue of the tcgen05 kernel is left with ONE per-column factor (inv2)
+// instead of two: half the column-table traffic and one FMA per element less.
+// The slots are the first three unused entries in (ky, kx) order: kx in [ws, rstride).
+__host__ __device__ inline void dm_desc_slots(int ws, int k[3]) {
+    const int r = dm_row_stride(ws);
+    int n = 0;
+    for (int ky = 0; ky < ws && n < 3; ++ky)
+        for (int kx = ws; kx < r && n < 3; ++kx) k[n++] = ky * r + kx;
+}
+void dm_desc_special_slots(int ws, int k[3]) { dm_desc_slots(ws, k); }
+
+// the three bf16 parts of a float32 value (hi + mid + lo == v exactly for |v| in the normal range)
+__device__ __forceinline__ void dm_split3(float v, float part[3]) {
+    const float hi = __bfloat162float(__float2bfloat16_rn(v));
+    const float r1 = __fsub_rn(v, hi);
+    const float mid = __bfloat162float(__float2bfloat16_rn(r1));
+    const float r2 = __fsub_rn(r1, mid);
+    part[0] = hi; part[1] = mid; part[2] = __bfloat162float(__float2bfloat16_rn(r2));
+}
+// value of correction slot j for a window with residual sum rs: side 1 -> S', side 2 -> part j of -S'/K
+__device__ __forceinline__ float dm_slot_value(int side, int j, int rs, int K) {
+    if (side == 1) return (float)rs;
+    if (side != 2) return 0.0f;
+    float part[3];
+    dm_split3(-__fdiv_rn((float)rs, (float)K), part);
+    return part[j];
+}
+
 extern "C" int dm_kpad(int ws) {
     int k = ws * dm_row_stride(ws);
     return ((k + 63) / 64) * 64;       // multiple of 64 bf16 = one 128-byte swizzle row
@@ -31,16 +66,15 @@ __device__ __forceinline__ void dm_write_stats(dm_stat* stat, long long n_patche
     const bool flat = (rq == 0);
     const float inv = flat ? 0.0f : __frcp_rn(__fsqrt_rn(var));
     stat[pidx] = make_float4(s, inv, sk, (float)mean);
-    // compact column table of the tcgen05 epilogue: per pair of patches {sk0, sk1, inv0, inv1}
-    float* ct = reinterpret_cast<float*>(stat + n_patches) + (pidx >> 1) * 4 + (pidx & 1);
-    ct[0] = sk; ct[2] = inv;
+    // compact column table of the tcgen05 epilogue: inv alone (the S'/K term rides in the correction slots)
+    reinterpret_cast<float*>(stat + n_patches)[pidx] = inv;
 }
 
 // Generic kernel (any odd ws <= 31, any grid): one warp per patch, two passes over the window.
 __global__ void __launch_bounds__(256)
 dm_descriptor_kernel(const uint8_t* __restrict__ scene, int pitch,
                      const int32_t* __restrict__ origin_yx, long long n_patches,
-                     int t0, int t1, int ws, int kpad,
+                     int t0, int t1, int ws, int kpad, int side,
                      __nv_bfloat16* __restrict__ desc, dm_stat* __restrict__ stat) {
     const int lane = threadIdx.x & 31;
     const long long warp = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -62,11 +96,15 @@ dm_descriptor_kernel(const uint8_t* __restrict__ scene, int pitch,
     for (int o = 16; o > 0; o >>= 1) { sum += __shfl_xor_sync(0xffffffffu, sum, o); sq += __shfl_xor_sync(0xffffffffu, sq, o); }
     const int mean = dm_round_mean(sum, K);
     __nv_bfloat16* row = desc + (size_t)warp * kpad;
+    int slot[3];
+    dm_desc_slots(ws, slot);
+    const int rs = sum - K * mean;
     for (int k = lane; k < kpad; k += 32) {
         const int ky = k / rstr, kx = k - ky * rstr;
-        int v = 0;
-        if (ky < ws && kx < ws) v = (int)base[ky * pitch + kx] - mean;
-        row[k] = __float2bfloat16((float)v);
+        float v = 0.f;
+        if (ky < ws && kx < ws) v = (float)((int)base[ky * pitch + kx] - mean);
+        for (int j = 0; j < 3; ++j) if (k == slot[j]) v = dm_slot_value(side, j, rs, K);
+        row[k] = __float2bfloat16(v);
     }
     if (lane == 0) dm_write_stats(stat, n_patches, warp, K, sum, sq, mean);
 }
@@ -81,7 +119,7 @@ template <int WS>
 __global__ void __launch_bounds__(256)
 dm_descriptor_row_kernel(const uint8_t* __restrict__ scene, int pitch,
                          const int32_t* __restrict__ origin_yx, long long n_groups, long long n_patches,
-                         int t0, int t1, dm_fastdiv fd_jb, dm_fastdiv fd_t0,
+                         int t0, int t1, dm_fastdiv fd_jb, dm_fastdiv fd_t0, int side,
                          __nv_bfloat16* __restrict__ desc, dm_stat* __restrict__ stat) {
     constexpr int K = WS * WS;
     constexpr int RSTR = WS <= 8 ? 8 : 16;
@@ -166,24 +204,38 @@ dm_descriptor_row_kernel(const uint8_t* __restrict__ scene, int pitch,
     }
     // the statistics (a division, a square root and a reciprocal, ~60 instructions) once for the
     // eight patches in parallel instead of once per patch behind a one-lane branch
-    if (live && gl < 8) dm_write_stats(stat, n_patches, p0 + gl, K, myS, myQ, myMean);
+    __syncwarp();                       // the slot stores below overwrite zeros other lanes of the group have just stored
+    if (live && gl < 8) {
+        dm_write_stats(stat, n_patches, p0 + gl, K, myS, myQ, myMean);
+        // correction slots (dm_desc_slots; zero so far): three 2-byte stores per patch, by the same eight lanes
+        if (side != 0) {
+            constexpr int NF = RSTR - WS;                           // unused entries per window row
+            const int rs = myS - K * myMean;
+            float part[3] = {(float)rs, (float)rs, (float)rs};
+            if (side == 2) dm_split3(-__fdiv_rn((float)rs, (float)K), part);
+            __nv_bfloat16* row = desc + (size_t)(p0 + gl) * KPAD;
+#pragma unroll
+            for (int j = 0; j < 3; ++j) row[(j / NF) * RSTR + WS + j % NF] = __float2bfloat16_rn(part[j]);
+        }
+    }
 }
 
 template <int WS>
 static void launch_descriptor_row(const uint8_t* scene, int pitch, const int32_t* origin, long long n_patches,
-                                  int t0, int t1, void* desc, float* stat, cudaStream_t st) {
+                                  int t0, int t1, int side, void* desc, float* stat, cudaStream_t st) {
     constexpr int RSTR = WS <= 8 ? 8 : 16;
     constexpr int GPW = RSTR == 16 ? 1 : 4;
     const long long n_groups = n_patches / 8;
     const long long warps = (n_groups + GPW - 1) / GPW;
     dm_descriptor_row_kernel<WS><<<dm_div_up(warps, 8), 256, 0, st>>>(scene, pitch, origin, n_groups, n_patches, t0, t1,
-                                                                       dm_make_fastdiv((uint32_t)(t1 >> 3)), dm_make_fastdiv((uint32_t)t0),
+                                                                       dm_make_fastdiv((uint32_t)(t1 >> 3)), dm_make_fastdiv((uint32_t)t0), side,
                                                                        (__nv_bfloat16*)desc, (dm_stat*)stat);
 }
 
 extern "C" int dm_descriptors(const uint8_t* scene_dev, int scene_h, int scene_w, int pitch,
-                              const int32_t* origin_yx_dev, int n_tiles, int t0, int t1, int ws,
+                              const int32_t* origin_yx_dev, int n_tiles, int t0, int t1, int ws, int side,
                               void* desc_bf16_dev, float* stat_dev, void* stream) {
+    DM_REQUIRE(side >= 0 && side <= 2, DM_ERR_INVALID, "dm_descriptors: side must be 1 (patch image), 2 (search image) or 0 (got %d)", side);
     DM_REQUIRE(ws >= 1 && (ws & 1) && ws <= 31, DM_ERR_INVALID, "dm_descriptors: window_size must be odd and <= 31 (got %d)", ws);
     DM_REQUIRE(t0 > 0 && t1 > 0 && n_tiles > 0, DM_ERR_INVALID, "dm_descriptors: empty grid");
     DM_REQUIRE(scene_h >= t0 + ws - 1 && scene_w >= t1 + ws - 1 && pitch >= scene_w, DM_ERR_INVALID,
@@ -192,17 +244,17 @@ extern "C" int dm_descriptors(const uint8_t* scene_dev, int scene_h, int scene_w
     cudaStream_t st = (cudaStream_t)stream;
     const bool rowk = (t1 % 8 == 0) && n_patches / 8 < (1LL << 32);
     switch (rowk ? ws : 0) {
-        case 3:  launch_descriptor_row<3>(scene_dev, pitch, origin_yx_dev, n_patches, t0, t1, desc_bf16_dev, stat_dev, st); break;
-        case 5:  launch_descriptor_row<5>(scene_dev, pitch, origin_yx_dev, n_patches, t0, t1, desc_bf16_dev, stat_dev, st); break;
-        case 7:  launch_descriptor_row<7>(scene_dev, pitch, origin_yx_dev, n_patches, t0, t1, desc_bf16_dev, stat_dev, st); break;
-        case 9:  launch_descriptor_row<9>(scene_dev, pitch, origin_yx_dev, n_patches, t0, t1, desc_bf16_dev, stat_dev, st); break;
-        case 11: launch_descriptor_row<11>(scene_dev, pitch, origin_yx_dev, n_patches, t0, t1, desc_bf16_dev, stat_dev, st); break;
-        case 13: launch_descriptor_row<13>(scene_dev, pitch, origin_yx_dev, n_patches, t0, t1, desc_bf16_dev, stat_dev, st); break;
-        case 15: launch_descriptor_row<15>(scene_dev, pitch, origin_yx_dev, n_patches, t0, t1, desc_bf16_dev, stat_dev, st); break;
+        case 3:  launch_descriptor_row<3>(scene_dev, pitch, origin_yx_dev, n_patches, t0, t1, side, desc_bf16_dev, stat_dev, st); break;
+        case 5:  launch_descriptor_row<5>(scene_dev, pitch, origin_yx_dev, n_patches, t0, t1, side, desc_bf16_dev, stat_dev, st); break;
+        case 7:  launch_descriptor_row<7>(scene_dev, pitch, origin_yx_dev, n_patches, t0, t1, side, desc_bf16_dev, stat_dev, st); break;
+        case 9:  launch_descriptor_row<9>(scene_dev, pitch, origin_yx_dev, n_patches, t0, t1, side, desc_bf16_dev, stat_dev, st); break;
+        case 11: launch_descriptor_row<11>(scene_dev, pitch, origin_yx_dev, n_patches, t0, t1, side, desc_bf16_dev, stat_dev, st); break;
+        case 13: launch_descriptor_row<13>(scene_dev, pitch, origin_yx_dev, n_patches, t0, t1, side, desc_bf16_dev, stat_dev, st); break;
+        case 15: launch_descriptor_row<15>(scene_dev, pitch, origin_yx_dev, n_patches, t0, t1, side, desc_bf16_dev, stat_dev, st); break;
         default: {
             const int warps = 8;
             dm_descriptor_kernel<<<dm_div_up(n_patches, warps), warps * 32, 0, st>>>(
-                scene_dev, pitch, origin_yx_dev, n_patches, t0, t1, ws, dm_kpad(ws),
+                scene_dev, pitch, origin_yx_dev, n_patches, t0, t1, ws, dm_kpad(ws), side,
                 (__nv_bfloat16*)desc_bf16_dev, (dm_stat*)stat_dev);
         }
     }

@@ -9,7 +9,7 @@
 #include "../../include/dmstereo.h"
 
 int dm_correlation_simt(const void* desc1, const float* stat1, const void* desc2, const float* stat2,
-                        int n_tiles, int p, int kpad, int method, float* raw, cudaStream_t stream);
+                        int n_tiles, int p, int kpad, int ws, int method, float* raw, cudaStream_t stream);
 
 // tcgen05 / TMEM / TMA engine (correlation_umma.cu)
 bool dm_correlation_umma_supported(int p, int kpad);

@@ -318,7 +318,11 @@ dm_final_quad_kernel(const FinalArgs a, long long n_quads) {
         const int m2 = (int)sq.w, S2 = (int)sq.x;
         const int dot = sum_ab - m2 * S1 - m1 * S2 - K * m1 * m2;
         const float z = dm_zncc_partial((float)dot, s1.x, sq.z, normed ? sq.y : 1.0f);
-        return dm_normalize(dm_zncc_finish(z, s1.y, flat1, normed), mn, mx, rinv);
+        // mn / mx come from the tensor-core kernel, whose correction terms are accumulated with a few ulp of
+        // rounding; the value recomputed here is exact and may undercut mn by that much -- it is the slice
+        // minimum then, i.e. 0 (a negative base would turn x ** 1.4 into NaN).  NaN stays NaN.
+        const float r = dm_normalize(dm_zncc_finish(z, s1.y, flat1, normed), mn, mx, rinv);
+        return r < 0.0f ? 0.0f : r;
     };
     // 16 bytes of a against region row `row`, window starting at byte `bo` (dynamic)
     auto row_dot = [&](const uint32_t (&aq)[4], int row, int bo) -> uint32_t {
@@ -491,8 +495,8 @@ int dm_fused_solve_chunk(dm_ctx* ctx, const dm_fused_args* a, int ck) {
         if ((rc = tm.begin(ck)) != DM_OK) return rc;
         dm_tile_origin_kernel2<<<dm_div_up(nt, 128), 128, 0, st>>>(fb.origin, fb.tinfo, nt, a->first_tile, a->len0, a->len1, a->s0, a->s1, a->scene_h);
         DM_LAUNCH_CHECK();
-        if ((rc = dm_descriptors(a->img1, a->scene_h * a->n_scenes, a->scene_w, a->scene_w, fb.origin, nt, t0, t1, a->ws, fb.desc1, fb.stat1, st)) != DM_OK) return rc;
-        if ((rc = dm_descriptors(a->img2, a->scene_h * a->n_scenes, a->scene_w, a->scene_w, fb.origin, nt, t0, t1, a->ws, fb.desc2, fb.stat2, st)) != DM_OK) return rc;
+        if ((rc = dm_descriptors(a->img1, a->scene_h * a->n_scenes, a->scene_w, a->scene_w, fb.origin, nt, t0, t1, a->ws, 1, fb.desc1, fb.stat1, st)) != DM_OK) return rc;
+        if ((rc = dm_descriptors(a->img2, a->scene_h * a->n_scenes, a->scene_w, a->scene_w, fb.origin, nt, t0, t1, a->ws, 2, fb.desc2, fb.stat2, st)) != DM_OK) return rc;
         ctx->launches[DM_STAGE_DESCRIPTORS] += 3;
         if ((rc = tm.end()) != DM_OK) return rc;
     }

@@ -122,6 +122,20 @@ __device__ __forceinline__ void zncc_partial2(float& v0, float& v1, float ns1, f
         "mov.b64 {%0, %1}, rc; }"
         : "+f"(v0), "+f"(v1) : "f"(ns1), "f"(s2k0), "f"(s2k1), "f"(inv0), "f"(inv1));
 }
+// (v0, v1) *= (f0, f1): FMUL2, each lane IEEE-rn
+__device__ __forceinline__ void mul2(float& v0, float& v1, float f0, float f1) {
+    asm("{ .reg .b64 ra, rb;\n\t"
+        "mov.b64 ra, {%0, %1};\n\t"
+        "mov.b64 rb, {%2, %3};\n\t"
+        "mul.rn.f32x2 ra, ra, rb;\n\t"
+        "mov.b64 {%0, %1}, ra; }"
+        : "+f"(v0), "+f"(v1) : "f"(f0), "f"(f1));
+}
+__device__ __forceinline__ float lds32(uint32_t saddr) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(saddr) : "memory");
+    return v;
+}
 __device__ __forceinline__ float max3(float a, float b, float c) {
     float r;
     asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));

@@ -125,11 +125,7 @@ def set_workspace_limit(nbytes):
         m.set_workspace_limit(nbytes)
 
 
-def pinned_empty(shape, dtype):
-    """numpy array backed by page-locked host memory (torch owns the allocation)."""
-    torch = _native.require_cuda()
-    t = torch.empty(tuple(int(x) for x in shape), dtype=getattr(torch, np.dtype(dtype).name), pin_memory=True)
-    return t.numpy()
+pinned_empty = _native.pinned_empty       # page-locked result arrays from a small pool (see _native.pinned_empty)
 
 
 def solve_batch(imgs1, imgs2, image_size=[32, 32], stride=[32, 32], window_size=5,

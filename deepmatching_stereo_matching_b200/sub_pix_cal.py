@@ -25,7 +25,7 @@ def sub_pix_cal(arr, co_map, direction=0, ratio=100.):
     return out.cpu().numpy()
 
 
-def sub_pix_cal_batch(d_maps, co_maps, directions, ratio=100., chunks=8):
+def sub_pix_cal_batch(d_maps, co_maps, directions, ratio=100., chunks=16):
     """sub_pix_cal for a batch: d_maps (n, n_modes, S0, S1), co_maps (n, S0, S1), directions[m] per
     plane -> (n, n_modes, S0, S1) float64; each slice identical to sub_pix_cal(d_maps[b, m],
     co_maps[b], directions[m]).  The batch goes through the device in ``chunks`` pieces on two
@@ -39,7 +39,7 @@ def sub_pix_cal_batch(d_maps, co_maps, directions, ratio=100., chunks=8):
     if any(d not in (0, 1) for d in directions):
         raise ValueError('direction must be 0 or 1')
     n = a_h.shape[0]
-    res = torch.empty(a_h.shape, dtype=torch.float64, pin_memory=True)
+    res = torch.from_numpy(_native.pinned_empty(tuple(a_h.shape), np.float64))
     lib = _native.lib()
     cur = torch.cuda.current_stream()
     streams = [torch.cuda.Stream(), torch.cuda.Stream()]

@@ -72,13 +72,17 @@ int         dm_device_cc(void);
  * the patch's rounded mean, exact), zero padded to kpad, plus the window statistics:
  * stat_dev holds DM_STAT_FLOATS (6) floats per patch -- first n*P float4 {S', inv, S'/K,
  * mean} with S' the residual sum and inv = 1/sqrt(sum a'^2 - S'^2/K) (0 for a flat
- * window), then n*P/2 float4 {S'/K (even), S'/K (odd), inv (even), inv (odd)} per pair
- * of patches (the compact column table of the tcgen05 epilogue).  kpad = dm_kpad(ws).
+ * window), then n*P floats inv again (the compact column table of the tcgen05 epilogue; the
+ * rest is padding).  kpad = dm_kpad(ws).
+ * side: which operand of the correlation the rows are for.  Three unused entries of every row
+ * (a window row occupies ws of its 8 / 16 entries) carry the ZNCC correction -S1' S2'/K into the
+ * contraction: 1 = patch image (image 1): they hold S'; 2 = search image (image 2): they hold the
+ * three bf16 parts of -S'/K; 0 = zeros.  dm_correlation expects desc1 with side 1, desc2 with side 2.
  */
 #define DM_STAT_FLOATS 6
 int dm_kpad(int ws);
 int dm_descriptors(const uint8_t* scene_dev, int scene_h, int scene_w, int pitch,
-                   const int32_t* origin_yx_dev, int n_tiles, int t0, int t1, int ws,
+                   const int32_t* origin_yx_dev, int n_tiles, int t0, int t1, int ws, int side,
                    void* desc_bf16_dev, float* stat_dev, void* stream);
 
 /* ---------------------------------------------------------------- correlation ------

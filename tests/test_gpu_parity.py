@@ -75,8 +75,11 @@ def test_correlation_and_pyramid_vs_reference(dm, name, engine):
 
 
 @pytest.mark.parametrize('t0,t1,ws,n', [(16, 16, 5, 3), (8, 32, 3, 2), (32, 32, 5, 5), (32, 32, 15, 2), (64, 64, 15, 3), (32, 64, 7, 2)])
-def test_tcgen05_correlation_bit_identical_to_simt(dm, t0, t1, ws, n, pair_mode):
-    """Both engines accumulate exact integers, so raw ZNCC must agree bit for bit."""
+def test_tcgen05_correlation_agrees_with_simt(dm, t0, t1, ws, n, pair_mode):
+    """Both engines accumulate the same exact integer products.  The CUDA-core engine applies the
+    -S1' S2'/K term with one FMA; the tensor-core engine gets it from the three correction entries of
+    the descriptor rows, whose accumulation rounds by at most a few ulp of the accumulator
+    (|acc| < 2^24): raw ZNCC within 5e-7, the un-normalised numerator within 4."""
     import torch
     from deepmatching_stereo_matching_b200 import _native
     from deepmatching_stereo_matching_b200.synth import texture
@@ -88,10 +91,10 @@ def test_tcgen05_correlation_bit_identical_to_simt(dm, t0, t1, ws, n, pair_mode)
     origin = torch.tensor([[k % 7, 13 * k] for k in range(n)], dtype=torch.int32, device='cuda')
     P, kpad = t0 * t1, lib.dm_kpad(ws)
     bufs = []
-    for sc in (s1, s2):
+    for side, sc in ((1, s1), (2, s2)):
         desc = torch.empty((n * P, kpad), dtype=torch.bfloat16, device='cuda')
         stat = torch.empty((n * P * 6,), dtype=torch.float32, device='cuda')
-        _native.check(lib.dm_descriptors(_native.ptr(sc), H, W, W, _native.ptr(origin), n, t0, t1, ws,
+        _native.check(lib.dm_descriptors(_native.ptr(sc), H, W, W, _native.ptr(origin), n, t0, t1, ws, side,
                                          _native.ptr(desc), _native.ptr(stat), _native.stream_ptr()))
         bufs += [desc, stat]
     for method in (_native.TM_CCOEFF_NORMED, _native.TM_CCOEFF):
@@ -103,7 +106,11 @@ def test_tcgen05_correlation_bit_identical_to_simt(dm, t0, t1, ws, n, pair_mode)
             torch.cuda.synchronize()
             out.append(raw.cpu().numpy())
         assert not np.isnan(out[1]).any()
-        assert np.array_equal(out[0], out[1])
+        if method == _native.TM_CCOEFF_NORMED:
+            assert np.abs(out[0] - out[1]).max() <= 5e-7
+        else:
+            assert np.abs(out[0] - out[1]).max() <= 4.0 and np.allclose(out[0], out[1], rtol=1e-6, atol=4.0)
+        print('ws %d method %d: engines differ in %.4f of the entries, max %.2e' % (ws, method, np.mean(out[0] != out[1]), np.abs(out[0] - out[1]).max()))
     # and the SIMT engine against the oracle for the first tile
     i1 = s1[:t0 + e2, :t1 + e2].cpu().numpy()
     i2 = s2[:t0 + e2, :t1 + e2].cpu().numpy()
@@ -130,10 +137,10 @@ def test_correlation_engines_are_repeatable(dm, T, ws, n, pair_mode):
     origin = torch.tensor([[k % 9, 11 * k] for k in range(n)], dtype=torch.int32, device='cuda')
     P, kpad = T * T, lib.dm_kpad(ws)
     bufs = []
-    for sc in (s1, s2):
+    for side, sc in ((1, s1), (2, s2)):
         desc = torch.empty((n * P, kpad), dtype=torch.bfloat16, device='cuda')
         stat = torch.empty((n * P * 6,), dtype=torch.float32, device='cuda')
-        _native.check(lib.dm_descriptors(_native.ptr(sc), H, W, W, _native.ptr(origin), n, T, T, ws, _native.ptr(desc), _native.ptr(stat), _native.stream_ptr()))
+        _native.check(lib.dm_descriptors(_native.ptr(sc), H, W, W, _native.ptr(origin), n, T, T, ws, side, _native.ptr(desc), _native.ptr(stat), _native.stream_ptr()))
         bufs += [desc, stat]
     ref = torch.empty((n * P * P,), dtype=torch.float32, device='cuda')
     _native.check(lib.dm_correlation(*[_native.ptr(b) for b in bufs], n, P, kpad, ws, 5, _native.CORR_SIMT, _native.ptr(ref), _native.stream_ptr()))
@@ -150,16 +157,17 @@ def test_correlation_engines_are_repeatable(dm, T, ws, n, pair_mode):
                 first = cur.clone()
                 assert not torch.isnan(out).any()
                 if engine == _native.CORR_UMMA:
-                    assert torch.equal(cur, ref.view(torch.int32))
+                    assert (out - ref).abs().max().item() <= 5e-7
             else:
                 assert torch.equal(cur, first)
 
 
 @pytest.mark.parametrize('T,ws,n', [(16, 5, 3), (32, 5, 5), (32, 15, 2), (64, 15, 3), (64, 3, 2), (128, 5, 1)])
 def test_pooled_epilogue_equals_maxpool_of_raw_zncc(dm, T, ws, n, pair_mode):
-    """The pooled tcgen05 epilogue against torch's max_pool2d(3, 2, 1) of the
-    SIMT engine's raw ZNCC: min-max, clamp and the row factor are monotone, so the pooled map,
-    the per-patch minimum and the per-patch maximum of the pooled map must agree bit for bit."""
+    """The pooled tcgen05 epilogue against torch's max_pool2d(3, 2, 1) of the raw ZNCC the same
+    tensor-core engine materialises (identical accumulators): clamp and the row factor are
+    monotone, so the pooled map, the per-patch minimum and the per-patch maximum of the pooled map
+    must agree bit for bit; and within 5e-7 of the CUDA-core engine's."""
     import torch
     from deepmatching_stereo_matching_b200 import _native
     from deepmatching_stereo_matching_b200.synth import texture
@@ -171,14 +179,18 @@ def test_pooled_epilogue_equals_maxpool_of_raw_zncc(dm, T, ws, n, pair_mode):
     origin = torch.tensor([[k % 9, 11 * k] for k in range(n)], dtype=torch.int32, device='cuda')
     P, kpad = T * T, lib.dm_kpad(ws)
     bufs = []
-    for sc in (s1, s2):
+    for side, sc in ((1, s1), (2, s2)):
         desc = torch.empty((n * P, kpad), dtype=torch.bfloat16, device='cuda')
         stat = torch.empty((n * P * 6,), dtype=torch.float32, device='cuda')
-        _native.check(lib.dm_descriptors(_native.ptr(sc), H, W, W, _native.ptr(origin), n, T, T, ws, _native.ptr(desc), _native.ptr(stat), _native.stream_ptr()))
+        _native.check(lib.dm_descriptors(_native.ptr(sc), H, W, W, _native.ptr(origin), n, T, T, ws, side, _native.ptr(desc), _native.ptr(stat), _native.stream_ptr()))
         bufs += [desc, stat]
     for method in (_native.TM_CCOEFF_NORMED, _native.TM_CCOEFF):
         raw = torch.empty((n * P, 1, T, T), dtype=torch.float32, device='cuda')
-        _native.check(lib.dm_correlation(*[_native.ptr(b) for b in bufs], n, P, kpad, ws, method, _native.CORR_SIMT, _native.ptr(raw), _native.stream_ptr()))
+        simt = torch.empty((n * P, 1, T, T), dtype=torch.float32, device='cuda')
+        _native.check(lib.dm_correlation(*[_native.ptr(b) for b in bufs], n, P, kpad, ws, method, _native.CORR_SIMT, _native.ptr(simt), _native.stream_ptr()))
+        _native.check(lib.dm_correlation(*[_native.ptr(b) for b in bufs], n, P, kpad, ws, method, _native.CORR_UMMA, _native.ptr(raw), _native.stream_ptr()))
+        if method == _native.TM_CCOEFF_NORMED:
+            assert (raw - simt).abs().max().item() <= 5e-7
         want = torch.nn.functional.max_pool2d(raw, 3, 2, 1).reshape(n * P, P // 4)
         want_min = raw.reshape(n * P, P).min(dim=1).values
         want_max = want.max(dim=1).values
@@ -321,7 +333,7 @@ def test_image_cut_solver_with_displacement_filter(dm, mode, num, win, fused_exp
     s2.log_flg = False
     s2._cut_and_pool()
     s2._execute_matching_per_tile(list(d.shape[1:]))
-    assert np.array_equal(s2.d_map, d, equal_nan=True) and np.array_equal(s2.out_map, sc, equal_nan=True)
+    _same_up_to_accumulation_rounding(s2.d_map, s2.out_map, d, sc, exact=not fused_expected)
     # "bit-exact given identical correlation inputs": the oracle's top-down pass + filter on the GPU's own
     # (float32) pyramid of a tile must reproduce the GPU's matches exactly -- whatever differs from the
     # float64 oracle below comes from the float32 level values alone
@@ -376,6 +388,25 @@ def test_feature_value_general_sizes(dm):
     assert np.abs(c - g['normed_small']).max() <= 6e-5
 
 
+def _same_up_to_accumulation_rounding(d_a, s_a, d_b, s_b, exact):
+    """The batched solver against the tile-by-tile class path.  On the materialising path both run the same
+    kernels on the same values: bit for bit.  The fused path recomputes the level-0 values of its last
+    step from exact integer dot products, while the class path reads them from the map the tensor-core
+    kernel materialised (correction terms accumulated with a few ulp of rounding): same matches, scores
+    within 1e-6, sub-pixel shifts within 1e-4 except where the parabola is ill conditioned."""
+    assert np.array_equal(np.isnan(d_a), np.isnan(d_b)) and np.array_equal(np.isnan(s_a), np.isnan(s_b))
+    if exact:
+        assert np.array_equal(d_a, d_b, equal_nan=True) and np.array_equal(s_a, s_b, equal_nan=True)
+        return
+    ok = ~np.isnan(d_a)
+    print('batched vs tile by tile: %.5f of the values differ by more than 0.5, %.5f by more than 1e-4' % (
+        np.mean(np.abs(d_a - d_b)[ok] > 0.5), np.mean(np.abs(d_a - d_b)[ok] > 1e-4)))
+    assert np.mean(np.abs(d_a - d_b)[ok] > 0.5) <= 1e-3
+    assert np.mean(np.abs(d_a - d_b)[ok] > 1e-4) <= 2e-3
+    so = ~np.isnan(s_a)
+    assert np.mean(np.abs(s_a - s_b)[so] > 1e-6) <= 1e-3
+
+
 def _end_to_end_tile(dm, img1, img2, ws, sub_pix):
     co = dm.Correlation_map(img1, img2, window_size=ws)
     co()
@@ -424,7 +455,7 @@ def test_image_cut_solver_vs_reference(dm, name):
     s2.log_flg = False
     s2._cut_and_pool()
     s2._execute_matching_per_tile(list(d.shape[1:]))
-    assert np.array_equal(s2.d_map, d) and np.array_equal(s2.out_map, sc)
+    _same_up_to_accumulation_rounding(s2.d_map, s2.out_map, d, sc, exact=not s.info.used_fused)
 
 
 @pytest.mark.parametrize('shape,size,stride,ws,sub', [((96, 96), 16, 12, 5, True), ((200, 168), 32, 30, 5, True),
@@ -491,40 +522,54 @@ def test_fused_path_flat_patch_nan(dm):
 
 
 def test_descriptor_kernels_agree(dm):
-    """The 8-patches-per-group descriptor kernel and the generic one write identical rows/stats."""
+    """The 8-patches-per-group descriptor kernel and the generic one write identical rows/stats, on
+    both sides (patch image: the correction entries hold S'; search image: the three bf16 parts of
+    -S'/K), and the rows match numpy."""
     import torch
     from deepmatching_stereo_matching_b200 import _native
     from deepmatching_stereo_matching_b200.synth import texture
     lib = _native.lib()
     for ws in (3, 5, 7, 9, 11, 13, 15):
         e2 = ws - 1
-        for (t0, t1) in ((8, 16), (4, 12)):           # t1 % 8 == 0 -> row kernel, else generic
-            pass
         sc = torch.from_numpy(texture((40 + e2, 60 + e2), seed=ws)).cuda()
         H, W = sc.shape
         origin = torch.tensor([[3, 5], [7, 20]], dtype=torch.int32, device='cuda')
         kpad = lib.dm_kpad(ws)
-        out = []
-        for (t0, t1, ox) in ((8, 16, 0), (8, 12, 0)):
-            desc = torch.zeros((2 * t0 * t1, kpad), dtype=torch.bfloat16, device='cuda')
-            stat = torch.zeros((2 * t0 * t1 * 6,), dtype=torch.float32, device='cuda')
-            _native.check(lib.dm_descriptors(_native.ptr(sc), H, W, W, _native.ptr(origin), 2, t0, t1, ws,
-                                             _native.ptr(desc), _native.ptr(stat), _native.stream_ptr()))
-            out.append((desc.float().cpu().numpy().reshape(2, t0, t1, kpad), stat[:2 * t0 * t1 * 4].cpu().numpy().reshape(2, t0, t1, 4)))
-        (da, sa), (db, sb) = out
-        assert np.array_equal(da[:, :, :12], db) and np.array_equal(sa[:, :, :12], sb)
-        # and against numpy: centred window values in the k = ky*rstride + kx layout
-        img = sc.cpu().numpy().astype(np.int64)
         rstr = 8 if ws <= 8 else 16
-        for (n, i, j) in ((0, 0, 0), (1, 7, 11), (0, 3, 9)):
-            oy, ox = origin[n].tolist()
-            win = img[oy + i:oy + i + ws, ox + j:ox + j + ws]
-            mean = (2 * win.sum() + ws * ws) // (2 * ws * ws)
-            exp = np.zeros(kpad)
-            for ky in range(ws):
-                exp[ky * rstr:ky * rstr + ws] = win[ky] - mean
-            assert np.array_equal(db[n, i, j], exp)
-            assert sb[n, i, j, 3] == mean and sb[n, i, j, 0] == (win - mean).sum()
+        slots = [ky * rstr + kx for ky in range(ws) for kx in range(ws, rstr)][:3]
+        for side in (1, 2, 0):
+            out = []
+            for (t0, t1) in ((8, 16), (8, 12)):           # t1 % 8 == 0 -> row kernel, else generic
+                desc = torch.zeros((2 * t0 * t1, kpad), dtype=torch.bfloat16, device='cuda')
+                stat = torch.zeros((2 * t0 * t1 * 6,), dtype=torch.float32, device='cuda')
+                _native.check(lib.dm_descriptors(_native.ptr(sc), H, W, W, _native.ptr(origin), 2, t0, t1, ws, side,
+                                                 _native.ptr(desc), _native.ptr(stat), _native.stream_ptr()))
+                st = stat.cpu().numpy()
+                inv_table = st[2 * t0 * t1 * 4:2 * t0 * t1 * 5].reshape(2, t0, t1)
+                out.append((desc.float().cpu().numpy().reshape(2, t0, t1, kpad), st[:2 * t0 * t1 * 4].reshape(2, t0, t1, 4), inv_table))
+            (da, sa, ia), (db, sb, ib) = out
+            assert np.array_equal(da[:, :, :12], db) and np.array_equal(sa[:, :, :12], sb) and np.array_equal(ia[:, :, :12], ib)
+            assert np.array_equal(ib, sb[..., 1])             # the compact column table is inv
+            # and against numpy: centred window values in the k = ky*rstride + kx layout
+            img = sc.cpu().numpy().astype(np.int64)
+            for (n, i, j) in ((0, 0, 0), (1, 7, 11), (0, 3, 9)):
+                oy, ox = origin[n].tolist()
+                win = img[oy + i:oy + i + ws, ox + j:ox + j + ws]
+                mean = (2 * win.sum() + ws * ws) // (2 * ws * ws)
+                exp = np.zeros(kpad)
+                for ky in range(ws):
+                    exp[ky * rstr:ky * rstr + ws] = win[ky] - mean
+                rs = int((win - mean).sum())
+                got = db[n, i, j].copy()
+                if side == 1:
+                    assert all(got[k] == rs for k in slots)
+                elif side == 2:
+                    c = -np.float32(rs) / np.float32(ws * ws)
+                    assert np.float32(got[slots[0]]) + np.float32(got[slots[1]]) + np.float32(got[slots[2]]) == c
+                    assert abs(got[slots[1]]) <= abs(c) * 2.0 ** -8 + 1e-30 and abs(got[slots[2]]) <= abs(c) * 2.0 ** -16 + 1e-30
+                got[slots] = 0
+                assert np.array_equal(got, exp)
+                assert sb[n, i, j, 3] == mean and sb[n, i, j, 0] == rs
 
 
 def test_oracle_tile_t64_ws15(dm):

@@ -13,10 +13,10 @@ H = W = max(1024, t0 + ws + 60 * 15)
 s1 = torch.from_numpy(texture((H, W), seed=1)).cuda(); s2 = torch.from_numpy(texture((H, W), seed=2)).cuda()
 origin = torch.tensor([[60 * ((k % 225) // 15), 60 * (k % 15)] for k in range(n)], dtype=torch.int32, device='cuda')
 bufs = []
-for sc in (s1, s2):
+for side, sc in ((1, s1), (2, s2)):
     desc = torch.empty((n * P, kpad), dtype=torch.bfloat16, device='cuda')
     stat = torch.empty((n * P * 6,), dtype=torch.float32, device='cuda')
-    _native.check(lib.dm_descriptors(_native.ptr(sc), H, W, W, _native.ptr(origin), n, t0, t1, ws, _native.ptr(desc), _native.ptr(stat), _native.stream_ptr()))
+    _native.check(lib.dm_descriptors(_native.ptr(sc), H, W, W, _native.ptr(origin), n, t0, t1, ws, side, _native.ptr(desc), _native.ptr(stat), _native.stream_ptr()))
     bufs += [desc, stat]
 raw = torch.empty((n * P * (P // 4) + 8 * n * P,), dtype=torch.float32, device='cuda')
 for engine in engines:

@@ -11,9 +11,9 @@ s1 = torch.from_numpy(texture((H, W), seed=31)).cuda(); s2 = torch.from_numpy(te
 origin = torch.tensor([[k % 9, 11 * k] for k in range(n)], dtype=torch.int32, device='cuda')
 P, kpad = T * T, lib.dm_kpad(ws)
 b = []
-for sc in (s1, s2):
+for side, sc in ((1, s1), (2, s2)):
     desc = torch.zeros((n * P, kpad), dtype=torch.bfloat16, device='cuda'); stat = torch.zeros((n * P * 6,), dtype=torch.float32, device='cuda')
-    _native.check(lib.dm_descriptors(_native.ptr(sc), H, W, W, _native.ptr(origin), n, T, T, ws, _native.ptr(desc), _native.ptr(stat), _native.stream_ptr()))
+    _native.check(lib.dm_descriptors(_native.ptr(sc), H, W, W, _native.ptr(origin), n, T, T, ws, side, _native.ptr(desc), _native.ptr(stat), _native.stream_ptr()))
     b += [desc, stat]
 ref = torch.empty((n, P, P), dtype=torch.float32, device='cuda')
 _native.check(lib.dm_correlation(*[_native.ptr(x) for x in b], n, P, kpad, ws, 5, 1, _native.ptr(ref), _native.stream_ptr()))

@@ -14,10 +14,10 @@ for (T, ws, n) in [(32, 5, 20), (32, 7, 6), (64, 15, 9), (16, 5, 36), (64, 5, 7)
     P, kpad = T * T, lib.dm_kpad(ws)
     def descs():
         out = []
-        for sc in (s1, s2):
+        for side, sc in ((1, s1), (2, s2)):
             desc = torch.full((n * P, kpad), 7.0, dtype=torch.bfloat16, device='cuda')
             stat = torch.full((n * P * 6,), 7.0, dtype=torch.float32, device='cuda')
-            _native.check(lib.dm_descriptors(_native.ptr(sc), H, W, W, _native.ptr(origin), n, T, T, ws, _native.ptr(desc), _native.ptr(stat), _native.stream_ptr()))
+            _native.check(lib.dm_descriptors(_native.ptr(sc), H, W, W, _native.ptr(origin), n, T, T, ws, side, _native.ptr(desc), _native.ptr(stat), _native.stream_ptr()))
             out += [desc, stat]
         return out
     b0 = descs()
