@@ -125,6 +125,22 @@ dm_descriptor_row_kernel(const uint8_t* __restrict__ scene, int pitch,
     constexpr int RSTR = WS <= 8 ? 8 : 16;
     constexpr int KPAD = ((WS * RSTR + 63) / 64) * 64;
     constexpr int LPG = RSTR == 16 ? 32 : 8;                          // lanes per group
+    // correction slots (dm_desc_slots): S' is an integer in [-K/2, K/2], so the three bf16 parts of -S'/K
+    // (side 2) come from a table of K + 1 entries built once per CTA
+    // Small windows (rstride 8: one lane per window row, the three slots in one lane) take the slot values
+    // inside the row stores; large ones (two lanes per row, the slots in three lanes) are cheaper with three
+    // 2-byte stores per patch after the loop (measured: ws 5 1.14 -> 0.94 ms on 64 x 512^2, ws 15 0.187 vs 0.208 ms).
+    constexpr int NF = RSTR - WS;                                     // unused entries per window row
+    constexpr bool SLOT_IN_LOOP = RSTR == 8;
+    __shared__ float slot_tab[3][SLOT_IN_LOOP ? K / 2 * 2 + 2 : 1];
+    if (SLOT_IN_LOOP && side == 2) {
+        for (int idx = threadIdx.x; idx <= K / 2 * 2; idx += blockDim.x) {
+            float part[3];
+            dm_split3(-__fdiv_rn((float)(idx - K / 2), (float)K), part);
+            slot_tab[0][idx] = part[0]; slot_tab[1][idx] = part[1]; slot_tab[2][idx] = part[2];
+        }
+        __syncthreads();
+    }
     constexpr int GPW = 32 / LPG;                                     // groups per warp
     const int lane = threadIdx.x & 31, gl = lane % LPG;
     const unsigned gmask = LPG == 32 ? 0xffffffffu : (0xffu << (lane & ~7));
@@ -193,6 +209,19 @@ dm_descriptor_row_kernel(const uint8_t* __restrict__ scene, int pitch,
             f[5] = __uint_as_float(__byte_perm(h2, 0x4B000000u, 0x7651)) - off;
             f[6] = __uint_as_float(__byte_perm(h2, 0x4B000000u, 0x7652)) - off;
             f[7] = __uint_as_float(__byte_perm(h2, 0x4B000000u, 0x7653)) - off;
+            if (SLOT_IN_LOOP && side != 0) {
+                const int rs = S - K * mean;                        // |rs| <= K/2
+#pragma unroll
+                for (int j = 0; j < 3; ++j) {
+                    constexpr int dummy = 0; (void)dummy;
+                    const int sky = j / NF, skx = WS + j % NF;      // the j-th unused entry in (ky, kx) order
+                    if (ky == sky && hf == skx / 8) {
+                        const float sv = side == 1 ? (float)rs : slot_tab[j][rs + K / 2];
+#pragma unroll
+                        for (int u = 0; u < 8; ++u) if (u == skx % 8) f[u] = sv;
+                    }
+                }
+            }
             __nv_bfloat162 b0 = __floats2bfloat162_rn(f[0], f[1]), b1 = __floats2bfloat162_rn(f[2], f[3]);
             __nv_bfloat162 b2 = __floats2bfloat162_rn(f[4], f[5]), b3 = __floats2bfloat162_rn(f[6], f[7]);
             uint4 pk;
@@ -204,12 +233,10 @@ dm_descriptor_row_kernel(const uint8_t* __restrict__ scene, int pitch,
     }
     // the statistics (a division, a square root and a reciprocal, ~60 instructions) once for the
     // eight patches in parallel instead of once per patch behind a one-lane branch
-    __syncwarp();                       // the slot stores below overwrite zeros other lanes of the group have just stored
+    if (!SLOT_IN_LOOP) __syncwarp();    // the slot stores below overwrite zeros other lanes of the group have just stored
     if (live && gl < 8) {
         dm_write_stats(stat, n_patches, p0 + gl, K, myS, myQ, myMean);
-        // correction slots (dm_desc_slots; zero so far): three 2-byte stores per patch, by the same eight lanes
-        if (side != 0) {
-            constexpr int NF = RSTR - WS;                           // unused entries per window row
+        if (!SLOT_IN_LOOP && side != 0) {
             const int rs = myS - K * myMean;
             float part[3] = {(float)rs, (float)rs, (float)rs};
             if (side == 2) dm_split3(-__fdiv_rn((float)rs, (float)K), part);

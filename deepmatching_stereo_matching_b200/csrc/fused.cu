@@ -135,6 +135,7 @@ struct FinalArgs {
     const uint8_t* img1; const uint8_t* img2; int pitch;
     const int32_t* origin; const int32_t* tinfo; const dm_stat* stat1; const dm_stat* stat2;
     dm_fastdiv fd_pq, fd_hb, fd_s0, fd_s1;     // divisors PQ = (t0/2)(t1/2), t1/2, s0, s1
+    dm_fastdiv fd_p, fd_t1;                    // divisors P = t0 t1, t1 (patch-per-thread kernel)
     const float* rowmin; const float* rowmax;
     const int32_t* parent;      // level-1 matches [n][2][t0/2][t1/2]
     int t0, t1, ws, normed, sub_pix, scene_h;
@@ -465,6 +466,142 @@ dm_final_quad_kernel(const FinalArgs a, long long n_quads) {
     a.out_map[(size_t)sc * plane + pix] = (double)score;
 }
 
+// ---------------------------------------------------------------------------------------
+// Final level, one THREAD per patch (round 2).  The warp-per-quad kernel above spends ~1300 warp
+// instructions per quad (7300 thread instructions per patch at ws 15, the same at ws 5) on staging,
+// shuffles and reductions around 13 window correlations that are 13 x ws x ceil(ws/4) DP4As.  Here a
+// thread keeps its own patch in registers (ws rows of packed bytes, fetched as aligned 32-bit words +
+// one funnel shift each) and walks every candidate window of image 2 the same way: no shared memory,
+// no shuffles, no reductions; neighbouring threads are neighbouring patches, so their loads fall into
+// the same cache lines and their plane stores are contiguous.  Same arithmetic, same order of the
+// comparisons: bit-identical to the kernel above (tests/test_gpu_parity.py).
+// misc/Matching.py:58-78,98-139,165-209 + misc/Calc_difference.py:36-48 + the paste of
+// misc/image_cut_solver.py:165-175.
+// ---------------------------------------------------------------------------------------
+template <int WS>
+__global__ void __launch_bounds__(128)
+dm_final_patch_kernel(const FinalArgs a, long long n_patches) {
+    constexpr int K = WS * WS;
+    constexpr int NW = (WS + 3) / 4;                       // packed words per window row
+    constexpr uint32_t LASTMASK = (WS % 4) ? ((1u << (8 * (WS % 4))) - 1u) : 0xffffffffu;
+    const long long tl = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (tl >= n_patches) return;
+    const uint32_t t = (uint32_t)tl;                       // a launch starts at a tile boundary and never holds 2^32 patches
+    const int T0 = a.t0, T1 = a.t1, P = T0 * T1;
+    const uint32_t nrel = dm_fd_div(t, a.fd_p);
+    const int n = a.tile0 + (int)nrel;                     // tile inside the chunk
+    const int p = (int)(t - nrel * (uint32_t)P);
+    const int i = (int)dm_fd_div((uint32_t)p, a.fd_t1), j = p - i * T1;
+    const int4 ti = __ldg(reinterpret_cast<const int4*>(a.tinfo) + n);      // (gi, gj, scene, -)
+    const int gi = ti.x, gj = ti.y, sc = ti.z;
+    // misc/image_cut_solver.py:165-175: a pixel belongs to the covering tile with the largest index
+    if (min(gi + (int)dm_fd_div((uint32_t)i, a.fd_s0), a.len0 - 1) != gi || min(gj + (int)dm_fd_div((uint32_t)j, a.fd_s1), a.len1 - 1) != gj) return;
+    const int oy = a.origin[2 * n], ox = a.origin[2 * n + 1];
+    const bool normed = a.normed != 0;
+    const int hA = T0 >> 1, hB = T1 >> 1, PQ = hA * hB;
+    // misc/Matching.py:116-124: p_dot = 2 * parent match + o
+    const int pq = (i >> 1) * hB + (j >> 1);
+    const size_t pb = (size_t)n * 2 * PQ;
+    const int d0 = 2 * a.parent[pb + pq] + (i & 1), d1 = 2 * a.parent[pb + PQ + pq] + (j & 1);
+
+    const dm_stat s1 = a.stat1[(size_t)n * P + p];
+    const bool flat1 = (s1.y == 0.0f);
+    const float4 pmn = reinterpret_cast<const float4*>(a.rowmin)[(size_t)n * P + p], pmx = reinterpret_cast<const float4*>(a.rowmax)[(size_t)n * P + p];
+    const float mn = dm_min_nan(dm_min_nan(pmn.x, pmn.y), dm_min_nan(pmn.z, pmn.w));
+    const float mx = dm_max_nan(dm_max_nan(pmx.x, pmx.y), dm_max_nan(pmx.z, pmx.w)), rinv = dm_range_inv(mn, mx);
+    const dm_stat* st2 = a.stat2 + (size_t)n * P;
+    const int m1 = (int)s1.w, S1 = (int)s1.x;
+
+    // WS bytes starting at `src` as NW packed words: aligned 32-bit loads (only words that hold a needed
+    // byte) + funnel shifts, bytes beyond the window masked off
+    auto load_row = [&](const uint8_t* src, uint32_t (&out)[NW]) {
+        const uintptr_t addr = reinterpret_cast<uintptr_t>(src);
+        const uint32_t* ap = reinterpret_cast<const uint32_t*>(addr & ~(uintptr_t)3);
+        const int off = (int)(addr & 3);
+        uint32_t w[NW + 1];
+#pragma unroll
+        for (int k = 0; k <= NW; ++k) w[k] = (4 * k < off + WS) ? __ldg(ap + k) : 0u;
+#pragma unroll
+        for (int k = 0; k < NW; ++k) out[k] = __funnelshift_r(w[k], w[k + 1], 8 * off);
+        out[NW - 1] &= LASTMASK;
+    };
+    uint32_t aw[WS][NW];                                   // this thread's patch
+    {
+        const uint8_t* b1 = a.img1 + (size_t)(oy + i) * a.pitch + ox + j;
+#pragma unroll
+        for (int ky = 0; ky < WS; ++ky) load_row(b1 + (size_t)ky * a.pitch, aw[ky]);
+    }
+    // min-maxed (not yet rectified) co_map value of position (qy,qx): exact integer sum a*b over the window,
+    // then the same formula as everywhere else (see dm_final_quad_kernel::value_at)
+    auto value_at = [&](int qy, int qx) -> float {
+        const uint8_t* b2 = a.img2 + (size_t)(oy + qy) * a.pitch + ox + qx;
+        uint32_t acc = 0;
+#pragma unroll
+        for (int ky = 0; ky < WS; ++ky) {
+            uint32_t bw[NW];
+            load_row(b2 + (size_t)ky * a.pitch, bw);
+#pragma unroll
+            for (int k = 0; k < NW; ++k) acc = __dp4a(aw[ky][k], bw[k], acc);
+        }
+        const dm_stat sq = st2[qy * T1 + qx];
+        const int m2 = (int)sq.w, S2 = (int)sq.x;
+        const int dot = (int)acc - m2 * S1 - m1 * S2 - K * m1 * m2;
+        const float z = dm_zncc_partial((float)dot, s1.x, sq.z, normed ? sq.y : 1.0f);
+        const float r = dm_normalize(dm_zncc_finish(z, s1.y, flat1, normed), mn, mx, rinv);
+        return r < 0.0f ? 0.0f : r;                        // see dm_final_quad_kernel
+    };
+
+    // ---- misc/Matching.py:58-78 on the recomputed 3x3 window (zero padding outside)
+    float best = 0.f, centre = 0.f;
+    int bi = 0;
+    bool best_nan = false;
+#pragma unroll 1
+    for (int s = 0; s < 9; ++s) {
+        const int qy = d0 + s / 3 - 1, qx = d1 + s % 3 - 1;
+        float v = 0.0f;
+        if (qy >= 0 && qy < T0 && qx >= 0 && qx < T1) v = value_at(qy, qx);
+        if (s == 4) centre = v;
+        if (s == 0) { best = v; best_nan = (v != v); }
+        else if (!best_nan && (v > best || v != v)) { best = v; bi = s; best_nan = (v != v); }
+    }
+    best = dm_rectify(best); centre = dm_rectify(centre);
+    if (best < DM_NEAR_ZERO_F) { bi = 4; best = centre; }
+    const int c0 = d0 + bi / 3 - 1, c1 = d1 + bi % 3 - 1;
+    const float score = best + centre;
+
+    // ---- misc/Matching.py:165-209 parabola fit (index -1 wraps, upper edge skipped)
+    double mrow = (double)c0, mcol = (double)c1;
+    if (a.sub_pix) {
+        const bool in = c0 >= 0 && c0 < T0 && c1 >= 0 && c1 < T1;
+        const float r0 = best;
+        if (in && c0 + 1 < T0) {
+            const float v0 = dm_rectify(value_at(c0 + 1, c1)), v1 = dm_rectify(value_at(c0 == 0 ? T0 - 1 : c0 - 1, c1));
+            if (r0 > v0 && r0 > v1) mrow += dm_parabola_shift(r0, v0, v1);
+        }
+        if (in && c1 + 1 < T1) {
+            const float v2 = dm_rectify(value_at(c0, c1 + 1)), v3 = dm_rectify(value_at(c0, c1 == 0 ? T1 - 1 : c1 - 1));
+            if (r0 > v2 && r0 > v3) mcol += dm_parabola_shift(r0, v2, v3);
+        }
+    }
+
+    // ---- planes + paste (misc/Calc_difference.py:36-48, misc/image_cut_solver.py:165-175)
+    const int Y = a.s0 * gi + i, X = a.s1 * gj + j;
+    const double e0 = __dsub_rn((double)i, mrow), e1 = __dsub_rn((double)j, mcol);
+    const size_t plane = (size_t)a.out_h * a.out_w, pix = (size_t)Y * a.out_w + X;
+    for (int m = 0; m < a.n_modes; ++m) {
+        const double v = a.modes[m] == DM_MODE_ELEVATION ? e1
+                       : a.modes[m] == DM_MODE_ELEVATION2 ? e0
+                       : __dsqrt_rn(__fma_rn(e1, e1, __dmul_rn(e0, e0)));
+        a.d_map[((size_t)sc * a.n_modes + m) * plane + pix] = v;
+    }
+    a.out_map[(size_t)sc * plane + pix] = (double)score;
+}
+
+template <int WS>
+static void launch_final_patch(const FinalArgs& fa, long long n_patches, cudaStream_t st) {
+    dm_final_patch_kernel<WS><<<dm_div_up(n_patches, 128), 128, 0, st>>>(fa, n_patches);
+}
+
 template <int WS>
 static void launch_final_quad(const FinalArgs& fa, long long n_quads, cudaStream_t st) {
     dm_final_quad_kernel<WS><<<dm_div_up(n_quads, FQ_WARPS), 32 * FQ_WARPS, 0, st>>>(fa, n_quads);
@@ -631,6 +768,7 @@ int dm_fused_solve_chunk(dm_ctx* ctx, const dm_fused_args* a, int ck) {
         fa.origin = fb.origin; fa.tinfo = fb.tinfo;
         fa.fd_pq = dm_make_fastdiv((uint32_t)(P / 4)); fa.fd_hb = dm_make_fastdiv((uint32_t)(t1 >> 1));
         fa.fd_s0 = dm_make_fastdiv((uint32_t)a->s0); fa.fd_s1 = dm_make_fastdiv((uint32_t)a->s1);
+        fa.fd_p = dm_make_fastdiv((uint32_t)P); fa.fd_t1 = dm_make_fastdiv((uint32_t)t1);
         fa.stat1 = (const dm_stat*)fb.stat1; fa.stat2 = (const dm_stat*)fb.stat2;
         fa.rowmin = fb.rowmin; fa.rowmax = fb.rowmax; fa.parent = fb.match[cur];
         fa.t0 = t0; fa.t1 = t1; fa.ws = a->ws; fa.normed = a->method == DM_TM_CCOEFF_NORMED; fa.sub_pix = a->sub_pix;
@@ -650,7 +788,18 @@ int dm_fused_solve_chunk(dm_ctx* ctx, const dm_fused_args* a, int ck) {
             if (t_end <= t_begin) continue;
             fa.tile0 = t_begin;
             const long long nq = (long long)(t_end - t_begin) * (P / 4);
-            switch (a->ws) {
+            static const bool per_quad = getenv("DM_FINAL_QUAD") != nullptr;      // measurement aid: the warp-per-quad kernel
+            if (!per_quad) switch (a->ws) {
+                case 3: launch_final_patch<3>(fa, nq * 4, st); break;
+                case 5: launch_final_patch<5>(fa, nq * 4, st); break;
+                case 7: launch_final_patch<7>(fa, nq * 4, st); break;
+                case 9: launch_final_patch<9>(fa, nq * 4, st); break;
+                case 11: launch_final_patch<11>(fa, nq * 4, st); break;
+                case 13: launch_final_patch<13>(fa, nq * 4, st); break;
+                case 15: launch_final_patch<15>(fa, nq * 4, st); break;
+                default: DM_REQUIRE(false, DM_ERR_UNSUPPORTED, "fused path supports odd window sizes 3..15 (got %d)", a->ws);
+            }
+            else switch (a->ws) {
                 case 3: launch_final_quad<3>(fa, nq, st); break;
                 case 5: launch_final_quad<5>(fa, nq, st); break;
                 case 7: launch_final_quad<7>(fa, nq, st); break;

@@ -880,3 +880,50 @@ def test_row_argmax_kernel(dm):
         assert np.array_equal(arg.cpu().numpy(), np.argmax(want_rows, axis=-1))
         _native.check(_native.lib().dm_row_argmax(_native.ptr(dev), n, t0, t1, _native.ptr(arg), None, _native.stream_ptr()))
         assert np.array_equal(arg.cpu().numpy(), np.argmax(want_rows, axis=-1))
+
+
+def test_final_level_kernels_agree(dm, tmp_path):
+    """The final level of the fused path exists twice: one thread per patch (product) and one warp per quad
+    of patches (DM_FINAL_QUAD=1, the round-1 kernel, kept as a measurement aid).  Same arithmetic and the
+    same order of comparisons: the planes must agree bit for bit -- window sizes 3..15, non-square grids,
+    TM_CCOEFF, a flat patch (NaN), with and without the parabola fit.  (The switch is read once per
+    process, so each variant runs in its own interpreter.)"""
+    import os
+    import subprocess
+    import sys
+    code = r'''
+import sys, numpy as np
+sys.path.insert(0, %r)
+import deepmatching_stereo_matching_b200 as dm
+from deepmatching_stereo_matching_b200.synth import stereo_pair
+out = {}
+for k, (shape, size, stride, ws, feat, sub) in enumerate([((200, 264), (32, 32), (30, 30), 15, 'cv2.TM_CCOEFF_NORMED', True),
+                                                         ((150, 230), (16, 64), (12, 50), 3, 'cv2.TM_CCOEFF_NORMED', True),
+                                                         ((120, 120), (16, 16), (14, 14), 5, 'cv2.TM_CCOEFF', True),
+                                                         ((160, 160), (32, 32), (32, 32), 7, 'cv2.TM_CCOEFF_NORMED', False),
+                                                         ((140, 200), (32, 32), (28, 28), 9, 'cv2.TM_CCOEFF_NORMED', True),
+                                                         ((140, 140), (16, 16), (16, 16), 11, 'cv2.TM_CCOEFF_NORMED', True),
+                                                         ((150, 150), (32, 32), (30, 30), 13, 'cv2.TM_CCOEFF_NORMED', True)]):
+    i1, i2 = stereo_pair(shape, seed=40 + k, mode='sine', amp=4)
+    if k == 2:
+        i1 = i1.copy(); i1[30:35, 40:45] = 77           # a flat patch
+    s = dm.ImageCutSolver(i1, i2, image_size=list(size), stride=list(stride), window_size=ws, feature_name=feat,
+                          degree_map_mode=['elevation', 'elevation2', 'distance'], sub_pix=sub)
+    s.log_flg = False; s.fused = 1; s.devices = [0]
+    d, sc = s()
+    assert s.info.used_fused == 1
+    out['d%%d' %% k] = d; out['s%%d' %% k] = sc
+np.savez(sys.argv[1], **out)
+''' % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))),)
+    res = []
+    for name, env in (('patch', {}), ('quad', {'DM_FINAL_QUAD': '1'})):
+        path = str(tmp_path / (name + '.npz'))
+        e = dict(os.environ); e.pop('DM_FINAL_QUAD', None); e.update(env)
+        r = subprocess.run([sys.executable, '-c', code, path], env=e, capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stderr[-2000:]
+        res.append(np.load(path))
+    a, b = res
+    assert sorted(a.files) == sorted(b.files) and len(a.files) == 14
+    assert np.isnan(a['s2']).any()
+    for k in a.files:
+        assert np.array_equal(a[k], b[k], equal_nan=True), k
