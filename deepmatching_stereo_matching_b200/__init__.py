@@ -12,7 +12,8 @@ from .Correlation_map import Correlation_map        # noqa: F401
 from .Matching import Matching                      # noqa: F401
 from .Calc_difference import Calc_difference        # noqa: F401
 from .sub_pix_cal import sub_pix_cal                # noqa: F401
-from .optimize_loop import image_threshold          # noqa: F401
+from .optimize_loop import image_threshold, optimize_loop   # noqa: F401
+from .opt_loop import make_weight, optimize_loop_bilateral_horizon, optimize_loop_bilateral_vertical   # noqa: F401
 from .image_cut_solver import ImageCutSolver        # noqa: F401
 from .raw_read import RawRead                       # noqa: F401
 from .bilateral import bilateral_filter             # noqa: F401

@@ -56,6 +56,9 @@ SIGNATURES = {
     'dm_match_map': (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
     'dm_cal_map': (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
     'dm_sub_pix_cal': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_double, c_void_p, c_void_p]),
+    'dm_optimize_loop': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_double, c_void_p, c_void_p, c_void_p]),
+    'dm_make_weight': (c_int, [c_void_p, c_int, c_int, c_int, c_double, c_double, c_void_p, c_void_p, c_void_p]),
+    'dm_optimize_loop_bilateral': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     'dm_bilateral_u8': (c_int, [c_void_p, c_int, c_int, c_int, c_double, c_double, c_void_p, c_void_p]),
     'dm_ctx_create': (c_int, [POINTER(c_void_p)]),
     'dm_ctx_destroy': (None, [c_void_p]),

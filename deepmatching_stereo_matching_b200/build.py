@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 LIB = os.path.join(HERE, 'libdmstereo.so')
 SOURCES = ['capi.cu', 'descriptors.cu', 'correlation_simt.cu', 'correlation_umma.cu', 'pyramid.cu',
-           'backtrack.cu', 'fused.cu', 'bilateral.cu', 'multi.cu']
+           'backtrack.cu', 'fused.cu', 'bilateral.cu', 'multi.cu', 'gauss_seidel.cu']
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17',
               '-fmad=false',            # contraction off: FMAs are written explicitly where wanted
               '-Xcompiler', '-fPIC', '-Xcompiler', '-O2']

@@ -492,7 +492,11 @@ int launch3(const CUtensorMap& mapA, const CUtensorMap& mapB, const Params& prm,
     }
     // persistent grid of CTA pairs: one 2-CTA cluster per TPC
     const int units = prm.n_items / 2;
-    const int pairs = units < max_pairs ? units : max_pairs;
+    int pairs = units < max_pairs ? units : max_pairs;
+    {   // measurement aid: DM_CORR_MAX_PAIRS caps the persistent grid (the other SMs stay free for a second stream)
+        static const int cap = getenv("DM_CORR_MAX_PAIRS") ? atoi(getenv("DM_CORR_MAX_PAIRS")) : 0;
+        if (cap > 0 && pairs > cap) pairs = cap;
+    }
     cudaLaunchConfig_t cfg = {};
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;

@@ -173,6 +173,22 @@ int dm_sub_pix_cal(const double* arr_dev, const double* co_map_dev, int s0, int 
 int dm_bilateral_u8(const uint8_t* src_dev, int h, int w, int d, double sigma_color, double sigma_space,
                     uint8_t* dst_dev, void* stream);
 
+/* ---------------------------------------------------------------- Gauss-Seidel post-process
+ * The reference's sequential in-place smoothing loops (its `if 0:` branch, optimize_looper.py:55-74), in the
+ * reference's own visiting order: only cells that cannot see each other are computed side by side (anti-diagonals,
+ * lockstep columns, skewed diagonals).  float64, bit-identical to the reference given the same inputs.
+ * All arrays are double (s0, s1) on the device; diff_dev is scratch of s0*s1 doubles; error_dev receives the
+ * sequentially accumulated |old - new| the reference returns.
+ *   dm_optimize_loop            misc/optimize_loop.py:15-37 (clamp to [0,10], forward sweep, "reverse" sweep), in place
+ *   dm_make_weight              misc/opt_loop.py:66-85: gw (w,w), cw (s0-e, s1-e, w, w), w = 2 e + 1 (exp: CUDA's, <= 1 ulp from numpy's)
+ *   dm_optimize_loop_bilateral  misc/opt_loop.py:16-63, horizon (vertical = 0) or vertical (1), in place */
+int dm_optimize_loop(double* img_dev, const double* coef_dev, int s0, int s1, int exclusion, double alpha,
+                     double* diff_dev, double* error_dev, void* stream);
+int dm_make_weight(const double* guide_dev, int s0, int s1, int exclusion, double sigma0, double sigma1,
+                   double* gw_dev, double* cw_dev, void* stream);
+int dm_optimize_loop_bilateral(double* img_dev, const double* cw_dev, const double* gw_dev, const double* coef_dev,
+                               int s0, int s1, int exclusion, int vertical, double* diff_dev, double* error_dev, void* stream);
+
 /* ---------------------------------------------------------------- scene solver -----
  * Replaces ImageCutSolver._cut_and_pool/_solver/_execute_matching
  * (misc/image_cut_solver.py:95-184) for a whole scene or for a strip of tile rows.

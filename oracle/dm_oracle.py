@@ -563,3 +563,113 @@ def raw_read(path, size=(6000, 6000), rate=1):
     """misc/raw_read.py:36-45 -- int8 read, * rate, cast to uint8 (wraps)."""
     c = np.fromfile(path, dtype=np.int8, count=size[0] * size[1]).reshape(1, size[1], size[0])
     return (c * rate)[0].astype(np.uint8)
+
+
+# --------------------------------------------------------------------------------------
+# Gauss-Seidel post-process (the reference's dead `if 0:` branch, optimize_looper.py:55-74)
+# --------------------------------------------------------------------------------------
+def optimize_loop(img_dis, coefficient, alpha, exclusion, size):
+    """misc/optimize_loop.py:15-37 -- clamp to [0, 10], one forward and one backward in-place sweep of
+    d <- (-a d + alpha (left + right + up + down)) / (-a + 4 alpha), a = coefficient[i, j].
+    The reference visits the cells one by one in row-major (then reversed) order; a cell only reads
+    its four neighbours, so all cells of an anti-diagonal i + j = t are independent and the sweep can
+    run diagonal by diagonal -- the order the CUDA kernel uses.  Bit-identical to the sequential loops.
+    Returns (img_dis, error) with error = the sequentially accumulated |old - new| of the backward sweep."""
+    d = image_threshold(np.asarray(img_dis), threshold=[0, 10]).astype(np.float64)
+    co = np.asarray(coefficient, dtype=np.float64)
+    lo0, hi0, lo1, hi1 = exclusion, size[0] - exclusion - 1, exclusion, size[1] - exclusion - 1     # half-open
+    if hi0 <= lo0 or hi1 <= lo1:
+        return d, 0.0
+
+    def update(i, j):
+        sum_d = d[i, j - 1] + d[i, j + 1] + d[i - 1, j] + d[i + 1, j]
+        a = co[i, j]
+        return (-a * d[i, j] + alpha * sum_d) / (-a + 4.0 * alpha)
+
+    for t in range(lo0 + lo1, hi0 + hi1 - 1):
+        i = np.arange(max(lo0, t - (hi1 - 1)), min(hi0 - 1, t - lo1) + 1)
+        d[i, t - i] = update(i, t - i)
+    # "Reverse" sweep (misc/optimize_loop.py:26-36).  The reference flips the indices INSIDE the inner loop:
+    # j is rebound by `for j`, but i keeps its value across inner iterations, so `i = size[0] - i - 1`
+    # flips it on the first inner iteration, flips it BACK on the second, and so on.  Visit k of outer
+    # iteration o therefore is the cell (R - o, C - k) for even k and (lo0 + o, C - k) for odd k
+    # (R = size0 - lo0 - 1, C = size1 - lo1 - 1): even-k columns are walked bottom-up, odd-k columns
+    # top-down.  A cell's vertical neighbours belong to its own column chain; its horizontal neighbours
+    # belong to the other kind of column and were visited at o' = R - lo0 - o -- strictly earlier or later
+    # except at the one step 2 o = R - lo0, where all columns sit on the same row and the visit order along
+    # k decides.  So all columns advance in lockstep over o (independent within a step), and that one
+    # middle row is walked sequentially.
+    R, C = size[0] - lo0 - 1, size[1] - lo1 - 1
+    n0, n1 = hi0 - lo0, hi1 - lo1
+    k = np.arange(n1)
+    cols = C - k
+    diff = np.zeros((n0, n1))
+    for o in range(n0):
+        rows = np.where(k % 2 == 0, R - o, lo0 + o)
+        if 2 * o == R - lo0:
+            for kk in range(n1):
+                new = update(rows[kk], cols[kk])
+                diff[o, kk] = np.abs(d[rows[kk], cols[kk]] - new)
+                d[rows[kk], cols[kk]] = new
+        else:
+            new = update(rows, cols)
+            diff[o] = np.abs(d[rows, cols] - new)
+            d[rows, cols] = new
+    visit = diff.ravel()                                             # the reference's visiting order
+    error = float(np.add.accumulate(visit)[-1]) if visit.size else 0.0
+    return d, error
+
+
+def make_weight(guide_img, exclusion, size, sigma):
+    """misc/opt_loop.py:66-85 -> (gausian_weight (w, w), color_weight_matrix (S0 - e, S1 - e, w, w))."""
+    e = exclusion
+    w = 2 * e + 1
+    g = np.asarray(guide_img, dtype=np.float64)
+    k = np.arange(w) - e
+    gw = np.exp(-((k[:, None] ** 2 + k[None, :] ** 2).astype(np.float64)) / (2.0 * sigma[1] ** 2))
+    cw = np.zeros([size[0] - e, size[1] - e, w, w])
+    from numpy.lib.stride_tricks import sliding_window_view
+    win = sliding_window_view(g, (w, w))                             # win[i - e, j - e] = g[i-e:i+e+1, j-e:j+e+1]
+    n0, n1 = size[0] - 2 * e - 1, size[1] - 2 * e - 1                # cells i in [e, S0 - e - 1)
+    if n0 > 0 and n1 > 0:
+        sub = win[:n0, :n1]
+        c = sub[:, :, e, e][:, :, None, None] - sub
+        cw[:n0, :n1] = np.exp(-1 * c * c / (2.0 * sigma[0] ** 2))
+    return gw, cw
+
+
+def optimize_loop_bilateral(img_dis, color_weight_matrix, gausian_weight, coefficient, alpha, exclusion, size, vertical=False):
+    """misc/opt_loop.py:16-63 (horizon / vertical): in-place sweep of the bilateral-weighted update over
+    the (2e+1)^2 window.  A cell reads every cell of its window, the earlier ones already updated: all
+    cells with the same j + (e + 1) i are independent (the last updated cell a cell needs, (i-1, j+e), lies
+    one step earlier), which is the order used here and by the CUDA kernel.  `a` and `b` use the
+    CONSTANT entries coefficient[e, e], coefficient[e, e +- 1] (or [e +- 1, e]) exactly as the reference does.
+    Returns (img_dis, error)."""
+    e = exclusion
+    d = np.asarray(img_dis, dtype=np.float64)                        # in place, like the reference
+    co = np.asarray(coefficient, dtype=np.float64)
+    gw = np.asarray(gausian_weight, dtype=np.float64)
+    lo0, hi0, lo1, hi1 = e, size[0] - e - 1, e, size[1] - e - 1
+    cp, cm = (co[e + 1, e], co[e - 1, e]) if vertical else (co[e, e + 1], co[e, e - 1])
+    a = -(co[e, e] - (cp + cm) / 2.0)
+    shift = (cp - cm) / 2.0 / (-2.0 * co[e, e] + cp + cm)
+    diff = np.zeros_like(d)
+    off = np.arange(-e, e + 1)
+    for t in range(lo1 + (e + 1) * lo0, (hi1 - 1) + (e + 1) * (hi0 - 1) + 1):
+        i = np.arange(lo0, hi0)
+        j = t - (e + 1) * i
+        ok = (j >= lo1) & (j < hi1)
+        i, j = i[ok], j[ok]
+        if i.size == 0:
+            continue
+        sub = d[(i[:, None] + off[None, :])[:, :, None], (j[:, None] + off[None, :])[:, None, :]]     # (n, w, w)
+        cw = color_weight_matrix[i - e, j - e]
+        b = d[i, j] - shift
+        num = np.array([(gw * cw[k] * sub[k]).sum() for k in range(i.size)])
+        den = np.array([(gw * cw[k]).sum() for k in range(i.size)])
+        new = (-a * b + num) / (-a + den)
+        diff[i, j] = np.abs(d[i, j] - new)
+        d[i, j] = new
+    visit = diff[lo0:hi0, lo1:hi1].ravel()
+    error = float(np.add.accumulate(visit)[-1]) if visit.size else 0.0
+    return d, error

@@ -927,3 +927,56 @@ np.savez(sys.argv[1], **out)
     assert np.isnan(a['s2']).any()
     for k in a.files:
         assert np.array_equal(a[k], b[k], equal_nan=True), k
+
+
+def test_gauss_seidel_loops_bit_exact(dm):
+    """The reference's sequential in-place smoothing loops (its `if 0:` branch, optimize_looper.py:55-74) through the
+    `misc.*` import paths: misc/optimize_loop.py::optimize_loop and misc/opt_loop.py::optimize_loop_bilateral_*
+    against the live reference's outputs -- same bits, including the sequentially accumulated error -- and
+    make_weight within an ulp (CUDA's exp against numpy's)."""
+    from misc.optimize_loop import optimize_loop
+    from misc.opt_loop import make_weight, optimize_loop_bilateral_horizon, optimize_loop_bilateral_vertical
+    g = load_golden('gauss_seidel')
+    size = g['d'].shape
+    for k in range(3):
+        alpha, exclusion, loops = g['ol%d_cfg' % k]
+        x = g['d'].copy()
+        errs = []
+        for _ in range(int(loops)):
+            y, err = optimize_loop(x, g['co'], float(alpha), int(exclusion), size)
+            assert y is not x                        # the reference clamps into a new array
+            x = y
+            errs.append(err)
+        assert np.array_equal(x, g['ol%d_out' % k]), k
+        assert np.array_equal(np.array(errs), g['ol%d_err' % k]), k
+    for k in range(2):
+        s0, s1, exclusion, loops = g['bl%d_cfg' % k]
+        sigma = np.array([int(s0), int(s1)])
+        gw, cw = make_weight(g['d'], int(exclusion), size, sigma)
+        assert gw.shape == g['bl%d_gw' % k].shape and cw.shape == g['bl%d_cw' % k].shape
+        assert np.allclose(gw, g['bl%d_gw' % k], rtol=4e-16, atol=0) and np.allclose(cw, g['bl%d_cw' % k], rtol=4e-16, atol=0)
+        assert np.array_equal(cw == 0, g['bl%d_cw' % k] == 0)
+        for name, fn in (('h', optimize_loop_bilateral_horizon), ('v', optimize_loop_bilateral_vertical)):
+            x = g['d'].copy()
+            errs = []
+            for _ in range(int(loops)):
+                y, err = fn(x, g['bl%d_cw' % k], g['bl%d_gw' % k], g['co'], 0.008, int(exclusion), size)
+                assert y is x                        # in place, like the reference
+                errs.append(err)
+            assert np.array_equal(x, g['bl%d_%s_out' % (k, name)]), (k, name)
+            assert np.array_equal(np.array(errs), g['bl%d_%s_err' % (k, name)]), (k, name)
+            # with the library's own weights: the same to rounding
+            x2, _ = fn(g['d'].copy(), cw, gw, g['co'], 0.008, int(exclusion), size)
+            x3, _ = fn(g['d'].copy(), g['bl%d_cw' % k], g['bl%d_gw' % k], g['co'], 0.008, int(exclusion), size)
+            assert np.allclose(x2, x3, rtol=1e-12, atol=1e-12)
+    # a larger plane against the oracle (a window sum of 13 x 13 = 169 > 128 terms takes numpy's recursive split)
+    rng = np.random.default_rng(3)
+    d = rng.normal(size=(70, 90)) * 2 + 4
+    co = rng.random((70, 90)) + 0.3
+    a, ea = optimize_loop(d, co, 0.01, 2, d.shape)
+    b, eb = O.optimize_loop(d, co, 0.01, 2, d.shape)
+    assert np.array_equal(a, b) and ea == eb
+    gw, cw = O.make_weight(d, 6, d.shape, np.array([3, 4]))
+    a, ea = optimize_loop_bilateral_vertical(d.copy(), cw, gw, co, 0.008, 6, d.shape)
+    b, eb = O.optimize_loop_bilateral(d.copy(), cw, gw, co, 0.008, 6, d.shape, vertical=True)
+    assert np.array_equal(a, b) and ea == eb

@@ -182,3 +182,31 @@ def test_oracle_bilateral_filter_vs_cv2():
             assert np.abs(got.astype(int) - g[k].astype(int)).max() <= 1, k
         n += 1
     assert n == 8
+
+
+def test_gauss_seidel_wavefront_restatement_is_bit_exact():
+    """The reference's sequential in-place Gauss-Seidel loops (misc/optimize_loop.py:15-37,
+    misc/opt_loop.py:16-85) restated diagonal by diagonal: same bits as the live reference, including
+    the sequentially accumulated error."""
+    g = load_golden('gauss_seidel')
+    size = g['d'].shape
+    for k in range(3):
+        alpha, exclusion, loops = g['ol%d_cfg' % k]
+        x = g['d'].copy()
+        errs = []
+        for _ in range(int(loops)):
+            x, err = O.optimize_loop(x, g['co'], float(alpha), int(exclusion), size)
+            errs.append(err)
+        assert np.array_equal(x, g['ol%d_out' % k]) and np.array_equal(np.array(errs), g['ol%d_err' % k])
+    for k in range(2):
+        s0, s1, exclusion, loops = g['bl%d_cfg' % k]
+        gw, cw = O.make_weight(g['d'], int(exclusion), size, np.array([int(s0), int(s1)]))
+        assert np.array_equal(gw, g['bl%d_gw' % k]) and np.array_equal(cw, g['bl%d_cw' % k])
+        for name, vertical in (('h', False), ('v', True)):
+            x = g['d'].copy()
+            errs = []
+            for _ in range(int(loops)):
+                x, err = O.optimize_loop_bilateral(x, cw, gw, g['co'], 0.008, int(exclusion), size, vertical=vertical)
+                errs.append(err)
+            assert np.array_equal(x, g['bl%d_%s_out' % (k, name)]), (k, name)
+            assert np.array_equal(np.array(errs), g['bl%d_%s_err' % (k, name)]), (k, name)
