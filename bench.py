@@ -667,7 +667,7 @@ def run_ours(args):
         kern_name = {'descriptors': 'dm_descriptor_row_kernel', 'correlation': 'dm_correlation_umma_kernel',
                      'normalize': 'dm_aggregate_first_kernel' if fused else 'dm_minmax_rectify_kernel',
                      'aggregate': 'dm_aggregate_kernel', 'backtrack': 'dm_upper_tail_kernel' if fused else 'dm_backtrack_kernel',
-                     'planes': 'dm_final_quad_kernel' if fused else 'dm_planes_kernel'}
+                     'planes': 'dm_final_patch_kernel' if fused else 'dm_planes_kernel'}
         traffic = {}
         tp = os.path.join(REPO, 'profiles', 'ncu_traffic.json')       # dram bytes per launch from ncu --set full (C2 only)
         if os.path.exists(tp) and name == 'c2':
