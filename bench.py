@@ -549,6 +549,7 @@ def run_ours(args):
     if B == 1 and world > 1:
         mosaic = SharedHostMosaic((solver.n_planes, solver.out_h, solver.out_w), np.float64)
     e2e_counter = [0]
+    e2e_stamps = []          # N > 1: per step (this rank's own upload + solve + copies, then waiting for the slowest rank)
 
     def e2e_step():
         if B == 1 and world == 1:
@@ -559,9 +560,12 @@ def run_ours(args):
             return s()
         if B == 1:
             e2e_counter[0] += 1
+            ta_ = time.perf_counter()
             solver.solve_host_into(h1, h2, mosaic)   # upload of the strip's rows, solve, finished rows streamed into the shared host mosaic
+            tb_ = time.perf_counter()
             mosaic.publish(e2e_counter[0])
             mosaic.wait(e2e_counter[0])              # the whole mosaic has landed
+            e2e_stamps.append((tb_ - ta_, time.perf_counter() - tb_))
             return mosaic.array
         dm_, om_ = solve_batch(h1[p_lo:p_hi], h2[p_lo:p_hi], image_size=[T, T], stride=[STRIDE, STRIDE], window_size=WS,
                                degree_map_mode=MODES, sub_pix=SUB_PIX, fused=args.fused, devices=[local_rank])
@@ -580,6 +584,17 @@ def run_ours(args):
     barrier()
     e2e_s = max_over_ranks(time.perf_counter() - t0)
     e2e = {'value': out_px * e2e_steps / 1e6 / e2e_s, 'unit': 'MP/s', 'steps': e2e_steps, 'ms_per_step': 1e3 * e2e_s / e2e_steps}
+    if world > 1 and B == 1:
+        # where an end-to-end step goes: every rank's own part (upload + solve + streamed copies) and its wait for the
+        # slowest rank, over the timed steps -- event stamps instead of a profiler timeline
+        own = float(np.mean([x[0] for x in e2e_stamps[-e2e_steps:]])) * 1e3
+        wait = float(np.mean([x[1] for x in e2e_stamps[-e2e_steps:]])) * 1e3
+        allv = [None] * world
+        dist.all_gather_object(allv, (own, wait, int(solver.tiles[1] - solver.tiles[0])))
+        if rank == 0:
+            e2e['timeline_ms'] = {'own_part_per_rank': [round(v[0], 3) for v in allv], 'wait_for_slowest_per_rank': [round(v[1], 3) for v in allv],
+                                  'tiles_per_rank': [v[2] for v in allv],
+                                  'reading': 'a step lasts max(own part) + the flag round; ranks that finish early wait'}
     if B == 1:
         rows_in = [input_rows(l // len1, (h - 1) // len1 + 1, STRIDE, T, WS) for (l, h) in solver.tile_parts if h > l]
         e2e['h2d_bytes_per_step'] = int(sum(2 * (bb - aa) * c['shape'][1] for aa, bb in rows_in))

@@ -59,6 +59,7 @@ SIGNATURES = {
     'dm_optimize_loop': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_double, c_void_p, c_void_p, c_void_p]),
     'dm_make_weight': (c_int, [c_void_p, c_int, c_int, c_int, c_double, c_double, c_void_p, c_void_p, c_void_p]),
     'dm_optimize_loop_bilateral': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    'dm_sub_pix_cal_host_batch': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, POINTER(c_int32), c_double, c_void_p]),
     'dm_bilateral_u8': (c_int, [c_void_p, c_int, c_int, c_int, c_double, c_double, c_void_p, c_void_p]),
     'dm_ctx_create': (c_int, [POINTER(c_void_p)]),
     'dm_ctx_destroy': (None, [c_void_p]),
@@ -211,6 +212,12 @@ class Context(object):
     def set_workspace_limit(self, nbytes):
         check(lib().dm_ctx_set_workspace_limit(self._h, int(nbytes)))
 
+    def sub_pix_cal_host_batch(self, d_maps_np, co_maps_np, directions, ratio, out_np):
+        n, n_planes, s0, s1 = d_maps_np.shape
+        dirs = (c_int32 * n_planes)(*[int(d) for d in directions])
+        check(lib().dm_sub_pix_cal_host_batch(self._h, c_void_p(d_maps_np.ctypes.data), c_void_p(co_maps_np.ctypes.data), int(n), int(n_planes),
+                                              int(s0), int(s1), dirs, float(ratio), c_void_p(out_np.ctypes.data)))
+
     def stage_ms(self):
         ms = (c_float * len(STAGES))()
         ln = (c_int * len(STAGES))()
@@ -239,6 +246,19 @@ class Context(object):
         return info
 
 
+_CTX = {}
+
+
+def current_context():
+    """One dm_ctx (workspace, staging buffers) per CUDA device of this process, for the current device."""
+    torch = require_cuda()
+    dev = torch.cuda.current_device()
+    if dev not in _CTX:
+        _CTX[dev] = Context(workspace_limit=WORKSPACE_LIMIT[0])
+    return _CTX[dev]
+
+
+WORKSPACE_LIMIT = [None]
 GATHER_P2P, GATHER_NCCL = 0, 1
 
 

@@ -83,6 +83,8 @@ extern "C" void dm_ctx_destroy(dm_ctx* ctx) {
     for (auto e : ctx->band_ev) cudaEventDestroy(e);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     if (ctx->h2d_stream) cudaStreamDestroy(ctx->h2d_stream);
+    for (int k = 0; k < 2; ++k) if (ctx->sp_stream[k]) cudaStreamDestroy(ctx->sp_stream[k]);
+    cudaFree(ctx->sp_buf);
     if (ctx->up_ev) cudaEventDestroy(ctx->up_ev);
     for (auto& g : ctx->upper_graphs) cudaGraphExecDestroy(g.exec);
     if (ctx->capture_stream) cudaStreamDestroy(ctx->capture_stream);
@@ -683,4 +685,50 @@ extern "C" int dm_solve_scene_stream(dm_ctx* ctx, const dm_scene_params* prm,
     if (rc != DM_OK) return rc;
     if (info_out) *info_out = info;
     return DM_OK;
+}
+
+// sub_pix_cal (misc/sub_pix_cal.py:22-53) for a batch of planes in HOST memory (config 4: 64 pairs, two planes
+// each).  The batch goes through the device in pieces on two streams, each with its own staging slot: the upload
+// of piece k+1, the kernels of piece k and the download of piece k-1 share the PCIe link in both directions.
+extern "C" int dm_sub_pix_cal_host_batch(dm_ctx* ctx, const double* d_maps_host, const double* co_maps_host, int n, int n_planes,
+                                         int s0, int s1, const int32_t* directions, double ratio, double* out_host) {
+    DM_REQUIRE(ctx && d_maps_host && co_maps_host && out_host && directions && n > 0 && n_planes > 0 && s0 > 0 && s1 > 0,
+               DM_ERR_INVALID, "dm_sub_pix_cal_host_batch: bad arguments");
+    for (int m = 0; m < n_planes; ++m)
+        DM_REQUIRE(directions[m] == 0 || directions[m] == 1, DM_ERR_INVALID, "dm_sub_pix_cal_host_batch: direction %d", directions[m]);
+    const size_t plane = (size_t)s0 * s1;
+    int piece = (int)((((size_t)8 << 20) + plane * sizeof(double) - 1) / (plane * sizeof(double)));      // ~8 MB of scores per piece
+    if (piece > n) piece = n;
+    if (piece * 8 > n && n >= 8) piece = n / 8;                 // at least eight pieces in flight over the two streams
+    if (piece < 1) piece = 1;
+    const size_t slot = (size_t)piece * (2 * n_planes + 1) * plane;         // doubles: planes in, scores in, planes out
+    if (2 * slot * sizeof(double) > ctx->sp_bytes) {
+        for (int k = 0; k < 2; ++k) if (ctx->sp_stream[k]) DM_CUDA_CHECK(cudaStreamSynchronize(ctx->sp_stream[k]));
+        cudaFree(ctx->sp_buf); ctx->sp_buf = nullptr; ctx->sp_bytes = 0;
+        DM_CUDA_CHECK(cudaMalloc(&ctx->sp_buf, 2 * slot * sizeof(double)));
+        ctx->sp_bytes = 2 * slot * sizeof(double);
+    }
+    for (int k = 0; k < 2; ++k)
+        if (!ctx->sp_stream[k]) DM_CUDA_CHECK(cudaStreamCreateWithFlags(&ctx->sp_stream[k], cudaStreamNonBlocking));
+    int rc = DM_OK;
+    for (int b0 = 0, k = 0; b0 < n && rc == DM_OK; b0 += piece, ++k) {
+        const int nb = b0 + piece <= n ? piece : n - b0;
+        cudaStream_t st = ctx->sp_stream[k & 1];
+        double* din = ctx->sp_buf + (size_t)(k & 1) * slot;
+        double* cin = din + (size_t)piece * n_planes * plane;
+        double* dout = cin + (size_t)piece * plane;
+        DM_CUDA_CHECK(cudaMemcpyAsync(din, d_maps_host + (size_t)b0 * n_planes * plane, (size_t)nb * n_planes * plane * sizeof(double), cudaMemcpyHostToDevice, st));
+        DM_CUDA_CHECK(cudaMemcpyAsync(cin, co_maps_host + (size_t)b0 * plane, (size_t)nb * plane * sizeof(double), cudaMemcpyHostToDevice, st));
+        for (int b = 0; b < nb && rc == DM_OK; ++b)
+            for (int m = 0; m < n_planes && rc == DM_OK; ++m)
+                rc = dm_sub_pix_cal(din + ((size_t)b * n_planes + m) * plane, cin + (size_t)b * plane, s0, s1, directions[m], ratio,
+                                    dout + ((size_t)b * n_planes + m) * plane, st);
+        if (rc == DM_OK)
+            DM_CUDA_CHECK(cudaMemcpyAsync(out_host + (size_t)b0 * n_planes * plane, dout, (size_t)nb * n_planes * plane * sizeof(double), cudaMemcpyDeviceToHost, st));
+    }
+    for (int k = 0; k < 2; ++k) {
+        cudaError_t e = cudaStreamSynchronize(ctx->sp_stream[k]);
+        if (rc == DM_OK) DM_CUDA_CHECK(e);
+    }
+    return rc;
 }

@@ -70,6 +70,9 @@ struct dm_ctx {
         long long rows_done = 0, row_end = 0;       // stacked scene rows [.., rows_done) are on the device (or on their way)
     } up;
     int device = 0;                                 // the CUDA device this context was created on
+    // dm_sub_pix_cal_host_batch: two streams, each with its own staging slot (planes in, scores in, planes out)
+    cudaStream_t sp_stream[2] = {nullptr, nullptr};
+    double* sp_buf = nullptr; size_t sp_bytes = 0;
     // CUDA graphs of the upper-pyramid + top-down launch sequence (fused.cu), keyed by what they depend on
     struct UpperGraph {
         const void* ws; int nt, t0, t1, levels, kpad, filter_num, filter_win, filter_mode;   // kpad: the carve-up of the workspace (level / match offsets) depends on it

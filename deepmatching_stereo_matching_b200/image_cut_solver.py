@@ -16,16 +16,12 @@ from .Correlation_map import Correlation_map
 from .Matching import Matching
 from .Calc_difference import Calc_difference
 
-_CTX = {}
+_CTX = _native._CTX            # one dm_ctx per CUDA device of this process (shared with sub_pix_cal_batch)
 
 
 def _context():
     """One dm_ctx (workspace, staging buffers) per CUDA device of this process."""
-    torch = _native.require_cuda()
-    dev = torch.cuda.current_device()
-    if dev not in _CTX:
-        _CTX[dev] = _native.Context(workspace_limit=_WS_LIMIT)
-    return _CTX[dev]
+    return _native.current_context()
 
 
 _MULTI = {}
@@ -120,6 +116,7 @@ def set_workspace_limit(nbytes):
     fit are processed in equal chunks of tiles (default limit: 48 GB)."""
     global _WS_LIMIT
     _WS_LIMIT = int(nbytes)
+    _native.WORKSPACE_LIMIT[0] = int(nbytes)
     _context().set_workspace_limit(nbytes)
     for m in _MULTI.values():
         m.set_workspace_limit(nbytes)

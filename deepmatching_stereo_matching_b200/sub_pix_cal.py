@@ -25,38 +25,20 @@ def sub_pix_cal(arr, co_map, direction=0, ratio=100.):
     return out.cpu().numpy()
 
 
-def sub_pix_cal_batch(d_maps, co_maps, directions, ratio=100., chunks=16):
+def sub_pix_cal_batch(d_maps, co_maps, directions, ratio=100.):
     """sub_pix_cal for a batch: d_maps (n, n_modes, S0, S1), co_maps (n, S0, S1), directions[m] per
     plane -> (n, n_modes, S0, S1) float64; each slice identical to sub_pix_cal(d_maps[b, m],
-    co_maps[b], directions[m]).  The batch goes through the device in ``chunks`` pieces on two
-    streams, so the upload of one piece, the kernels of the previous one and the download of the one
-    before share the PCIe link in both directions (page-locked inputs, e.g. solve_batch's results)."""
-    torch = _native.require_cuda()
-    a_h = torch.from_numpy(np.ascontiguousarray(d_maps, dtype=np.float64))
-    c_h = torch.from_numpy(np.ascontiguousarray(co_maps, dtype=np.float64))
-    if a_h.dim() != 4 or c_h.dim() != 3 or a_h.shape[0] != c_h.shape[0] or a_h.shape[2:] != c_h.shape[1:] or len(directions) != a_h.shape[1]:
+    co_maps[b], directions[m]).  One library call (dm_sub_pix_cal_host_batch): the batch crosses the
+    device in pieces on two streams, so the upload of one piece, the kernels of the previous one and
+    the download of the one before share the PCIe link in both directions (page-locked inputs, e.g.
+    solve_batch's results, make the copies asynchronous)."""
+    _native.require_cuda()
+    a = np.ascontiguousarray(d_maps, dtype=np.float64)
+    c = np.ascontiguousarray(co_maps, dtype=np.float64)
+    if a.ndim != 4 or c.ndim != 3 or a.shape[0] != c.shape[0] or a.shape[2:] != c.shape[1:] or len(directions) != a.shape[1]:
         raise ValueError('d_maps (n, n_modes, S0, S1), co_maps (n, S0, S1), one direction per plane')
     if any(d not in (0, 1) for d in directions):
         raise ValueError('direction must be 0 or 1')
-    n = a_h.shape[0]
-    res = torch.from_numpy(_native.pinned_empty(tuple(a_h.shape), np.float64))
-    lib = _native.lib()
-    cur = torch.cuda.current_stream()
-    streams = [torch.cuda.Stream(), torch.cuda.Stream()]
-    step = max(1, -(-n // max(1, int(chunks))))
-    for k, b0 in enumerate(range(0, n, step)):
-        b1 = min(n, b0 + step)
-        st = streams[k % 2]
-        st.wait_stream(cur)
-        with torch.cuda.stream(st):
-            a = a_h[b0:b1].cuda(non_blocking=True)
-            c = c_h[b0:b1].cuda(non_blocking=True)
-            out = torch.empty_like(a)
-            for b in range(b1 - b0):
-                for m in range(a.shape[1]):
-                    _native.check(lib.dm_sub_pix_cal(_native.ptr(a[b, m]), _native.ptr(c[b]), a.shape[2], a.shape[3], int(directions[m]),
-                                                     float(ratio), _native.ptr(out[b, m]), _native.stream_ptr()))
-            res[b0:b1].copy_(out, non_blocking=True)
-    for st in streams:
-        st.synchronize()
-    return res.numpy()
+    res = _native.pinned_empty(a.shape, np.float64)
+    _native.current_context().sub_pix_cal_host_batch(a, c, directions, ratio, res)
+    return res

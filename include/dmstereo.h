@@ -59,6 +59,9 @@ extern "C" {
  * one CTA per work item.  Both produce bit-identical results; a tuning / test knob. */
 int         dm_correlation_set_pair_mode(int mode);
 
+/* a context owns the device workspace and the staging buffers of the scene solvers (dm_ctx_create, below) */
+typedef struct dm_ctx dm_ctx;
+
 int         dm_version(void);
 const char* dm_last_error(void);
 /* compute capability of the current device as major*10+minor, or <0 */
@@ -166,6 +169,13 @@ int dm_cal_map(const double* map_dev, int t0, int t1, int mode, double* out_dev,
 int dm_sub_pix_cal(const double* arr_dev, const double* co_map_dev, int s0, int s1,
                    int direction, double ratio, double* out_dev, void* stream);
 
+/* sub_pix_cal for a batch of planes in HOST memory (config 4 of BASELINE.json: 64 pairs, sub_pix_cal on both
+ * planes): d_maps double [n][n_planes][s0][s1], co_maps double [n][s0][s1], directions[n_planes] -> out like d_maps.
+ * The batch crosses the device in pieces on two streams (upload, kernels and download of neighbouring pieces
+ * overlap); page-locked arrays make the copies asynchronous.  Synchronous: returns when out_host is complete. */
+int dm_sub_pix_cal_host_batch(dm_ctx* ctx, const double* d_maps_host, const double* co_maps_host, int n, int n_planes,
+                              int s0, int s1, const int32_t* directions, double ratio, double* out_host);
+
 /* cv2.bilateralFilter(plane.astype('uint8'), d, sigma_color, sigma_space) -- the live branch of the
  * reference's post-process (optimize_looper.py:76-77, d = 2*exclusion+1).  uint8 (h,w) planes;
  * OpenCV's own 8-bit algorithm (BORDER_REFLECT_101, float32 weights, cvRound), bit-identical
@@ -231,8 +241,6 @@ typedef struct dm_scene_info {
     int32_t chunk_tiles;            /* tiles per batch                                    */
     int32_t kernel_launches;        /* kernels enqueued by the last solve                 */
 } dm_scene_info;
-
-typedef struct dm_ctx dm_ctx;
 
 int  dm_ctx_create(dm_ctx** out);                 /* on the current CUDA device          */
 void dm_ctx_destroy(dm_ctx* ctx);

@@ -606,8 +606,8 @@ def test_batch_of_pairs_equals_one_by_one(dm):
     # the batched, pipelined refinement equals the plane-by-plane one
     from deepmatching_stereo_matching_b200.sub_pix_cal import sub_pix_cal_batch
     ref_batch = np.stack([np.stack([dm.sub_pix_cal(d[b, m], sc[b], direction=dr) for m, dr in ((0, 1), (1, 0))]) for b in range(3)])
-    for chunks in (1, 2, 8):
-        assert np.array_equal(sub_pix_cal_batch(d, sc, [1, 0], chunks=chunks), ref_batch, equal_nan=True)
+    assert np.array_equal(sub_pix_cal_batch(d, sc, [1, 0]), ref_batch, equal_nan=True)
+    assert np.array_equal(sub_pix_cal_batch(np.concatenate([d] * 7), np.concatenate([sc] * 7), [1, 0]), np.concatenate([ref_batch] * 7), equal_nan=True)   # several pieces per stream
     # the post-hoc refinement of config 4 (direction rule of image_cut_solver.py:137) vs the oracle
     rd, rs = O.image_cut_solver(pairs[0][0], pairs[0][1], (32, 32), (32, 32), 5, ('elevation', 'elevation2'), True)
     got = dm.sub_pix_cal(d[0, 0], sc[0], direction=1)

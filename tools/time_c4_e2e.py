@@ -30,6 +30,5 @@ ms, _ = t(lambda: ctx.solve_device(prm, d1, d2, dd, oo))
 print('dm_solve_scene (device-resident) %.2f ms' % ms)
 ms, (d, s) = t(lambda: solve_batch(h1, h2, **kw))
 print('solve_batch %.2f ms' % ms)
-for ch in (1, 4, 8, 16):
-    ms, r = t(lambda: sub_pix_cal_batch(d, s, [1, 0], chunks=ch))
-    print('sub_pix_cal_batch chunks=%d %.2f ms' % (ch, ms))
+ms, r = t(lambda: sub_pix_cal_batch(d, s, [1, 0]), n=10)
+print('sub_pix_cal_batch %.2f ms' % ms)
