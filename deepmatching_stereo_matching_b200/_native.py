@@ -68,6 +68,7 @@ SIGNATURES = {
     'dm_ctx_set_workspace_limit': (c_int, [c_void_p, c_size_t]),
     'dm_ctx_workspace_bytes': (c_size_t, [c_void_p]),
     'dm_scene_geometry': (c_int, [POINTER(SceneParams), POINTER(SceneInfo)]),
+    'dm_owned_rectangles': (c_int, [POINTER(SceneParams), POINTER(c_int32), POINTER(c_int32)]),
     'dm_solve_scene': (c_int, [c_void_p, POINTER(SceneParams), c_void_p, c_void_p, c_void_p, c_void_p, POINTER(SceneInfo)]),
     'dm_solve_scene_host': (c_int, [c_void_p, POINTER(SceneParams), c_void_p, c_void_p, c_void_p, c_void_p, POINTER(SceneInfo)]),
     'dm_solve_scene_stream': (c_int, [c_void_p, POINTER(SceneParams), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, POINTER(SceneInfo)]),
@@ -158,8 +159,9 @@ def pinned_empty(shape, dtype):
     t = pool.pop() if pool else torch.empty(key, dtype=torch.uint8, pin_memory=True)
     base = t.numpy()                                                # owns the reference to t; every view keeps it alive
 
-    def give_back(pool=pool, t=t):
-        if len(pool) < 4:
+    def give_back(pool=pool, t=t, key=key):
+        # keep at most four buffers of a size and 8 GiB in all; the rest goes back to the allocator
+        if len(pool) < 4 and sum(k * len(v) for k, v in _PINNED_POOL.items()) + key <= (8 << 30):
             pool.append(t)
     weakref.finalize(base, give_back)
     return base[:nbytes].view(dt).reshape(shape)
@@ -311,6 +313,14 @@ class MultiContext(object):
 
     def synchronize(self):
         check(lib().dm_multi_synchronize(self._h))
+
+
+def owned_rectangles(prm):
+    """[(row_lo, row_hi, col_lo, col_hi), ...]: the rectangles of the mosaic the tiles of ``prm`` own."""
+    rects = (c_int32 * 12)()
+    n = c_int32()
+    check(lib().dm_owned_rectangles(byref(prm), rects, byref(n)))
+    return [tuple(int(rects[4 * k + i]) for i in range(4)) for k in range(n.value)]
 
 
 def partition_tile_rows(len0, n):

@@ -732,3 +732,18 @@ extern "C" int dm_sub_pix_cal_host_batch(dm_ctx* ctx, const double* d_maps_host,
     }
     return rc;
 }
+
+// geometry only: the rectangles of the mosaic the tiles of `prm` own (rows [r0,r1) x columns [c0,c1) each)
+extern "C" int dm_owned_rectangles(const dm_scene_params* prm, int32_t* rects /* [3][4] = {r0, r1, c0, c1} */, int32_t* n_rects) {
+    DM_REQUIRE(prm && rects && n_rects, DM_ERR_INVALID, "dm_owned_rectangles: null argument");
+    dm_scene_info info;
+    int rc = dm_scene_geometry(prm, &info);
+    if (rc != DM_OK) return rc;
+    long long ta, tb;
+    if ((rc = dm_tile_range(prm, info.len0, info.len1, &ta, &tb)) != DM_OK) return rc;
+    OwnedRect r[3];
+    const int n = owned_rects(info.len0, info.len1, prm->s0, prm->s1, info.out_h, info.out_w, ta, tb, r);
+    for (int k = 0; k < n; ++k) { rects[4 * k] = r[k].r0; rects[4 * k + 1] = r[k].r1; rects[4 * k + 2] = r[k].c0; rects[4 * k + 3] = r[k].c1; }
+    *n_rects = n;
+    return DM_OK;
+}

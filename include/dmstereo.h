@@ -251,6 +251,11 @@ size_t dm_ctx_workspace_bytes(const dm_ctx* ctx);
 /* geometry only (no GPU work): fills info for the given params */
 int dm_scene_geometry(const dm_scene_params* prm, dm_scene_info* info);
 
+/* geometry only: the (at most three) rectangles of the mosaic the tiles of `prm` own -- the tail of the first
+ * tile row of the range, whole tile rows, the head of its last tile row; rects[k] = {row_lo, row_hi, col_lo, col_hi}.
+ * (A pixel belongs to the covering tile with the largest index, misc/image_cut_solver.py:165-175.) */
+int dm_owned_rectangles(const dm_scene_params* prm, int32_t* rects /* [3][4] */, int32_t* n_rects);
+
 /* Device-resident solve.  img*_dev: uint8 [scene_h][scene_w].  d_map_dev: double
  * [n_modes][out_h][out_w], out_map_dev: double [out_h][out_w]; only rows
  * [row_lo,row_hi) are written.  Asynchronous on the ctx stream. */

@@ -503,11 +503,12 @@ def tile_grid(img_shape, image_size, stride, ws):
 
 def image_cut_solver(img1, img2, image_size=(32, 32), stride=(32, 32), ws=5,
                      modes=('elevation',), sub_pix_on=True, method=TM_CCOEFF_NORMED,
-                     tile_rows=None, filtering=None):
+                     tile_rows=None, filtering=None, tiles=None):
     """misc/image_cut_solver.py:95-113,144-184 -> (d_map (nmodes,S0',S1'), out_map (S0',S1')).
 
-    ``tile_rows=(lo,hi)`` restricts the solve to tile-row indices lo..hi-1 (everything
-    else is left NaN) -- used to check the multi-GPU strip partition.
+    ``tile_rows=(lo,hi)`` restricts the solve to tile-row indices lo..hi-1, ``tiles=(a,b)`` to the
+    tiles a..b-1 in row-major order (everything else is left NaN; pixels of the range that later tiles of
+    the range paste over are overwritten as usual) -- used to check the multi-GPU partitions.
     """
     ln, trimmed = tile_grid(img1.shape, image_size, stride, ws)
     if ln[0] <= 0 or ln[1] <= 0:
@@ -518,6 +519,8 @@ def image_cut_solver(img1, img2, image_size=(32, 32), stride=(32, 32), ws=5,
     lo, hi = (0, ln[0]) if tile_rows is None else tile_rows
     for j in range(ln[1]):
         for i in range(lo, hi):
+            if tiles is not None and not (tiles[0] <= i * ln[1] + j < tiles[1]):
+                continue                                         # a range of tiles in row-major order (the multi-GPU shares)
             y, x = stride[0] * i, stride[1] * j
             d, s = solve_tile(img1[y:y + trimmed[0], x:x + trimmed[1]],
                               img2[y:y + trimmed[0], x:x + trimmed[1]], ws, modes, sub_pix_on, method, filtering)

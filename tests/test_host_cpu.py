@@ -245,3 +245,58 @@ def test_tile_range_geometry():
             _native.scene_geometry(_native.scene_params(*args, tiles=bad))
     with pytest.raises(_native.DmError):        # a tile range and a strip of tile rows exclude each other
         _native.scene_geometry(_native.scene_params(*args, tile_rows=(0, 3), tiles=(0, 10)))
+
+
+@pytest.mark.parametrize('shape,size,stride,ws', [((200, 264), (32, 32), (30, 30), 5), ((150, 230), (16, 64), (12, 50), 3),
+                                                   ((300, 300), (32, 32), (40, 36), 7), ((140, 140), (16, 16), (16, 16), 3)])
+def test_owned_rectangles_cover_exactly_what_the_paste_order_leaves(shape, size, stride, ws):
+    """dm_owned_rectangles against a brute-force paste in the reference's order (j outer, i inner,
+    later tiles overwrite, misc/image_cut_solver.py:165-175): for every way of cutting the tiles into
+    contiguous ranges the rectangles of a range are exactly the pixels whose final owner lies in it."""
+    from deepmatching_stereo_matching_b200 import _native
+    args = (shape, size, stride, ws, 'cv2.TM_CCOEFF_NORMED', ['elevation'], True)
+    info = _native.scene_geometry(_native.scene_params(*args))
+    n = info.len0 * info.len1
+    owner = np.full((info.out_h, info.out_w), -1, dtype=np.int64)
+    for j in range(info.len1):
+        for i in range(info.len0):
+            owner[stride[0] * i:stride[0] * i + size[0], stride[1] * j:stride[1] * j + size[1]] = i * info.len1 + j
+    rng = np.random.default_rng(n)
+    for parts in (1, 2, 3, 5, 8):
+        cuts = [0] + sorted(rng.choice(np.arange(1, n), size=min(parts, n) - 1, replace=False).tolist()) + [n]
+        seen = np.zeros_like(owner)
+        for a, b in zip(cuts[:-1], cuts[1:]):
+            rects = _native.owned_rectangles(_native.scene_params(*args, tiles=(a, b)))
+            assert 1 <= len(rects) <= 3
+            mask = np.zeros(owner.shape, bool)
+            for r0, r1, c0, c1 in rects:
+                assert 0 <= r0 < r1 <= info.out_h and 0 <= c0 < c1 <= info.out_w
+                assert not mask[r0:r1, c0:c1].any()                  # the rectangles of a range are disjoint
+                mask[r0:r1, c0:c1] = True
+            want = (owner >= a) & (owner < b)
+            # where the stride exceeds the tile there are pixels no tile writes (np.empty in the reference, zeros
+            # here): the rectangles carry them along, what counts is the owned pixels
+            assert np.array_equal(mask & (owner >= 0), want), (a, b)
+            seen += mask
+        assert (seen == 1).all()                                     # the ranges' rectangles tile the mosaic: every pixel exactly once
+
+
+def test_tile_ranges_paste_like_the_whole_scene():
+    """The oracle restricted to ranges of tiles, each range pasted through its owned rectangles into one
+    mosaic, equals the whole-scene solve: the host-side contract of the multi-GPU shares."""
+    from conftest import load_golden
+    from deepmatching_stereo_matching_b200 import _native
+    g = load_golden('solver_96_t16_s12_ws5')
+    size, stride, ws = tuple(int(x) for x in g['image_size']), tuple(int(x) for x in g['stride']), int(g['ws'])
+    modes = tuple(str(m) for m in g['modes'])
+    args = (g['img1'].shape, size, stride, ws, 'cv2.TM_CCOEFF_NORMED', list(modes), bool(g['sub_pix']))
+    info = _native.scene_geometry(_native.scene_params(*args))
+    parts = _native.partition_tile_rows(info.len0 * info.len1, 3)
+    d_all = np.full(g['d_map'].shape, np.nan); s_all = np.full(g['out_map'].shape, np.nan)
+    for a, b in parts:
+        d, s = O.image_cut_solver(g['img1'], g['img2'], size, stride, ws, modes, bool(g['sub_pix']), tiles=(a, b))
+        for r0, r1, c0, c1 in _native.owned_rectangles(_native.scene_params(*args, tiles=(a, b))):
+            d_all[:, r0:r1, c0:c1] = d[:, r0:r1, c0:c1]
+            s_all[r0:r1, c0:c1] = s[r0:r1, c0:c1]
+    d_ref, s_ref = O.image_cut_solver(g['img1'], g['img2'], size, stride, ws, modes, bool(g['sub_pix']))
+    assert np.array_equal(d_all, d_ref, equal_nan=True) and np.array_equal(s_all, s_ref, equal_nan=True)
