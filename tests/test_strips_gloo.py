@@ -50,8 +50,24 @@ def _worker(rank, world, port, q):
         shared = mosaic.array.copy()
         dist.barrier()
         mosaic.close()
+        # the tile-granular shares of the streaming paths: this rank's range of tiles, pasted through the
+        # rectangles it owns (dm_owned_rectangles) into a second shared mosaic
+        from deepmatching_stereo_matching_b200 import _native
+        args = (g['img1'].shape, size, stride, ws, 'cv2.TM_CCOEFF_NORMED', list(modes), bool(g['sub_pix']))
+        tparts = partition_tile_rows(ln[0] * ln[1], world)
+        ta, tb = tparts[rank]
+        d2, s2 = O.image_cut_solver(g['img1'], g['img2'], size, stride, ws, modes, bool(g['sub_pix']), tiles=(ta, tb))
+        mine = np.concatenate([d2, s2[None]], 0)
+        mosaic2 = SharedHostMosaic(tuple(local.shape), np.float64)
+        for r0, r1, c0, c1 in _native.owned_rectangles(_native.scene_params(*args, tiles=(ta, tb))):
+            mosaic2.array[:, r0:r1, c0:c1] = mine[:, r0:r1, c0:c1]
+        mosaic2.publish(1)
+        mosaic2.wait(1)
+        shared2 = mosaic2.array.copy()
+        dist.barrier()
+        mosaic2.close()
         if rank == 0:
-            q.put((full.numpy(), shared))
+            q.put((full.numpy(), shared, shared2))
         else:
             assert full is None
     finally:
@@ -67,7 +83,7 @@ def test_two_rank_strip_gather_equals_whole_scene():
     procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
     for p in procs:
         p.start()
-    full, shared = q.get(timeout=240)
+    full, shared, shared2 = q.get(timeout=240)
     for p in procs:
         p.join(60)
         assert p.exitcode == 0
@@ -78,3 +94,5 @@ def test_two_rank_strip_gather_equals_whole_scene():
     assert np.array_equal(full[-1], s, equal_nan=True)
     # the mosaic assembled in shared host memory (every rank writes its own strip) is the same
     assert np.array_equal(shared, full, equal_nan=True)
+    # ... and so is the one assembled from tile ranges through their owned rectangles
+    assert np.array_equal(shared2, full, equal_nan=True)
