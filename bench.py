@@ -52,6 +52,7 @@ SUB_PIX = True
 FEATURE = 'cv2.TM_CCOEFF_NORMED'
 
 CONFIGS = {
+    'c1': dict(shape=(256, 256), ws=5, T=32, stride=32, seed=0, batch=1),       # BASELINE configs[0]: the reference's own CPU-runnable case (a parity case, tests/golden/solver_c1_*)
     'c2': dict(shape=(1024, 1024), ws=15, T=64, stride=60, seed=1, batch=1),
     'c3': dict(shape=(4096, 4096), ws=15, T=64, stride=60, seed=2, batch=1),
     'c4': dict(shape=(512, 512), ws=5, T=32, stride=32, seed=100, batch=64, post=True),

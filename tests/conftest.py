@@ -22,7 +22,7 @@ def load_golden(name):
 
 TILE_CASES = ['tile_16x16_ws5_noise', 'tile_16x16_ws5_sine', 'tile_8x32_ws3', 'tile_32x8_ws5',
               'tile_16x16_ws15', 'tile_8x8_ws5_flat', 'tile_16x16_ws5_ccoeff']
-SOLVER_CASES = ['solver_96_t16_s12_ws5', 'solver_80x112_t16_s16_ws3']
+SOLVER_CASES = ['solver_96_t16_s12_ws5', 'solver_80x112_t16_s16_ws3', 'solver_c1_256_t32_s32_ws5']   # the last one: BASELINE.json configs[0]
 
 # tolerance of the float32 ZNCC + min-max against the live reference: OpenCV's own
 # float32 cross-correlation is ~2e-6 (up to 4e-5 on low-contrast ws=3 patches) away from

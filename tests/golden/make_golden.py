@@ -81,8 +81,8 @@ def tile_case(name, t0, t1, ws, mode, plain, seed, feature='cv2.TM_CCOEFF_NORMED
     save(name, **out)
 
 
-def solver_case(name, shape, image_size, stride, ws, modes, sub_pix, seed, mode='sine'):
-    img1, img2 = synth.stereo_pair(shape, seed=seed, mode=mode, amp=3)
+def solver_case(name, shape, image_size, stride, ws, modes, sub_pix, seed, mode='sine', amp=3):
+    img1, img2 = synth.stereo_pair(shape, seed=seed, mode=mode, amp=amp)
     with contextlib.redirect_stdout(io.StringIO()), contextlib.redirect_stderr(io.StringIO()):
         s = ImageCutSolver(img1, img2, image_size=list(image_size), stride=list(stride), window_size=ws,
                            degree_map_mode=list(modes), sub_pix=sub_pix)
@@ -133,5 +133,7 @@ if __name__ == '__main__':
     tile_case('tile_32x32_ws5', 32, 32, 5, 'sine', False, 9, keep_levels_from=2)
     solver_case('solver_96_t16_s12_ws5', (96, 96), (16, 16), (12, 12), 5, ('elevation', 'elevation2'), True, 10)
     solver_case('solver_80x112_t16_s16_ws3', (80, 112), (16, 16), (16, 16), 3, ('distance', 'elevation'), False, 12)
+    # BASELINE.json configs[0]: 256 x 256 pair, ws 5, image_size 32, stride 32 -> 36 tiles, 192 x 192
+    solver_case('solver_c1_256_t32_s32_ws5', (256, 256), (32, 32), (32, 32), 5, ('elevation', 'elevation2'), True, 0, amp=8)
     feature_case()
     subpix2d_case()
