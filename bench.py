@@ -414,14 +414,33 @@ def run_ours(args):
         d2 = torch.zeros(c['shape'], dtype=torch.uint8, device='cuda')
         d1[a:b].copy_(torch.from_numpy(h1[a:b])); d2[a:b].copy_(torch.from_numpy(h2[a:b]))      # a rank holds only the rows its strip reads
         planes = solver.alloc_planes()
-        peer = PeerMosaic((solver.n_planes, solver.out_h, solver.out_w)) if world > 1 else None
-        gather_name = 'none (one GPU)' if world == 1 else \
+        peer, peer_error = None, None
+        if world > 1:
+            # the mosaic in rank 0's memory, mapped into every rank through CUDA IPC; if the box does not allow that
+            # (no peer access, IPC disabled in a container) every rank falls back to the NCCL gather for `value`
+            try:
+                if os.environ.get('DM_BENCH_NO_PEER'):
+                    raise RuntimeError('DM_BENCH_NO_PEER is set')
+                peer = PeerMosaic((solver.n_planes, solver.out_h, solver.out_w))
+            except Exception as exc:                 # noqa: BLE001 -- reported in the line, not swallowed
+                peer_error = '%s: %s' % (type(exc).__name__, exc)
+            flags = [None] * world
+            dist.all_gather_object(flags, peer_error)
+            if any(f is not None for f in flags):
+                if peer is not None:
+                    peer.close()
+                peer = None
+                peer_error = next(f for f in flags if f is not None)
+        gather_name = 'none (one GPU)' if world == 1 else (
             'finished row bands streamed into rank 0\'s mosaic over NVLink peer memory (CUDA IPC) while the strip is still being solved'
+            if peer is not None else 'NCCL point-to-point gather of the owned rows after the solve (peer mosaic unavailable: %s)' % peer_error)
 
         def step():
             if world == 1:
                 solver.solve_local(d1, d2, planes)
                 return planes
+            if peer is None:
+                return step_nccl()
             solver.solve_into(d1, d2, planes, peer)
             return peer.tensor
 
@@ -516,7 +535,7 @@ def run_ours(args):
         g1.record()
         barrier()
         gms = max_over_ranks(g0.elapsed_time(g1))
-        checks['nccl_gather_equals_streamed_mosaic'] = bool(torch.equal(planes, peer.tensor)) if rank == 0 else None
+        checks['nccl_gather_equals_streamed_mosaic'] = bool(torch.equal(planes, peer.tensor)) if (rank == 0 and peer is not None) else None
         gather_nccl = {'value': out_px * args.steps / 1e6 / (gms * 1e-3), 'unit': 'MP/s', 'ms_per_step': gms / args.steps,
                        'how': 'solve the strip, then point-to-point NCCL transfers of the owned rows (float64) to rank 0'}
 
@@ -538,7 +557,10 @@ def run_ours(args):
             q1.record()
             torch.cuda.synchronize()
             qms = q0.elapsed_time(q1) / reps
-            checks['strips_equal_single_gpu_solve'] = bool(torch.equal(planes, peer.tensor))      # bit for bit
+            if peer is not None:
+                checks['strips_equal_single_gpu_solve'] = bool(torch.equal(planes, peer.tensor))      # bit for bit
+            elif got_planes is not None:
+                checks['strips_equal_single_gpu_solve'] = bool(np.array_equal(planes.cpu().numpy()[None], got_planes, equal_nan=True))
             single = {'value': out_px / 1e6 / (qms * 1e-3), 'unit': 'MP/s', 'ms_per_step': qms, 'n_gpus': 1,
                       'how': 'the same workload solved by rank 0 alone (device-resident), for the strong-scaling ratio'}
             sctx.close()
@@ -621,7 +643,8 @@ def run_ours(args):
     if mosaic is not None:
         barrier()
         if rank == 0:
-            checks['host_mosaic_equals_streamed_mosaic'] = bool(np.array_equal(mosaic.array, peer.tensor.cpu().numpy(), equal_nan=True))
+            ref_ = peer.tensor.cpu().numpy() if peer is not None else got_planes[0]
+            checks['host_mosaic_equals_streamed_mosaic'] = bool(np.array_equal(mosaic.array, ref_, equal_nan=True))
         mosaic.close()
     if raw_paths is not None:
         for p_ in raw_paths:
