@@ -980,3 +980,30 @@ def test_gauss_seidel_loops_bit_exact(dm):
     a, ea = optimize_loop_bilateral_vertical(d.copy(), cw, gw, co, 0.008, 6, d.shape)
     b, eb = O.optimize_loop_bilateral(d.copy(), cw, gw, co, 0.008, 6, d.shape, vertical=True)
     assert np.array_equal(a, b) and ea == eb
+
+
+@pytest.mark.parametrize('kind', ['plain_noise', 'two_level'])
+def test_correction_slots_on_high_contrast_input(dm, kind):
+    """The tensor-core engine adds the three correction terms (-S1' * parts of S2'/K) to an accumulator that
+    can be as large as 2^23..2^24 on high-contrast input (uniform noise; a random 0 / 255 pattern where
+    |a'| reaches 255): co_map must stay within 2e-6 of the exact float64 oracle there as well, and the
+    tensor-core and CUDA-core engines within 5e-7 of each other."""
+    from deepmatching_stereo_matching_b200.synth import texture
+    rng = np.random.default_rng(77)
+    if kind == 'plain_noise':
+        i1 = texture((78, 78), seed=91, plain_noise=True)
+        i2 = texture((78, 78), seed=92, plain_noise=True)
+    else:
+        i1 = (rng.integers(0, 2, size=(78, 78)) * 255).astype(np.uint8)
+        i2 = i1.copy()
+        flip = rng.random((78, 78)) < 0.2
+        i2[flip] = 255 - i2[flip]
+    exact = O.initial_co_map(i1, i2, 15)
+    got = {}
+    for engine in (0, 1):                                # 0 = auto (tcgen05 at P = 4096), 1 = CUDA cores
+        co = dm.Correlation_map(i1, i2, window_size=15)
+        co._create_atomic_patch()
+        co._create_simple_initial_co_map(engine=engine)
+        got[engine] = np.asarray(co.co_map)
+        assert np.abs(got[engine] - exact).max() <= 2e-6, (kind, engine)
+    assert np.abs(got[0] - got[1]).max() <= 5e-7
