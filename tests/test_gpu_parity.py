@@ -987,7 +987,7 @@ def test_correction_slots_on_high_contrast_input(dm, kind):
     """The tensor-core engine adds the three correction terms (-S1' * parts of S2'/K) to an accumulator that
     can be as large as 2^23..2^24 on high-contrast input (uniform noise; a random 0 / 255 pattern where
     |a'| reaches 255): co_map must stay within 2e-6 of the exact float64 oracle there as well, and the
-    tensor-core and CUDA-core engines within 5e-7 of each other."""
+    tensor-core and CUDA-core engines within 1e-6 of each other (min-maxed values)."""
     from deepmatching_stereo_matching_b200.synth import texture
     rng = np.random.default_rng(77)
     if kind == 'plain_noise':
@@ -1006,4 +1006,4 @@ def test_correction_slots_on_high_contrast_input(dm, kind):
         co._create_simple_initial_co_map(engine=engine)
         got[engine] = np.asarray(co.co_map)
         assert np.abs(got[engine] - exact).max() <= 2e-6, (kind, engine)
-    assert np.abs(got[0] - got[1]).max() <= 5e-7
+    assert np.abs(got[0] - got[1]).max() <= 1e-6
