@@ -279,6 +279,8 @@ __device__ __forceinline__ void tail_aggregate(const float* __restrict__ in, int
 __global__ void __launch_bounds__(256)
 dm_upper_tail_kernel(const TailArgs a) {
     extern __shared__ __align__(16) float tail_smem[];
+    dm_pdl_wait();                  // level ks comes from the aggregation kernel in front
+    dm_pdl_launch_dependents();
     const int n = blockIdx.x, L = a.L, ks = a.ks;
     // shared levels ks+1 .. L-1, then two match buffers of [2][cells of level 2]
     float* slevel[16];
@@ -358,7 +360,7 @@ int dm_upper_tail(float* const* levels_dev, int n_tiles, int t0, int t1, int lev
     size_t floats = 0;
     for (int k = a.ks + 1; k < levels; ++k) { const size_t c = (size_t)(t0 >> k) * (t1 >> k); floats += c * c; }
     const size_t smem = floats * 4 + (size_t)4 * (t0 >> 2) * (t1 >> 2) * 4;
-    dm_upper_tail_kernel<<<n_tiles, 256, smem, stream>>>(a);
+    dm_launch_dep(DM_PDL_UPPER, dm_upper_tail_kernel, dim3((unsigned)n_tiles), dim3(256), smem, stream, a);
     DM_LAUNCH_CHECK();
     return DM_OK;
 }

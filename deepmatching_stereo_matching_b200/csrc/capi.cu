@@ -21,6 +21,15 @@ void dm_set_error(const char* fmt, ...) {
 }
 
 extern "C" const char* dm_last_error(void) { return g_err; }
+
+// programmatic dependent launch between the kernels of a chunk (dm_common.cuh); DM_PDL = mask of DM_PDL_*
+#define DM_PDL_DEFAULT 0
+static thread_local bool g_pdl_suppressed = false;
+bool dm_pdl_enabled(int which) {
+    static const int mask = getenv("DM_PDL") ? atoi(getenv("DM_PDL")) : DM_PDL_DEFAULT;
+    return (mask & which) != 0 && !g_pdl_suppressed;
+}
+void dm_pdl_suppress(bool off) { g_pdl_suppressed = off; }
 extern "C" int dm_version(void) { return 100; }
 
 extern "C" int dm_device_cc(void) {
@@ -509,9 +518,10 @@ extern "C" int dm_solve_scene(dm_ctx* ctx, const dm_scene_params* prm,
             if ((rc = tm.begin(ck)) != DM_OK) return rc;
             dm_tile_origin_kernel<<<dm_div_up(nt, 128), 128, 0, st>>>(tb.origin, nt, first, info.len0, info.len1, prm->s0, prm->s1, prm->scene_h);
             DM_LAUNCH_CHECK();
-            if ((rc = dm_descriptors(img1_dev, prm->scene_h * ns, prm->scene_w, prm->scene_w, tb.origin, nt, t0, t1, prm->ws, 1, tb.desc1, tb.stat1, st)) != DM_OK) return rc;
-            if ((rc = dm_descriptors(img2_dev, prm->scene_h * ns, prm->scene_w, prm->scene_w, tb.origin, nt, t0, t1, prm->ws, 2, tb.desc2, tb.stat2, st)) != DM_OK) return rc;
-            ctx->launches[DM_STAGE_DESCRIPTORS] += 3;
+            int n_desc = 0;
+            if ((rc = dm_descriptors_both(img1_dev, img2_dev, prm->scene_h * ns, prm->scene_w, prm->scene_w, tb.origin, nt, t0, t1, prm->ws,
+                                          tb.desc1, tb.stat1, tb.desc2, tb.stat2, st, &n_desc)) != DM_OK) return rc;
+            ctx->launches[DM_STAGE_DESCRIPTORS] += 1 + n_desc;
             if ((rc = tm.end()) != DM_OK) return rc;
         }
         {

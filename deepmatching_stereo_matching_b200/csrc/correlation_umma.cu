@@ -141,6 +141,10 @@ dm_correlation_umma_kernel(const __grid_constant__ CUtensorMap mapA, const __gri
     if (PAIR) umma::cluster_sync_all();     // the peer's barriers are initialised before anything signals them
     umma::tc_fence_after();
     const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
+    // programmatic dependent launch: everything above (barriers, TMEM, tensor-map prefetch, cluster sync) ran
+    // while the descriptor kernel was still draining; its rows and statistics are read only from here on
+    dm_pdl_wait();
+    dm_pdl_launch_dependents();
 
     // register re-partitioning between the warpgroups (setmaxnreg): the producer / MMA
     // warpgroup keeps 40 registers per thread, the two epilogue warpgroups get 232
@@ -486,7 +490,7 @@ int launch3(const CUtensorMap& mapA, const CUtensorMap& mapB, const Params& prm,
     }
     if (!PAIR) {
         const int grid = prm.n_items < sms ? prm.n_items : sms;
-        kern<<<grid, THREADS, SMEM_BYTES, stream>>>(mapA, mapB, prm);
+        DM_CUDA_CHECK(dm_launch_dep(DM_PDL_CORR, kern, dim3((unsigned)grid), dim3(THREADS), SMEM_BYTES, stream, mapA, mapB, prm));
         DM_LAUNCH_CHECK();
         return DM_OK;
     }
@@ -498,11 +502,13 @@ int launch3(const CUtensorMap& mapA, const CUtensorMap& mapB, const Params& prm,
         if (cap > 0 && pairs > cap) pairs = cap;
     }
     cudaLaunchConfig_t cfg = {};
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;        // dm_common.cuh: the prologue overlaps the descriptor kernel's tail
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.gridDim = dim3(2 * pairs); cfg.blockDim = dim3(THREADS); cfg.dynamicSmemBytes = SMEM_BYTES; cfg.stream = stream;
-    cfg.attrs = attr; cfg.numAttrs = 1;
+    cfg.attrs = attr; cfg.numAttrs = dm_pdl_enabled(DM_PDL_CORR) ? 2 : 1;
     DM_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, mapA, mapB, prm));
     DM_LAUNCH_CHECK();
     return DM_OK;

@@ -7,7 +7,10 @@
 // residual sum S' is bounded by K/2, which keeps the fp32 ZNCC numerator
 // dot - S1'*S2'/K free of cancellation.  Row layout [n][P][kpad], K-major, zero padded:
 // the layout TMA loads straight into 128B-swizzled shared memory for tcgen05.mma.
+#include <cstdlib>
+
 #include "dm_common.cuh"
+#include "dm_internal.h"
 
 // K layout of a descriptor row: k = ky * rstride + kx with rstride = 8 / 16 / 32 (window rows
 // padded to a power of two, so a lane owns 8 consecutive entries of ONE window row); both
@@ -120,7 +123,12 @@ __global__ void __launch_bounds__(256)
 dm_descriptor_row_kernel(const uint8_t* __restrict__ scene, int pitch,
                          const int32_t* __restrict__ origin_yx, long long n_groups, long long n_patches,
                          int t0, int t1, dm_fastdiv fd_jb, dm_fastdiv fd_t0, int side,
-                         __nv_bfloat16* __restrict__ desc, dm_stat* __restrict__ stat) {
+                         __nv_bfloat16* __restrict__ desc, dm_stat* __restrict__ stat,
+                         const uint8_t* __restrict__ scene_b, __nv_bfloat16* __restrict__ desc_b, dm_stat* __restrict__ stat_b) {
+    dm_pdl_wait();                  // the tile origins come from the kernel in front
+    dm_pdl_launch_dependents();
+    // both images of a pair in one launch (dm_descriptors_both): grid row 1 is the search image
+    if (blockIdx.y) { scene = scene_b; desc = desc_b; stat = stat_b; side = 2; }
     constexpr int K = WS * WS;
     constexpr int RSTR = WS <= 8 ? 8 : 16;
     constexpr int KPAD = ((WS * RSTR + 63) / 64) * 64;
@@ -192,7 +200,16 @@ dm_descriptor_row_kernel(const uint8_t* __restrict__ scene, int pitch,
         const uint32_t hi = __funnelshift_r(w[(q >> 2) + 1], w[(q >> 2) + 2], 8 * (q & 3)) & mhi;
         const int s = (int)__dp4a(lo, 0x01010101u, __dp4a(hi, 0x01010101u, 0u));
         const int sq = (int)__dp4a(lo, lo, __dp4a(hi, hi, 0u));
-        const int S = __reduce_add_sync(gmask, s), Q = __reduce_add_sync(gmask, sq);
+        // window sums over the lanes of the group.  A whole warp (two lanes per window row) uses REDUX; the four
+        // 8-lane groups of a warp would each bring their own member mask, which the compiler serialises group by
+        // group behind WARPSYNC / ENDCOLLECTIVE (47 convergence regions in the ws = 5 kernel) -- three full-warp
+        // butterfly steps stay inside the aligned groups of 8 and cost six shuffles
+        int S = s, Q = sq;
+        if (LPG == 32) { S = __reduce_add_sync(gmask, s); Q = __reduce_add_sync(gmask, sq); }
+        else {
+#pragma unroll
+            for (int o = 1; o < LPG; o <<= 1) { S += __shfl_xor_sync(0xffffffffu, S, o); Q += __shfl_xor_sync(0xffffffffu, Q, o); }
+        }
         const int mean = dm_round_mean(S, K);
         if (!live) continue;
         if (gl * 8 < KPAD) {
@@ -249,14 +266,45 @@ dm_descriptor_row_kernel(const uint8_t* __restrict__ scene, int pitch,
 
 template <int WS>
 static void launch_descriptor_row(const uint8_t* scene, int pitch, const int32_t* origin, long long n_patches,
-                                  int t0, int t1, int side, void* desc, float* stat, cudaStream_t st) {
+                                  int t0, int t1, int side, void* desc, float* stat, cudaStream_t st,
+                                  const uint8_t* scene_b = nullptr, void* desc_b = nullptr, float* stat_b = nullptr) {
     constexpr int RSTR = WS <= 8 ? 8 : 16;
     constexpr int GPW = RSTR == 16 ? 1 : 4;
     const long long n_groups = n_patches / 8;
     const long long warps = (n_groups + GPW - 1) / GPW;
-    dm_descriptor_row_kernel<WS><<<dm_div_up(warps, 8), 256, 0, st>>>(scene, pitch, origin, n_groups, n_patches, t0, t1,
-                                                                       dm_make_fastdiv((uint32_t)(t1 >> 3)), dm_make_fastdiv((uint32_t)t0), side,
-                                                                       (__nv_bfloat16*)desc, (dm_stat*)stat);
+    dim3 grid((unsigned)dm_div_up(warps, 8), scene_b ? 2 : 1);
+    dm_launch_dep(DM_PDL_DESC, dm_descriptor_row_kernel<WS>, grid, dim3(256), 0, st, scene, pitch, origin, n_groups, n_patches, t0, t1,
+                  dm_make_fastdiv((uint32_t)(t1 >> 3)), dm_make_fastdiv((uint32_t)t0), side,
+                  (__nv_bfloat16*)desc, (dm_stat*)stat, scene_b, (__nv_bfloat16*)desc_b, (dm_stat*)stat_b);
+}
+
+// Descriptors of both images of a pair (side 1 = patch image, side 2 = search image) over the same tile origins:
+// one launch with a two-row grid where the row kernel applies, else two launches.  *launches = kernels launched.
+int dm_descriptors_both(const uint8_t* img1, const uint8_t* img2, int scene_h, int scene_w, int pitch,
+                        const int32_t* origin_yx_dev, int n_tiles, int t0, int t1, int ws,
+                        void* desc1, float* stat1, void* desc2, float* stat2, cudaStream_t st, int* launches) {
+    static const bool split = getenv("DM_DESC_SPLIT") != nullptr;        // measurement aid: one launch per image
+    const long long n_patches = (long long)n_tiles * t0 * t1;
+    const bool rowk = (t1 % 8 == 0) && n_patches / 8 < (1LL << 32) && ws >= 3 && ws <= 15 && (ws & 1);
+    const bool sized = scene_h >= t0 + ws - 1 && scene_w >= t1 + ws - 1 && pitch >= scene_w && t0 > 0 && t1 > 0 && n_tiles > 0;
+    if (split || !rowk || !sized) {
+        int rc = dm_descriptors(img1, scene_h, scene_w, pitch, origin_yx_dev, n_tiles, t0, t1, ws, 1, desc1, stat1, st);
+        if (rc != DM_OK) return rc;
+        if (launches) *launches = 2;
+        return dm_descriptors(img2, scene_h, scene_w, pitch, origin_yx_dev, n_tiles, t0, t1, ws, 2, desc2, stat2, st);
+    }
+    switch (ws) {
+        case 3:  launch_descriptor_row<3>(img1, pitch, origin_yx_dev, n_patches, t0, t1, 1, desc1, stat1, st, img2, desc2, stat2); break;
+        case 5:  launch_descriptor_row<5>(img1, pitch, origin_yx_dev, n_patches, t0, t1, 1, desc1, stat1, st, img2, desc2, stat2); break;
+        case 7:  launch_descriptor_row<7>(img1, pitch, origin_yx_dev, n_patches, t0, t1, 1, desc1, stat1, st, img2, desc2, stat2); break;
+        case 9:  launch_descriptor_row<9>(img1, pitch, origin_yx_dev, n_patches, t0, t1, 1, desc1, stat1, st, img2, desc2, stat2); break;
+        case 11: launch_descriptor_row<11>(img1, pitch, origin_yx_dev, n_patches, t0, t1, 1, desc1, stat1, st, img2, desc2, stat2); break;
+        case 13: launch_descriptor_row<13>(img1, pitch, origin_yx_dev, n_patches, t0, t1, 1, desc1, stat1, st, img2, desc2, stat2); break;
+        default: launch_descriptor_row<15>(img1, pitch, origin_yx_dev, n_patches, t0, t1, 1, desc1, stat1, st, img2, desc2, stat2); break;
+    }
+    DM_LAUNCH_CHECK();
+    if (launches) *launches = 1;
+    return DM_OK;
 }
 
 extern "C" int dm_descriptors(const uint8_t* scene_dev, int scene_h, int scene_w, int pitch,

@@ -106,6 +106,34 @@ __device__ __forceinline__ int dm_round_mean(int sum, int k) {
     return (2 * sum + k) / (2 * k);
 }
 
+// ---- programmatic dependent launch (PDL) -----------------------------------------------
+// The launches of a chunk form one dependent chain on one stream.  A kernel launched through dm_launch_dep
+// carries cudaLaunchAttributeProgrammaticStreamSerialization: its CTAs may become resident -- and run whatever
+// precedes dm_pdl_wait(): barrier init, TMEM allocation, tensor-map prefetch -- while the last wave of the kernel in
+// front of it drains.  dm_pdl_wait() returns once that kernel has COMPLETED and its writes are visible, so the data
+// dependency is exactly the stream order; every kernel of the chain calls it first thing, before any early
+// return, which keeps completion transitive (K_c waits for K_b, whose threads all waited for K_a).  Launched
+// without the attribute both instructions are no-ops.  dm_pdl_launch_dependents() early in a kernel only lets the
+// next grid be scheduled once every CTA of this one is resident or done; it takes nothing away from this grid.
+__device__ __forceinline__ void dm_pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void dm_pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+enum { DM_PDL_DESC = 1, DM_PDL_CORR = 2, DM_PDL_FIRST = 4, DM_PDL_UPPER = 8, DM_PDL_FINAL = 16 };      // which launches carry the attribute
+bool dm_pdl_enabled(int which); // capi.cu: DM_PDL = bit mask over the launches above
+void dm_pdl_suppress(bool off); // this thread launches without the attribute until told otherwise (graph-capture fallback)
+
+template <typename... KArgs, typename... Args>
+static inline cudaError_t dm_launch_dep(int which, void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cudaLaunchAttribute attr[1];
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    if (dm_pdl_enabled(which)) {
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+    }
+    return cudaLaunchKernelEx(&cfg, kern, args...);
+}
+
 static inline int dm_div_up(long long a, long long b) { return (int)((a + b - 1) / b); }
 
 // Exact unsigned 32-bit division by a runtime constant (Granlund & Montgomery, round-up method):

@@ -35,6 +35,9 @@ bool dm_upper_tail_supported(int t0, int t1, int levels);
 int dm_upper_tail_first_level(int t0, int t1, int levels);
 int dm_upper_tail(float* const* levels_dev, int n_tiles, int t0, int t1, int levels, int32_t* match1_dev, cudaStream_t stream);
 
+int dm_descriptors_both(const uint8_t* img1, const uint8_t* img2, int scene_h, int scene_w, int pitch,
+                        const int32_t* origin_yx_dev, int n_tiles, int t0, int t1, int ws,
+                        void* desc1, float* stat1, void* desc2, float* stat2, cudaStream_t st, int* launches);   // descriptors.cu
 int dm_desc_kreal(int ws);      // ws * row stride of the descriptor K layout (descriptors.cu)
 
 struct dm_ctx {

@@ -86,6 +86,8 @@ __global__ void dm_tile_origin_kernel2(int32_t* origin, int32_t* tinfo, int n, i
 __global__ void __launch_bounds__(256)
 dm_aggregate_first_kernel(const float* __restrict__ pooled, const float* __restrict__ rowmin,
                           const float* __restrict__ rowmax, int t0, int t1, float* __restrict__ out) {
+    dm_pdl_wait();                  // the pooled map and the row minima / maxima come from the correlation kernel
+    dm_pdl_launch_dependents();
     // blockIdx.x = parent (n, I, J) flattened; threads cover the P/16 float4 of its map
     const int P = t0 * t1, Q4 = P >> 4;
     const int hA = t0 >> 1, hB = t1 >> 1;
@@ -484,6 +486,8 @@ dm_final_patch_kernel(const FinalArgs a, long long n_patches) {
     constexpr int K = WS * WS;
     constexpr int NW = (WS + 3) / 4;                       // packed words per window row
     constexpr uint32_t LASTMASK = (WS % 4) ? ((1u << (8 * (WS % 4))) - 1u) : 0xffffffffu;
+    dm_pdl_wait();                  // before the early exits: the grid must not complete ahead of the kernel in front
+    dm_pdl_launch_dependents();
     const long long tl = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (tl >= n_patches) return;
     const uint32_t t = (uint32_t)tl;                       // a launch starts at a tile boundary and never holds 2^32 patches
@@ -599,7 +603,7 @@ dm_final_patch_kernel(const FinalArgs a, long long n_patches) {
 
 template <int WS>
 static void launch_final_patch(const FinalArgs& fa, long long n_patches, cudaStream_t st) {
-    dm_final_patch_kernel<WS><<<dm_div_up(n_patches, 128), 128, 0, st>>>(fa, n_patches);
+    dm_launch_dep(DM_PDL_FINAL, dm_final_patch_kernel<WS>, dim3((unsigned)dm_div_up(n_patches, 128)), dim3(128), 0, st, fa, n_patches);
 }
 
 template <int WS>
@@ -632,9 +636,10 @@ int dm_fused_solve_chunk(dm_ctx* ctx, const dm_fused_args* a, int ck) {
         if ((rc = tm.begin(ck)) != DM_OK) return rc;
         dm_tile_origin_kernel2<<<dm_div_up(nt, 128), 128, 0, st>>>(fb.origin, fb.tinfo, nt, a->first_tile, a->len0, a->len1, a->s0, a->s1, a->scene_h);
         DM_LAUNCH_CHECK();
-        if ((rc = dm_descriptors(a->img1, a->scene_h * a->n_scenes, a->scene_w, a->scene_w, fb.origin, nt, t0, t1, a->ws, 1, fb.desc1, fb.stat1, st)) != DM_OK) return rc;
-        if ((rc = dm_descriptors(a->img2, a->scene_h * a->n_scenes, a->scene_w, a->scene_w, fb.origin, nt, t0, t1, a->ws, 2, fb.desc2, fb.stat2, st)) != DM_OK) return rc;
-        ctx->launches[DM_STAGE_DESCRIPTORS] += 3;
+        int n_desc = 0;
+        if ((rc = dm_descriptors_both(a->img1, a->img2, a->scene_h * a->n_scenes, a->scene_w, a->scene_w, fb.origin, nt, t0, t1, a->ws,
+                                      fb.desc1, fb.stat1, fb.desc2, fb.stat2, st, &n_desc)) != DM_OK) return rc;
+        ctx->launches[DM_STAGE_DESCRIPTORS] += 1 + n_desc;
         if ((rc = tm.end()) != DM_OK) return rc;
     }
     {
@@ -653,8 +658,10 @@ int dm_fused_solve_chunk(dm_ctx* ctx, const dm_fused_args* a, int ck) {
         // 64 threads making four or more trips each, not 256 threads and one trip: 32 small CTAs stay
         // resident per SM and a CTA's loads overlap its own arithmetic (C2: 0.838 -> 0.676 ms, 7.0 TB/s;
         // a variant that also gave the CTAs of small maps several parents was slower)
-        const int threads = q4 >= 256 ? 64 : (q4 < 32 ? 32 : q4);
-        dm_aggregate_first_kernel<<<(unsigned)parents, threads, 0, st>>>(fb.pooled, fb.rowmin, fb.rowmax, t0, t1, fb.level[1]);
+        static const int threads_env = getenv("DM_FIRST_THREADS") ? atoi(getenv("DM_FIRST_THREADS")) : 0;   // measurement aid
+        const int threads = threads_env > 0 ? threads_env : (q4 >= 256 ? 64 : (q4 < 32 ? 32 : q4));
+        dm_launch_dep(DM_PDL_FIRST, dm_aggregate_first_kernel, dim3((unsigned)parents), dim3(threads), 0, st,
+                      (const float*)fb.pooled, (const float*)fb.rowmin, (const float*)fb.rowmax, t0, t1, fb.level[1]);
         DM_LAUNCH_CHECK();
         ctx->launches[DM_STAGE_NORMALIZE] += 1;
         if ((rc = tm.end()) != DM_OK) return rc;
@@ -741,17 +748,25 @@ int dm_fused_solve_chunk(dm_ctx* ctx, const dm_fused_args* a, int ck) {
             dm_ctx::UpperGraph g;
             g.ws = ctx->ws; g.nt = nt; g.t0 = t0; g.t1 = t1; g.levels = L; g.kpad = a->kpad;
             g.filter_num = a->filter_num; g.filter_win = a->filter_win; g.filter_mode = a->filter_mode;
-            DM_CUDA_CHECK(cudaStreamBeginCapture(ctx->capture_stream, cudaStreamCaptureModeThreadLocal));
-            rc = run_agg(ctx->capture_stream, &g.n_agg);
-            if (rc == DM_OK) rc = run_bt(ctx->capture_stream, &g.n_bt);
-            cudaGraph_t graph = nullptr;
-            cudaError_t ce = cudaStreamEndCapture(ctx->capture_stream, &graph);
-            if (rc != DM_OK) { if (graph) cudaGraphDestroy(graph); return rc; }
+            // the launches carry the programmatic-dependent-launch attribute (programmatic edges between the kernel
+            // nodes); should a driver refuse those in a capture, the sequence is captured once more without it
+            cudaError_t ce = cudaSuccess;
+            for (int attempt = 0; attempt < 2; ++attempt) {
+                DM_CUDA_CHECK(cudaStreamBeginCapture(ctx->capture_stream, cudaStreamCaptureModeThreadLocal));
+                rc = run_agg(ctx->capture_stream, &g.n_agg);
+                if (rc == DM_OK) rc = run_bt(ctx->capture_stream, &g.n_bt);
+                cudaGraph_t graph = nullptr;
+                ce = cudaStreamEndCapture(ctx->capture_stream, &graph);
+                if (rc == DM_OK && ce == cudaSuccess) ce = cudaGraphInstantiate(&g.exec, graph, 0);
+                if (graph) cudaGraphDestroy(graph);
+                if (rc == DM_OK && ce == cudaSuccess) break;
+                if (attempt == 0 && dm_pdl_enabled(DM_PDL_UPPER)) { cudaGetLastError(); dm_pdl_suppress(true); rc = DM_OK; continue; }
+                break;
+            }
+            dm_pdl_suppress(false);
+            if (rc != DM_OK) return rc;
             DM_CUDA_CHECK(ce);
             g.final_cur = cur;
-            ce = cudaGraphInstantiate(&g.exec, graph, 0);
-            cudaGraphDestroy(graph);
-            DM_CUDA_CHECK(ce);
             ctx->upper_graphs.push_back(g);
             ug = &ctx->upper_graphs.back();
         }

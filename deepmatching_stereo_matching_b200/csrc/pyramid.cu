@@ -10,6 +10,7 @@
 // reads them back with 128-bit loads and hands the one-column halo between lanes with a
 // warp shuffle.
 #include <atomic>
+#include <cstdlib>
 
 #include "dm_common.cuh"
 
@@ -114,9 +115,11 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
 // Requirements of this kernel: D % 4 == 0 (16-byte rows), C even.
 __global__ void __launch_bounds__(256)
 dm_aggregate_kernel(const float* __restrict__ in, long long n_parents, int A, int B, int C, int D,
-                    int pp, int rb, int rect, dm_fastdiv fd_xp, dm_fastdiv fd_oc, float* __restrict__ out) {
+                    int pp, int rb, int rect, int merged, dm_fastdiv fd_xp, dm_fastdiv fd_oc, float* __restrict__ out) {
     extern __shared__ __align__(16) float smem[];
     __shared__ __align__(8) uint64_t bar;
+    dm_pdl_wait();                  // the level below comes from the kernel in front
+    dm_pdl_launch_dependents();
     const int hA = A >> 1, hB = B >> 1, oc = C >> 1, od = D >> 1;
     const long long parent0 = (long long)blockIdx.x * pp;
     const int npar = (int)min((long long)pp, n_parents - parent0);
@@ -133,7 +136,23 @@ dm_aggregate_kernel(const float* __restrict__ in, long long n_parents, int A, in
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
-    if (threadIdx.x == 0) {
+    if (threadIdx.x == 0 && merged) {
+        // whole slices, all parents of the CTA in one parent row I: the children (2I + c, 2J0 .. 2J0 + 2 pp - 1)
+        // of one child row are 2 pp consecutive slices of the input -- TWO bulk copies per CTA instead of 4 pp,
+        // and one index decode instead of pp (a 512^2 / image_size 32 level 1: 2 x 16 KiB instead of 32 x 1 KiB,
+        // each behind four 64-bit divisions of its own)
+        const int J0 = (int)(parent0 % hB);
+        const long long t = parent0 / hB;
+        const int I = (int)(t % hA);
+        const long long nn = t / hA;
+        const uint32_t run_bytes = chunk_bytes * 2u * (uint32_t)npar;
+        mbar_expect_tx(&bar, 2u * run_bytes);
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+            const size_t child = ((size_t)nn * A + (2 * I + c)) * B + 2 * J0;
+            bulk_g2s(smem + (size_t)c * 2 * npar * chunk, in + child * slice, run_bytes, &bar);
+        }
+    } else if (threadIdx.x == 0) {
         mbar_expect_tx(&bar, chunk_bytes * 4u * (uint32_t)npar);
         for (int k = 0; k < npar; ++k) {
             long long par = parent0 + k;
@@ -172,7 +191,9 @@ dm_aggregate_kernel(const float* __restrict__ in, long long n_parents, int A, in
         float sum0 = 0.f, sum1 = 0.f;
 #pragma unroll
         for (int ch = 0; ch < 4; ++ch) {
-            const float* base = smem + (size_t)(k * 4 + ch) * chunk;
+            // staged slice of child ch of parent k: parent-major, or (merged) the two child rows one after the other
+            const int slot = merged ? (ch >> 1) * 2 * npar + 2 * k + (ch & 1) : k * 4 + ch;
+            const float* base = smem + (size_t)slot * chunk;
             float m0 = NEG, m1 = NEG;
 #pragma unroll
             for (int dy = -1; dy <= 1; ++dy) {
@@ -274,7 +295,8 @@ extern "C" int dm_aggregate(const float* in_dev, int n, int a, int b, int c, int
     // (32 KiB for the small upper levels: a CTA there lives only a few microseconds, and six resident
     //  CTAs hide the load -> compute -> exit chain better than three: 0.234 -> 0.205 ms for level 1 -> 2 of C2)
     const size_t full = (size_t)4 * c * d * sizeof(float);          // four whole child slices
-    const size_t budget = full <= 16 * 1024 ? 32 * 1024 : 64 * 1024;
+    static const int budget_kb = getenv("DM_AGG_BUDGET_KB") ? atoi(getenv("DM_AGG_BUDGET_KB")) : 0;     // measurement aid
+    const size_t budget = budget_kb > 0 && full <= 16 * 1024 ? (size_t)budget_kb * 1024 : (full <= 16 * 1024 ? 32 * 1024 : 64 * 1024);
     int pp = 1, rb = oc;
     if (full <= budget) {
         pp = (int)(budget / full);
@@ -288,6 +310,13 @@ extern "C" int dm_aggregate(const float* in_dev, int n, int a, int b, int c, int
         if (rb > oc) rb = oc;
     }
     const int bands = dm_div_up(oc, rb);
+    // one band and the parents of a CTA inside one parent row: the staged slices are two contiguous runs of the input
+    static const bool no_merge = getenv("DM_AGG_NO_MERGE") != nullptr;     // measurement aid: one bulk copy per child slice
+    int merged = 0;
+    if (bands == 1 && !no_merge) {
+        while (pp > 1 && (b / 2) % pp != 0) --pp;
+        merged = 1;
+    }
     const int rows_staged = (bands == 1) ? c : 2 * rb + 1;
     const size_t smem = (size_t)pp * 4 * rows_staged * d * sizeof(float);
     DM_REQUIRE(smem <= 200 * 1024, DM_ERR_UNSUPPORTED, "dm_aggregate: row of %d floats too wide for shared memory", d);
@@ -301,7 +330,8 @@ extern "C" int dm_aggregate(const float* in_dev, int n, int a, int b, int c, int
         }
     }
     dim3 grid((unsigned)dm_div_up(n_parents, pp), bands);
-    dm_aggregate_kernel<<<grid, 256, smem, st>>>(in_dev, n_parents, a, b, c, d, pp, rb, rectify, dm_make_fastdiv((uint32_t)(d >> 2)), dm_make_fastdiv((uint32_t)oc), out_dev);
+    dm_launch_dep(DM_PDL_UPPER, dm_aggregate_kernel, grid, dim3(256), smem, st, in_dev, n_parents, a, b, c, d, pp, rb, rectify, merged,
+                  dm_make_fastdiv((uint32_t)(d >> 2)), dm_make_fastdiv((uint32_t)oc), out_dev);
     DM_LAUNCH_CHECK();
     return DM_OK;
 }

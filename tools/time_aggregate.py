@@ -3,8 +3,9 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from deepmatching_stereo_matching_b200 import _native
 lib = _native.lib()
-n = 225
-for (A, C) in ((32, 32), (16, 16)):
+# level transitions of the fused path: C2 (225 tiles, image_size 64): level 1 -> 2 and 2 -> 3; C4 (a quarter of the
+# 12544 tiles of 64 x 512^2, image_size 32): level 1 -> 2.  Knobs: DM_AGG_NO_MERGE, DM_AGG_BUDGET_KB, DM_PDL.
+for (n, A, C) in ((225, 32, 32), (225, 16, 16), (3136, 16, 16)):
     x = torch.rand((n, A, A, C, C), dtype=torch.float32, device='cuda')
     y = torch.empty((n, A // 2, A // 2, C // 2, C // 2), dtype=torch.float32, device='cuda')
     for _ in range(3):
@@ -21,4 +22,4 @@ for (A, C) in ((32, 32), (16, 16)):
         tot += e0.elapsed_time(e1)
     ms = tot / 10
     gb = (x.numel() + y.numel()) * 4 / 1e9
-    print('level %dx%d  %.4f ms  %.0f GB/s' % (A, C, ms, gb / ms * 1e3))
+    print('n %d level %dx%d  %.4f ms  %.0f GB/s' % (n, A, C, ms, gb / ms * 1e3), flush=True)
