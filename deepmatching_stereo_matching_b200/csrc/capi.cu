@@ -23,7 +23,7 @@ void dm_set_error(const char* fmt, ...) {
 extern "C" const char* dm_last_error(void) { return g_err; }
 
 // programmatic dependent launch between the kernels of a chunk (dm_common.cuh); DM_PDL = mask of DM_PDL_*
-#define DM_PDL_DEFAULT 0
+#define DM_PDL_DEFAULT DM_PDL_CORR
 static thread_local bool g_pdl_suppressed = false;
 bool dm_pdl_enabled(int which) {
     static const int mask = getenv("DM_PDL") ? atoi(getenv("DM_PDL")) : DM_PDL_DEFAULT;

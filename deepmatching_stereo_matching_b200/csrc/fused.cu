@@ -130,6 +130,80 @@ dm_aggregate_first_kernel(const float* __restrict__ pooled, const float* __restr
     }
 }
 
+// Small maps (P/16 <= 64 float4 per parent map, image_size <= 32): one WARP per parent, warps striding over the
+// parents of a persistent grid.  With one 64-thread CTA per parent a 64 x 512^2 batch is 3.2 million CTAs of ~400
+// instructions each, and the rate at which CTAs can be handed out -- not HBM, not the instruction count -- bounds
+// the kernel (four parents per CTA: -5 %; cooperative statistics alone: nothing).  A lane owns TRIPS float4
+// columns of the parent's map; all its loads (TRIPS x 4 map loads + the statistics of child lane & 3) are issued
+// before any arithmetic.  Same operations in the same order as dm_aggregate_first_kernel: bit-identical level 1.
+template <int TRIPS>
+__global__ void __launch_bounds__(256, 4)
+dm_aggregate_first_small_kernel(const float* __restrict__ pooled, const float* __restrict__ rowmin,
+                                const float* __restrict__ rowmax, int t0, int t1, unsigned n_parents,
+                                dm_fastdiv fd_hb, dm_fastdiv fd_ha, float* __restrict__ out) {
+    dm_pdl_wait();
+    dm_pdl_launch_dependents();
+    const int P = t0 * t1, Q4 = P >> 4;
+    const int hA = t0 >> 1, hB = t1 >> 1;
+    const int lane = threadIdx.x & 31, c = lane & 3;
+    const unsigned warps = gridDim.x * (blockDim.x >> 5);
+    for (unsigned par = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); par < n_parents; par += warps) {
+        const unsigned t = dm_fd_div(par, fd_hb);
+        const int J = (int)(par - t * (unsigned)hB);
+        const unsigned nn = dm_fd_div(t, fd_ha);
+        const int I = (int)(t - nn * (unsigned)hA);
+        const size_t p00 = (size_t)nn * P + (size_t)(2 * I) * t1 + 2 * J;
+        const float4* src[4];
+        src[0] = reinterpret_cast<const float4*>(pooled) + p00 * (size_t)Q4;
+        src[1] = src[0] + Q4;
+        src[2] = src[0] + (size_t)t1 * (size_t)Q4;
+        src[3] = src[2] + Q4;
+        float4 v[TRIPS][4];
+#pragma unroll
+        for (int tr = 0; tr < TRIPS; ++tr) {
+            const int m4 = lane + 32 * tr;
+            if (m4 < Q4) {
+#pragma unroll
+                for (int ch = 0; ch < 4; ++ch) v[tr][ch] = __ldg(src[ch] + m4);
+            }
+        }
+        const size_t p = p00 + (size_t)(c >> 1) * t1 + (c & 1);
+        const float4 pmn = __ldg(reinterpret_cast<const float4*>(rowmin) + p), pmx = __ldg(reinterpret_cast<const float4*>(rowmax) + p);
+        const float cmn = dm_min_nan(dm_min_nan(pmn.x, pmn.y), dm_min_nan(pmn.z, pmn.w));
+        const float cmx = dm_max_nan(dm_max_nan(pmx.x, pmx.y), dm_max_nan(pmx.z, pmx.w));
+        const float cinv = dm_range_inv(cmn, cmx);
+        float mn[4], mx[4], rinv[4];
+#pragma unroll
+        for (int ch = 0; ch < 4; ++ch) {
+            mn[ch] = __shfl_sync(0xffffffffu, cmn, ch);
+            mx[ch] = __shfl_sync(0xffffffffu, cmx, ch);
+            rinv[ch] = __shfl_sync(0xffffffffu, cinv, ch);
+        }
+        float4* dst = reinterpret_cast<float4*>(out) + (size_t)par * Q4;
+#pragma unroll
+        for (int tr = 0; tr < TRIPS; ++tr) {
+            const int m4 = lane + 32 * tr;
+            if (m4 < Q4) {
+                float4 sum;
+#pragma unroll
+                for (int ch = 0; ch < 4; ++ch) {
+                    float4 r;
+                    r.x = dm_rectify(dm_normalize(v[tr][ch].x, mn[ch], mx[ch], rinv[ch]));
+                    r.y = dm_rectify(dm_normalize(v[tr][ch].y, mn[ch], mx[ch], rinv[ch]));
+                    r.z = dm_rectify(dm_normalize(v[tr][ch].z, mn[ch], mx[ch], rinv[ch]));
+                    r.w = dm_rectify(dm_normalize(v[tr][ch].w, mn[ch], mx[ch], rinv[ch]));
+                    if (ch == 0) sum = r;
+                    else { sum.x = __fadd_rn(sum.x, r.x); sum.y = __fadd_rn(sum.y, r.y); sum.z = __fadd_rn(sum.z, r.z); sum.w = __fadd_rn(sum.w, r.w); }
+                }
+                float4 o;
+                o.x = dm_rectify(__fmul_rn(sum.x, 0.25f)); o.y = dm_rectify(__fmul_rn(sum.y, 0.25f));
+                o.z = dm_rectify(__fmul_rn(sum.z, 0.25f)); o.w = dm_rectify(__fmul_rn(sum.w, 0.25f));
+                dst[m4] = o;
+            }
+        }
+    }
+}
+
 // ---------------------------------------------------------------------------------------
 // Final level: arguments.
 // ---------------------------------------------------------------------------------------
@@ -656,12 +730,25 @@ int dm_fused_solve_chunk(dm_ctx* ctx, const dm_fused_args* a, int ck) {
         const long long parents = (long long)nt * (P / 4);
         const int q4 = P / 16;
         // 64 threads making four or more trips each, not 256 threads and one trip: 32 small CTAs stay
-        // resident per SM and a CTA's loads overlap its own arithmetic (C2: 0.838 -> 0.676 ms, 7.0 TB/s;
-        // a variant that also gave the CTAs of small maps several parents was slower)
-        static const int threads_env = getenv("DM_FIRST_THREADS") ? atoi(getenv("DM_FIRST_THREADS")) : 0;   // measurement aid
-        const int threads = threads_env > 0 ? threads_env : (q4 >= 256 ? 64 : (q4 < 32 ? 32 : q4));
-        dm_launch_dep(DM_PDL_FIRST, dm_aggregate_first_kernel, dim3((unsigned)parents), dim3(threads), 0, st,
-                      (const float*)fb.pooled, (const float*)fb.rowmin, (const float*)fb.rowmax, t0, t1, fb.level[1]);
+        // resident per SM and a CTA's loads overlap its own arithmetic (C2: 0.838 -> 0.676 ms, 7.0 TB/s)
+        const int threads = q4 >= 256 ? 64 : (q4 < 32 ? 32 : q4);
+        static const bool first_cta = getenv("DM_FIRST_CTA") != nullptr;       // measurement aid: one CTA per parent for small maps too
+        if (q4 <= 64 && !first_cta) {
+            // small maps: a persistent grid of warps striding over the parents (dm_aggregate_first_small_kernel)
+            int dev = 0, sms = 148, per_sm = 4;
+            auto sk = q4 > 32 ? dm_aggregate_first_small_kernel<2> : dm_aggregate_first_small_kernel<1>;
+            DM_CUDA_CHECK(cudaGetDevice(&dev));
+            DM_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+            DM_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sk, 256, 0));
+            long long blocks = (long long)sms * (per_sm > 0 ? per_sm : 1);
+            if (blocks > (parents + 7) / 8) blocks = (parents + 7) / 8;
+            DM_CUDA_CHECK(dm_launch_dep(DM_PDL_FIRST, sk, dim3((unsigned)blocks), dim3(256), 0, st,
+                                        (const float*)fb.pooled, (const float*)fb.rowmin, (const float*)fb.rowmax, t0, t1, (unsigned)parents,
+                                        dm_make_fastdiv((uint32_t)(t1 >> 1)), dm_make_fastdiv((uint32_t)(t0 >> 1)), fb.level[1]));
+        } else {
+            DM_CUDA_CHECK(dm_launch_dep(DM_PDL_FIRST, dm_aggregate_first_kernel, dim3((unsigned)parents), dim3(threads), 0, st,
+                                        (const float*)fb.pooled, (const float*)fb.rowmin, (const float*)fb.rowmax, t0, t1, fb.level[1]));
+        }
         DM_LAUNCH_CHECK();
         ctx->launches[DM_STAGE_NORMALIZE] += 1;
         if ((rc = tm.end()) != DM_OK) return rc;
