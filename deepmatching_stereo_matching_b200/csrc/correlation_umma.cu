@@ -80,6 +80,7 @@ struct Params {
     float* raw;                 // MODE_RAW : [n][P][P]
     float* pooled;              // MODE_POOL: [n][P][P/4]
     float* rowmin; float* rowmax;   // MODE_POOL: [n][P][4] partial min / max: each column half writes its value twice
+    int pair_flush;                 // MODE_POOL, D == 64: the two column halves of a patch row leave as one 128-byte line (below)
 };
 
 enum { MODE_RAW = 0, MODE_POOL = 1, MODE_NULL = 2 };   // MODE_NULL: drain TMEM only (measurement aid)
@@ -253,6 +254,18 @@ dm_correlation_umma_kernel(const __grid_constant__ CUtensorMap mapA, const __gri
         const int wsw = (lane >> 1) & 3;                // XOR swizzle of this lane's own staging row
         float4* stgA_mine = reinterpret_cast<float4*>(stgA + lane * STG_STRIDE);
         float4* stgB_mine = reinterpret_cast<float4*>(stgB + lane * STG_STRIDE);
+        // Pair flush (MODE_POOL, D == 64).  The warps e and e + 4 own the two column halves of the same 32 + 32 patch
+        // rows; flushed separately, every store instruction writes 8 rows x 64 B -- half a line per row, 8 L1
+        // wavefronts for 512 bytes.  Here both warps stage into two SHARED regions instead (rows of 32 floats, the
+        // 16-byte slots XOR-swizzled by row & 7: conflict-free both ways) -- the first warp's region collects
+        // accumulator half A, the second warp's half B --, meet at a named barrier, and each flushes ONE region as
+        // whole 128-byte lines: 4 rows x 128 B per store instruction, half the global-store wavefronts.
+        constexpr bool PF_SHAPE = (MODE == MODE_POOL && D == 64);
+        const bool pf = PF_SHAPE && prm.pair_flush != 0;
+        float* regionX = smemStg + (size_t)quarter * (2 * 32 * STG_STRIDE);
+        float* regionY = smemStg + (size_t)(quarter + 4) * (2 * 32 * STG_STRIDE);
+        float4* xs_mine = reinterpret_cast<float4*>(regionX + lane * 32);
+        float4* ys_mine = reinterpret_cast<float4*>(regionY + lane * 32);
         int acc = 0; uint32_t accph = 0; int cst = 0; uint32_t cph = 0;
         const uint32_t t_empty_lead = PAIR ? umma::mapa_u32(t_empty, 0) : 0;     // the leader's MMA warp waits for both CTAs' epilogues
         for (int unit = slot; unit < n_units; unit += n_slots) {
@@ -287,6 +300,27 @@ dm_correlation_umma_kernel(const __grid_constant__ CUtensorMap mapA, const __gri
 #pragma unroll
                 for (int it = 0; it < 4; ++it) *reinterpret_cast<float4*>(dst + (size_t)(it * 8) * ostride) = v[it];
                 __syncwarp();
+            };
+            // pair flush: this warp writes the 32 rows x 32 floats of ITS region (ch 0: half A, ch 1: half B)
+            auto flush_pair = [&](size_t col) {
+                asm volatile("bar.sync %0, 64;" ::"r"(1 + quarter) : "memory");      // both column halves are staged
+                const uint32_t sa = umma::smem_u32(ch ? regionY : regionX);
+                float* wout = ch ? woutB : woutA;
+#pragma unroll
+                for (int hb = 0; hb < 2; ++hb) {
+                    float4 v[4];
+#pragma unroll
+                    for (int it = 0; it < 4; ++it) {
+                        const int row = (hb * 4 + it) * 4 + (lane >> 3);
+                        v[it] = umma::lds128(sa + (uint32_t)((row * 32 + (((lane & 7) ^ (row & 7)) << 2)) * 4));
+                    }
+#pragma unroll
+                    for (int it = 0; it < 4; ++it) {
+                        const int row = (hb * 4 + it) * 4 + (lane >> 3);
+                        *reinterpret_cast<float4*>(wout + (size_t)row * ostride + col + (size_t)((lane & 7) << 2)) = v[it];
+                    }
+                }
+                asm volatile("bar.sync %0, 64;" ::"r"(1 + quarter) : "memory");      // the regions may be overwritten
             };
             for (int j = 0; j < NT; ++j) {
                 umma::mbar_wait(c_full + cst, cph);
@@ -403,14 +437,23 @@ dm_correlation_umma_kernel(const __grid_constant__ CUtensorMap mapA, const __gri
                                 const int ol = (D == 128) ? xh : (r >> 1) * HWQ + xh;
                                 if ((ol & 3) == 0) { obA.x = oA; obB.x = oB; } else if ((ol & 3) == 1) { obA.y = oA; obB.y = oB; }
                                 else if ((ol & 3) == 2) { obA.z = oA; obB.z = oB; } else { obA.w = oA; obB.w = oB; }
-                                if ((ol & 3) == 3) { stgA_mine[((ol & 15) >> 2) ^ wsw] = obA; stgB_mine[((ol & 15) >> 2) ^ wsw] = obB; }
+                                if ((ol & 3) == 3) {
+                                    if (PF_SHAPE && pf) {
+                                        const int slot = (ch * 4 + ((ol & 15) >> 2)) ^ (lane & 7);
+                                        xs_mine[slot] = obA; ys_mine[slot] = obB;
+                                    } else { stgA_mine[((ol & 15) >> 2) ^ wsw] = obA; stgB_mine[((ol & 15) >> 2) ^ wsw] = obB; }
+                                }
                                 if ((ol & 15) == 15) {
-                                    // first pooled row / column of the group; segments of min(16, D/4) floats, one per pooled row
-                                    constexpr int SEG = HWQ < 16 ? HWQ : 16;
-                                    const size_t col = (D == 128) ? (size_t)(j >> 1) * DH + (size_t)ch * HWQ + (ol - 15)
-                                                                  : (size_t)j * (BN / 4) + (size_t)ch * HWQ;
-                                    flush16(stgA, woutA, col, SEG, DH);
-                                    flush16(stgB, woutB, col, SEG, DH);
+                                    if (PF_SHAPE && pf) {
+                                        flush_pair((size_t)j * (BN / 4));
+                                    } else {
+                                        // first pooled row / column of the group; segments of min(16, D/4) floats, one per pooled row
+                                        constexpr int SEG = HWQ < 16 ? HWQ : 16;
+                                        const size_t col = (D == 128) ? (size_t)(j >> 1) * DH + (size_t)ch * HWQ + (ol - 15)
+                                                                      : (size_t)j * (BN / 4) + (size_t)ch * HWQ;
+                                        flush16(stgA, woutA, col, SEG, DH);
+                                        flush16(stgB, woutB, col, SEG, DH);
+                                    }
                                 }
                             }
                         }
@@ -566,6 +609,7 @@ static int fill_params(Params& prm, CUtensorMap& mapA, CUtensorMap& mapB, CUtens
     if (prm.ksteps <= 0 || prm.ksteps > kpad / UMMA_K) prm.ksteps = kpad / UMMA_K;
     prm.n_items = n_tiles * prm.items_per_tile;
     prm.raw = prm.pooled = prm.rowmin = prm.rowmax = nullptr;
+    prm.pair_flush = 0;
     return DM_OK;
 }
 
@@ -597,6 +641,8 @@ int dm_correlation_umma_pool(const void* desc1, const float* stat1, const void* 
     int rc = fill_params(prm, mapA, mapB, mapBp, desc1, stat1, desc2, stat2, n_tiles, t0 * t1, kpad, kreal);
     if (rc != DM_OK) return rc;
     prm.pooled = pooled; prm.rowmin = rowmin; prm.rowmax = rowmax;
+    static const bool no_pair_flush = getenv("DM_CORR_NO_PAIR_FLUSH") != nullptr;       // measurement aid: every warp flushes its own half rows
+    prm.pair_flush = no_pair_flush ? 0 : 1;
     const bool normed = method == DM_TM_CCOEFF_NORMED;
     if (t1 == 128) return launch<MODE_POOL, 128>(mapA, mapB, mapBp, prm, normed, stream);
     if (t1 == 64) return launch<MODE_POOL, 64>(mapA, mapB, mapBp, prm, normed, stream);
