@@ -260,6 +260,8 @@ dm_correlation_umma_kernel(const __grid_constant__ CUtensorMap mapA, const __gri
         // 16-byte slots XOR-swizzled by row & 7: conflict-free both ways) -- the first warp's region collects
         // accumulator half A, the second warp's half B --, meet at a named barrier, and each flushes ONE region as
         // whole 128-byte lines: 4 rows x 128 B per store instruction, half the global-store wavefronts.
+        // (Measured at D == 32 as well -- two pooled rows of 16 per N-tile, a thread contributing 8 + 8 floats of the
+        // row's 32 -- bit-identical, but no faster there: 3.865 vs 3.875 ms on 64 x 512^2, ws 5; left on the per-warp flush.)
         constexpr bool PF_SHAPE = (MODE == MODE_POOL && D == 64);
         const bool pf = PF_SHAPE && prm.pair_flush != 0;
         float* regionX = smemStg + (size_t)quarter * (2 * 32 * STG_STRIDE);
@@ -439,6 +441,7 @@ dm_correlation_umma_kernel(const __grid_constant__ CUtensorMap mapA, const __gri
                                 else if ((ol & 3) == 2) { obA.z = oA; obB.z = oB; } else { obA.w = oA; obB.w = oB; }
                                 if ((ol & 3) == 3) {
                                     if (PF_SHAPE && pf) {
+                                        // 16-byte slot inside the row's 32 floats: this column half's 16 floats of the pooled row
                                         const int slot = (ch * 4 + ((ol & 15) >> 2)) ^ (lane & 7);
                                         xs_mine[slot] = obA; ys_mine[slot] = obB;
                                     } else { stgA_mine[((ol & 15) >> 2) ^ wsw] = obA; stgB_mine[((ol & 15) >> 2) ^ wsw] = obB; }
