@@ -112,9 +112,11 @@ def kernels(tag, rep, path_name):
     tp = os.path.join(PROF, 'ncu_traffic.json')
     traffic = json.load(open(tp)) if os.path.exists(tp) else {}
     t = traffic.setdefault(path_name, {})
+    seen = {}
     for d in res:
         name = d['kernel'].split('<')[0]
-        t[name] = max(t.get(name, 0), d['dram_read_bytes'] + d['dram_write_bytes'])     # the largest launch of that kernel
+        seen[name] = max(seen.get(name, 0), d['dram_read_bytes'] + d['dram_write_bytes'])     # the largest launch of that kernel in THIS report
+    t.update(seen)
     json.dump(traffic, open(tp, 'w'), indent=1, sort_keys=True)
     print('wrote', tag + '_kernels.csv/.md and ncu_traffic.json')
 
