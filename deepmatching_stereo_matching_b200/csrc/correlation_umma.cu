@@ -73,6 +73,25 @@ constexpr size_t OFF_CS = OFF_STG + (size_t)EPI_WARPS * STG_BYTES;
 constexpr size_t OFF_BAR = OFF_CS + CS_STAGES * CS_BYTES;
 constexpr size_t SMEM_BYTES = 1024 /*align slack*/ + OFF_BAR + 256;
 
+// Per-instance carve-up.  WIDE (pooled epilogue at D == 128): a thread completes 32 consecutive pooled floats of a
+// patch row per map-row pair -- a whole 128-byte line -- but 16-float staging rows made it leave as two 64-byte
+// pieces (8 rows x 64 B per store instruction: 8 L1 wavefronts for 512 bytes).  Staging rows of 32 floats need
+// 8 KiB per epilogue warp; the 32 KiB come from the B ring (4 stages of 8 KiB = one N-tile of K blocks on CTA
+// pairs, 2 of 16 KiB on a single CTA) and from the column-table ring (2 stages).
+template <bool WIDE, bool PAIR>
+struct Layout {
+    static constexpr int NSTG = PAIR ? (WIDE ? 4 : STAGES_PAIR) : (WIDE ? 2 : STAGES);
+    static constexpr int B_STAGE = PAIR ? BOX_BYTES / 2 : BOX_BYTES;
+    static constexpr int CSN = WIDE ? 2 : CS_STAGES;
+    static constexpr int STG_WARP = WIDE ? 2 * STG_BYTES : STG_BYTES;
+    static constexpr size_t O_STG = OFF_B + (size_t)NSTG * B_STAGE;
+    static constexpr size_t O_CS = O_STG + (size_t)EPI_WARPS * STG_WARP;
+    static constexpr size_t O_BAR = O_CS + (size_t)CSN * CS_BYTES;
+    static constexpr size_t SMEM = 1024 /*align slack*/ + O_BAR + 256;
+};
+static_assert(Layout<false, true>::SMEM == SMEM_BYTES && Layout<false, false>::SMEM == SMEM_BYTES, "the default carve-up is the one above");
+static_assert(Layout<true, true>::SMEM <= 227 * 1024 && Layout<true, false>::SMEM <= 227 * 1024, "wide staging does not fit");
+
 struct Params {
     const dm_stat* stat1;       // [n*P] float4 {S', inv, S'/K, mean}
     const float* inv2;          // [n*P] inv of the windows of image 2 (compact table written by dm_descriptors)
@@ -88,7 +107,7 @@ enum { MODE_RAW = 0, MODE_POOL = 1, MODE_NULL = 2 };   // MODE_NULL: drain TMEM 
 // PAIR: the CTA pair of a 2-CTA cluster works on 512 patches of one tile (256 per CTA, epilogue
 // unchanged) with tcgen05.mma.cta_group::2 (M = 256 across the pair, N = 128): each CTA fetches
 // only HALF of every B tile from its own shared memory and streams only half of B from L2.
-template <int MODE, int D, bool NORMED, bool PAIR>      // D = positions per map row (T1); only used by MODE_POOL
+template <int MODE, int D, bool NORMED, bool PAIR, bool WIDE>      // D = positions per map row (T1); only used by MODE_POOL
 __global__ void __launch_bounds__(THREADS, 1)
 dm_correlation_umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const Params prm) {
     extern __shared__ uint8_t smem_raw[];
@@ -96,12 +115,15 @@ dm_correlation_umma_kernel(const __grid_constant__ CUtensorMap mapA, const __gri
     uint8_t* smem = smem_raw + ((1024u - (umma::smem_u32(smem_raw) & 1023u)) & 1023u);
     uint8_t* smemA = smem + OFF_A;
     uint8_t* smemB = smem + OFF_B;
-    float* smemStg = reinterpret_cast<float*>(smem + OFF_STG);
-    uint8_t* smemCs = smem + OFF_CS;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
+    using L = Layout<WIDE, PAIR>;
+    static_assert(!WIDE || (MODE == MODE_POOL && D == 128), "wide staging exists for the pooled epilogue at D == 128");
+    float* smemStg = reinterpret_cast<float*>(smem + L::O_STG);
+    uint8_t* smemCs = smem + L::O_CS;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::O_BAR);
     uint64_t* a_full = bars;
     uint64_t* a_empty = bars + 1;
-    constexpr int NSTG = PAIR ? STAGES_PAIR : STAGES;
+    constexpr int NSTG = L::NSTG;
+    constexpr int CSN = L::CSN;
     constexpr int ISSUERS = 1;              // 2: warps 1 and 2 of the leader each issue the MMAs of one accumulator half
     constexpr int B_STAGE_BYTES = PAIR ? BOX_BYTES / 2 : BOX_BYTES;
     uint64_t* b_full = bars + 2;
@@ -109,8 +131,8 @@ dm_correlation_umma_kernel(const __grid_constant__ CUtensorMap mapA, const __gri
     uint64_t* t_full = bars + 2 + 2 * NSTG;
     uint64_t* t_empty = bars + 4 + 2 * NSTG;
     uint64_t* c_full = bars + 6 + 2 * NSTG;
-    uint64_t* c_empty = bars + 6 + 2 * NSTG + CS_STAGES;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 6 + 2 * NSTG + 2 * CS_STAGES);
+    uint64_t* c_empty = bars + 6 + 2 * NSTG + CSN;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 6 + 2 * NSTG + 2 * CSN);
 
     const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;   // provably warp-uniform
     const int P = prm.P, KB = prm.KB, NT = P / BN;
@@ -128,7 +150,7 @@ dm_correlation_umma_kernel(const __grid_constant__ CUtensorMap mapA, const __gri
         umma::mbar_init(a_empty, ISSUERS);
         for (int s = 0; s < NSTG; ++s) { umma::mbar_init(b_full + s, 1); umma::mbar_init(b_empty + s, ISSUERS); }
         for (int s = 0; s < 2; ++s) { umma::mbar_init(t_full + s, ISSUERS); umma::mbar_init(t_empty + s, (PAIR ? 2 : 1) * EPI_WARPS); }
-        for (int s = 0; s < CS_STAGES; ++s) { umma::mbar_init(c_full + s, 1); umma::mbar_init(c_empty + s, EPI_WARPS); }
+        for (int s = 0; s < CSN; ++s) { umma::mbar_init(c_full + s, 1); umma::mbar_init(c_empty + s, EPI_WARPS); }
         umma::fence_barrier_init();
         umma::tma_prefetch_desc(&mapA);
         umma::tma_prefetch_desc(&mapB);
@@ -197,7 +219,7 @@ dm_correlation_umma_kernel(const __grid_constant__ CUtensorMap mapA, const __gri
                     umma::bulk_g2s(smemCs + (size_t)cst * CS_BYTES, prm.inv2 + ((size_t)tile * P + (size_t)j * BN), CS_BYTES, c_full + cst);
                 }
                 __syncwarp();
-                if (++cst == CS_STAGES) { cst = 0; cph ^= 1; }
+                if (++cst == CSN) { cst = 0; cph ^= 1; }
             }
         }
     } else if ((warp == 1 || (ISSUERS == 2 && warp == 2)) && rank == 0) {
@@ -249,8 +271,10 @@ dm_correlation_umma_kernel(const __grid_constant__ CUtensorMap mapA, const __gri
         const int ch = e >> 2;                          // which half of every map row's columns
         constexpr int DH = D / 2;                       // columns of a map row handled by this thread
         constexpr int HWQ = (MODE == MODE_POOL) ? D / 4 : 1;    // pooled outputs per map row per thread
-        float* stgA = smemStg + (size_t)e * (2 * 32 * STG_STRIDE);
-        float* stgB = stgA + 32 * STG_STRIDE;
+        float* stgA = smemStg + (size_t)e * (L::STG_WARP / 4);
+        float* stgB = stgA + (WIDE ? 32 * 32 : 32 * STG_STRIDE);
+        float4* wideA_mine = reinterpret_cast<float4*>(stgA + lane * 32);      // WIDE: rows of 32 floats, 16-byte slots XOR-swizzled by row & 7
+        float4* wideB_mine = reinterpret_cast<float4*>(stgB + lane * 32);
         const int wsw = (lane >> 1) & 3;                // XOR swizzle of this lane's own staging row
         float4* stgA_mine = reinterpret_cast<float4*>(stgA + lane * STG_STRIDE);
         float4* stgB_mine = reinterpret_cast<float4*>(stgB + lane * STG_STRIDE);
@@ -301,6 +325,26 @@ dm_correlation_umma_kernel(const __grid_constant__ CUtensorMap mapA, const __gri
                 float* dst = wout + (size_t)(lane >> 2) * ostride + col + (size_t)(f4 / seg) * segstride + (f4 % seg);
 #pragma unroll
                 for (int it = 0; it < 4; ++it) *reinterpret_cast<float4*>(dst + (size_t)(it * 8) * ostride) = v[it];
+                __syncwarp();
+            };
+            // WIDE: 32 staged floats per lane -> the warp writes 4 rows x 128 B per store instruction
+            auto flush32 = [&](const float* stg, float* wout, size_t col) {
+                __syncwarp();
+                const uint32_t sa = umma::smem_u32(stg);
+#pragma unroll
+                for (int hb = 0; hb < 2; ++hb) {
+                    float4 v[4];
+#pragma unroll
+                    for (int it = 0; it < 4; ++it) {
+                        const int row = (hb * 4 + it) * 4 + (lane >> 3);
+                        v[it] = umma::lds128(sa + (uint32_t)((row * 32 + (((lane & 7) ^ (row & 7)) << 2)) * 4));
+                    }
+#pragma unroll
+                    for (int it = 0; it < 4; ++it) {
+                        const int row = (hb * 4 + it) * 4 + (lane >> 3);
+                        *reinterpret_cast<float4*>(wout + (size_t)row * ostride + col + (size_t)((lane & 7) << 2)) = v[it];
+                    }
+                }
                 __syncwarp();
             };
             // pair flush: this warp writes the 32 rows x 32 floats of ITS region (ch 0: half A, ch 1: half B)
@@ -444,9 +488,17 @@ dm_correlation_umma_kernel(const __grid_constant__ CUtensorMap mapA, const __gri
                                         // 16-byte slot inside the row's 32 floats: this column half's 16 floats of the pooled row
                                         const int slot = (ch * 4 + ((ol & 15) >> 2)) ^ (lane & 7);
                                         xs_mine[slot] = obA; ys_mine[slot] = obB;
+                                    } else if (WIDE) {
+                                        wideA_mine[(ol >> 2) ^ (lane & 7)] = obA; wideB_mine[(ol >> 2) ^ (lane & 7)] = obB;
                                     } else { stgA_mine[((ol & 15) >> 2) ^ wsw] = obA; stgB_mine[((ol & 15) >> 2) ^ wsw] = obB; }
                                 }
-                                if ((ol & 15) == 15) {
+                                if (WIDE) {
+                                    if (ol == 31) {         // the thread's 32 pooled floats of this pooled row: one line per patch row
+                                        const size_t col = (size_t)(j >> 1) * DH + (size_t)ch * HWQ;
+                                        flush32(stgA, woutA, col);
+                                        flush32(stgB, woutB, col);
+                                    }
+                                } else if ((ol & 15) == 15) {
                                     if (PF_SHAPE && pf) {
                                         flush_pair((size_t)j * (BN / 4));
                                     } else {
@@ -470,7 +522,7 @@ dm_correlation_umma_kernel(const __grid_constant__ CUtensorMap mapA, const __gri
                     umma::mbar_arrive(c_empty + cst);
                 }
                 if (++acc == 2) { acc = 0; accph ^= 1; }
-                if (++cst == CS_STAGES) { cst = 0; cph ^= 1; }
+                if (++cst == CSN) { cst = 0; cph ^= 1; }
             }
             if (MODE == MODE_POOL) {
                 // partial min / max of this column half; flat patch: OpenCV's map is all ones
@@ -506,14 +558,15 @@ dm_encode_tiled_fn get_encode_fn() {
 
 std::atomic<int> g_pair_mode{-1};       // -1: CTA pairs whenever the shape allows, 0: never, 1: same as -1 (dm_correlation_set_pair_mode)
 
-template <int MODE, int D, bool NORMED, bool PAIR>
+template <int MODE, int D, bool NORMED, bool PAIR, bool WIDE>
 int launch3(const CUtensorMap& mapA, const CUtensorMap& mapB, const Params& prm, cudaStream_t stream) {
+    constexpr size_t SMEM_BYTES = Layout<WIDE, PAIR>::SMEM;
     // per-device state: cudaFuncSetAttribute and the cluster occupancy belong to the device, and one
     // process may drive several devices from several threads (dm_multi_*).  -1 = not configured yet;
     // two threads racing on the same device compute the same values.
     constexpr int MAX_DEV = 64;
     static std::atomic<int> state[MAX_DEV];         // 0 = unconfigured, else 1 + co-resident CTA pairs
-    auto kern = dm_correlation_umma_kernel<MODE, D, NORMED, PAIR>;
+    auto kern = dm_correlation_umma_kernel<MODE, D, NORMED, PAIR, WIDE>;
     int dev = 0, sms = 0;
     DM_CUDA_CHECK(cudaGetDevice(&dev));
     DM_REQUIRE(dev >= 0 && dev < MAX_DEV, DM_ERR_UNSUPPORTED, "tcgen05 correlation: device index %d not supported", dev);
@@ -563,8 +616,14 @@ int launch3(const CUtensorMap& mapA, const CUtensorMap& mapB, const Params& prm,
 template <int MODE, int D, bool NORMED>
 int launch2(const CUtensorMap& mapA, const CUtensorMap& mapB, const CUtensorMap& mapB_pair, const Params& prm, cudaStream_t stream) {
     // a pair's work unit is two consecutive items of the same tile
-    if (g_pair_mode.load(std::memory_order_relaxed) != 0 && prm.items_per_tile % 2 == 0) return launch3<MODE, D, NORMED, true>(mapA, mapB_pair, prm, stream);
-    return launch3<MODE, D, NORMED, false>(mapA, mapB, prm, stream);
+    const bool pair = g_pair_mode.load(std::memory_order_relaxed) != 0 && prm.items_per_tile % 2 == 0;
+    if constexpr (MODE == MODE_POOL && D == 128) {
+        static const bool no_wide = getenv("DM_CORR_NO_WIDE") != nullptr;        // measurement aid: 16-float staging rows, deeper B ring
+        if (!no_wide) return pair ? launch3<MODE, D, NORMED, true, true>(mapA, mapB_pair, prm, stream)
+                                  : launch3<MODE, D, NORMED, false, true>(mapA, mapB, prm, stream);
+    }
+    if (pair) return launch3<MODE, D, NORMED, true, false>(mapA, mapB_pair, prm, stream);
+    return launch3<MODE, D, NORMED, false, false>(mapA, mapB, prm, stream);
 }
 
 template <int MODE, int D>
