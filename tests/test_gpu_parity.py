@@ -929,6 +929,54 @@ np.savez(sys.argv[1], **out)
         assert np.array_equal(a[k], b[k], equal_nan=True), k
 
 
+def test_launch_and_store_variants_agree(dm, tmp_path):
+    """Round 2's second session changed HOW several stages launch, stage and store -- never what they compute: the pooled
+    epilogue's pair flush (image_size 64) and 32-float staging rows (128), the two-copy upper aggregation, the
+    persistent first aggregation of small maps, both images' descriptors in one launch (and the 8-lane window sums by
+    shuffles), programmatic dependent launch.  Each has a switch back to the form it replaced (INTEGRATION.md section 2);
+    the planes of four scenes -- tiles of 16, 32, 64 and 128 -- must agree bit for bit between the product, all switches
+    thrown, and the attribute on every launch of the chain.  (The switches are read once per process.)"""
+    import os
+    import subprocess
+    import sys
+    code = r'''
+import sys, numpy as np
+sys.path.insert(0, %r)
+import deepmatching_stereo_matching_b200 as dm
+from deepmatching_stereo_matching_b200.synth import stereo_pair
+out = {}
+for k, (shape, size, stride, ws) in enumerate([((150, 150), (16, 16), (14, 14), 5), ((260, 300), (32, 32), (32, 32), 5),
+                                                ((340, 400), (64, 64), (60, 60), 15), ((400, 400), (128, 128), (124, 124), 15)]):
+    i1, i2 = stereo_pair(shape, seed=70 + k, mode='sine', amp=size[0] // 8)
+    s = dm.ImageCutSolver(i1, i2, image_size=list(size), stride=list(stride), window_size=ws,
+                          degree_map_mode=['elevation', 'elevation2'], sub_pix=True)
+    s.log_flg = False; s.fused = 1; s.devices = [0]
+    d, sc = s()
+    assert s.info.used_fused == 1
+    out['d%%d' %% k] = d; out['s%%d' %% k] = sc
+np.savez(sys.argv[1], **out)
+''' % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))),)
+    switches = ['DM_CORR_NO_PAIR_FLUSH', 'DM_CORR_NO_WIDE', 'DM_AGG_NO_MERGE', 'DM_FIRST_CTA', 'DM_DESC_SPLIT', 'DM_PDL']
+    res = []
+    for name, env in (('product', {}), ('replaced', {'DM_CORR_NO_PAIR_FLUSH': '1', 'DM_CORR_NO_WIDE': '1', 'DM_AGG_NO_MERGE': '1',
+                                                     'DM_FIRST_CTA': '1', 'DM_DESC_SPLIT': '1', 'DM_PDL': '0'}),
+                      ('pdl_everywhere', {'DM_PDL': '31'})):
+        path = str(tmp_path / (name + '.npz'))
+        e = dict(os.environ)
+        for k in switches:
+            e.pop(k, None)
+        e.update(env)
+        r = subprocess.run([sys.executable, '-c', code, path], env=e, capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stderr[-2000:]
+        res.append(np.load(path))
+    a = res[0]
+    assert len(a.files) == 8
+    for other in res[1:]:
+        assert sorted(a.files) == sorted(other.files)
+        for k in a.files:
+            assert np.array_equal(a[k], other[k], equal_nan=True), k
+
+
 def test_gauss_seidel_loops_bit_exact(dm):
     """The reference's sequential in-place smoothing loops (its `if 0:` branch, optimize_looper.py:55-74) through the
     `misc.*` import paths: misc/optimize_loop.py::optimize_loop and misc/opt_loop.py::optimize_loop_bilateral_*
