@@ -109,7 +109,8 @@ enum { MODE_RAW = 0, MODE_POOL = 1, MODE_NULL = 2 };   // MODE_NULL: drain TMEM 
 // only HALF of every B tile from its own shared memory and streams only half of B from L2.
 template <int MODE, int D, bool NORMED, bool PAIR, bool WIDE>      // D = positions per map row (T1); only used by MODE_POOL
 __global__ void __launch_bounds__(THREADS, 1)
-dm_correlation_umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const Params prm) {
+dm_correlation_umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
+                           const __grid_constant__ CUtensorMap mapO, const Params prm) {
     extern __shared__ uint8_t smem_raw[];
     // keep shared-space provenance: offset the array instead of round-tripping through integers
     uint8_t* smem = smem_raw + ((1024u - (umma::smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -288,6 +289,9 @@ dm_correlation_umma_kernel(const __grid_constant__ CUtensorMap mapA, const __gri
         // row's 32 -- bit-identical, but no faster there: 3.865 vs 3.875 ms on 64 x 512^2, ws 5; left on the per-warp flush.)
         constexpr bool PF_SHAPE = (MODE == MODE_POOL && D == 64);
         const bool pf = PF_SHAPE && prm.pair_flush != 0;
+        // pair_flush == 2 (DM_CORR_TMA_STORE, measurement): the staged region leaves as ONE 2-D bulk tensor store
+        // (the XOR-by-row layout is the tensor map's 128-byte swizzle) instead of 8 LDS.128 + 8 STG.128 per lane
+        const bool pf_tma = PF_SHAPE && prm.pair_flush == 2;
         float* regionX = smemStg + (size_t)quarter * (2 * 32 * STG_STRIDE);
         float* regionY = smemStg + (size_t)(quarter + 4) * (2 * 32 * STG_STRIDE);
         float4* xs_mine = reinterpret_cast<float4*>(regionX + lane * 32);
@@ -349,6 +353,16 @@ dm_correlation_umma_kernel(const __grid_constant__ CUtensorMap mapA, const __gri
             };
             // pair flush: this warp writes the 32 rows x 32 floats of ITS region (ch 0: half A, ch 1: half B)
             auto flush_pair = [&](size_t col) {
+                if (PF_SHAPE && pf_tma) {
+                    umma::fence_proxy_async();                                        // this thread's staging writes -> async proxy
+                    asm volatile("bar.sync %0, 64;" ::"r"(1 + quarter) : "memory");  // both column halves are staged and fenced
+                    if (lane == 0) {
+                        umma::tma_store_2d(&mapO, ch ? regionY : regionX, (int)col, (int)(wrow + (ch ? BM : 0)));
+                        umma::bulk_commit();
+                    }
+                    __syncwarp();
+                    return;             // the regions are released at the next N-tile's first staging write (below)
+                }
                 asm volatile("bar.sync %0, 64;" ::"r"(1 + quarter) : "memory");      // both column halves are staged
                 const uint32_t sa = umma::smem_u32(ch ? regionY : regionX);
                 float* wout = ch ? woutB : woutA;
@@ -408,6 +422,11 @@ dm_correlation_umma_kernel(const __grid_constant__ CUtensorMap mapA, const __gri
                     constexpr int dummy = 0; (void)dummy;
                     const int xo = (s * SW) % DH;           // first column of the step inside this thread's row half
                     const int r = (s * SW) / DH;            // map row inside the N-tile
+                    if (PF_SHAPE && s == NSTEP / 2 && pf_tma) {
+                        // the previous N-tile's tensor store has read this region (half an N-tile ago at least)
+                        if (lane == 0) umma::bulk_wait_read0();
+                        asm volatile("bar.sync %0, 64;" ::"r"(1 + quarter) : "memory");
+                    }
                     umma::tmem_wait_ld();                   // step s (and its halo) is in registers
                     // halo of THIS step must be consumed before the next step's halo load overwrites it
                     float zhA = -CUDART_INF_F, zhB = -CUDART_INF_F;
@@ -532,6 +551,7 @@ dm_correlation_umma_kernel(const __grid_constant__ CUtensorMap mapA, const __gri
                 { const float v = (NORMED && flatB) ? 1.0f : rmaxB; prm.rowmax[4 * prowB + 2 * ch] = v; prm.rowmax[4 * prowB + 2 * ch + 1] = v; }
             }
             if (MODE == MODE_NULL && rmaxA == 12345.678f) prm.raw[prowA] = rmaxA;     // keep the loads alive
+            if (PF_SHAPE && pf_tma && lane == 0) umma::bulk_wait0();                    // the unit's tensor stores are performed
         }
 
     }
@@ -559,8 +579,22 @@ dm_encode_tiled_fn get_encode_fn() {
 std::atomic<int> g_pair_mode{-1};       // -1: CTA pairs whenever the shape allows, 0: never, 1: same as -1 (dm_correlation_set_pair_mode)
 
 template <int MODE, int D, bool NORMED, bool PAIR, bool WIDE>
-int launch3(const CUtensorMap& mapA, const CUtensorMap& mapB, const Params& prm, cudaStream_t stream) {
+int launch3(const CUtensorMap& mapA, const CUtensorMap& mapB, const Params& prm_in, cudaStream_t stream) {
     constexpr size_t SMEM_BYTES = Layout<WIDE, PAIR>::SMEM;
+    Params prm = prm_in;
+    CUtensorMap mapO = mapA;            // placeholder unless the pooled map leaves by tensor stores
+    if (MODE == MODE_POOL && D == 64 && prm.pair_flush == 2) {
+        dm_encode_tiled_fn enc = get_encode_fn();
+        DM_REQUIRE(enc != nullptr, DM_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+        const uint64_t rows = (uint64_t)prm.n_items * (HALVES * BM);
+        cuuint64_t gdim[2] = {(cuuint64_t)(prm.P / 4), rows};
+        cuuint64_t gstride[1] = {(cuuint64_t)prm.P};                 // P / 4 floats per patch row
+        cuuint32_t box[2] = {32, 32};
+        cuuint32_t estr[2] = {1, 1};
+        CUresult r = enc(&mapO, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, prm.pooled, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                         CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        DM_REQUIRE(r == CUDA_SUCCESS, DM_ERR_CUDA, "cuTensorMapEncodeTiled (pooled map) failed with %d", (int)r);
+    }
     // per-device state: cudaFuncSetAttribute and the cluster occupancy belong to the device, and one
     // process may drive several devices from several threads (dm_multi_*).  -1 = not configured yet;
     // two threads racing on the same device compute the same values.
@@ -589,7 +623,7 @@ int launch3(const CUtensorMap& mapA, const CUtensorMap& mapB, const Params& prm,
     }
     if (!PAIR) {
         const int grid = prm.n_items < sms ? prm.n_items : sms;
-        DM_CUDA_CHECK(dm_launch_dep(DM_PDL_CORR, kern, dim3((unsigned)grid), dim3(THREADS), SMEM_BYTES, stream, mapA, mapB, prm));
+        DM_CUDA_CHECK(dm_launch_dep(DM_PDL_CORR, kern, dim3((unsigned)grid), dim3(THREADS), SMEM_BYTES, stream, mapA, mapB, mapO, prm));
         DM_LAUNCH_CHECK();
         return DM_OK;
     }
@@ -608,7 +642,7 @@ int launch3(const CUtensorMap& mapA, const CUtensorMap& mapB, const Params& prm,
     attr[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.gridDim = dim3(2 * pairs); cfg.blockDim = dim3(THREADS); cfg.dynamicSmemBytes = SMEM_BYTES; cfg.stream = stream;
     cfg.attrs = attr; cfg.numAttrs = dm_pdl_enabled(DM_PDL_CORR) ? 2 : 1;
-    DM_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, mapA, mapB, prm));
+    DM_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, mapA, mapB, mapO, prm));
     DM_LAUNCH_CHECK();
     return DM_OK;
 }
@@ -704,7 +738,8 @@ int dm_correlation_umma_pool(const void* desc1, const float* stat1, const void* 
     if (rc != DM_OK) return rc;
     prm.pooled = pooled; prm.rowmin = rowmin; prm.rowmax = rowmax;
     static const bool no_pair_flush = getenv("DM_CORR_NO_PAIR_FLUSH") != nullptr;       // measurement aid: every warp flushes its own half rows
-    prm.pair_flush = no_pair_flush ? 0 : 1;
+    static const bool tma_store = getenv("DM_CORR_TMA_STORE") != nullptr;               // measurement: the pair regions leave by 2-D tensor stores
+    prm.pair_flush = no_pair_flush ? 0 : (tma_store ? 2 : 1);
     const bool normed = method == DM_TM_CCOEFF_NORMED;
     if (t1 == 128) return launch<MODE_POOL, 128>(mapA, mapB, mapBp, prm, normed, stream);
     if (t1 == 64) return launch<MODE_POOL, 64>(mapA, mapB, mapBp, prm, normed, stream);
