@@ -99,7 +99,7 @@ struct Params {
     float* raw;                 // MODE_RAW : [n][P][P]
     float* pooled;              // MODE_POOL: [n][P][P/4]
     float* rowmin; float* rowmax;   // MODE_POOL: [n][P][4] partial min / max: each column half writes its value twice
-    int pair_flush;                 // MODE_POOL, D == 64: the two column halves of a patch row leave as one 128-byte line (below)
+    int pair_flush;                 // MODE_POOL: 0 per-warp flush, 1 pair flush (D == 64 / 32), 2 + tensor stores (also D == 128): the two column halves of a patch row leave as one 128-byte line (below)
 };
 
 enum { MODE_RAW = 0, MODE_POOL = 1, MODE_NULL = 2 };   // MODE_NULL: drain TMEM only (measurement aid)
@@ -279,19 +279,22 @@ dm_correlation_umma_kernel(const __grid_constant__ CUtensorMap mapA, const __gri
         const int wsw = (lane >> 1) & 3;                // XOR swizzle of this lane's own staging row
         float4* stgA_mine = reinterpret_cast<float4*>(stgA + lane * STG_STRIDE);
         float4* stgB_mine = reinterpret_cast<float4*>(stgB + lane * STG_STRIDE);
-        // Pair flush (MODE_POOL, D == 64).  The warps e and e + 4 own the two column halves of the same 32 + 32 patch
+        // Pair flush (MODE_POOL, D == 64 and 32).  The warps e and e + 4 own the two column halves of the same 32 + 32 patch
         // rows; flushed separately, every store instruction writes 8 rows x 64 B -- half a line per row, 8 L1
         // wavefronts for 512 bytes.  Here both warps stage into two SHARED regions instead (rows of 32 floats, the
         // 16-byte slots XOR-swizzled by row & 7: conflict-free both ways) -- the first warp's region collects
         // accumulator half A, the second warp's half B --, meet at a named barrier, and each flushes ONE region as
         // whole 128-byte lines: 4 rows x 128 B per store instruction, half the global-store wavefronts.
-        // (Measured at D == 32 as well -- two pooled rows of 16 per N-tile, a thread contributing 8 + 8 floats of the
-        // row's 32 -- bit-identical, but no faster there: 3.865 vs 3.875 ms on 64 x 512^2, ws 5; left on the per-warp flush.)
-        constexpr bool PF_SHAPE = (MODE == MODE_POOL && D == 64);
+        // At D == 32 an N-tile holds two pooled rows of 16: the same 32 consecutive floats per patch row, a thread
+        // contributing 8 + 8 of them (with LDS + STG flushes that was no faster than the per-warp flush, 3.865 vs 3.875 ms
+        // on 64 x 512^2 at ws 5; it pays once the region leaves by a tensor store).
+        constexpr bool PF_SHAPE = (MODE == MODE_POOL && (D == 64 || D == 32));
         const bool pf = PF_SHAPE && prm.pair_flush != 0;
-        // pair_flush == 2 (DM_CORR_TMA_STORE, measurement): the staged region leaves as ONE 2-D bulk tensor store
-        // (the XOR-by-row layout is the tensor map's 128-byte swizzle) instead of 8 LDS.128 + 8 STG.128 per lane
+        // pair_flush == 2 (the default): a staged region of 32 rows x 128 B leaves as ONE 2-D bulk tensor store -- the
+        // XOR-by-row layout IS the tensor map's 128-byte swizzle -- instead of 8 LDS.128 + 8 STG.128 per lane; the
+        // region is handed back (cp.async.bulk.wait_group.read) right before its next staging write.
         const bool pf_tma = PF_SHAPE && prm.pair_flush == 2;
+        const bool wide_tma = WIDE && prm.pair_flush == 2;
         float* regionX = smemStg + (size_t)quarter * (2 * 32 * STG_STRIDE);
         float* regionY = smemStg + (size_t)(quarter + 4) * (2 * 32 * STG_STRIDE);
         float4* xs_mine = reinterpret_cast<float4*>(regionX + lane * 32);
@@ -422,7 +425,11 @@ dm_correlation_umma_kernel(const __grid_constant__ CUtensorMap mapA, const __gri
                     constexpr int dummy = 0; (void)dummy;
                     const int xo = (s * SW) % DH;           // first column of the step inside this thread's row half
                     const int r = (s * SW) / DH;            // map row inside the N-tile
-                    if (PF_SHAPE && s == NSTEP / 2 && pf_tma) {
+                    if (WIDE && s == 0 && wide_tma && (j & 1)) {
+                        if (lane == 0) umma::bulk_wait_read0();     // the previous pooled row's stores have read this warp's regions
+                        __syncwarp();
+                    }
+                    if (PF_SHAPE && s == DH / SW && pf_tma) {       // first step of the N-tile's first odd map row
                         // the previous N-tile's tensor store has read this region (half an N-tile ago at least)
                         if (lane == 0) umma::bulk_wait_read0();
                         asm volatile("bar.sync %0, 64;" ::"r"(1 + quarter) : "memory");
@@ -504,8 +511,11 @@ dm_correlation_umma_kernel(const __grid_constant__ CUtensorMap mapA, const __gri
                                 else if ((ol & 3) == 2) { obA.z = oA; obB.z = oB; } else { obA.w = oA; obB.w = oB; }
                                 if ((ol & 3) == 3) {
                                     if (PF_SHAPE && pf) {
-                                        // 16-byte slot inside the row's 32 floats: this column half's 16 floats of the pooled row
-                                        const int slot = (ch * 4 + ((ol & 15) >> 2)) ^ (lane & 7);
+                                        // 16-byte slot inside the row's 32 floats: D == 64: one pooled row, this half's 16 floats;
+                                        // D == 32: two pooled rows of 16, this half's 8 floats of each
+                                        const int k4 = (ol & 15) >> 2;
+                                        const int lslot = (D == 64) ? ch * 4 + k4 : (k4 >> 1) * 4 + ch * 2 + (k4 & 1);
+                                        const int slot = lslot ^ (lane & 7);
                                         xs_mine[slot] = obA; ys_mine[slot] = obB;
                                     } else if (WIDE) {
                                         wideA_mine[(ol >> 2) ^ (lane & 7)] = obA; wideB_mine[(ol >> 2) ^ (lane & 7)] = obB;
@@ -514,8 +524,19 @@ dm_correlation_umma_kernel(const __grid_constant__ CUtensorMap mapA, const __gri
                                 if (WIDE) {
                                     if (ol == 31) {         // the thread's 32 pooled floats of this pooled row: one line per patch row
                                         const size_t col = (size_t)(j >> 1) * DH + (size_t)ch * HWQ;
-                                        flush32(stgA, woutA, col);
-                                        flush32(stgB, woutB, col);
+                                        if (wide_tma) {
+                                            umma::fence_proxy_async();
+                                            __syncwarp();
+                                            if (lane == 0) {
+                                                umma::tma_store_2d(&mapO, stgA, (int)col, (int)wrow);
+                                                umma::tma_store_2d(&mapO, stgB, (int)col, (int)(wrow + BM));
+                                                umma::bulk_commit();
+                                            }
+                                            __syncwarp();
+                                        } else {
+                                            flush32(stgA, woutA, col);
+                                            flush32(stgB, woutB, col);
+                                        }
                                     }
                                 } else if ((ol & 15) == 15) {
                                     if (PF_SHAPE && pf) {
@@ -551,7 +572,7 @@ dm_correlation_umma_kernel(const __grid_constant__ CUtensorMap mapA, const __gri
                 { const float v = (NORMED && flatB) ? 1.0f : rmaxB; prm.rowmax[4 * prowB + 2 * ch] = v; prm.rowmax[4 * prowB + 2 * ch + 1] = v; }
             }
             if (MODE == MODE_NULL && rmaxA == 12345.678f) prm.raw[prowA] = rmaxA;     // keep the loads alive
-            if (PF_SHAPE && pf_tma && lane == 0) umma::bulk_wait0();                    // the unit's tensor stores are performed
+            if ((pf_tma || wide_tma) && lane == 0) umma::bulk_wait0();                  // the unit's tensor stores are performed
         }
 
     }
@@ -583,7 +604,7 @@ int launch3(const CUtensorMap& mapA, const CUtensorMap& mapB, const Params& prm_
     constexpr size_t SMEM_BYTES = Layout<WIDE, PAIR>::SMEM;
     Params prm = prm_in;
     CUtensorMap mapO = mapA;            // placeholder unless the pooled map leaves by tensor stores
-    if (MODE == MODE_POOL && D == 64 && prm.pair_flush == 2) {
+    if (MODE == MODE_POOL && (D == 64 || D == 32 || WIDE) && prm.pair_flush == 2) {
         dm_encode_tiled_fn enc = get_encode_fn();
         DM_REQUIRE(enc != nullptr, DM_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
         const uint64_t rows = (uint64_t)prm.n_items * (HALVES * BM);
@@ -738,8 +759,8 @@ int dm_correlation_umma_pool(const void* desc1, const float* stat1, const void* 
     if (rc != DM_OK) return rc;
     prm.pooled = pooled; prm.rowmin = rowmin; prm.rowmax = rowmax;
     static const bool no_pair_flush = getenv("DM_CORR_NO_PAIR_FLUSH") != nullptr;       // measurement aid: every warp flushes its own half rows
-    static const bool tma_store = getenv("DM_CORR_TMA_STORE") != nullptr;               // measurement: the pair regions leave by 2-D tensor stores
-    prm.pair_flush = no_pair_flush ? 0 : (tma_store ? 2 : 1);
+    static const bool no_tma_store = getenv("DM_CORR_NO_TMA_STORE") != nullptr;         // measurement aid: LDS.128 + STG.128 flushes of the staged regions
+    prm.pair_flush = no_pair_flush ? 0 : (no_tma_store ? 1 : 2);
     const bool normed = method == DM_TM_CCOEFF_NORMED;
     if (t1 == 128) return launch<MODE_POOL, 128>(mapA, mapB, mapBp, prm, normed, stream);
     if (t1 == 64) return launch<MODE_POOL, 64>(mapA, mapB, mapBp, prm, normed, stream);

@@ -932,7 +932,7 @@ np.savez(sys.argv[1], **out)
 def test_launch_and_store_variants_agree(dm, tmp_path):
     """Round 2's second session changed HOW several stages launch, stage and store -- never what they compute: the pooled
     epilogue's pair flush (image_size 64) and 32-float staging rows (128), the two-copy upper aggregation, the
-    persistent first aggregation of small maps, both images' descriptors in one launch (and the 8-lane window sums by
+    bulk tensor stores those regions leave by, the persistent first aggregation of small maps, both images' descriptors in one launch (and the 8-lane window sums by
     shuffles), programmatic dependent launch.  Each has a switch back to the form it replaced (INTEGRATION.md section 2);
     the planes of four scenes -- tiles of 16, 32, 64 and 128 -- must agree bit for bit between the product, all switches
     thrown, and the attribute on every launch of the chain.  (The switches are read once per process.)"""
@@ -956,11 +956,11 @@ for k, (shape, size, stride, ws) in enumerate([((150, 150), (16, 16), (14, 14), 
     out['d%%d' %% k] = d; out['s%%d' %% k] = sc
 np.savez(sys.argv[1], **out)
 ''' % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))),)
-    switches = ['DM_CORR_NO_PAIR_FLUSH', 'DM_CORR_NO_WIDE', 'DM_AGG_NO_MERGE', 'DM_FIRST_CTA', 'DM_DESC_SPLIT', 'DM_PDL']
+    switches = ['DM_CORR_NO_PAIR_FLUSH', 'DM_CORR_NO_WIDE', 'DM_CORR_NO_TMA_STORE', 'DM_AGG_NO_MERGE', 'DM_FIRST_CTA', 'DM_DESC_SPLIT', 'DM_PDL']
     res = []
     for name, env in (('product', {}), ('replaced', {'DM_CORR_NO_PAIR_FLUSH': '1', 'DM_CORR_NO_WIDE': '1', 'DM_AGG_NO_MERGE': '1',
                                                      'DM_FIRST_CTA': '1', 'DM_DESC_SPLIT': '1', 'DM_PDL': '0'}),
-                      ('pdl_everywhere', {'DM_PDL': '31'})):
+                      ('flush_by_loads_and_stores', {'DM_CORR_NO_TMA_STORE': '1'}), ('pdl_everywhere', {'DM_PDL': '31'})):
         path = str(tmp_path / (name + '.npz'))
         e = dict(os.environ)
         for k in switches:
