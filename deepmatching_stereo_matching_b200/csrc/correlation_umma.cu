@@ -31,9 +31,13 @@
 //                              dependency chains interleave.  The one halo column at the
 //                              split comes from a 1-column TMEM load.  Software pipelined
 //                              in steps of 8 columns (loads of step s+1 in flight during
-//                              step s), FFMA2/FMUL2 packed math, 3-input min/max.  Results
-//                              leave through a per-warp shared-memory transpose so that
-//                              every store instruction writes 8 rows x 64 B.
+//                              step s), FFMA2/FMUL2 packed math, 3-input min/max.  Pooled
+//                              results are staged in shared memory as regions of 32 rows x
+//                              128 B (the layout of a 128-byte-swizzled TMA box; at D = 64 / 32
+//                              the two column halves of a row meet there, staged by the warp
+//                              pair e, e + 4) and leave by 2-D bulk tensor stores; the raw mode
+//                              and D = 16 keep a per-warp transpose + LDS/STG flush (8 rows x
+//                              64 B per store instruction).
 // B traffic: every CTA streams the tile's whole position matrix once per item; with
 // M = 256 rows per item that is 32 B/clk/SM from L2 at the MMA's full rate.
 #include <atomic>
