@@ -711,6 +711,15 @@ def run_ours(args):
         tp = os.path.join(REPO, 'profiles', 'ncu_traffic.json')       # dram bytes per launch from ncu --set full (C2 only)
         if os.path.exists(tp) and name == 'c2':
             traffic = json.load(open(tp)).get('fused' if fused else 'materialising', {})
+        elif os.path.exists(tp) and fused:
+            # other shapes: the correlation kernel's measured DRAM bytes per tile, scaled to the tiles of one launch
+            try:
+                per_tile = json.load(open(tp)).get('correlation_per_tile', {}).get('t%d_ws%d' % (T, WS))
+                n_launch = int(st_launch.get('correlation', 0))
+                if per_tile and n_launch > 0:
+                    traffic = {'dm_correlation_umma_kernel': float(per_tile) * tiles / n_launch}
+            except Exception:
+                traffic = {}
         kernels = {}
         for k, cands in work.items():
             if acc.get(k, 0) <= 0:
