@@ -219,6 +219,23 @@ def test_bench_arms_print_the_same_config():
     assert bench.config_dict('c4', 2)['tiles'] == 12544
 
 
+def test_ncu_traffic_table_is_what_bench_reads():
+    """bench.py takes roofline.traffic from profiles/ncu_traffic.json: per launch of the C2 step, and per tile of the
+    correlation kernel for the other shapes; a broken table would take the bench line with it."""
+    import json
+    import bench
+    t = json.load(open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'profiles', 'ncu_traffic.json')))
+    for k in ('dm_correlation_umma_kernel', 'dm_aggregate_first_kernel', 'dm_aggregate_kernel', 'dm_descriptor_row_kernel'):
+        assert t['fused'][k] > 0
+    for name, c in bench.CONFIGS.items():
+        v = t['correlation_per_tile'].get('t%d_ws%d' % (c['T'], c['ws']))
+        assert v is not None and v > 0, name
+        # never below the algorithmic bytes of a tile: the pooled map written once, both descriptor blocks read once
+        P = c['T'] ** 2
+        kpad = 64 if c['ws'] <= 7 else 256
+        assert v >= 4.0 * P * P / 4 + 2 * P * kpad * 2 * 0.5
+
+
 def test_oracle_margins_follow_the_matching():
     """matching_margins walks the same path as matching() and its margins are positive distances."""
     from deepmatching_stereo_matching_b200.synth import stereo_pair
